@@ -46,6 +46,59 @@ int mpu_mtgemm_wgrad(const void* X, long long rowsX, int Cx, int ldX, const void
                      int co_valid, int a_lbo, int a_sbo, int b_lbo, int b_sbo, int kstep_bytes,
                      void* stream);
 
+/* ---- 2D U-Net engine ------------------------------------------------------------------------------
+ * Replaces the Keras model built by mpunet/models/unet.py:26-216 (`UNet`, selected by name through
+ * mpunet/models/model_init.py:10-13) and what the callers do with it: `model.predict`
+ * (utils/fusion/fuse_and_predict.py:88), `model.fit` train step (train/trainer.py:246-257 with the
+ * loss/optimizer of bin/defaults/MultiPlanar/train_hparams.yaml:108,125-126).
+ * filters[l] = int(64 * 2^l * sqrt(complexity_factor)) for l = 0..depth (unet.py:91,120,195). */
+typedef struct MpuUNetConfig {
+  int H, W;            /* slice size ("dim"), divisible by 2^depth */
+  int n_channels;      /* input image channels */
+  int n_classes;       /* <= 16 */
+  int depth;           /* number of 2x2 max-pools (reference: 4) */
+  int filters[8];      /* encoder levels 0..depth-1, then bottom */
+  int max_batch;
+  int training;        /* 1: allocate gradient buffers */
+  float bn_eps;        /* Keras default 1e-3 */
+  float bn_momentum;   /* Keras default 0.99 */
+} MpuUNetConfig;
+
+typedef struct MpuLayerInfo {
+  char name[64];       /* Keras layer name (unet.py:119-179; head = "conv2d") */
+  int kind;            /* 0 = conv, 1 = batch-norm */
+  int ksize, cin, cout, k_phys, co_phys, c0_phys;
+  long long off0, off1; /* conv: kernel [k*k][co_phys][k_phys], bias [co_phys]; bn: gamma, beta (param buffer) */
+  long long off2, off3; /* bn: moving mean, moving variance (bn_state buffer) */
+} MpuLayerInfo;
+
+int mpu_unet_sizes(const MpuUNetConfig* cfg, long long* n_params, long long* n_bn_state,
+                   long long* workspace_bytes);
+/* params / grads / adam_m / adam_v: float[n_params]; bn_state: float[n_bn_state]; all caller-owned. */
+int mpu_unet_create(const MpuUNetConfig* cfg, float* params, float* grads, float* adam_m, float* adam_v,
+                    float* bn_state, void* workspace, long long workspace_bytes, void* stream,
+                    void** handle);
+int mpu_unet_destroy(void* handle);
+int mpu_unet_num_layers(void* handle);
+int mpu_unet_layer_info(void* handle, int idx, MpuLayerInfo* out);
+/* rebuild the bf16 GEMM operand copies after `params` changed (load_weights / external update) */
+int mpu_unet_sync_weights(void* handle, void* stream);
+/* the zero-bordered bf16 input tensor [B*(H+2)*(W+2)][cin_phys] the plane sampler writes into */
+int mpu_unet_input_buffer(void* handle, void** ptr, int* cin_phys, long long* rows);
+/* fp32 NHWC [B,H,W,n_channels] -> input buffer (what Keras' predict/fit receives) */
+int mpu_unet_pack_input(void* handle, const float* x_nhwc, int B, void* stream);
+/* model.predict_on_batch: softmax probabilities fp32 [B,H,W,n_classes]; bn_training=0 uses moving stats */
+int mpu_unet_forward(void* handle, int B, int bn_training, float* probs_out, void* stream);
+/* forward + sparse categorical cross-entropy (x sample weight) + backward; gradients land in `grads`.
+ * labels uint8 [B,H,W]; loss_sum (device double) receives the SUM of per-pixel weighted losses;
+ * grad_scale multiplies dlogits (1 = Keras' sum-of-unreduced-losses semantics). */
+int mpu_unet_train_step(void* handle, int B, const unsigned char* labels, const float* sample_w,
+                        float grad_scale, double* loss_sum, float* probs_opt, void* stream);
+/* Keras Adam step t (1-based) over the whole parameter buffer, then mpu_unet_sync_weights */
+int mpu_unet_adam(void* handle, float lr, float beta1, float beta2, float eps, int step,
+                  float grad_scale, void* stream);
+int mpu_unet_debug_buffer(void* handle, int level, int which, void** ptr, long long* rows, int* C);
+
 #ifdef __cplusplus
 }
 #endif

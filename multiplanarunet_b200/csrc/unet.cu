@@ -1,0 +1,803 @@
+// U-Net engine: owns the layer table, the activation/gradient workspace layout and the kernel schedule
+// for forward, train step (forward + sparse-CE + backward) and Adam.  Graph = mpunet/models/unet.py:
+// encoder (:114-134), bottom (:136-146), up path (:148-180), 1x1 softmax head (:211-214).
+//
+// Data layout: every activation is a zero-bordered NHWC bf16 matrix [B*(H+2)*(W+2)][C_phys]
+// (C_phys = channels rounded up to 8; padded channels stay exactly zero in forward and backward).
+// All convolutions run as multi-tap GEMMs on tcgen05 (mtgemm.cu); BN / pool / head / Adam are the
+// HBM-bound kernels of elementwise.cu.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/mpunet_b200.h"
+#include "common.h"
+#include "elementwise.cuh"
+#include "mtgemm.cuh"
+
+namespace mpu {
+
+typedef __nv_bfloat16 bf16;
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+struct ConvL {
+  std::string name;
+  int ksize;            // 3, 2 (upsample-conv) or 1 (head)
+  int cin, cout;        // logical (Keras) channels; cin counts both concat halves
+  int k_phys, co_phys;  // physical K (input channels incl. padding, both concat halves) and outputs
+  int c0_phys;          // physical channels of concat source 0 (== k_phys when single source)
+  int ntap_master;      // 9 / 4 / 1
+  int ntap_gemm;        // 9 / 9 pairs / 1
+  long long w_off, b_off;  // float offsets into the flat parameter buffer
+  bf16* wf = nullptr;   // forward operand [ntap_gemm][co_phys][k_phys]
+  bf16* wd = nullptr;   // dgrad operand   [ntap_gemm][k_phys][co_phys]
+};
+
+struct BnL {
+  std::string name;
+  int c, c_phys;
+  long long g_off, b_off;  // gamma / beta in the parameter buffer
+  long long m_off, v_off;  // moving mean / variance in the bn_state buffer
+  float *scale = nullptr, *shift = nullptr, *mean = nullptr, *rstd = nullptr;
+  double* sums = nullptr;  // [2][c_phys]
+};
+
+struct Level {
+  Geo g;
+  int C;  // physical channels at this level
+  // encoder / bottom
+  bf16 *a1 = nullptr, *a2 = nullptr, *b = nullptr, *pooled = nullptr;  // pooled: geometry of level+1
+  // up path (levels 0..depth-1)
+  bf16 *u = nullptr, *bn1 = nullptr, *c2 = nullptr, *c3 = nullptr, *bn2 = nullptr;
+  // gradients / scratch
+  bf16 *gout = nullptr;   // grad wrt this level's block output (bn2_l, or bottom BN for the last level)
+  bf16 *s1 = nullptr, *s2 = nullptr, *dcat = nullptr, *dzu = nullptr, *dpool = nullptr;
+};
+
+struct UNet {
+  MpuUNetConfig cfg;
+  int depth;
+  int cin_phys;
+  std::vector<ConvL> convs;  // enc l: [2l], [2l+1]; bottom: [2d], [2d+1]; up i: [2d+2+3i .. +2]; head last
+  std::vector<BnL> bns;      // enc l: [l]; bottom: [d]; up i: [d+1+2i] (BN1), [d+2+2i] (BN2)
+  std::vector<Level> lv;     // 0..depth
+  long long n_params = 0, n_bn_state = 0;
+  float *params = nullptr, *grads = nullptr, *adam_m = nullptr, *adam_v = nullptr, *bn_state = nullptr;
+  char* ws = nullptr;
+  long long ws_bytes = 0, ws_used = 0;
+  bf16* x_in = nullptr;      // [rows0][cin_phys]
+  float* dwc = nullptr;      // scratch for collapsed upsample-conv weight gradients
+  long long dwc_floats = 0;
+  bool training_buffers = false;
+  bool weights_synced = false;
+
+  ConvL& enc_conv(int l, int j) { return convs[2 * l + j]; }
+  ConvL& up_conv(int i, int j) { return convs[2 * (depth + 1) + 3 * i + j]; }
+  ConvL& head() { return convs.back(); }
+  BnL& enc_bn(int l) { return bns[l]; }
+  BnL& up_bn(int i, int j) { return bns[depth + 1 + 2 * i + j]; }
+};
+
+// ---- construction ---------------------------------------------------------------------------------
+static int build_tables(UNet& u) {
+  const MpuUNetConfig& c = u.cfg;
+  u.depth = c.depth;
+  if (c.depth < 1 || c.depth > 6) {
+    set_error("unet: depth %d not supported", c.depth);
+    return MPU_ERR_ARG;
+  }
+  if (c.H % (1 << c.depth) || c.W % (1 << c.depth)) {
+    set_error("unet: H=%d W=%d must be divisible by 2^depth", c.H, c.W);
+    return MPU_ERR_ARG;
+  }
+  u.cin_phys = round_up(c.n_channels, 8);
+  long long off = 0, soff = 0;
+  auto add_conv = [&](const std::string& name, int ks, int cin, int cout, int k_phys, int co_phys,
+                      int c0_phys) {
+    ConvL L;
+    L.name = name;
+    L.ksize = ks;
+    L.cin = cin;
+    L.cout = cout;
+    L.k_phys = k_phys;
+    L.co_phys = co_phys;
+    L.c0_phys = c0_phys;
+    L.ntap_master = ks * ks;
+    L.ntap_gemm = ks == 2 ? 9 : ks * ks;
+    L.w_off = off;
+    off += (long long)L.ntap_master * co_phys * k_phys;
+    L.b_off = off;
+    off += co_phys;
+    u.convs.push_back(L);
+  };
+  auto add_bn = [&](const std::string& name, int ch) {
+    BnL B;
+    B.name = name;
+    B.c = ch;
+    B.c_phys = round_up(ch, 8);
+    B.g_off = off;
+    off += B.c_phys;
+    B.b_off = off;
+    off += B.c_phys;
+    B.m_off = soff;
+    soff += B.c_phys;
+    B.v_off = soff;
+    soff += B.c_phys;
+    u.bns.push_back(B);
+  };
+  char nm[64];
+  int cin = c.n_channels, cin_p = u.cin_phys;
+  for (int l = 0; l <= c.depth; ++l) {
+    const int f = c.filters[l], fp = round_up(f, 8);
+    const char* pre = l < c.depth ? "encoder_L%d" : "bottom";
+    char base[48];
+    snprintf(base, sizeof(base), pre, l);
+    snprintf(nm, sizeof(nm), "%s_conv1", base);
+    add_conv(nm, 3, cin, f, cin_p, fp, cin_p);
+    snprintf(nm, sizeof(nm), "%s_conv2", base);
+    add_conv(nm, 3, f, f, fp, fp, fp);
+    cin = f;
+    cin_p = fp;
+  }
+  for (int l = 0; l <= c.depth; ++l) {
+    if (l < c.depth) snprintf(nm, sizeof(nm), "encoder_L%d_BN", l);
+    else snprintf(nm, sizeof(nm), "bottom_BN");
+    add_bn(nm, c.filters[l]);
+  }
+  for (int i = 0; i < c.depth; ++i) {
+    const int l = c.depth - 1 - i;
+    const int f = c.filters[l], fp = round_up(f, 8);
+    snprintf(nm, sizeof(nm), "upsample_L%d_conv1", i);
+    add_conv(nm, 2, cin, f, cin_p, fp, cin_p);
+    snprintf(nm, sizeof(nm), "upsample_L%d_conv2", i);
+    add_conv(nm, 3, 2 * f, f, 2 * fp, fp, fp);
+    snprintf(nm, sizeof(nm), "upsample_L%d_conv3", i);
+    add_conv(nm, 3, f, f, fp, fp, fp);
+    snprintf(nm, sizeof(nm), "upsample_L%d_BN1", i);
+    add_bn(nm, f);
+    snprintf(nm, sizeof(nm), "upsample_L%d_BN2", i);
+    add_bn(nm, f);
+    cin = f;
+    cin_p = fp;
+  }
+  add_conv("conv2d", 1, cin, c.n_classes, cin_p, c.n_classes, cin_p);
+  u.n_params = off;
+  u.n_bn_state = soff;
+  return MPU_OK;
+}
+
+template <typename T>
+static T* bump(UNet& u, long long count, bool dry) {
+  long long bytes = (count * (long long)sizeof(T) + 1023) / 1024 * 1024;
+  T* p = dry ? nullptr : reinterpret_cast<T*>(u.ws + u.ws_used);
+  u.ws_used += bytes;
+  return p;
+}
+
+static void layout_workspace(UNet& u, bool dry) {
+  const MpuUNetConfig& c = u.cfg;
+  u.ws_used = 0;
+  const int B = c.max_batch;
+  u.lv.assign(c.depth + 1, Level());
+  for (int l = 0; l <= c.depth; ++l) {
+    Level& L = u.lv[l];
+    L.g = Geo{B, c.H >> l, c.W >> l};
+    L.C = round_up(c.filters[l], 8);
+  }
+  u.x_in = bump<bf16>(u, u.lv[0].g.rows() * u.cin_phys, dry);
+  const bool tr = c.training != 0;
+  for (int l = 0; l <= c.depth; ++l) {
+    Level& L = u.lv[l];
+    const long long n = L.g.rows() * L.C;
+    L.a1 = bump<bf16>(u, n, dry);
+    L.a2 = bump<bf16>(u, n, dry);
+    L.b = bump<bf16>(u, n, dry);
+    if (l < c.depth) {
+      L.pooled = bump<bf16>(u, u.lv[l + 1].g.rows() * L.C, dry);
+      L.u = bump<bf16>(u, n, dry);
+      L.bn1 = bump<bf16>(u, n, dry);
+      L.c2 = bump<bf16>(u, n, dry);
+      L.c3 = bump<bf16>(u, n, dry);
+      L.bn2 = bump<bf16>(u, n, dry);
+    }
+    if (tr) {
+      L.gout = bump<bf16>(u, n, dry);
+      L.s1 = bump<bf16>(u, n, dry);
+      L.s2 = bump<bf16>(u, n, dry);
+      if (l < c.depth) {
+        L.dcat = bump<bf16>(u, 2 * n, dry);
+        L.dzu = bump<bf16>(u, 4 * u.lv[l + 1].g.rows() * L.C, dry);
+        L.dpool = bump<bf16>(u, u.lv[l + 1].g.rows() * L.C, dry);
+      }
+    }
+  }
+  long long dwc = 0;
+  for (ConvL& L : u.convs) {
+    const long long n = (long long)L.ntap_gemm * L.co_phys * L.k_phys;
+    if (L.ksize == 1) continue;  // head runs on CUDA cores from the fp32 master
+    L.wf = bump<bf16>(u, n, dry);
+    L.wd = bump<bf16>(u, n, dry);
+    if (L.ksize == 2 && n > dwc) dwc = n;
+  }
+  u.dwc_floats = dwc;
+  u.dwc = tr ? bump<float>(u, dwc, dry) : nullptr;
+  for (BnL& b : u.bns) {
+    b.scale = bump<float>(u, b.c_phys, dry);
+    b.shift = bump<float>(u, b.c_phys, dry);
+    b.mean = bump<float>(u, b.c_phys, dry);
+    b.rstd = bump<float>(u, b.c_phys, dry);
+    b.sums = bump<double>(u, 2 * b.c_phys, dry);
+  }
+}
+
+// ---- GEMM wrappers ----------------------------------------------------------------------------------
+static int pick_bn(int n_valid) {
+  if (n_valid <= 256) return round_up(n_valid, 16);
+  const int tiles = (n_valid + 255) / 256;
+  return round_up((n_valid + tiles - 1) / tiles, 16);
+}
+
+static void taps3x3(int Wp, int* off) {
+  for (int ky = 0; ky < 3; ++ky)
+    for (int kx = 0; kx < 3; ++kx) off[ky * 3 + kx] = (ky - 1) * Wp + (kx - 1);
+}
+
+// out[rows][n_phys] = act( sum_taps A[m+off] . W[tap]^T + bias ), same-resolution (3x3 or dgrad).
+static int gemm_same(const bf16* A0, int C0, int ldA0, const bf16* A1, int C1, int ldA1, const bf16* W,
+                     int ntap, int n_phys, int k_total, Geo g, bf16* out, int ldo, const float* bias,
+                     const bf16* mask, int ldm, int relu, cudaStream_t st) {
+  FwdParams p;
+  memset(&p, 0, sizeof(p));
+  const long long rows = g.rows();
+  MPU_TRY(make_tmap_2d(&p.tmA0, A0, rows, C0, ldA0, 64, 128));
+  p.chunks0 = (C0 + 63) / 64;
+  if (A1) {
+    MPU_TRY(make_tmap_2d(&p.tmA1, A1, rows, C1, ldA1, 64, 128));
+    p.chunks1 = (C1 + 63) / 64;
+    p.kofs1 = C0;
+  }
+  p.BN = pick_bn(n_phys);
+  MPU_TRY(make_tmap_2d(&p.tmB, W, (long long)ntap * n_phys, k_total, k_total, 64, p.BN));
+  p.ntaps = ntap;
+  if (ntap == 9) {
+    taps3x3(g.Wp(), p.tap_a_off);
+  } else {
+    p.tap_a_off[0] = 0;
+  }
+  for (int t = 0; t < ntap; ++t) p.tap_w[t] = t;
+  p.w_rows_per_tap = n_phys;
+  p.M_rows = (int)rows;
+  p.n_valid = n_phys;
+  p.map = RowMap{g.Hp(), g.Wp(), g.Hp(), g.Wp(), 1, 0, 0};
+  p.out = out;
+  p.ldo = ldo;
+  p.bias = bias;
+  p.mask = mask;
+  p.ldm = ldm;
+  p.relu = relu;
+  return launch_fwd(p, st);
+}
+
+// nearest-2x upsample + 2x2 SAME conv + bias + ReLU as four phase GEMMs on the low-res grid.
+static int gemm_upconv(const bf16* X, int Cx, Geo glo, const ConvL& L, const float* bias, Geo ghi,
+                       bf16* out, cudaStream_t st) {
+  for (int a = 0; a < 2; ++a)
+    for (int b = 0; b < 2; ++b) {
+      FwdParams p;
+      memset(&p, 0, sizeof(p));
+      MPU_TRY(make_tmap_2d(&p.tmA0, X, glo.rows(), Cx, Cx, 64, 128));
+      p.chunks0 = (Cx + 63) / 64;
+      p.BN = pick_bn(L.co_phys);
+      MPU_TRY(make_tmap_2d(&p.tmB, L.wf, 9ll * L.co_phys, L.k_phys, L.k_phys, 64, p.BN));
+      p.ntaps = 0;
+      for (int i = 0; i < 9; ++i) {
+        const UpPair pr = up_pair(i);
+        if (pr.a == a && pr.b == b) {
+          p.tap_a_off[p.ntaps] = pr.di * glo.Wp() + pr.dj;
+          p.tap_w[p.ntaps] = i;
+          ++p.ntaps;
+        }
+      }
+      p.w_rows_per_tap = L.co_phys;
+      p.M_rows = (int)glo.rows();
+      p.n_valid = L.co_phys;
+      p.map = RowMap{glo.Hp(), glo.Wp(), ghi.Hp(), ghi.Wp(), 2, a, b};
+      p.out = out;
+      p.ldo = L.co_phys;
+      p.bias = bias;
+      p.relu = 1;
+      MPU_TRY(launch_fwd(p, st));
+    }
+  return MPU_OK;
+}
+
+// dIn[m_lo] = sum over the 9 (phase, tap) pairs of dZ[phase][m_lo - off] . Wc[pair]  (dZ phase-major)
+static int gemm_upconv_dgrad(const bf16* dzu, const ConvL& L, Geo glo, bf16* out, cudaStream_t st) {
+  FwdParams p;
+  memset(&p, 0, sizeof(p));
+  const long long rows_lo = glo.rows();
+  MPU_TRY(make_tmap_2d(&p.tmA0, dzu, 4 * rows_lo, L.co_phys, L.co_phys, 64, 128));
+  p.chunks0 = (L.co_phys + 63) / 64;
+  p.BN = pick_bn(L.k_phys);
+  MPU_TRY(make_tmap_2d(&p.tmB, L.wd, 9ll * L.k_phys, L.co_phys, L.co_phys, 64, p.BN));
+  p.ntaps = 9;
+  for (int i = 0; i < 9; ++i) {
+    const UpPair pr = up_pair(i);
+    p.tap_a_off[i] = (int)((pr.a * 2 + pr.b) * rows_lo) - (pr.di * glo.Wp() + pr.dj);
+    p.tap_w[i] = i;
+  }
+  p.w_rows_per_tap = L.k_phys;
+  p.M_rows = (int)rows_lo;
+  p.n_valid = L.k_phys;
+  p.map = RowMap{glo.Hp(), glo.Wp(), glo.Hp(), glo.Wp(), 1, 0, 0};
+  p.out = out;
+  p.ldo = L.k_phys;
+  return launch_fwd(p, st);
+}
+
+// taps per wgrad CTA: bounded by TMEM (G*BN <= 512 columns) and by shared memory (>= 3 stages of
+// G x 16 KB of X tiles + the dY tile)
+static int wgrad_group(int BN) {
+  int G = 512 / BN;
+  return G > 3 ? 3 : G;
+}
+
+static int wgrad_common(WgradParams& p, int ci_valid, int co_valid, long long rows, cudaStream_t st) {
+  p.ci_valid = ci_valid;
+  p.co_valid = co_valid;
+  p.ci_tiles = (ci_valid + 127) / 128;
+  p.co_tiles = (co_valid + p.BN - 1) / p.BN;
+  p.kblocks = (int)((rows + 63) / 64);
+  const int base = p.ci_tiles * p.co_tiles * p.ngroups;
+  int splits = (2 * num_sms() + base - 1) / base;
+  if (splits < 1) splits = 1;
+  if (splits > p.kblocks) splits = p.kblocks;
+  p.kblocks_per_split = (p.kblocks + splits - 1) / splits;
+  p.splits = (p.kblocks + p.kblocks_per_split - 1) / p.kblocks_per_split;
+  p.a_lbo = 8192;
+  p.a_sbo = 1024;
+  p.b_lbo = 8192;
+  p.b_sbo = 1024;
+  p.kstep_bytes = 2048;
+  return launch_wgrad(p, st);
+}
+
+// dW[tap][co][col0 + ci] += sum_m X[m+off_tap][ci] * dZ[m][co]   (3x3 / 1-tap, same resolution)
+static int wgrad_same(const bf16* X, int Cx, int ldX, const bf16* dZ, int Cz, int ntap, Geo g,
+                      float* dW, int ldw, int co_phys, int col0, cudaStream_t st) {
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  const long long rows = g.rows();
+  MPU_TRY(make_tmap_2d(&p.tmX, X, rows, Cx, ldX, 64, 64));
+  MPU_TRY(make_tmap_2d(&p.tmDY, dZ, rows, Cz, Cz, 64, 64));
+  p.ntaps = ntap;
+  if (ntap == 9) taps3x3(g.Wp(), p.tap_x_off);
+  for (int t = 0; t < ntap; ++t) p.tap_w[t] = t;
+  p.BN = pick_bn(Cz);
+  const int G = wgrad_group(p.BN);
+  p.ngroups = 0;
+  for (int t = 0; t < ntap; t += G) {
+    p.groups[p.ngroups] = WgradGroup{t, (ntap - t) < G ? (ntap - t) : G, 0};
+    ++p.ngroups;
+  }
+  p.dW = dW;
+  p.ldw = ldw;
+  p.w_rows_per_tap = co_phys;
+  p.dw_col0 = col0;
+  return wgrad_common(p, Cx, Cz, rows, st);
+}
+
+// collapsed upsample-conv weight gradient: dWc[pair][co][ci] = sum_m X[m + off][ci] * dZ[phase][m][co]
+static int wgrad_upconv(const bf16* X, int Cx, const bf16* dzu, const ConvL& L, Geo glo, float* dwc,
+                        cudaStream_t st) {
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  const long long rows_lo = glo.rows();
+  MPU_TRY(make_tmap_2d(&p.tmX, X, rows_lo, Cx, Cx, 64, 64));
+  MPU_TRY(make_tmap_2d(&p.tmDY, dzu, 4 * rows_lo, L.co_phys, L.co_phys, 64, 64));
+  p.ntaps = 9;
+  p.BN = pick_bn(L.co_phys);
+  const int G = wgrad_group(p.BN);
+  p.ngroups = 0;
+  int i = 0;
+  while (i < 9) {
+    const UpPair pr = up_pair(i);
+    int n = 0;
+    while (i + n < 9 && n < G) {
+      const UpPair q = up_pair(i + n);
+      if (q.a != pr.a || q.b != pr.b) break;
+      ++n;
+    }
+    p.groups[p.ngroups] = WgradGroup{i, n, (int)((pr.a * 2 + pr.b) * rows_lo)};
+    ++p.ngroups;
+    i += n;
+  }
+  for (int t = 0; t < 9; ++t) {
+    const UpPair pr = up_pair(t);
+    p.tap_x_off[t] = pr.di * glo.Wp() + pr.dj;
+    p.tap_w[t] = t;
+  }
+  p.dW = dwc;
+  p.ldw = L.k_phys;
+  p.w_rows_per_tap = L.co_phys;
+  p.dw_col0 = 0;
+  return wgrad_common(p, Cx, L.co_phys, rows_lo, st);
+}
+
+// ---- schedule -------------------------------------------------------------------------------------
+static Geo geo_b(const UNet& u, int l, int B) {
+  Geo g = u.lv[l].g;
+  g.B = B;
+  return g;
+}
+
+static int bn_forward(UNet& u, BnL& bn, const bf16* y, Geo g, bf16* b, bf16* pooled, int training,
+                      cudaStream_t st) {
+  const float* P = u.params;
+  if (training) MPU_TRY(launch_channel_stats(y, g.rows(), bn.c_phys, bn.c_phys, bn.sums, st));
+  MPU_TRY(launch_bn_finalize(bn.sums, (double)g.pixels(), P + bn.g_off, P + bn.b_off,
+                             u.bn_state + bn.m_off, u.bn_state + bn.v_off, u.cfg.bn_eps,
+                             u.cfg.bn_momentum, training, bn.c_phys, bn.scale, bn.shift, bn.mean, bn.rstd,
+                             st));
+  return launch_bn_apply(y, bn.scale, bn.shift, b, pooled, g, bn.c_phys, st);
+}
+
+static int sync_weights(UNet& u, cudaStream_t st) {
+  for (ConvL& L : u.convs) {
+    if (L.ksize == 1) continue;
+    if (L.ksize == 3)
+      MPU_TRY(launch_prep_conv(u.params + L.w_off, L.wf, L.wd, 9, L.co_phys, L.k_phys, 1, st));
+    else
+      MPU_TRY(launch_prep_upconv(u.params + L.w_off, L.wf, L.wd, L.co_phys, L.k_phys, st));
+  }
+  u.weights_synced = true;
+  return MPU_OK;
+}
+
+static int forward(UNet& u, int B, int training, cudaStream_t st) {
+  if (!u.weights_synced) MPU_TRY(sync_weights(u, st));
+  const int d = u.depth;
+  const float* P = u.params;
+  const bf16* x = u.x_in;
+  int cx = u.cin_phys;
+  for (int l = 0; l <= d; ++l) {
+    Level& L = u.lv[l];
+    const Geo g = geo_b(u, l, B);
+    ConvL& c1 = u.enc_conv(l, 0);
+    ConvL& c2 = u.enc_conv(l, 1);
+    MPU_TRY(gemm_same(x, cx, cx, nullptr, 0, 0, c1.wf, 9, c1.co_phys, c1.k_phys, g, L.a1, L.C,
+                      P + c1.b_off, nullptr, 0, 1, st));
+    MPU_TRY(gemm_same(L.a1, L.C, L.C, nullptr, 0, 0, c2.wf, 9, c2.co_phys, c2.k_phys, g, L.a2, L.C,
+                      P + c2.b_off, nullptr, 0, 1, st));
+    MPU_TRY(bn_forward(u, u.enc_bn(l), L.a2, g, L.b, l < d ? L.pooled : nullptr, training, st));
+    x = l < d ? L.pooled : L.b;
+    cx = L.C;
+  }
+  for (int i = 0; i < d; ++i) {
+    const int l = d - 1 - i;
+    Level& L = u.lv[l];
+    const Geo g = geo_b(u, l, B), glo = geo_b(u, l + 1, B);
+    ConvL& c1 = u.up_conv(i, 0);
+    ConvL& c2 = u.up_conv(i, 1);
+    ConvL& c3 = u.up_conv(i, 2);
+    MPU_TRY(gemm_upconv(x, cx, glo, c1, P + c1.b_off, g, L.u, st));
+    MPU_TRY(bn_forward(u, u.up_bn(i, 0), L.u, g, L.bn1, nullptr, training, st));
+    MPU_TRY(gemm_same(L.b, L.C, L.C, L.bn1, L.C, L.C, c2.wf, 9, c2.co_phys, c2.k_phys, g, L.c2, L.C,
+                      P + c2.b_off, nullptr, 0, 1, st));
+    MPU_TRY(gemm_same(L.c2, L.C, L.C, nullptr, 0, 0, c3.wf, 9, c3.co_phys, c3.k_phys, g, L.c3, L.C,
+                      P + c3.b_off, nullptr, 0, 1, st));
+    MPU_TRY(bn_forward(u, u.up_bn(i, 1), L.c3, g, L.bn2, nullptr, training, st));
+    x = L.bn2;
+    cx = L.C;
+  }
+  return MPU_OK;
+}
+
+static int bn_backward(UNet& u, BnL& bn, const bf16* y, const bf16* gA, int ldA, const bf16* gP, Geo g,
+                       bf16* dz, int phase_major, float* dbias, cudaStream_t st) {
+  BnBwdArgs a;
+  a.y = y;
+  a.gA = gA;
+  a.ldA = ldA;
+  a.gP = gP;
+  a.scale = bn.scale;
+  a.shift = bn.shift;
+  a.mean = bn.mean;
+  a.rstd = bn.rstd;
+  a.gamma = u.params + bn.g_off;
+  a.g = g;
+  a.C = bn.c_phys;
+  MPU_TRY(launch_bn_bwd_reduce(a, bn.sums, st));
+  return launch_bn_bwd_apply(a, bn.sums, dz, phase_major, u.grads + bn.g_off, u.grads + bn.b_off, dbias,
+                             st);
+}
+
+// conv-ReLU-conv-ReLU-BN block backward given dz2 (gradient at the second conv's pre-activation):
+// wgrad conv2, dgrad conv2 (masked by a1 -> dz1), bias1, wgrad conv1, optional dgrad conv1.
+static int block_tail_backward(UNet& u, ConvL& c1, ConvL& c2, const bf16* xin0, int cx0, const bf16* xin1,
+                               int cx1, const bf16* a1, const bf16* dz2, bf16* dz1, bf16* dxin, int C,
+                               Geo g, cudaStream_t st) {
+  float* G = u.grads;
+  MPU_TRY(wgrad_same(a1, C, C, dz2, C, 9, g, G + c2.w_off, c2.k_phys, c2.co_phys, 0, st));
+  MPU_TRY(gemm_same(dz2, C, C, nullptr, 0, 0, c2.wd, 9, c2.k_phys, c2.co_phys, g, dz1, C, nullptr, a1,
+                    C, 0, st));
+  MPU_TRY(launch_colsum(dz1, g.rows(), C, C, G + c1.b_off, st));
+  MPU_TRY(wgrad_same(xin0, cx0, cx0, dz1, C, 9, g, G + c1.w_off, c1.k_phys, c1.co_phys, 0, st));
+  if (xin1)
+    MPU_TRY(wgrad_same(xin1, cx1, cx1, dz1, C, 9, g, G + c1.w_off, c1.k_phys, c1.co_phys, cx0, st));
+  if (dxin)
+    MPU_TRY(gemm_same(dz1, C, C, nullptr, 0, 0, c1.wd, 9, c1.k_phys, c1.co_phys, g, dxin, c1.k_phys,
+                      nullptr, nullptr, 0, 0, st));
+  return MPU_OK;
+}
+
+static int backward(UNet& u, int B, cudaStream_t st) {
+  const int d = u.depth;
+  float* G = u.grads;
+  // up path, from the output resolution down
+  for (int l = 0; l < d; ++l) {
+    const int i = d - 1 - l;
+    Level& L = u.lv[l];
+    Level& Lo = u.lv[l + 1];
+    const Geo g = geo_b(u, l, B), glo = geo_b(u, l + 1, B);
+    ConvL& c1 = u.up_conv(i, 0);
+    ConvL& c2 = u.up_conv(i, 1);
+    ConvL& c3 = u.up_conv(i, 2);
+    // BN2 backward: gradient wrt bn2_l is in L.gout
+    MPU_TRY(bn_backward(u, u.up_bn(i, 1), L.c3, L.gout, L.C, nullptr, g, L.s1, 0, G + c3.b_off, st));
+    // conv3 / conv2 ([skip | bn1] concat input) backward; dgrad of conv2 -> dcat [rows][2C]
+    MPU_TRY(block_tail_backward(u, c2, c3, L.b, L.C, L.bn1, L.C, L.c2, L.s1, L.s2, L.dcat, L.C, g, st));
+    // BN1 backward on the second half of dcat -> dz of the upsample-conv, phase-major
+    MPU_TRY(bn_backward(u, u.up_bn(i, 0), L.u, L.dcat + L.C, 2 * L.C, nullptr, g, L.dzu, 1,
+                        G + c1.b_off, st));
+    // upsample-conv backward
+    const bf16* xin = (l + 1 == d) ? Lo.b : Lo.bn2;
+    MPU_CUDA(cudaMemsetAsync(u.dwc, 0, sizeof(float) * 9 * c1.co_phys * c1.k_phys, st));
+    MPU_TRY(wgrad_upconv(xin, Lo.C, L.dzu, c1, glo, u.dwc, st));
+    MPU_TRY(launch_fold_upconv_grad(u.dwc, G + c1.w_off, c1.co_phys, c1.k_phys, st));
+    MPU_TRY(gemm_upconv_dgrad(L.dzu, c1, glo, Lo.gout, st));
+  }
+  // bottom + encoder
+  for (int l = d; l >= 0; --l) {
+    Level& L = u.lv[l];
+    const Geo g = geo_b(u, l, B);
+    ConvL& c1 = u.enc_conv(l, 0);
+    ConvL& c2 = u.enc_conv(l, 1);
+    if (l == d) {
+      MPU_TRY(bn_backward(u, u.enc_bn(l), L.a2, L.gout, L.C, nullptr, g, L.s1, 0, G + c2.b_off, st));
+    } else {
+      // skip gradient = first half of dcat_l; pooled gradient = dpool_l (from level l+1's conv1 dgrad)
+      MPU_TRY(bn_backward(u, u.enc_bn(l), L.a2, L.dcat, 2 * L.C, L.dpool, g, L.s1, 0, G + c2.b_off, st));
+    }
+    const bf16* xin = l == 0 ? u.x_in : u.lv[l - 1].pooled;
+    const int cx = l == 0 ? u.cin_phys : u.lv[l - 1].C;
+    bf16* dxin = l == 0 ? nullptr : u.lv[l - 1].dpool;
+    MPU_TRY(block_tail_backward(u, c1, c2, xin, cx, nullptr, 0, L.a1, L.s1, L.s2, dxin, L.C, g, st));
+  }
+  return MPU_OK;
+}
+
+}  // namespace mpu
+
+// ======================================================================================================
+using namespace mpu;
+
+extern "C" {
+
+static int check_cfg(const MpuUNetConfig* cfg) {
+  if (!cfg) {
+    set_error("unet: null config");
+    return MPU_ERR_ARG;
+  }
+  if (cfg->max_batch < 1 || cfg->n_classes < 1 || cfg->n_classes > 16 || cfg->n_channels < 1) {
+    set_error("unet: bad config (max_batch=%d n_classes=%d n_channels=%d)", cfg->max_batch,
+              cfg->n_classes, cfg->n_channels);
+    return MPU_ERR_ARG;
+  }
+  return MPU_OK;
+}
+
+int mpu_unet_sizes(const MpuUNetConfig* cfg, long long* n_params, long long* n_bn_state,
+                   long long* workspace_bytes) {
+  MPU_TRY(check_cfg(cfg));
+  UNet u;
+  u.cfg = *cfg;
+  MPU_TRY(build_tables(u));
+  layout_workspace(u, true);
+  if (n_params) *n_params = u.n_params;
+  if (n_bn_state) *n_bn_state = u.n_bn_state;
+  if (workspace_bytes) *workspace_bytes = u.ws_used;
+  return MPU_OK;
+}
+
+int mpu_unet_create(const MpuUNetConfig* cfg, float* params, float* grads, float* adam_m, float* adam_v,
+                    float* bn_state, void* workspace, long long workspace_bytes, void* stream,
+                    void** handle) {
+  MPU_TRY(check_cfg(cfg));
+  if (!params || !bn_state || !workspace || !handle) {
+    set_error("unet_create: null buffer");
+    return MPU_ERR_ARG;
+  }
+  if (cfg->training && (!grads || !adam_m || !adam_v)) {
+    set_error("unet_create: training handle needs grads / adam buffers");
+    return MPU_ERR_ARG;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_error("unet_create: no CUDA device (this library has no CPU fallback)");
+    return MPU_ERR_CUDA;
+  }
+  UNet* u = new UNet();
+  u->cfg = *cfg;
+  int rc = build_tables(*u);
+  if (rc != MPU_OK) {
+    delete u;
+    return rc;
+  }
+  layout_workspace(*u, true);
+  if (u->ws_used > workspace_bytes) {
+    set_error("unet_create: workspace too small (%lld < %lld bytes)", workspace_bytes, u->ws_used);
+    delete u;
+    return MPU_ERR_NOMEM;
+  }
+  u->params = params;
+  u->grads = grads;
+  u->adam_m = adam_m;
+  u->adam_v = adam_v;
+  u->bn_state = bn_state;
+  u->ws = reinterpret_cast<char*>(workspace);
+  u->ws_bytes = workspace_bytes;
+  const long long need = u->ws_used;
+  layout_workspace(*u, false);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // zero borders / padded channels once; kernels only ever write interiors
+  cudaError_t e = cudaMemsetAsync(workspace, 0, (size_t)need, st);
+  if (e != cudaSuccess) {
+    set_error("unet_create: memset failed: %s", cudaGetErrorString(e));
+    delete u;
+    return MPU_ERR_CUDA;
+  }
+  *handle = u;
+  return MPU_OK;
+}
+
+int mpu_unet_destroy(void* handle) {
+  delete reinterpret_cast<UNet*>(handle);
+  return MPU_OK;
+}
+
+int mpu_unet_num_layers(void* handle) {
+  UNet* u = reinterpret_cast<UNet*>(handle);
+  return (int)(u->convs.size() + u->bns.size());
+}
+
+int mpu_unet_layer_info(void* handle, int idx, MpuLayerInfo* out) {
+  UNet* u = reinterpret_cast<UNet*>(handle);
+  if (!u || !out || idx < 0 || idx >= (int)(u->convs.size() + u->bns.size())) {
+    set_error("layer_info: bad index %d", idx);
+    return MPU_ERR_ARG;
+  }
+  memset(out, 0, sizeof(*out));
+  if (idx < (int)u->convs.size()) {
+    const ConvL& L = u->convs[idx];
+    snprintf(out->name, sizeof(out->name), "%s", L.name.c_str());
+    out->kind = 0;
+    out->ksize = L.ksize;
+    out->cin = L.cin;
+    out->cout = L.cout;
+    out->k_phys = L.k_phys;
+    out->co_phys = L.co_phys;
+    out->c0_phys = L.c0_phys;
+    out->off0 = L.w_off;
+    out->off1 = L.b_off;
+  } else {
+    const BnL& b = u->bns[idx - u->convs.size()];
+    snprintf(out->name, sizeof(out->name), "%s", b.name.c_str());
+    out->kind = 1;
+    out->cout = b.c;
+    out->co_phys = b.c_phys;
+    out->off0 = b.g_off;
+    out->off1 = b.b_off;
+    out->off2 = b.m_off;
+    out->off3 = b.v_off;
+  }
+  return MPU_OK;
+}
+
+int mpu_unet_sync_weights(void* handle, void* stream) {
+  return sync_weights(*reinterpret_cast<UNet*>(handle), reinterpret_cast<cudaStream_t>(stream));
+}
+
+int mpu_unet_input_buffer(void* handle, void** ptr, int* cin_phys, long long* rows) {
+  UNet* u = reinterpret_cast<UNet*>(handle);
+  if (ptr) *ptr = u->x_in;
+  if (cin_phys) *cin_phys = u->cin_phys;
+  if (rows) *rows = u->lv[0].g.rows();
+  return MPU_OK;
+}
+
+int mpu_unet_pack_input(void* handle, const float* x_nhwc, int B, void* stream) {
+  UNet* u = reinterpret_cast<UNet*>(handle);
+  if (B < 1 || B > u->cfg.max_batch) {
+    set_error("pack_input: batch %d outside [1,%d]", B, u->cfg.max_batch);
+    return MPU_ERR_ARG;
+  }
+  return launch_pack_input(x_nhwc, geo_b(*u, 0, B), u->cfg.n_channels, u->cin_phys, u->x_in,
+                           reinterpret_cast<cudaStream_t>(stream));
+}
+
+int mpu_unet_forward(void* handle, int B, int bn_training, float* probs_out, void* stream) {
+  UNet* u = reinterpret_cast<UNet*>(handle);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (B < 1 || B > u->cfg.max_batch) {
+    set_error("forward: batch %d outside [1,%d]", B, u->cfg.max_batch);
+    return MPU_ERR_ARG;
+  }
+  MPU_TRY(forward(*u, B, bn_training, st));
+  const ConvL& H = u->head();
+  return launch_head_infer(u->lv[0].bn2, geo_b(*u, 0, B), u->lv[0].C, u->params + H.w_off,
+                           u->params + H.b_off, u->cfg.n_classes, probs_out, st);
+}
+
+int mpu_unet_train_step(void* handle, int B, const unsigned char* labels, const float* sample_w,
+                        float grad_scale, double* loss_sum, float* probs_opt, void* stream) {
+  UNet* u = reinterpret_cast<UNet*>(handle);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (!u->cfg.training) {
+    set_error("train_step: handle was created with training=0");
+    return MPU_ERR_STATE;
+  }
+  if (B < 1 || B > u->cfg.max_batch) {
+    set_error("train_step: batch %d outside [1,%d]", B, u->cfg.max_batch);
+    return MPU_ERR_ARG;
+  }
+  MPU_CUDA(cudaMemsetAsync(u->grads, 0, sizeof(float) * u->n_params, st));
+  MPU_CUDA(cudaMemsetAsync(loss_sum, 0, sizeof(double), st));
+  MPU_TRY(forward(*u, B, 1, st));
+  const ConvL& H = u->head();
+  MPU_TRY(launch_head_train(u->lv[0].bn2, geo_b(*u, 0, B), u->lv[0].C, u->params + H.w_off,
+                            u->params + H.b_off, u->cfg.n_classes, labels, sample_w, grad_scale,
+                            u->lv[0].gout, u->grads + H.w_off, u->grads + H.b_off, loss_sum, probs_opt,
+                            st));
+  return backward(*u, B, st);
+}
+
+int mpu_unet_adam(void* handle, float lr, float beta1, float beta2, float eps, int step,
+                  float grad_scale, void* stream) {
+  UNet* u = reinterpret_cast<UNet*>(handle);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (!u->cfg.training) {
+    set_error("adam: handle was created with training=0");
+    return MPU_ERR_STATE;
+  }
+  const double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, step)) / (1.0 - pow((double)beta1, step));
+  MPU_TRY(launch_adam(u->params, u->grads, u->adam_m, u->adam_v, u->n_params, (float)lr_t, beta1, beta2,
+                      eps, grad_scale, st));
+  return sync_weights(*u, st);
+}
+
+// debug / test access to internal activations: which = 0:a1 1:a2 2:b 3:pooled 4:u 5:bn1 6:c2 7:c3 8:bn2
+// 9:gout 10:s1 11:s2 12:dcat 13:dzu 14:dpool
+int mpu_unet_debug_buffer(void* handle, int level, int which, void** ptr, long long* rows, int* C) {
+  UNet* u = reinterpret_cast<UNet*>(handle);
+  if (level < 0 || level > u->depth) {
+    set_error("debug_buffer: bad level");
+    return MPU_ERR_ARG;
+  }
+  Level& L = u->lv[level];
+  bf16* tab[15] = {L.a1, L.a2, L.b, L.pooled, L.u, L.bn1, L.c2, L.c3, L.bn2, L.gout, L.s1, L.s2,
+                   L.dcat, L.dzu, L.dpool};
+  if (which < 0 || which >= 15) {
+    set_error("debug_buffer: bad selector");
+    return MPU_ERR_ARG;
+  }
+  if (ptr) *ptr = tab[which];
+  if (rows) *rows = L.g.rows();
+  if (C) *C = L.C;
+  return MPU_OK;
+}
+
+}  // extern "C"

@@ -81,7 +81,9 @@ def conv_case(B, H, W, Cin, Cout, BN, cin_phys=None, cout_phys=None, relu=True, 
     err = (got - ref).abs()
     tol = 0.02 + 0.01 * ref.abs()
     bad = (err > tol).float().mean().item()
-    border = out.float().abs().sum() - out[:, 1:-1, 1:-1, :].float().abs().sum()
+    bm = torch.ones_like(out, dtype=torch.bool)
+    bm[:, 1:-1, 1:-1, :] = False
+    border = out[bm].float().abs().sum()
     padc = out[..., Cout:].float().abs().sum().item()
     print("  max_err=%.4g mean_err=%.4g frac_bad=%.4g ref_absmean=%.4g border_sum=%.4g padch_sum=%.4g" %
           (err.max().item(), err.mean().item(), bad, ref.abs().mean().item(), border.item(), padc))
