@@ -99,6 +99,51 @@ int mpu_unet_adam(void* handle, float lr, float beta1, float beta2, float eps, i
                   float grad_scale, void* stream);
 int mpu_unet_debug_buffer(void* handle, int level, int which, void** ptr, long long* rows, int* C);
 
+/* ---- oblique-plane sampler -------------------------------------------------------------------------
+ * Replaces ViewInterpolator.__call__ + scaler.transform per plane: mpunet/interpolation/
+ * view_interpolator.py:62-101, regular_grid_interpolator.py:204-223,252-270, sample_grid.py:227-239 and
+ * sequences/isotrophic_live_view_sequence_2d.py:103-117 (inference stacks :29-101, train batches :163-216).
+ *   vol [X][Y][Z][C] f32, labels [X][Y][Z] u8 (may be NULL); gx/gy/gz: float32 voxel axes
+ *   (sample_grid.py:93-98); h_inv_step[3]: 1/axis spacing (search seed only); h_rot: optional 3x3
+ *   (view_interpolator.py:54-60); planes: device double [n][10] = row-major basis [u v n] (9) + offset,
+ *   computed on the host exactly as sample_plane_at does; span = real_space_span;
+ *   h_bg_value[C] (f32), bg_class; h_center/h_scale[C]: RobustScaler statistics or NULL.
+ * Outputs (each optional): out_f32 [n][dim][dim][C]; out_padded_bf16 = the U-Net input tensor
+ * [n][dim+2][dim+2][cpad]; out_labels [n][dim][dim] u8. */
+int mpu_sample_planes(const float* vol, const unsigned char* labels, const int* h_dims, int C,
+                      const float* gx, const float* gy, const float* gz, const double* h_inv_step,
+                      const double* h_rot, const double* planes, int n_planes, int dim, double span,
+                      const float* h_bg_value, int bg_class, const double* h_center,
+                      const double* h_scale, float* out_f32, void* out_padded_bf16, int cpad,
+                      unsigned char* out_labels, void* stream);
+
+/* ---- multi-view mapping + fusion ---------------------------------------------------------------------
+ * Replaces map_real_space_pred per view (mpunet/utils/fusion/fuse_and_predict.py:92-137) fused with
+ * FusionLayer.call + argmax (models/fusion_model.py:38-39, bin/predict.py:349-366, utils/utils.py:311-328).
+ *   h_pred_ptrs[V]: device pointers, each [n_planes][dim][dim][C] f32 softmax of one view's plane stack;
+ *   inv_basis: device double [V][9]; ax: device double [dim] (in-plane axis); offsets: device double
+ *   [V][n_planes]; h_inv_step[1+V]: 1/spacing of ax and of each offsets row; h_dims[3] = volume shape;
+ *   h_affine3x3 / h_mean[3]: voxel->real transform and the centre get_voxel_grid_real_space subtracts
+ *   (sample_grid.py:101-130); W [V][C], b [C] fusion weights (sum_fusion=1: plain sum over views).
+ * Outputs (each optional): labels_out [X][Y][Z] u8; probs_out [X][Y][Z][C] f32; combined_out
+ * [V][X][Y][Z][C] f32 (the per-view mapped volumes, what the reference materialises). */
+int mpu_map_fuse(const void* const* h_pred_ptrs, int V, int C, int dim, int n_planes,
+                 const double* inv_basis, const double* ax, const double* offsets,
+                 const double* h_inv_step, const int* h_dims, const double* h_affine3x3,
+                 const double* h_mean, const float* W, const float* b, int sum_fusion,
+                 unsigned char* labels_out, float* probs_out, float* combined_out, void* stream);
+
+/* ---- fusion-layer training ---------------------------------------------------------------------------
+ * Replaces FusionModel.fit's train step (bin/train_fusion.py:196-213; loss evaluate/loss_functions.py:
+ * 207-246 with uniform weights; regulariser models/fusion_model.py:9-11).  X [n][V][C] f32, y [n] u8.
+ * mpu_fusion_grad ADDS into accum (double [V*C + C + 1] = dW | db | sum of per-point losses); all-reduce
+ * accum across ranks, then mpu_fusion_adam applies mean gradient + regulariser with Keras Adam. */
+int mpu_fusion_grad(const float* X, const unsigned char* y, long long n, int V, int C, const float* W,
+                    const float* b, double* accum, void* stream);
+int mpu_fusion_adam(float* W, float* b, float* m, float* v, const double* accum, double n_points,
+                    int V, int C, float reg, float lr, float beta1, float beta2, float eps, int step,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

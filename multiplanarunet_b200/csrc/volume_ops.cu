@@ -1,0 +1,473 @@
+// Volume-side kernels of the mpunet hot path (CUDA cores, gather-bound; the 256^3 volume sits in L2):
+//   * oblique-plane trilinear / nearest sampler  (mpunet/interpolation/sample_grid.py:192-244,
+//     regular_grid_interpolator.py:204-223,252-270, view_interpolator.py:62-101,
+//     sequences/isotrophic_live_view_sequence_2d.py:103-117, preprocessing/scaling.py:75-88)
+//   * multi-view nearest mapping + fusion + argmax (utils/fusion/fuse_and_predict.py:92-137,
+//     models/fusion_model.py:38-39, bin/predict.py:349-366, utils/utils.py:311-328)
+//   * fusion-layer training step (evaluate/loss_functions.py:207-246, models/fusion_model.py:9-11)
+// Index math is float64 in the reference's operation order (explicit _rn intrinsics: no FMA
+// contraction) so gathers are bit-exact; see oracle/sampler.py and oracle/fusion.py.
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "../../include/mpunet_b200.h"
+#include "common.h"
+
+namespace mpu {
+
+namespace {
+
+constexpr int kMaxCh = 8;
+constexpr int kMaxViews = 16;
+constexpr int kMaxClasses = 16;
+
+// i = searchsorted(g, x, 'left') - 1 clamped to [0, n-2]  ==  largest i with g[i] < x (clamped).
+template <typename T>
+__device__ __forceinline__ int find_cell(const T* __restrict__ g, int n, double x, double inv_step) {
+  int i = (int)floor((x - (double)g[0]) * inv_step);
+  i = max(0, min(n - 2, i));
+  while (i < n - 2 && (double)g[i + 1] < x) ++i;
+  while (i > 0 && !((double)g[i] < x)) --i;
+  return i;
+}
+
+__device__ __forceinline__ double dot3(const double* m, double a, double b, double c) {
+  // BLAS-style accumulate: ((m0*a) + m1*b) + m2*c with fused multiply-adds
+  return fma(m[2], c, fma(m[1], b, __dmul_rn(m[0], a)));
+}
+
+struct SamplerParams {
+  const float* vol;       // [X][Y][Z][C]
+  const uint8_t* labels;  // [X][Y][Z] or null
+  int X, Y, Z, C;
+  const float *gx, *gy, *gz;  // float32 voxel axes (sample_grid.py:93-98)
+  double inv_step[3];
+  const double* planes;   // [n][10]: basis row-major 3x3 (columns u v n), offset
+  int n_planes, dim;
+  double ax_start, ax_step;  // in-plane axis: idx*step + start (np.mgrid semantics)
+  int has_rot;
+  double rot[9];
+  float bg_value[kMaxCh];
+  int bg_class;
+  int apply_scaler;
+  double center[kMaxCh], scale[kMaxCh];
+  float* out_f32;          // [n][dim][dim][C] or null
+  __nv_bfloat16* out_pad;  // zero-bordered [n][dim+2][dim+2][cpad] or null
+  int cpad;
+  uint8_t* out_lab;        // [n][dim][dim] or null
+};
+
+__global__ void sample_planes_kernel(const SamplerParams p) {
+  const long long total = (long long)p.n_planes * p.dim * p.dim;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % p.dim);
+    const long long t0 = idx / p.dim;
+    const int i = (int)(t0 % p.dim);
+    const int pl = (int)(t0 / p.dim);
+    const double* P = p.planes + (size_t)pl * 10;
+    const double a = __dadd_rn(__dmul_rn((double)i, p.ax_step), p.ax_start);
+    const double b = __dadd_rn(__dmul_rn((double)j, p.ax_step), p.ax_start);
+    const double off = P[9];
+    double q[3];
+    q[0] = dot3(P + 0, a, b, off);
+    q[1] = dot3(P + 3, a, b, off);
+    q[2] = dot3(P + 6, a, b, off);
+    if (p.has_rot) {
+      const double r0 = dot3(p.rot + 0, q[0], q[1], q[2]);
+      const double r1 = dot3(p.rot + 3, q[0], q[1], q[2]);
+      const double r2 = dot3(p.rot + 6, q[0], q[1], q[2]);
+      q[0] = r0; q[1] = r1; q[2] = r2;
+    }
+    const float* gs[3] = {p.gx, p.gy, p.gz};
+    const int ns[3] = {p.X, p.Y, p.Z};
+    int ci[3];
+    double tt[3];
+    bool oob = false;
+    for (int k = 0; k < 3; ++k) {
+      const float* g = gs[k];
+      const int n = ns[k];
+      const int c = find_cell(g, n, q[k], p.inv_step[k]);
+      ci[k] = c;
+      const float den = __fsub_rn(g[c + 1], g[c]);  // float32 axis difference, as numpy computes it
+      tt[k] = __ddiv_rn(__dsub_rn(q[k], (double)g[c]), (double)den);
+      oob = oob || q[k] < (double)g[0] || q[k] > (double)g[n - 1];
+    }
+    const long long sY = (long long)p.Z * p.C, sX = (long long)p.Y * sY;
+    const long long base = (long long)ci[0] * sX + (long long)ci[1] * sY + (long long)ci[2] * p.C;
+    for (int c = 0; c < p.C; ++c) {
+      double acc = 0.0;
+      if (!oob) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int dx = (e >> 2) & 1, dy = (e >> 1) & 1, dz = e & 1;
+          double w = dx ? tt[0] : __dsub_rn(1.0, tt[0]);
+          w = __dmul_rn(w, dy ? tt[1] : __dsub_rn(1.0, tt[1]));
+          w = __dmul_rn(w, dz ? tt[2] : __dsub_rn(1.0, tt[2]));
+          const float v = __ldg(p.vol + base + dx * sX + dy * sY + dz * p.C + c);
+          acc = __dadd_rn(acc, __dmul_rn((double)v, w));
+        }
+      } else {
+        acc = (double)p.bg_value[c];
+      }
+      float val = (float)acc;
+      if (p.apply_scaler) {
+        const float t = (float)__dsub_rn((double)val, p.center[c]);
+        val = (float)__ddiv_rn((double)t, p.scale[c]);
+      }
+      if (p.out_f32) p.out_f32[idx * p.C + c] = val;
+      if (p.out_pad) {
+        const long long row = (long long)pl * (p.dim + 2) * (p.dim + 2) + (long long)(i + 1) * (p.dim + 2) + (j + 1);
+        p.out_pad[row * p.cpad + c] = __float2bfloat16_rn(val);
+      }
+    }
+    if (p.out_lab) {
+      int lab = p.bg_class;
+      if (!oob && p.labels) {
+        const int s0 = tt[0] <= 0.5 ? ci[0] : ci[0] + 1;
+        const int s1 = tt[1] <= 0.5 ? ci[1] : ci[1] + 1;
+        const int s2 = tt[2] <= 0.5 ? ci[2] : ci[2] + 1;
+        lab = p.labels[((long long)s0 * p.Y + s1) * p.Z + s2];
+      }
+      p.out_lab[idx] = (uint8_t)lab;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+struct MapFuseParams {
+  int X, Y, Z, C, V;
+  double affine[9];      // voxel -> real (3x3 part of the NIfTI affine)
+  double mean[3];        // centre subtracted by get_voxel_grid_real_space (sample_grid.py:117-118)
+  const float* pred[kMaxViews];      // per view [n_planes][dim][dim][C] softmax probabilities
+  const double* inv_basis;           // [V][9]
+  const double* ax;                  // [dim] in-plane axis (float64 linspace)
+  const double* offsets;             // [V][n_planes]
+  int dim, n_planes;
+  double inv_step_ax;
+  double inv_step_off[kMaxViews];
+  const float* W;                    // [V][C] fusion weights (null for sum fusion)
+  const float* b;                    // [C]
+  int sum_fusion;
+  uint8_t* labels_out;               // [X][Y][Z] or null
+  float* probs_out;                  // [X][Y][Z][C] or null
+  float* combined_out;               // [V][X][Y][Z][C] or null
+};
+
+__global__ void map_fuse_kernel(const MapFuseParams p) {
+  const long long total = (long long)p.X * p.Y * p.Z;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(idx % p.Z);
+    const long long t0 = idx / p.Z;
+    const int j = (int)(t0 % p.Y);
+    const int i = (int)(t0 / p.Y);
+    double xr[3];
+    xr[0] = __dsub_rn(dot3(p.affine + 0, (double)i, (double)j, (double)k), p.mean[0]);
+    xr[1] = __dsub_rn(dot3(p.affine + 3, (double)i, (double)j, (double)k), p.mean[1]);
+    xr[2] = __dsub_rn(dot3(p.affine + 6, (double)i, (double)j, (double)k), p.mean[2]);
+    float z[kMaxClasses];
+#pragma unroll
+    for (int c = 0; c < kMaxClasses; ++c) z[c] = 0.f;
+    for (int v = 0; v < p.V; ++v) {
+      const double* ib = p.inv_basis + v * 9;
+      double q[3];
+      q[0] = dot3(ib + 0, xr[0], xr[1], xr[2]);
+      q[1] = dot3(ib + 3, xr[0], xr[1], xr[2]);
+      q[2] = dot3(ib + 6, xr[0], xr[1], xr[2]);
+      const double* off = p.offsets + (size_t)v * p.n_planes;
+      int sel[3];
+      bool oob = false;
+      for (int a = 0; a < 3; ++a) {
+        const double* g = a < 2 ? p.ax : off;
+        const int n = a < 2 ? p.dim : p.n_planes;
+        const double inv = a < 2 ? p.inv_step_ax : p.inv_step_off[v];
+        const int c = find_cell(g, n, q[a], inv);
+        const double t = __ddiv_rn(__dsub_rn(q[a], g[c]), __dsub_rn(g[c + 1], g[c]));
+        sel[a] = t <= 0.5 ? c : c + 1;
+        oob = oob || q[a] < g[0] || q[a] > g[n - 1];
+      }
+      const float* src = p.pred[v] + (((long long)sel[2] * p.dim + sel[0]) * p.dim + sel[1]) * p.C;
+#pragma unroll
+      for (int c = 0; c < kMaxClasses; ++c) {
+        if (c < p.C) {
+          const float x = oob ? (c == 0 ? 1.f : 0.f) : __ldg(src + c);
+          if (p.combined_out) p.combined_out[((long long)v * total + idx) * p.C + c] = x;
+          if (p.sum_fusion) z[c] = __fadd_rn(z[c], x);
+          else z[c] = __fadd_rn(z[c], __fmul_rn(p.W[v * p.C + c], x));
+        }
+      }
+    }
+    float pr[kMaxClasses];
+    if (p.sum_fusion) {
+#pragma unroll
+      for (int c = 0; c < kMaxClasses; ++c) pr[c] = z[c];
+    } else {
+      float m = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < kMaxClasses; ++c)
+        if (c < p.C) {
+          z[c] = __fadd_rn(z[c], p.b[c]);
+          m = fmaxf(m, z[c]);
+        }
+      float s = 0.f;
+#pragma unroll
+      for (int c = 0; c < kMaxClasses; ++c)
+        if (c < p.C) {
+          pr[c] = expf(__fsub_rn(z[c], m));
+          s = __fadd_rn(s, pr[c]);
+        }
+#pragma unroll
+      for (int c = 0; c < kMaxClasses; ++c)
+        if (c < p.C) pr[c] = __fdiv_rn(pr[c], s);
+    }
+    int best = 0;
+    float bv = pr[0];
+#pragma unroll
+    for (int c = 1; c < kMaxClasses; ++c)
+      if (c < p.C && pr[c] > bv) {
+        bv = pr[c];
+        best = c;
+      }
+    if (p.labels_out) p.labels_out[idx] = (uint8_t)best;
+    if (p.probs_out) {
+#pragma unroll
+      for (int c = 0; c < kMaxClasses; ++c)
+        if (c < p.C) p.probs_out[idx * p.C + c] = pr[c];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fusion layer training: per point softmax(sum_v W*x + b), generalized dice (uniform weights),
+// analytic gradients; accum = [dW (V*C) | db (C) | loss] in double via block reduction + atomics.
+__global__ void fusion_grad_kernel(const float* __restrict__ X, const uint8_t* __restrict__ y,
+                                   long long n, int V, int C, const float* __restrict__ W,
+                                   const float* __restrict__ b, double* __restrict__ accum) {
+  extern __shared__ double fsm[];  // [warps][V*C + C + 1]
+  const int nacc = V * C + C + 1;
+  float loc[kMaxViews * kMaxClasses / 2 + kMaxClasses + 1];  // supports V*C <= 128
+  for (int k = 0; k < nacc; ++k) loc[k] = 0.f;
+  float w[kMaxViews * kMaxClasses / 2];
+  for (int k = 0; k < V * C; ++k) w[k] = W[k];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float* x = X + i * V * C;
+    float z[kMaxClasses], pr[kMaxClasses];
+    for (int c = 0; c < C; ++c) {
+      float s = 0.f;
+      for (int v = 0; v < V; ++v) s += w[v * C + c] * x[v * C + c];
+      z[c] = s + b[c];
+    }
+    float m = z[0];
+    for (int c = 1; c < C; ++c) m = fmaxf(m, z[c]);
+    float se = 0.f;
+    for (int c = 0; c < C; ++c) {
+      pr[c] = expf(z[c] - m);
+      se += pr[c];
+    }
+    const float inv = 1.f / se;
+    const int lab = y[i];
+    float dice_sum = 0.f, dp[kMaxClasses], dpp = 0.f;
+    for (int c = 0; c < C; ++c) {
+      pr[c] *= inv;
+      const float o = c == lab ? 1.f : 0.f;
+      const float num = 2.f * o * pr[c];
+      const float den = pr[c] + o + 1e-6f;
+      dice_sum += num / den;
+      dp[c] = -((2.f * o * den - num) / (den * den)) / (float)C;
+      dpp += dp[c] * pr[c];
+    }
+    loc[nacc - 1] += 1.f - dice_sum / (float)C;
+    for (int c = 0; c < C; ++c) {
+      const float dz = pr[c] * (dp[c] - dpp);
+      loc[V * C + c] += dz;
+      for (int v = 0; v < V; ++v) loc[v * C + c] += dz * x[v * C + c];
+    }
+  }
+  // warp reduce then block reduce in double
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int k = 0; k < nacc; ++k) {
+    double v = (double)loc[k];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) fsm[warp * nacc + k] = v;
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < nacc; k += blockDim.x) {
+    double s = 0;
+    for (int ww = 0; ww < nwarps; ++ww) s += fsm[ww * nacc + k];
+    atomicAdd(accum + k, s);
+  }
+}
+
+// Adam on the 35 fusion parameters (+ L2 regulariser gradients); one thread per parameter.
+__global__ void fusion_adam_kernel(float* W, float* b, float* m, float* v, const double* accum,
+                                   double n_points, int V, int C, float reg, float lr_t, float b1,
+                                   float b2, float eps) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nW = V * C;
+  if (k >= nW + C) return;
+  float* prm = k < nW ? W + k : b + (k - nW);
+  const float cnt = k < nW ? (float)nW : (float)C;
+  const float g = (float)(accum[k] / n_points) + reg * 2.f * (*prm) / cnt;
+  const float mi = b1 * m[k] + (1.f - b1) * g;
+  const float vi = b2 * v[k] + (1.f - b2) * g * g;
+  m[k] = mi;
+  v[k] = vi;
+  *prm = *prm - lr_t * mi / (sqrtf(vi) + eps);
+}
+
+inline int grid_for(long long work, int threads, int cap = 148 * 16) {
+  long long g = (work + threads - 1) / threads;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace
+}  // namespace mpu
+
+using namespace mpu;
+
+extern "C" {
+
+int mpu_sample_planes(const float* vol, const unsigned char* labels, const int* h_dims, int C,
+                      const float* gx, const float* gy, const float* gz, const double* h_inv_step,
+                      const double* h_rot,
+                      const double* planes, int n_planes, int dim, double span,
+                      const float* h_bg_value, int bg_class, const double* h_center,
+                      const double* h_scale, float* out_f32, void* out_padded_bf16, int cpad,
+                      unsigned char* out_labels, void* stream) {
+  if (!vol || !h_dims || !gx || !gy || !gz || !h_inv_step || !planes || n_planes < 1 || dim < 2) {
+    set_error("mpu_sample_planes: bad arguments");
+    return MPU_ERR_ARG;
+  }
+  if (C < 1 || C > kMaxCh) {
+    set_error("mpu_sample_planes: %d channels unsupported (max %d)", C, kMaxCh);
+    return MPU_ERR_ARG;
+  }
+  if (out_padded_bf16 && cpad < C) {
+    set_error("mpu_sample_planes: padded channel count %d < C=%d", cpad, C);
+    return MPU_ERR_ARG;
+  }
+  SamplerParams p;
+  memset(&p, 0, sizeof(p));
+  p.vol = vol;
+  p.labels = labels;
+  p.X = h_dims[0];
+  p.Y = h_dims[1];
+  p.Z = h_dims[2];
+  p.C = C;
+  p.gx = gx;
+  p.gy = gy;
+  p.gz = gz;
+  p.planes = planes;
+  p.n_planes = n_planes;
+  p.dim = dim;
+  // np.mgrid[-hd:hd:dim*1j] with hd = span // 2 (sample_grid.py:227-233)
+  const double hd = floor(span / 2.0);
+  p.ax_start = -hd;
+  p.ax_step = (hd - (-hd)) / (double)(dim - 1);
+  p.has_rot = h_rot != nullptr;
+  if (h_rot) memcpy(p.rot, h_rot, sizeof(double) * 9);
+  for (int c = 0; c < C; ++c) p.bg_value[c] = h_bg_value ? h_bg_value[c] : 0.f;
+  p.bg_class = bg_class;
+  p.apply_scaler = (h_center && h_scale) ? 1 : 0;
+  for (int c = 0; c < C; ++c) {
+    p.center[c] = h_center ? h_center[c] : 0.0;
+    p.scale[c] = h_scale ? h_scale[c] : 1.0;
+  }
+  p.out_f32 = out_f32;
+  p.out_pad = reinterpret_cast<__nv_bfloat16*>(out_padded_bf16);
+  p.cpad = cpad;
+  p.out_lab = out_labels;
+  // 1/spacing of each voxel axis: only seeds the cell search, the axis tables decide the result
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  for (int k = 0; k < 3; ++k) p.inv_step[k] = h_inv_step[k];
+  const long long total = (long long)n_planes * dim * dim;
+  sample_planes_kernel<<<grid_for(total, 256), 256, 0, st>>>(p);
+  MPU_CUDA(cudaGetLastError());
+  return MPU_OK;
+}
+
+int mpu_map_fuse(const void* const* h_pred_ptrs, int V, int C, int dim, int n_planes,
+                 const double* inv_basis, const double* ax, const double* offsets,
+                 const double* h_inv_step, const int* h_dims, const double* h_affine3x3,
+                 const double* h_mean, const float* W, const float* b, int sum_fusion,
+                 unsigned char* labels_out, float* probs_out, float* combined_out, void* stream) {
+  if (!h_pred_ptrs || V < 1 || V > kMaxViews || C < 1 || C > kMaxClasses || !inv_basis || !ax ||
+      !offsets || !h_inv_step || !h_dims || !h_affine3x3 || !h_mean) {
+    set_error("mpu_map_fuse: bad arguments (V=%d C=%d)", V, C);
+    return MPU_ERR_ARG;
+  }
+  if (!sum_fusion && (!W || !b)) {
+    set_error("mpu_map_fuse: fusion weights missing");
+    return MPU_ERR_ARG;
+  }
+  MapFuseParams p;
+  memset(&p, 0, sizeof(p));
+  p.X = h_dims[0];
+  p.Y = h_dims[1];
+  p.Z = h_dims[2];
+  p.C = C;
+  p.V = V;
+  memcpy(p.affine, h_affine3x3, sizeof(double) * 9);
+  memcpy(p.mean, h_mean, sizeof(double) * 3);
+  for (int v = 0; v < V; ++v) p.pred[v] = reinterpret_cast<const float*>(h_pred_ptrs[v]);
+  p.inv_basis = inv_basis;
+  p.ax = ax;
+  p.offsets = offsets;
+  p.dim = dim;
+  p.n_planes = n_planes;
+  p.inv_step_ax = h_inv_step[0];
+  // h_inv_step = [1/spacing of the in-plane axis, 1/spacing of each view's offset axis]
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  for (int v = 0; v < V; ++v) p.inv_step_off[v] = h_inv_step[1 + v];
+  p.W = W;
+  p.b = b;
+  p.sum_fusion = sum_fusion;
+  p.labels_out = labels_out;
+  p.probs_out = probs_out;
+  p.combined_out = combined_out;
+  const long long total = (long long)p.X * p.Y * p.Z;
+  map_fuse_kernel<<<grid_for(total, 256), 256, 0, st>>>(p);
+  MPU_CUDA(cudaGetLastError());
+  return MPU_OK;
+}
+
+int mpu_fusion_grad(const float* X, const unsigned char* y, long long n, int V, int C, const float* W,
+                    const float* b, double* accum, void* stream) {
+  if (!X || !y || !W || !b || !accum || V < 1 || C < 1 || C > kMaxClasses || V * C > 128) {
+    set_error("mpu_fusion_grad: bad arguments (V=%d C=%d)", V, C);
+    return MPU_ERR_ARG;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int threads = 256;
+  const int nacc = V * C + C + 1;
+  const size_t smem = sizeof(double) * (threads / 32) * nacc;
+  fusion_grad_kernel<<<grid_for(n, threads, 148 * 4), threads, smem, st>>>(X, y, n, V, C, W, b, accum);
+  MPU_CUDA(cudaGetLastError());
+  return MPU_OK;
+}
+
+int mpu_fusion_adam(float* W, float* b, float* m, float* v, const double* accum, double n_points,
+                    int V, int C, float reg, float lr, float beta1, float beta2, float eps, int step,
+                    void* stream) {
+  if (!W || !b || !m || !v || !accum || n_points <= 0) {
+    set_error("mpu_fusion_adam: bad arguments");
+    return MPU_ERR_ARG;
+  }
+  const double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, step)) / (1.0 - pow((double)beta1, step));
+  const int n = V * C + C;
+  fusion_adam_kernel<<<(n + 63) / 64, 64, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      W, b, m, v, accum, n_points, V, C, reg, (float)lr_t, beta1, beta2, eps);
+  MPU_CUDA(cudaGetLastError());
+  return MPU_OK;
+}
+
+}  // extern "C"

@@ -170,7 +170,10 @@ class UNet(object):
                 S[info["off2"]:info["off2"] + c].cpu().numpy().copy(),
                 S[info["off3"]:info["off3"] + c].cpu().numpy().copy()]
 
-    def _set_layer_weights(self, info, ws):
+    def _sync(self):
+        check(lib.mpu_unet_sync_weights(self._h, _C.current_stream()), "mpu_unet_sync_weights")
+
+    def _set_layer_weights(self, info, ws, sync=True):
         import torch
         P = self.params
         if info["kind"] == 0:
@@ -198,7 +201,8 @@ class UNet(object):
                 full = np.full(cp, pad, dtype=np.float32)
                 full[:c] = v
                 buf[off:off + cp] = torch.from_numpy(full).to(self.device)
-        check(lib.mpu_unet_sync_weights(self._h, _C.current_stream()), "mpu_unet_sync_weights")
+        if sync:
+            self._sync()
 
     def init_weights(self, seed=None):
         """Keras defaults: glorot_uniform kernels, zero biases, BN gamma=1 beta=0 mean=0 var=1."""
@@ -208,11 +212,12 @@ class UNet(object):
                 k, cin, co = info["ksize"], info["cin"], info["cout"]
                 limit = math.sqrt(6.0 / (k * k * cin + k * k * co))
                 kern = rng.uniform(-limit, limit, size=(k, k, cin, co)).astype(np.float32)
-                self._set_layer_weights(info, [kern, np.zeros(co, np.float32)])
+                self._set_layer_weights(info, [kern, np.zeros(co, np.float32)], sync=False)
             else:
                 c = info["cout"]
                 self._set_layer_weights(info, [np.ones(c, np.float32), np.zeros(c, np.float32),
-                                               np.zeros(c, np.float32), np.ones(c, np.float32)])
+                                               np.zeros(c, np.float32), np.ones(c, np.float32)], sync=False)
+        self._sync()
 
     def get_keras_weights(self):
         out = {}
@@ -231,9 +236,11 @@ class UNet(object):
                 continue
             d = weights[info["name"]]
             if info["kind"] == 0:
-                self._set_layer_weights(info, [d["kernel"], d["bias"]])
+                self._set_layer_weights(info, [d["kernel"], d["bias"]], sync=False)
             else:
-                self._set_layer_weights(info, [d["gamma"], d["beta"], d["moving_mean"], d["moving_variance"]])
+                self._set_layer_weights(info, [d["gamma"], d["beta"], d["moving_mean"], d["moving_variance"]],
+                                        sync=False)
+        self._sync()
 
     def get_flat_grads_as_keras(self):
         """Gradients of the last train step, in Keras layouts (tests / debugging)."""

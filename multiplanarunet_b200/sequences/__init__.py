@@ -1,0 +1,1 @@
+from .isotrophic_live_view_sequence_2d import IsotrophicLiveViewSequence2D, SyntheticImage  # noqa: F401

@@ -1,0 +1,199 @@
+"""Plane-sampling front-end, mirroring mpunet/sequences/isotrophic_live_view_sequence_2d.py on the GPU
+sampler: `get_view_from` builds whole inference stacks (reference :29-101, one launch instead of
+276 numpy planes x 7 threads) and `__getitem__` draws a training batch of random oblique planes
+(reference :119-216) with the foreground rules of isotrophic_live_view_sequence.py:70-128.
+
+Image objects are duck-typed like the reference's ImagePair (image/image_pair.py): `.image`
+[X,Y,Z,C] float32, `.labels` [X,Y,Z] uint8 | None, `.affine` 4x4, `.interpolator`
+(multiplanarunet_b200.interpolation.ViewInterpolator), `.scaler_center/.scaler_scale` (RobustScaler
+statistics, preprocessing/scaling.py:47-88), `.sample_weight`, `.predict_mode`.
+"""
+import numpy as np
+
+from ..interpolation import ViewInterpolator, plane_basis, view_offsets
+
+
+class SyntheticImage(object):
+    """Minimal ImagePair stand-in (what the sequence needs from image/image_pair.py:27-484):
+    bg_value = 1st percentile per channel (bin/defaults/MultiPlanar/train_hparams.yaml:130,
+    image_pair.py:469-484), scaler = RobustScaler median / IQR over all voxels."""
+
+    def __init__(self, image, labels=None, affine=None, bg_value="1pct", bg_class=0, sample_weight=1.0,
+                 device=None, identifier="synthetic"):
+        image = np.asarray(image, dtype=np.float32)
+        if image.ndim == 3:
+            image = image[..., None]
+        self.image = image
+        self.labels = None if labels is None else np.asarray(labels).astype(np.uint8)
+        self.affine = np.eye(4) if affine is None else np.asarray(affine, dtype=np.float64)
+        self.shape = image.shape
+        self.n_channels = image.shape[-1]
+        self.predict_mode = labels is None
+        self.sample_weight = float(sample_weight)
+        self.identifier = identifier
+        if isinstance(bg_value, str) and bg_value.endswith("pct"):
+            pct = float(bg_value[:-3])
+            bg_value = [float(np.percentile(image[..., c], pct)) for c in range(self.n_channels)]
+        self.bg_value = bg_value
+        flat = image.reshape(-1, self.n_channels)
+        q = np.percentile(flat, [25.0, 50.0, 75.0], axis=0)
+        self.scaler_center = q[1].astype(np.float64)
+        iqr = (q[2] - q[0]).astype(np.float64)
+        iqr[iqr == 0] = 1.0
+        self.scaler_scale = iqr
+        self.interpolator = ViewInterpolator(image, self.labels, self.affine, bg_value=bg_value,
+                                             bg_class=bg_class, device=device)
+
+    @property
+    def real_shape(self):
+        pix = np.linalg.norm(self.affine[:3, :3], axis=0)
+        return np.asarray(self.shape[:3]) * pix
+
+
+class IsotrophicLiveViewSequence2D(object):
+    def __init__(self, images, views, sample_dim, real_space_span, n_classes, batch_size=16,
+                 noise_sd=0.1, fg_batch_fraction=0.5, force_all_fg="auto", is_validation=False,
+                 label_crop=None, logger=None, **kwargs):
+        self.images = list(images) if isinstance(images, (list, tuple)) else [images]
+        self.views = np.asarray(views, dtype=np.float64)
+        self.sample_dim = int(sample_dim)
+        self.real_space_span = real_space_span
+        self.n_classes = int(n_classes)
+        self.batch_size = int(batch_size)
+        self.noise_sd = 0.0 if is_validation else noise_sd
+        self.fg_batch_fraction = fg_batch_fraction
+        self.force_all_fg_switch = force_all_fg
+        self.is_validation = is_validation
+        self.fg_classes = np.arange(1, self.n_classes)
+        self.label_crop = np.zeros((2, 2), dtype=int) if label_crop is None else label_crop
+        self.logger = logger or (lambda *a, **k: None)
+
+    # -- reference properties (isotrophic_live_view_sequence.py:70-90)
+    @property
+    def n_fg_slices(self):
+        return int(np.ceil(self.batch_size * self.fg_batch_fraction))
+
+    @property
+    def force_all_fg(self):
+        if isinstance(self.force_all_fg_switch, str) and self.force_all_fg_switch.lower() == "auto":
+            return self.batch_size > len(self.fg_classes)
+        return self.force_all_fg_switch
+
+    # -- inference stacks --------------------------------------------------------------------------
+    def get_view_stack_device(self, image, view, n_planes="same+20", out_padded=None, cpad=0,
+                              want_f32=True, want_labels=True):
+        """Device-native get_view_from: returns (X [n,dim,dim,C] f32 tensor|None, y tensor|None,
+        (axis, axis, offsets), inv_basis, basis).  With `out_padded` the planes go straight into the
+        U-Net's bf16 input tensor."""
+        dim, span = self.sample_dim, self.real_space_span
+        bounding = float(np.linalg.norm(np.asarray(image.real_shape) / 2)) if n_planes == "by_radius" else None
+        offsets = view_offsets(dim, span, n_planes, bounding)
+        basis = plane_basis(view, 0.)
+        X, y = image.interpolator.sample_planes(
+            basis, offsets, dim, span, center=image.scaler_center, scale=image.scaler_scale,
+            out_padded=out_padded, cpad=cpad, want_f32=want_f32,
+            want_labels=want_labels and not image.predict_mode)
+        hd = span // 2
+        g = np.linspace(-hd, hd, dim)
+        return X, y, (g, g, offsets), np.linalg.inv(basis), basis
+
+    def get_view_from(self, image, view, n_planes):
+        """Reference layout (…_2d.py:29-101): X [dim,dim,n,C] float32, y [dim,dim,n] uint8 | None,
+        (real_axis, real_axis, offsets), inv_basis."""
+        X, y, grid, inv_basis, _ = self.get_view_stack_device(image, view, n_planes)
+        Xn = np.ascontiguousarray(X.permute(1, 2, 0, 3).cpu().numpy())
+        yn = None if y is None else np.ascontiguousarray(y.permute(1, 2, 0).cpu().numpy())
+        return Xn, yn, grid, inv_basis
+
+    # -- training batches --------------------------------------------------------------------------
+    def _validate_lab_vec(self, present, has_fg, cur_bs):
+        new_mask = has_fg + present
+        if np.all(new_mask):
+            return True, new_mask
+        if np.sum(new_mask == 0) < (self.batch_size - cur_bs):
+            return True, new_mask
+        return False, has_fg
+
+    def _validate_lab(self, present, has_fg_count, cur_bs):
+        if np.any(present):
+            return True, 1
+        if (self.n_fg_slices - has_fg_count) < (self.batch_size - cur_bs):
+            return True, 0
+        return False, 0
+
+    def sample_batch_device(self, out_padded=None, cpad=0, max_tries=10, rng=np.random):
+        """One training batch of random oblique planes.  Candidate planes for every slot are drawn up
+        front (view, offset ~ U(-span//2, span//2), normal noise) and their LABELS sampled in one
+        launch; the sequential accept/reject rules of …_2d.py:119-161 then run on tiny per-plane
+        class-presence masks on the host, and only the accepted planes get the trilinear image pass.
+        Returns (x [B,dim,dim,C] f32 tensor | None if out_padded, y [B,dim,dim] uint8 tensor, w [B])."""
+        import torch
+        B, dim, span = self.batch_size, self.sample_dim, self.real_space_span
+        im_idx = rng.randint(0, len(self.images), B)
+        sphere_r = span // 2
+        chosen_bases = np.empty((B, 3, 3))
+        chosen_offs = np.empty(B)
+        has_fg_count, has_fg_vec = 0, np.zeros_like(self.fg_classes)
+        # candidates: B x max_tries planes, labels only
+        cand_bases = np.empty((B, max_tries, 3, 3))
+        cand_offs = np.empty((B, max_tries))
+        for s in range(B):
+            for t in range(max_tries):
+                view = self.views[rng.randint(0, len(self.views), 1)[0]]
+                cand_offs[s, t] = rng.uniform(-sphere_r, sphere_r, 1)[0]
+                cand_bases[s, t] = plane_basis(view, rng.normal(scale=self.noise_sd, size=3))
+        present = np.zeros((B, max_tries, len(self.fg_classes)), dtype=bool)
+        for i, image in enumerate(self.images):
+            slots = np.where(im_idx == i)[0]
+            if len(slots) == 0:
+                continue
+            _, lab = image.interpolator.sample_planes(cand_bases[slots].reshape(-1, 3, 3),
+                                                      cand_offs[slots].ravel(), dim, span,
+                                                      want_f32=False, want_labels=True)
+            onehot = torch.zeros(lab.shape[0], self.n_classes, dtype=torch.bool, device=lab.device)
+            onehot.scatter_(1, lab.view(lab.shape[0], -1).long(), True)
+            present[slots] = onehot[:, 1:].cpu().numpy().reshape(len(slots), max_tries, -1)
+        for s in range(B):
+            pick = max_tries - 1
+            for t in range(max_tries):
+                last = t == max_tries - 1
+                if self.force_all_fg and not last:
+                    ok, has_fg_vec = self._validate_lab_vec(present[s, t], has_fg_vec, s)
+                    if not ok:
+                        continue
+                ok, change = self._validate_lab(present[s, t], has_fg_count, s)
+                if ok or last:
+                    has_fg_count += change
+                    pick = t
+                    break
+            chosen_bases[s], chosen_offs[s] = cand_bases[s, pick], cand_offs[s, pick]
+        x = torch.empty(B, dim, dim, self.images[0].n_channels, dtype=torch.float32,
+                        device=self.images[0].interpolator.device) if out_padded is None else None
+        y = torch.empty(B, dim, dim, dtype=torch.uint8, device=self.images[0].interpolator.device)
+        w = np.empty(B, dtype=np.float32)
+        for i, image in enumerate(self.images):
+            slots = np.where(im_idx == i)[0]
+            if len(slots) == 0:
+                continue
+            contiguous = len(self.images) == 1
+            xi, yi = image.interpolator.sample_planes(
+                chosen_bases[slots], chosen_offs[slots], dim, span, center=image.scaler_center,
+                scale=image.scaler_scale, out_padded=out_padded if contiguous else None, cpad=cpad,
+                want_f32=(out_padded is None) or not contiguous, want_labels=True)
+            if x is not None:
+                x[torch.as_tensor(slots, device=x.device)] = xi
+            elif not contiguous:
+                raise NotImplementedError("direct U-Net input writes need a single resident image per rank")
+            y[torch.as_tensor(slots, device=y.device)] = yi
+            w[slots] = image.sample_weight
+        return x, y, w
+
+    def __getitem__(self, idx):
+        """Reference batch layout (…_2d.py:163-216 + prepare_batches): x [B,dim,dim,C] f32,
+        y [B,dim*dim,1] uint8, w [B]."""
+        x, y, w = self.sample_batch_device()
+        B = x.shape[0]
+        return x.cpu().numpy(), y.cpu().numpy().reshape(B, -1, 1), w.astype(np.float64)
+
+    def __len__(self):
+        return 10 ** 6

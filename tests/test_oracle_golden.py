@@ -1,0 +1,86 @@
+"""The CPU oracle reproduces the committed golden vectors, which were produced by the UNMODIFIED
+reference source (oracle/make_golden.py).  Bit-exact for images (float32), labels and gathers."""
+import os
+
+import numpy as np
+
+import golden_inputs as gi
+from oracle import fusion, sampler
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_sampler_matches_reference_goldens():
+    for case in gi.SAMPLER_CASES:
+        z = np.load(os.path.join(GOLD, "sampler_%s.npz" % case["name"]))
+        vol, lab, affine, bg = gi.sampler_volume(case)
+        k = 0
+        for view in case["views"]:
+            basis = sampler.plane_basis(view)
+            for off in case["offsets"]:
+                im, lb = sampler.sample_plane(vol, lab, case["pix"], basis, case["dim"], case["span"], off, bg, 0)
+                assert np.array_equal(np.linalg.inv(basis), z["inv_basis"][k])
+                assert np.array_equal(im, z["im"][k]), (case["name"], view, off)
+                assert np.array_equal(lb, z["lab"][k]), (case["name"], view, off)
+                hd = case["span"] // 2
+                assert np.array_equal(np.linspace(-hd, hd, case["dim"]), z["axis"][k])
+                k += 1
+
+
+def test_mapping_matches_reference_goldens():
+    for case in gi.MAPPING_CASES:
+        z = np.load(os.path.join(GOLD, "mapping_%s.npz" % case["name"]))
+        preds, grids, inv_bases, shape, affine = gi.mapping_inputs(case)
+        vg = fusion.voxel_grid_real_space(shape, affine[:3, :3])
+        assert np.array_equal(vg[:, :2, :2, :2], z["vgrid_corner"])
+        oob = 0.0
+        for v, (p, g, ib) in enumerate(zip(preds, grids, inv_bases)):
+            mapped = fusion.map_real_space_pred(np.moveaxis(p, 0, 2), g, ib, vg)
+            assert np.array_equal(mapped, z["mapped"][v].astype(np.float32))
+            oob += (mapped[..., 0] == 1.0).mean()
+        # the oblique views leave the volume corners outside the sampled stack -> one-hot background
+        assert 0.0 < oob / len(preds) < 0.9
+
+
+def test_view_offsets_and_plane_axis():
+    offs = sampler.view_offsets(256, 256.0, "same+20")
+    assert len(offs) == 276 and offs[0] == -offs[-1]
+    res = 256.0 / 255
+    assert np.isclose(offs[-1], (256.0 + 20 * res) / 2)
+    a = sampler.plane_axis(256, 256.0)
+    assert a[0] == -128.0 and np.isclose(a[-1], 128.0)
+
+
+def test_fusion_formulas():
+    rng = np.random.RandomState(0)
+    x = rng.rand(100, 6, 5).astype(np.float32)
+    W = np.ones((6, 5), np.float32)
+    b = np.zeros(5, np.float32)
+    p = fusion.fusion_forward(x, W, b)
+    assert np.allclose(p.sum(-1), 1, atol=1e-6)
+    # with unit weights the fused argmax equals the argmax of the plain view sum (monotone softmax)
+    assert np.array_equal(p.argmax(-1), x.sum(1).argmax(-1))
+    # analytic gradient vs central differences (float64)
+    y = rng.randint(0, 5, 100)
+    W = rng.uniform(0.5, 1.5, (6, 5))
+    b = 0.1 * rng.randn(5)
+    loss, dW, db = fusion.gdl_loss_and_grads(x, y, W, b)
+    eps = 1e-6
+    for (i, j) in [(0, 0), (3, 2), (5, 4)]:
+        Wp, Wm = W.copy(), W.copy()
+        Wp[i, j] += eps
+        Wm[i, j] -= eps
+        num = (fusion.gdl_loss_and_grads(x, y, Wp, b)[0] - fusion.gdl_loss_and_grads(x, y, Wm, b)[0]) / (2 * eps)
+        assert abs(num - dW[i, j]) < 1e-7
+    bp, bm = b.copy(), b.copy()
+    bp[1] += eps
+    bm[1] -= eps
+    num = (fusion.gdl_loss_and_grads(x, y, W, bp)[0] - fusion.gdl_loss_and_grads(x, y, W, bm)[0]) / (2 * eps)
+    assert abs(num - db[1]) < 1e-7
+
+
+def test_dice_all():
+    a = np.array([0, 1, 1, 2, 2, 2])
+    b = np.array([0, 1, 2, 2, 2, 0])
+    d = fusion.dice_all(a, b, 3)
+    assert np.allclose(d, [(1 + 2 * 1) / (1 + 2 + 1), (1 + 2 * 2) / (1 + 3 + 3)])

@@ -1,0 +1,77 @@
+"""Pins the oracle against the LIVE reference source where it is present (this container only; the
+GPU box has no /root/reference, so these tests skip there).  Wider sweep than the golden fixtures."""
+import numpy as np
+import pytest
+
+from conftest import has_reference
+from oracle import fusion, sampler
+
+pytestmark = pytest.mark.skipif(not has_reference(), reason="/root/reference not present")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    from oracle import ref_shim
+    return ref_shim.modules()
+
+
+def test_sampler_equals_reference(ref):
+    rng = np.random.RandomState(3)
+    vol = rng.randn(20, 16, 24, 2).astype(np.float32)
+    lab = rng.randint(0, 5, size=(20, 16, 24)).astype(np.uint8)
+    aff = np.eye(4)
+    ivi = ref.view_interpolator.ViewInterpolator(vol, lab, aff, bg_value=[0.5, -2.0], bg_class=0)
+    for view in [(0.3, 0.5, 0.8), (0, 0, 1), (0, 1, 0), (0.1, 0.1, 0.98), (-0.4, -0.4, 0.2)]:
+        basis = sampler.plane_basis(view)
+        for off in [-11.0, -0.37, 6.5]:
+            grid, g, inv = ref.sample_grid.sample_plane_at(view, sample_dim=28, real_space_span=26,
+                                                           offset_from_center=off, noise_sd=0., test_mode=True)
+            im_r, lab_r = ivi(grid)
+            pts = sampler.plane_points(basis, 28, 26, off)
+            assert np.array_equal(pts, np.moveaxis(grid[..., 0], 0, -1))
+            im_o, lab_o = sampler.sample_plane(vol, lab, (1, 1, 1), basis, 28, 26, off, [0.5, -2.0], 0)
+            assert np.array_equal(im_o, im_r) and np.array_equal(lab_o, lab_r)
+            assert np.array_equal(np.linalg.inv(basis), inv)
+
+
+def test_noisy_basis_equals_reference(ref):
+    for seed in range(5):
+        np.random.seed(seed)
+        grid, g, inv = ref.sample_grid.sample_plane_at((0.3, 0.5, 0.8), 8, 10, 1.0, noise_sd=0.1, test_mode=True)
+        np.random.seed(seed)
+        noise = np.random.normal(scale=0.1, size=3)
+        assert np.array_equal(np.linalg.inv(sampler.plane_basis((0.3, 0.5, 0.8), noise)), inv)
+
+
+def test_mapping_equals_reference(ref):
+    if ref.fuse_and_predict is None:
+        pytest.skip("fuse_and_predict not importable under the shim")
+    rng = np.random.RandomState(4)
+    shape = (14, 18, 12)
+
+    class Img:
+        pass
+    img = Img()
+    img.shape = shape + (1,)
+    img.affine = np.eye(4)
+    vg_r = ref.sample_grid.get_voxel_grid_real_space(img)
+    vg_o = fusion.voxel_grid_real_space(shape, np.eye(3))
+    assert np.array_equal(vg_r, vg_o)
+    pred = rng.rand(20, 20, 26, 3).astype(np.float32)
+    g = np.linspace(-9, 9, 20)
+    for view in [(0.3, 0.5, 0.8), (1, 0, 0)]:
+        ib = np.linalg.inv(sampler.plane_basis(view))
+        offs = sampler.view_offsets(20, 18, 26)
+        a = ref.fuse_and_predict.map_real_space_pred(pred, (g, g, offs), ib, vg_r)
+        b = fusion.map_real_space_pred(pred, (g, g, offs), ib, vg_o)
+        assert np.array_equal(a, b)
+
+
+def test_host_geometry_mirror_equals_reference(ref):
+    """The product's host-side plane geometry (multiplanarunet_b200.interpolation) against the reference."""
+    from multiplanarunet_b200.interpolation import sample_plane_at, view_offsets
+    for view in [(0.3, 0.5, 0.8), (0, 0, 1), (-0.7, 0.1, 0.2)]:
+        (basis, off), g, inv = sample_plane_at(view, 32, 30, 2.5, 0., test_mode=True)
+        grid, g_r, inv_r = ref.sample_grid.sample_plane_at(view, 32, 30, 2.5, 0., test_mode=True)
+        assert np.array_equal(inv, inv_r) and np.array_equal(g, g_r) and off == 2.5
+    assert np.array_equal(view_offsets(64, 64.0, "same+20"), sampler.view_offsets(64, 64.0, "same+20"))
