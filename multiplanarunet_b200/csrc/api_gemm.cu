@@ -35,33 +35,19 @@ int mpu_mtgemm_fwd(const void* A0, long long rowsA0, int C0, int ldA0, const voi
     set_error("mpu_mtgemm_fwd: bad arguments");
     return MPU_ERR_ARG;
   }
+  FwdDesc d;
+  memset(&d, 0, sizeof(d));
+  d.A0 = A0; d.rowsA0 = rowsA0; d.C0 = C0; d.ldA0 = ldA0;
+  d.A1 = A1; d.rowsA1 = rowsA1; d.C1 = C1; d.ldA1 = ldA1;
+  d.W = W; d.w_taps = w_taps; d.n_phys = n_phys; d.k_total = k_total;
+  d.ntaps = ntaps; d.tap_a_off = tap_a_off; d.tap_w = tap_w;
+  d.M_rows = M_rows;
+  d.BN = BN;
+  d.map = RowMap{Hp, Wp, oHp, oWp, s, py, px};
+  d.out = out; d.ldo = ldo; d.bias = bias; d.mask = mask; d.ldm = ldm; d.relu = relu;
+  d.stats = nullptr;
   FwdParams p;
-  memset(&p, 0, sizeof(p));
-  MPU_TRY(make_tmap_2d(&p.tmA0, A0, (uint64_t)rowsA0, (uint64_t)C0, (uint64_t)ldA0, 64, 128));
-  p.chunks0 = (C0 + 63) / 64;
-  if (A1) {
-    MPU_TRY(make_tmap_2d(&p.tmA1, A1, (uint64_t)rowsA1, (uint64_t)C1, (uint64_t)ldA1, 64, 128));
-    p.chunks1 = (C1 + 63) / 64;
-    p.kofs1 = C0;
-  }
-  MPU_TRY(make_tmap_2d(&p.tmB, W, (uint64_t)w_taps * n_phys, (uint64_t)k_total, (uint64_t)k_total, 64,
-                       (uint32_t)BN));
-  p.ntaps = ntaps;
-  for (int t = 0; t < ntaps; ++t) {
-    p.tap_a_off[t] = tap_a_off[t];
-    p.tap_w[t] = tap_w[t];
-  }
-  p.w_rows_per_tap = n_phys;
-  p.M_rows = M_rows;
-  p.n_valid = n_phys;
-  p.BN = BN;
-  p.map = RowMap{Hp, Wp, oHp, oWp, s, py, px};
-  p.out = reinterpret_cast<__nv_bfloat16*>(out);
-  p.ldo = ldo;
-  p.bias = bias;
-  p.mask = reinterpret_cast<const __nv_bfloat16*>(mask);
-  p.ldm = ldm;
-  p.relu = relu;
+  MPU_TRY(fwd_setup(p, d));
   return launch_fwd(p, reinterpret_cast<cudaStream_t>(stream));
 }
 
@@ -75,36 +61,23 @@ int mpu_mtgemm_wgrad(const void* X, long long rowsX, int Cx, int ldX, const void
     set_error("mpu_mtgemm_wgrad: bad arguments");
     return MPU_ERR_ARG;
   }
+  (void)ngroups; (void)group_first; (void)group_count; (void)a_lbo; (void)a_sbo; (void)b_lbo; (void)b_sbo;
+  (void)kstep_bytes; (void)ci_valid; (void)co_valid;
+  // per-tap dY offsets from the legacy group description
+  int dy_off[kMaxTaps] = {0};
+  for (int g = 0; g < ngroups; ++g)
+    for (int t = group_first[g]; t < group_first[g] + group_count[g] && t < ntaps; ++t) dy_off[t] = group_dy_off[g];
+  WgradDesc d;
+  memset(&d, 0, sizeof(d));
+  d.X = X; d.rowsX = rowsX; d.Cx = Cx; d.ldX = ldX;
+  d.dY = dY; d.rowsDY = rowsDY; d.Cy = Cy; d.ldDY = ldDY;
+  d.ntaps = ntaps; d.tap_x_off = tap_x_off; d.tap_dy_off = dy_off; d.tap_w = tap_w;
+  d.rows_total = rows_total;
+  d.BN = BN > 160 ? 0 : BN;
+  d.splits = splits;
+  d.dW = dW; d.ldw = ldw; d.w_rows_per_tap = w_rows_per_tap; d.dw_col0 = dw_col0;
   WgradParams p;
-  memset(&p, 0, sizeof(p));
-  MPU_TRY(make_tmap_2d(&p.tmX, X, (uint64_t)rowsX, (uint64_t)Cx, (uint64_t)ldX, 64, 64));
-  MPU_TRY(make_tmap_2d(&p.tmDY, dY, (uint64_t)rowsDY, (uint64_t)Cy, (uint64_t)ldDY, 64, 64));
-  p.ntaps = ntaps;
-  for (int t = 0; t < ntaps; ++t) {
-    p.tap_x_off[t] = tap_x_off[t];
-    p.tap_w[t] = tap_w[t];
-  }
-  p.ngroups = ngroups;
-  for (int g = 0; g < ngroups; ++g) p.groups[g] = WgradGroup{group_first[g], group_count[g], group_dy_off[g]};
-  p.BN = BN;
-  p.ci_tiles = (ci_valid + 127) / 128;
-  p.co_tiles = (co_valid + BN - 1) / BN;
-  p.kblocks = (rows_total + 63) / 64;
-  if (splits < 1) splits = 1;
-  if (splits > p.kblocks) splits = p.kblocks;
-  p.kblocks_per_split = (p.kblocks + splits - 1) / splits;
-  p.splits = (p.kblocks + p.kblocks_per_split - 1) / p.kblocks_per_split;
-  p.dW = dW;
-  p.ldw = ldw;
-  p.w_rows_per_tap = w_rows_per_tap;
-  p.dw_col0 = dw_col0;
-  p.ci_valid = ci_valid;
-  p.co_valid = co_valid;
-  p.a_lbo = a_lbo > 0 ? a_lbo : 8192;
-  p.a_sbo = a_sbo > 0 ? a_sbo : 1024;
-  p.b_lbo = b_lbo > 0 ? b_lbo : 8192;
-  p.b_sbo = b_sbo > 0 ? b_sbo : 1024;
-  p.kstep_bytes = kstep_bytes > 0 ? kstep_bytes : 2048;
+  MPU_TRY(wgrad_setup(p, d));
   return launch_wgrad(p, reinterpret_cast<cudaStream_t>(stream));
 }
 

@@ -1,64 +1,114 @@
 // tcgen05 / TMA / TMEM multi-tap GEMM kernels (sm_100a). See mtgemm.cuh for the math.
 //
-// Warp roles (256 threads, 1 CTA per SM):
-//   warp 0   : TMA producer (one elected lane)
-//   warp 1   : tcgen05.mma issuer (one elected lane)
-//   warp 2   : TMEM allocator / deallocator
-//   warps 4-7: epilogue (TMEM -> registers -> global), warp w owns TMEM lanes 32*(w%4)..+31
+// Measured facts these kernels are built around (B200, ncu + in-kernel cycle counters, profiles/):
+//   * a tcgen05.mma with both operands in shared memory costs ~165 cycles per issue whatever N is (the
+//     128-row A operand fetch), so every MMA is given the full N = 256: the forward/dgrad kernel puts
+//     the OUTPUT CHANNELS on the 128 MMA rows (weights = A operand) and 256 PIXELS on the columns;
+//   * issuing TMA / MMA from a divergent `lane == 0` branch makes ptxas wrap every UTCHMMA in an
+//     ELECT+BRA waterfall loop: producer / MMA warps run warp-uniform loops and issue from one
+//     elect.sync lane;
+//   * the 128B swizzle is applied on absolute shared-memory address bits: a descriptor whose start
+//     address is shifted by whole 128 B rows inside a TMA-written tile reads the shifted rows
+//     correctly with the base-offset field left at 0.  One activation "slab" load therefore serves
+//     the kx-1, kx, kx+1 taps of a 3x3 kernel row.
+//   * operand traffic L2 -> SM is the next bound (~42 B/clk/SM): slabs are shared across taps and
+//     rings of slabs / weight tiles keep the tensor pipe fed.
 #include "mtgemm.cuh"
 #include "ptx.cuh"
 #include "common.h"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace mpu {
 
 using namespace ptx;
 
-static constexpr int kThreads = 256;
-static constexpr int kSmemBudget = 232448 - 2048;  // 227 KB minus alignment slack + barrier block
-static constexpr int kABytes = 128 * 128;          // 128 rows x 64 bf16 (fwd A tile)
+// mbarrier wait that optionally accumulates the stall time (bring-up profiling of the role pipeline)
+__device__ __forceinline__ void timed_wait(uint32_t bar, uint32_t parity, long long* acc) {
+  if (acc) {
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    *acc += clock64() - t0;
+  } else {
+    mbar_wait(bar, parity);
+  }
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+static constexpr int kThreads = 256;       // wgrad kernel
+static constexpr int kFwdThreads = 384;    // fwd kernel: 4 control warps + 8 epilogue warps
+static constexpr int kSmemBudget = 232448 - 1024 - 1024 - 512;  // 227 KB minus launch slack, alignment, barriers
+
+static constexpr int kPT = 256;                              // pixels per CTA tile (MMA N)
+static constexpr uint32_t kSlabRows = kPT + 8;               // 264: room for tap shifts of up to 7 rows
+static constexpr uint32_t kSlabBytes = kSlabRows * 128u;     // 33792 (multiple of 1024)
+static constexpr uint32_t kWTileBytes = 128u * 128u;         // 128 output channels x 64 K
+static constexpr uint32_t kStageHalfBytes = 128u * 256u;     // epilogue staging: 128 pixels x 128 ch bf16
 
 // ------------------------------------------------------------------------------------------------
-// Forward-type kernel (also used for dgrad): persistent over (m_tile, n_tile), TMEM double-buffered.
+// Forward-type kernel (forward conv, dgrad, upsample-conv phases).  Persistent over CTA tiles of
+// 256 pixels x 128 output channels:  D[co, px] = sum_{tap, k-chunk} W_tap[co, k] * Slab[px + shift_tap, k]^T
+//   warp 0   : TMA producer   (activation slabs -> ring A, weight tiles -> ring W)
+//   warp 1   : tcgen05.mma issuer, fp32 accumulators in TMEM (2 stages x 256 columns)
+//   warp 2   : TMEM allocator
+//   warps 4-11: epilogue.  Thread = output channel (TMEM lane), 16 pixels per tcgen05.ld: bias + ReLU,
+//              bf16 rounding, optional per-channel sum / sum-of-squares (BatchNorm statistics or bias
+//              gradients, accumulated in registers across tiles), transpose through shared memory, then
+//              row-wise coalesced 16-byte stores (optional ReLU-backward mask applied there).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 1) mtgemm_fwd_kernel(const __grid_constant__ FwdParams p) {
+__global__ void __launch_bounds__(kFwdThreads, 1) mtgemm_fwd_kernel(const __grid_constant__ FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const int S = p.stages;
-  const uint32_t b_bytes = (uint32_t)p.BN * 128u;
-  const uint32_t stage_bytes = kABytes + b_bytes;
-  const uint32_t bar_base = smem_base + (uint32_t)S * stage_bytes;
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
-  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * S + s); };
-  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * S + 2 + s); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * S + 4);
-  volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int NA = p.a_slots, NW = p.w_slots;
+  const uint32_t a_base = smem_base;
+  const uint32_t w_base = a_base + (uint32_t)NA * kSlabBytes;
+  const uint32_t stg_off = (uint32_t)NA * kSlabBytes + (uint32_t)NW * kWTileBytes;  // 2 x 32 KB staging
+  const uint32_t orow_off = stg_off + 2u * kStageHalfBytes;                          // int[256]
+  const uint32_t bar_base = smem_base + orow_off + 1024u;
+  auto a_full = [&](int s) { return bar_base + 8u * s; };
+  auto a_empty = [&](int s) { return bar_base + 8u * (NA + s); };
+  auto w_full = [&](int s) { return bar_base + 8u * (2 * NA + s); };
+  auto w_empty = [&](int s) { return bar_base + 8u * (2 * NA + NW + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * NA + 2 * NW + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * NA + 2 * NW + 2 + s); };
+  const uint32_t tmem_slot_off = orow_off + 1024u + 8u * (2 * NA + 2 * NW + 4);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_al + tmem_slot_off);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
-    prefetch_tmap(&p.tmA0);
-    if (p.chunks1 > 0) prefetch_tmap(&p.tmA1);
-    prefetch_tmap(&p.tmB);
+    prefetch_tmap(&p.tmA0_hi);
+    prefetch_tmap(&p.tmA0_lo);
+    if (p.chunks1 > 0) {
+      prefetch_tmap(&p.tmA1_hi);
+      prefetch_tmap(&p.tmA1_lo);
+    }
+    prefetch_tmap(&p.tmW);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < S; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+    for (int s = 0; s < NA; ++s) {
+      mbar_init(a_full(s), 1);
+      mbar_init(a_empty(s), 1);
+    }
+    for (int s = 0; s < NW; ++s) {
+      mbar_init(w_full(s), 1);
+      mbar_init(w_empty(s), 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 128);
+      mbar_init(tempty_bar(s), 256);
     }
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, 512);
+    tmem_alloc(smem_base + tmem_slot_off, 512);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -68,132 +118,213 @@ __global__ void __launch_bounds__(kThreads, 1) mtgemm_fwd_kernel(const __grid_co
 
   const int total_tiles = p.m_tiles * p.n_tiles;
   const int kchunks = p.chunks0 + p.chunks1;
-  const int nk = p.ntaps * kchunks;
+  const bool prof = p.dbg != nullptr && blockIdx.x == 0;
+  long long w0 = 0, w1 = 0, w2 = 0;
+  const long long t_start = prof ? clock64() : 0;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m0 = (tile / p.n_tiles) * 128;
-        const int n0 = (tile % p.n_tiles) * p.BN;
-        for (int t = 0; t < p.ntaps; ++t) {
-          const int arow = m0 + p.tap_a_off[t];
-          const int wrow = p.tap_w[t] * p.w_rows_per_tap + n0;
-          for (int c = 0; c < kchunks; ++c) {
-            mbar_wait(empty_bar(s), ph ^ 1u);
-            const uint32_t a_dst = smem_base + (uint32_t)s * stage_bytes;
-            const uint32_t b_dst = a_dst + kABytes;
-            mbar_expect_tx(full_bar(s), stage_bytes);
-            int kcol;
-            if (c < p.chunks0) {
-              tma_load_2d(&p.tmA0, full_bar(s), a_dst, c * 64, arow);
-              kcol = c * 64;
-            } else {
-              tma_load_2d(&p.tmA1, full_bar(s), a_dst, (c - p.chunks0) * 64, arow);
-              kcol = p.kofs1 + (c - p.chunks0) * 64;
+    // ===== TMA producer (warp-uniform loop, one elected lane issues) =====
+    int as = 0, ws = 0;
+    uint32_t aph = 0, wph = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m0 = (tile / p.n_tiles) * kPT;
+      const int n0 = (tile % p.n_tiles) * 128;
+      for (int g = 0; g < p.ngroups; ++g) {
+        const TapGroup& G = p.groups[g];
+        const int arow = m0 + G.a_off;
+        for (int c = 0; c < kchunks; ++c) {
+          timed_wait(a_empty(as), aph ^ 1u, prof ? &w0 : nullptr);
+          const uint32_t a_dst = a_base + (uint32_t)as * kSlabBytes;
+          int kcol, ccol;
+          const CUtensorMap *mhi, *mlo;
+          if (c < p.chunks0) {
+            ccol = c * 64;
+            kcol = ccol;
+            mhi = &p.tmA0_hi;
+            mlo = &p.tmA0_lo;
+          } else {
+            ccol = (c - p.chunks0) * 64;
+            kcol = p.kofs1 + ccol;
+            mhi = &p.tmA1_hi;
+            mlo = &p.tmA1_lo;
+          }
+          if (elect_one()) {
+            mbar_expect_tx(a_full(as), kSlabBytes);
+            tma_load_2d(mhi, a_full(as), a_dst, ccol, arow);
+            tma_load_2d(mlo, a_full(as), a_dst + 136u * 128u, ccol, arow + 136);
+          }
+          __syncwarp();
+          if (++as == NA) { as = 0; aph ^= 1u; }
+          for (int t = 0; t < G.ntaps; ++t) {
+            timed_wait(w_empty(ws), wph ^ 1u, prof ? &w1 : nullptr);
+            if (elect_one()) {
+              mbar_expect_tx(w_full(ws), kWTileBytes);
+              tma_load_2d(&p.tmW, w_full(ws), w_base + (uint32_t)ws * kWTileBytes, kcol,
+                          G.w_idx[t] * p.w_rows_per_tap + n0);
             }
-            tma_load_2d(&p.tmB, full_bar(s), b_dst, kcol, wrow);
-            if (++s == S) { s = 0; ph ^= 1u; }
+            __syncwarp();
+            if (++ws == NW) { ws = 0; wph ^= 1u; }
           }
         }
       }
+    }
+    if (prof && lane == 0) {
+      p.dbg[0] = w0;
+      p.dbg[1] = w1;
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, p.BN, 0, 0);
-      int s = 0;
-      uint32_t ph = 0;
-      int as = 0;
-      uint32_t aph = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        mbar_wait(tempty_bar(as), aph ^ 1u);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)as * 256u;
-        for (int k = 0; k < nk; ++k) {
-          mbar_wait(full_bar(s), ph);
-          tc_fence_after();
-          const uint32_t a_addr = smem_base + (uint32_t)s * stage_bytes;
-          const uint64_t a_desc = make_desc_sw128(a_addr, 16, 1024);
-          const uint64_t b_desc = make_desc_sw128(a_addr + kABytes, 16, 1024);
+    // ===== MMA issuer =====
+    const uint32_t idesc = make_idesc_bf16(128, kPT, 0, 0);
+    int as = 0, ws = 0;
+    uint32_t aph = 0, wph = 0;
+    int acs = 0;
+    uint32_t acph = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      timed_wait(tempty_bar(acs), acph ^ 1u, prof ? &w2 : nullptr);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acs * kPT);
+      uint32_t first = 1;
+      for (int g = 0; g < p.ngroups; ++g) {
+        const TapGroup& G = p.groups[g];
+        for (int c = 0; c < kchunks; ++c) {
+          timed_wait(a_full(as), aph, prof ? &w0 : nullptr);
+          const uint32_t a_addr = a_base + (uint32_t)as * kSlabBytes;
+          // K=16 steps that hold real channels in this 64-channel chunk (the rest is TMA zero fill)
+          const int crem = c < p.chunks0 ? p.c0_valid - c * 64 : p.c1_valid - (c - p.chunks0) * 64;
+          const int ksteps = crem >= 64 ? 4 : (crem + 15) >> 4;
+          for (int t = 0; t < G.ntaps; ++t) {
+            timed_wait(w_full(ws), wph, prof ? &w1 : nullptr);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint64_t w_desc = make_desc_sw128(w_base + (uint32_t)ws * kWTileBytes, 16, 1024);
+              const uint64_t x_desc = make_desc_sw128(a_addr + (uint32_t)G.shift[t] * 128u, 16, 1024);
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            // advance 16 bf16 (32 B) along K inside the 128 B swizzle row: +2 in 16 B units
-            mma_bf16_ss(d_tmem, a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), idesc,
-                        (k | kk) != 0 ? 1u : 0u);
+              for (int kk = 0; kk < 4; ++kk) {
+                if (kk < ksteps)
+                  mma_bf16_ss(d_tmem, w_desc + (uint64_t)(kk * 2), x_desc + (uint64_t)(kk * 2), idesc,
+                              (first && kk == 0) ? 0u : 1u);
+              }
+              mma_commit(w_empty(ws));
+              if (t == G.ntaps - 1) mma_commit(a_empty(as));
+            }
+            __syncwarp();
+            first = 0;
+            if (++ws == NW) { ws = 0; wph ^= 1u; }
           }
-          mma_commit(empty_bar(s));
-          if (++s == S) { s = 0; ph ^= 1u; }
+          if (++as == NA) { as = 0; aph ^= 1u; }
         }
-        mma_commit(tfull_bar(as));
-        if (++as == 2) { as = 0; aph ^= 1u; }
       }
+      if (elect_one()) mma_commit(tfull_bar(acs));
+      __syncwarp();
+      if (++acs == 2) { acs = 0; acph ^= 1u; }
+    }
+    if (prof && lane == 0) {
+      p.dbg[2] = w0;
+      p.dbg[3] = w1;
+      p.dbg[4] = w2;
+      p.dbg[7] = clock64() - t_start;
     }
   } else if (warp >= 4) {
-    const int q = warp & 3;
-    int as = 0;
-    uint32_t aph = 0;
+    // ===== epilogue =====
+    const int q = warp & 3;              // TMEM lane quarter: channels q*32 .. q*32+31 of the tile
+    const int half = (warp - 4) >> 2;    // pixel half: columns half*128 .. +127
+    const int et = threadIdx.x - 128 - half * 128;  // 0..127 inside the half
+    const int ch_local = q * 32 + lane;
+    __nv_bfloat16* stg = reinterpret_cast<__nv_bfloat16*>(smem_al + stg_off + (uint32_t)half * kStageHalfBytes);
+    int* orow_s = reinterpret_cast<int*>(smem_al + orow_off) + half * 128;
     const int plane = p.map.Hp * p.map.Wp;
+    const bool prof_e = prof && warp == 4 && lane == 0;
+    int acs = 0;
+    uint32_t acph = 0;
+    float s_sum = 0.f, s_sq = 0.f;
+    int s_ch = -1;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m0 = (tile / p.n_tiles) * 128;
-      const int n0 = (tile % p.n_tiles) * p.BN;
-      const int m = m0 + q * 32 + lane;
-      bool valid = m < p.M_rows;
-      long long orow = 0;
-      {
-        const int img = m / plane;
-        const int rem = m - img * plane;
-        const int ya = rem / p.map.Wp;
-        const int xa = rem - ya * p.map.Wp;
-        valid = valid && ya >= 1 && ya <= p.map.Hp - 2 && xa >= 1 && xa <= p.map.Wp - 2;
-        orow = (long long)img * p.map.oHp * p.map.oWp +
-               (long long)(p.map.s * (ya - 1) + p.map.py + 1) * p.map.oWp +
-               (p.map.s * (xa - 1) + p.map.px + 1);
+      const int m0 = (tile / p.n_tiles) * kPT;
+      const int n0 = (tile % p.n_tiles) * 128;
+      const int ch = n0 + ch_local;
+      if (p.stats && ch != s_ch) {  // channel tile changed: flush the register accumulators
+        if (s_ch >= 0 && s_ch < p.n_valid) {
+          atomicAdd(p.stats + s_ch, (double)s_sum);
+          atomicAdd(p.stats + p.n_valid + s_ch, (double)s_sq);
+        }
+        s_sum = s_sq = 0.f;
+        s_ch = ch;
       }
-      mbar_wait(tfull_bar(as), aph);
+      // output row (or -1) of pixel `et` of this half
+      {
+        const int m = m0 + half * 128 + et;
+        int orow = -1;
+        if (m < p.M_rows) {
+          const int img = m / plane;
+          const int rem = m - img * plane;
+          const int ya = rem / p.map.Wp;
+          const int xa = rem - ya * p.map.Wp;
+          if (ya >= 1 && ya <= p.map.Hp - 2 && xa >= 1 && xa <= p.map.Wp - 2)
+            orow = img * p.map.oHp * p.map.oWp + (p.map.s * (ya - 1) + p.map.py + 1) * p.map.oWp +
+                   (p.map.s * (xa - 1) + p.map.px + 1);
+        }
+        orow_s[et] = orow;
+      }
+      named_bar_sync(1 + half, 128);
+      timed_wait(tfull_bar(acs), acph, prof_e ? &w0 : nullptr);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * 256u;
-      for (int c0 = 0; c0 < p.BN; c0 += 16) {
+      const long long te0 = prof_e ? clock64() : 0;
+      const float bias = (p.bias && ch < p.n_valid) ? __ldg(p.bias + ch) : 0.f;
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acs * kPT + half * 128);
+#pragma unroll 2
+      for (int c0 = 0; c0 < 128; c0 += 16) {
         uint32_t r[16];
         tmem_ld16(t_row + (uint32_t)c0, r);
         tmem_ld_wait();
-        const int n = n0 + c0;
-        if (valid && n < p.n_valid) {
-          float v[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-          if (p.bias) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (n + j < p.n_valid) v[j] += __ldg(p.bias + n + j);
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
-          }
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            if (n + h * 8 < p.n_valid) {
-              if (p.mask) {
-                const uint4 mk = *reinterpret_cast<const uint4*>(p.mask + orow * p.ldm + n + h * 8);
-                const __nv_bfloat16* mb = reinterpret_cast<const __nv_bfloat16*>(&mk);
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                  if (!(__bfloat162float(mb[j]) > 0.f)) v[h * 8 + j] = 0.f;
-              }
-              uint4 o;
-              __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                ob[j] = __floats2bfloat162_rn(v[h * 8 + 2 * j], v[h * 8 + 2 * j + 1]);
-              *reinterpret_cast<uint4*>(p.out + orow * p.ldo + n + h * 8) = o;
-            }
+        for (int j = 0; j < 16; ++j) {
+          float v = __uint_as_float(r[j]) + bias;
+          if (p.relu) v = fmaxf(v, 0.f);
+          const __nv_bfloat16 hb = __float2bfloat16_rn(v);
+          stg[(c0 + j) * 128 + ch_local] = hb;
+          if (p.stats && orow_s[c0 + j] >= 0) {
+            const float vr = __bfloat162float(hb);
+            s_sum += vr;
+            s_sq = fmaf(vr, vr, s_sq);
           }
         }
       }
       tc_fence_before();
-      mbar_arrive(tempty_bar(as));
-      if (++as == 2) { as = 0; aph ^= 1u; }
+      mbar_arrive(tempty_bar(acs));  // accumulator drained: the MMA warp may start the next tile
+      named_bar_sync(1 + half, 128);
+      // row-wise copy-out: 16 chunks of 16 B per pixel row (128 channels), 2 rows per warp instruction
+      {
+        const int nchunk = min(16, (p.n_valid - n0 + 7) >> 3);
+        const int sub = lane >> 4, chunk = lane & 15;
+        for (int r0 = q * 32; r0 < q * 32 + 32; r0 += 2) {
+          const int rr = r0 + sub;
+          const int orow = orow_s[rr];
+          if (orow >= 0 && chunk < nchunk) {
+            uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 128 + chunk * 8);
+            const long long o = (long long)orow;
+            if (p.mask) {
+              const uint4 mk = *reinterpret_cast<const uint4*>(p.mask + o * p.ldm + n0 + chunk * 8);
+              const __nv_bfloat16* mb = reinterpret_cast<const __nv_bfloat16*>(&mk);
+              __nv_bfloat16* vb = reinterpret_cast<__nv_bfloat16*>(&val);
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (!(__bfloat162float(mb[j]) > 0.f)) vb[j] = __float2bfloat16_rn(0.f);
+            }
+            *reinterpret_cast<uint4*>(p.out + o * p.ldo + n0 + chunk * 8) = val;
+          }
+        }
+      }
+      named_bar_sync(1 + half, 128);  // staging + row table are reused by the next tile
+      if (prof_e) w1 += clock64() - te0;
+      if (++acs == 2) { acs = 0; acph ^= 1u; }
+    }
+    if (p.stats && s_ch >= 0 && s_ch < p.n_valid) {
+      atomicAdd(p.stats + s_ch, (double)s_sum);
+      atomicAdd(p.stats + p.n_valid + s_ch, (double)s_sq);
+    }
+    if (prof_e) {
+      p.dbg[5] = w0;
+      p.dbg[6] = w1;
     }
   }
 
@@ -206,19 +337,22 @@ __global__ void __launch_bounds__(kThreads, 1) mtgemm_fwd_kernel(const __grid_co
 }
 
 // ------------------------------------------------------------------------------------------------
-// Wgrad kernel: one CTA = (ci tile of 128, co tile of BN, tap group, K split). MN-major operands
-// straight from the NHWC tensors (pixels are the contraction dim), fp32 atomics into dW.
+// Wgrad kernel: one CTA = (ci tile of 128, co tile of BN, tap group = one kernel row, K split).
+// MN-major operands straight from the NHWC tensors (pixels are the contraction dim): per 64-pixel K
+// block one X slab of 72 rows serves the group's taps through row-shifted descriptors, one dY tile
+// feeds all of them; fp32 accumulators in TMEM (one per tap), fp32 atomics into dW at the end.
 // ------------------------------------------------------------------------------------------------
+static constexpr uint32_t kWgSlabRows = 72;
+static constexpr uint32_t kWgAtomBytes = kWgSlabRows * 128u;  // 9216: one 64-channel atom of the slab
+
 __global__ void __launch_bounds__(kThreads, 1)
     mtgemm_wgrad_kernel(const __grid_constant__ WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int S = p.stages;
-  int gmax = 1;
-  for (int g = 0; g < p.ngroups; ++g) gmax = max(gmax, p.groups[g].count);
   const int nb = (p.BN + 63) / 64;
-  const uint32_t a_tap_bytes = 2u * 8192u;  // two 64-channel atoms x 64 K rows
-  const uint32_t stage_bytes = (uint32_t)gmax * a_tap_bytes + (uint32_t)nb * 8192u;
+  const uint32_t a_bytes = 2u * kWgAtomBytes;  // two 64-channel atoms (M = 128 input channels)
+  const uint32_t stage_bytes = a_bytes + (uint32_t)nb * 8192u;
   const uint32_t bar_base = smem_base + (uint32_t)S * stage_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
@@ -236,7 +370,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   const int gi = w % p.ngroups;   w /= p.ngroups;
   const int co_t = w % p.co_tiles; w /= p.co_tiles;
   const int ci_t = w;
-  const WgradGroup grp = p.groups[gi];
+  const WgradGroup& grp = p.groups[gi];
   const int ci0 = ci_t * 128, co0 = co_t * p.BN;
   const int kb0 = split * p.kblocks_per_split;
   const int kb1 = min(p.kblocks, kb0 + p.kblocks_per_split);
@@ -264,60 +398,59 @@ __global__ void __launch_bounds__(kThreads, 1)
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      const uint32_t tx = (uint32_t)grp.count * a_tap_bytes + (uint32_t)nb * 8192u;
-      for (int kb = kb0; kb < kb1; ++kb) {
-        const int r0 = kb * 64;
-        mbar_wait(empty_bar(s), ph ^ 1u);
-        const uint32_t st = smem_base + (uint32_t)s * stage_bytes;
-        mbar_expect_tx(full_bar(s), tx);
-        for (int g = 0; g < grp.count; ++g) {
-          const int xr = r0 + p.tap_x_off[grp.first + g];
-          tma_load_2d(&p.tmX, full_bar(s), st + (uint32_t)g * a_tap_bytes, ci0, xr);
-          tma_load_2d(&p.tmX, full_bar(s), st + (uint32_t)g * a_tap_bytes + 8192u, ci0 + 64, xr);
-        }
-        const uint32_t bst = st + (uint32_t)gmax * a_tap_bytes;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int kb = kb0; kb < kb1; ++kb) {
+      const int r0 = kb * 64;
+      mbar_wait(empty_bar(s), ph ^ 1u);
+      const uint32_t st = smem_base + (uint32_t)s * stage_bytes;
+      if (elect_one()) {
+        mbar_expect_tx(full_bar(s), stage_bytes);
+        tma_load_2d(&p.tmX, full_bar(s), st, ci0, r0 + grp.x_off);
+        tma_load_2d(&p.tmX, full_bar(s), st + kWgAtomBytes, ci0 + 64, r0 + grp.x_off);
         for (int j = 0; j < nb; ++j)
-          tma_load_2d(&p.tmDY, full_bar(s), bst + (uint32_t)j * 8192u, co0 + j * 64, r0 + grp.dy_off);
-        if (++s == S) { s = 0; ph ^= 1u; }
+          tma_load_2d(&p.tmDY, full_bar(s), st + a_bytes + (uint32_t)j * 8192u, co0 + j * 64,
+                      r0 + grp.dy_off);
       }
+      __syncwarp();
+      if (++s == S) { s = 0; ph ^= 1u; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, p.BN, 1, 1);
-      int s = 0;
-      uint32_t ph = 0;
-      for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait(full_bar(s), ph);
-        tc_fence_after();
+    const uint32_t idesc = make_idesc_bf16(128, p.BN, 1, 1);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int kb = 0; kb < nkb; ++kb) {
+      mbar_wait(full_bar(s), ph);
+      tc_fence_after();
+      if (elect_one()) {
         const uint32_t st = smem_base + (uint32_t)s * stage_bytes;
-        const uint32_t bst = st + (uint32_t)gmax * a_tap_bytes;
-        for (int g = 0; g < grp.count; ++g) {
+        const uint32_t bst = st + a_bytes;
+        for (int g = 0; g < grp.ntaps; ++g) {
           const uint32_t d_tmem = tmem_base + (uint32_t)(g * p.BN);
+          const uint32_t a0 = st + (uint32_t)grp.shift[g] * 128u;
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
-            const uint64_t a_desc = make_desc_sw128(
-                st + (uint32_t)g * a_tap_bytes + (uint32_t)(kk * p.kstep_bytes), p.a_lbo, p.a_sbo);
-            const uint64_t b_desc =
-                make_desc_sw128(bst + (uint32_t)(kk * p.kstep_bytes), p.b_lbo, p.b_sbo);
+            // K step = 16 pixel rows = 2048 B; M atoms (64 channels) kWgAtomBytes apart; N atoms 8192 B
+            const uint64_t a_desc = make_desc_sw128(a0 + (uint32_t)kk * 2048u, kWgAtomBytes, 1024);
+            const uint64_t b_desc = make_desc_sw128(bst + (uint32_t)kk * 2048u, 8192, 1024);
             mma_bf16_ss(d_tmem, a_desc, b_desc, idesc, (kb | kk) != 0 ? 1u : 0u);
           }
         }
         mma_commit(empty_bar(s));
-        if (++s == S) { s = 0; ph ^= 1u; }
       }
-      mma_commit(done_bar);
+      __syncwarp();
+      if (++s == S) { s = 0; ph ^= 1u; }
     }
+    if (elect_one()) mma_commit(done_bar);
+    __syncwarp();
   } else if (warp >= 4) {
     const int q = warp & 3;
     mbar_wait(done_bar, 0);
     tc_fence_after();
     if (nkb > 0) {
       const int ci = ci0 + q * 32 + lane;
-      for (int g = 0; g < grp.count; ++g) {
-        const int tw = p.tap_w[grp.first + g];
+      for (int g = 0; g < grp.ntaps; ++g) {
+        const int tw = grp.w_idx[g];
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * p.BN);
         for (int c0 = 0; c0 < p.BN; c0 += 16) {
           uint32_t r[16];
@@ -402,25 +535,99 @@ int num_sms() {
 static int g_fwd_attr_set = 0, g_wgrad_attr_set = 0;
 static constexpr int kDynSmem = 232448 - 1024;  // leave room for static smem (none) and the driver
 
+int pick_bn(int n_valid) { return (n_valid + 15) / 16 * 16 > 256 ? 256 : (n_valid + 15) / 16 * 16; }
+
+// bring-up knobs
+static int g_fwd_no_slab = 0;
+static long long* g_fwd_dbg = nullptr;
+extern "C" void mpu_debug_set_fwd_mode(int no_slab) { g_fwd_no_slab = no_slab; }
+// device pointer to 8 long longs: role stall cycles of CTA 0 for the next forward-type launches
+extern "C" void mpu_debug_set_fwd_profile(long long* dev_counters) { g_fwd_dbg = dev_counters; }
+
+int fwd_setup(FwdParams& p, const FwdDesc& d) {
+  static bool env_read = false;
+  if (!env_read) {  // bring-up override without a rebuild
+    if (const char* e = getenv("MPU_FWD_NO_SLAB")) g_fwd_no_slab = atoi(e);
+    env_read = true;
+  }
+  memset(&p, 0, sizeof(p));
+  if (!d.A0 || !d.W || !d.out || d.ntaps < 1 || d.ntaps > kMaxTaps) {
+    set_error("fwd_setup: bad arguments");
+    return MPU_ERR_ARG;
+  }
+  MPU_TRY(make_tmap_2d(&p.tmA0_hi, d.A0, (uint64_t)d.rowsA0, (uint64_t)d.C0, (uint64_t)d.ldA0, 64, 136));
+  MPU_TRY(make_tmap_2d(&p.tmA0_lo, d.A0, (uint64_t)d.rowsA0, (uint64_t)d.C0, (uint64_t)d.ldA0, 64, 128));
+  p.chunks0 = (d.C0 + 63) / 64;
+  p.c0_valid = d.C0;
+  p.c1_valid = d.C1;
+  if (d.A1) {
+    MPU_TRY(make_tmap_2d(&p.tmA1_hi, d.A1, (uint64_t)d.rowsA1, (uint64_t)d.C1, (uint64_t)d.ldA1, 64, 136));
+    MPU_TRY(make_tmap_2d(&p.tmA1_lo, d.A1, (uint64_t)d.rowsA1, (uint64_t)d.C1, (uint64_t)d.ldA1, 64, 128));
+    p.chunks1 = (d.C1 + 63) / 64;
+    p.kofs1 = d.C0;
+  }
+  MPU_TRY(make_tmap_2d(&p.tmW, d.W, (uint64_t)d.w_taps * d.n_phys, (uint64_t)d.k_total,
+                       (uint64_t)d.k_total, 64, 128));
+  // group taps that are < 8 rows apart (sorted by offset) into slabs of up to 3 taps
+  int order[kMaxTaps];
+  for (int i = 0; i < d.ntaps; ++i) order[i] = i;
+  for (int i = 1; i < d.ntaps; ++i)
+    for (int j = i; j > 0 && d.tap_a_off[order[j]] < d.tap_a_off[order[j - 1]]; --j) {
+      const int t = order[j];
+      order[j] = order[j - 1];
+      order[j - 1] = t;
+    }
+  p.ngroups = 0;
+  int i = 0;
+  while (i < d.ntaps) {
+    TapGroup& G = p.groups[p.ngroups++];
+    G.a_off = d.tap_a_off[order[i]];
+    G.ntaps = 0;
+    while (i < d.ntaps && G.ntaps < 3 && d.tap_a_off[order[i]] - G.a_off < 8 &&
+           (!g_fwd_no_slab || G.ntaps < 1)) {
+      G.shift[G.ntaps] = d.tap_a_off[order[i]] - G.a_off;
+      G.w_idx[G.ntaps] = d.tap_w[order[i]];
+      ++G.ntaps;
+      ++i;
+    }
+  }
+  p.w_rows_per_tap = d.n_phys;
+  p.M_rows = d.M_rows;
+  p.n_valid = d.n_phys;
+  p.map = d.map;
+  p.out = reinterpret_cast<__nv_bfloat16*>(d.out);
+  p.ldo = d.ldo;
+  p.bias = d.bias;
+  p.mask = reinterpret_cast<const __nv_bfloat16*>(d.mask);
+  p.ldm = d.ldm;
+  p.relu = d.relu;
+  p.stats = d.stats;
+  p.dbg = g_fwd_dbg;
+  const long long imgs = (d.M_rows + (long long)d.map.Hp * d.map.Wp - 1) / ((long long)d.map.Hp * d.map.Wp);
+  if ((long long)d.map.oHp * d.map.oWp * imgs > 2147483647LL) {
+    set_error("fwd_setup: output row index exceeds 32 bits");
+    return MPU_ERR_ARG;
+  }
+  return MPU_OK;
+}
+
 int launch_fwd(FwdParams& p, cudaStream_t stream) {
-  if (p.BN % 16 != 0 || p.BN < 16 || p.BN > 256) {
-    set_error("launch_fwd: BN=%d must be a multiple of 16 in [16,256]", p.BN);
+  const int fixed = 2 * (int)kStageHalfBytes + 1024;  // epilogue staging + row table
+  int NA = 2;
+  int NW = (kSmemBudget - fixed - NA * (int)kSlabBytes) / (int)kWTileBytes;
+  if (const char* e = getenv("MPU_FWD_NA")) {  // bring-up overrides
+    NA = atoi(e);
+    NW = (kSmemBudget - fixed - NA * (int)kSlabBytes) / (int)kWTileBytes;
+  }
+  if (NW > 8) NW = 8;
+  if (NA < 1 || NW < 2) {
+    set_error("launch_fwd: not enough shared memory (NA=%d NW=%d)", NA, NW);
     return MPU_ERR_ARG;
   }
-  if (p.ntaps < 1 || p.ntaps > kMaxTaps) {
-    set_error("launch_fwd: ntaps=%d out of range", p.ntaps);
-    return MPU_ERR_ARG;
-  }
-  const int stage_bytes = kABytes + p.BN * 128;
-  int S = kSmemBudget / stage_bytes;
-  if (S > 8) S = 8;
-  if (S < 2) {
-    set_error("launch_fwd: not enough shared memory for 2 stages");
-    return MPU_ERR_ARG;
-  }
-  p.stages = S;
-  p.m_tiles = (p.M_rows + 127) / 128;
-  p.n_tiles = (p.n_valid + p.BN - 1) / p.BN;
+  p.a_slots = NA;
+  p.w_slots = NW;
+  p.m_tiles = (p.M_rows + kPT - 1) / kPT;
+  p.n_tiles = (p.n_valid + 127) / 128;
   if (!g_fwd_attr_set) {
     MPU_CUDA(cudaFuncSetAttribute(mtgemm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   kDynSmem));
@@ -428,30 +635,92 @@ int launch_fwd(FwdParams& p, cudaStream_t stream) {
   }
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  mtgemm_fwd_kernel<<<grid, kThreads, kDynSmem, stream>>>(p);
+  mtgemm_fwd_kernel<<<grid, kFwdThreads, kDynSmem, stream>>>(p);
   MPU_CUDA(cudaGetLastError());
   return MPU_OK;
 }
 
+// co tile for wgrad: multiple of 16, at most 160 (3 tap accumulators x BN <= 512 TMEM columns),
+// chosen to minimise padding
+static int pick_bn_wgrad(int co) {
+  int best = 160, best_pad = 1 << 30;
+  for (int tiles = (co + 159) / 160; tiles <= (co + 159) / 160 + 2; ++tiles) {
+    const int bn = ((co + tiles - 1) / tiles + 15) / 16 * 16;
+    if (bn > 160 || bn < 16) continue;
+    const int pad = bn * tiles - co;
+    if (pad < best_pad) {
+      best_pad = pad;
+      best = bn;
+    }
+  }
+  return best;
+}
+
+int wgrad_setup(WgradParams& p, const WgradDesc& d) {
+  memset(&p, 0, sizeof(p));
+  if (!d.X || !d.dY || !d.dW || d.ntaps < 1 || d.ntaps > kMaxTaps) {
+    set_error("wgrad_setup: bad arguments");
+    return MPU_ERR_ARG;
+  }
+  p.BN = d.BN > 0 ? d.BN : pick_bn_wgrad(d.Cy);
+  if (p.BN % 16 != 0 || p.BN < 16 || 3 * p.BN > 512) {
+    set_error("wgrad_setup: BN=%d must be a multiple of 16 and <= 160", p.BN);
+    return MPU_ERR_ARG;
+  }
+  MPU_TRY(make_tmap_2d(&p.tmX, d.X, (uint64_t)d.rowsX, (uint64_t)d.Cx, (uint64_t)d.ldX, 64, kWgSlabRows));
+  MPU_TRY(make_tmap_2d(&p.tmDY, d.dY, (uint64_t)d.rowsDY, (uint64_t)d.Cy, (uint64_t)d.ldDY, 64, 64));
+  // sort taps by (dy_off, x_off); group taps of one dY plane whose X rows are < 8 apart
+  int order[kMaxTaps];
+  for (int i = 0; i < d.ntaps; ++i) order[i] = i;
+  auto less = [&](int a, int b) {
+    const int da = d.tap_dy_off ? d.tap_dy_off[a] : 0, db = d.tap_dy_off ? d.tap_dy_off[b] : 0;
+    if (da != db) return da < db;
+    return d.tap_x_off[a] < d.tap_x_off[b];
+  };
+  for (int i = 1; i < d.ntaps; ++i)
+    for (int j = i; j > 0 && less(order[j], order[j - 1]); --j) {
+      const int t = order[j];
+      order[j] = order[j - 1];
+      order[j - 1] = t;
+    }
+  p.ngroups = 0;
+  int i = 0;
+  while (i < d.ntaps) {
+    WgradGroup& G = p.groups[p.ngroups++];
+    G.x_off = d.tap_x_off[order[i]];
+    G.dy_off = d.tap_dy_off ? d.tap_dy_off[order[i]] : 0;
+    G.ntaps = 0;
+    while (i < d.ntaps && G.ntaps < 3 && d.tap_x_off[order[i]] - G.x_off < 8 &&
+           (d.tap_dy_off ? d.tap_dy_off[order[i]] : 0) == G.dy_off) {
+      G.shift[G.ntaps] = d.tap_x_off[order[i]] - G.x_off;
+      G.w_idx[G.ntaps] = d.tap_w[order[i]];
+      ++G.ntaps;
+      ++i;
+    }
+  }
+  p.ci_valid = d.Cx;
+  p.co_valid = d.Cy;
+  p.ci_tiles = (d.Cx + 127) / 128;
+  p.co_tiles = (d.Cy + p.BN - 1) / p.BN;
+  p.kblocks = (int)((d.rows_total + 63) / 64);
+  const int base = p.ci_tiles * p.co_tiles * p.ngroups;
+  int splits = d.splits > 0 ? d.splits : (2 * num_sms() + base - 1) / base;
+  if (splits < 1) splits = 1;
+  if (splits > p.kblocks) splits = p.kblocks;
+  p.kblocks_per_split = (p.kblocks + splits - 1) / splits;
+  p.splits = (p.kblocks + p.kblocks_per_split - 1) / p.kblocks_per_split;
+  p.dW = d.dW;
+  p.ldw = d.ldw;
+  p.w_rows_per_tap = d.w_rows_per_tap;
+  p.dw_col0 = d.dw_col0;
+  return MPU_OK;
+}
+
 int launch_wgrad(WgradParams& p, cudaStream_t stream) {
-  if (p.BN % 16 != 0 || p.BN < 16 || p.BN > 256) {
-    set_error("launch_wgrad: BN=%d must be a multiple of 16 in [16,256]", p.BN);
-    return MPU_ERR_ARG;
-  }
-  int gmax = 1;
-  for (int g = 0; g < p.ngroups; ++g) gmax = p.groups[g].count > gmax ? p.groups[g].count : gmax;
-  if (gmax * p.BN > 512) {
-    set_error("launch_wgrad: group %d x BN %d exceeds 512 TMEM columns", gmax, p.BN);
-    return MPU_ERR_ARG;
-  }
   const int nb = (p.BN + 63) / 64;
-  const int stage_bytes = gmax * 16384 + nb * 8192;
+  const int stage_bytes = 2 * (int)kWgAtomBytes + nb * 8192;
   int S = kSmemBudget / stage_bytes;
   if (S > 8) S = 8;
-  if (S < 2) {
-    set_error("launch_wgrad: not enough shared memory for 2 stages");
-    return MPU_ERR_ARG;
-  }
   p.stages = S;
   if (!g_wgrad_attr_set) {
     MPU_CUDA(cudaFuncSetAttribute(mtgemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

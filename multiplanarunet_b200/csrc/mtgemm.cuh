@@ -1,7 +1,8 @@
 // Multi-tap GEMM on tcgen05 tensor cores — the one contraction every conv of the mpunet 2D U-Net
 // reduces to once activations live in zero-bordered ("padded-linear") NHWC bf16 layout:
 //
-//   forward / dgrad :  D[m, n]   = sum_t sum_c  A[m + a_off[t], c] * W[t][n][c]        (K-major operands)
+//   forward / dgrad :  D[n, m]   = sum_t sum_c  W[t][n][c] * A[m + a_off[t], c]        (K-major operands;
+//                      output channels n on the 128 MMA rows, 256 pixels m on the MMA columns)
 //   wgrad           :  dW[t][n][c] = sum_m      X[m + x_off[t], c] * dY[m + dy_off, n]  (MN-major operands)
 //
 // A / X / dY are 2-D row-major matrices [rows][channels]; a tap shift is a pure row offset because
@@ -25,18 +26,27 @@ struct RowMap {
   int py, px;        // output phase: out (y,x) = (s*(ya-1)+py+1, s*(xa-1)+px+1)
 };
 
+// Taps whose row offsets differ by < 8 share one shared-memory "slab" of A rows: the slab is loaded once
+// and each tap's MMA reads it through a descriptor whose start address is shifted by whole 128 B rows.
+struct TapGroup {
+  int a_off;                     // row offset of the slab relative to the anchor row
+  int ntaps;                     // 1..3
+  int shift[3];                  // extra row shift of each tap inside the slab (0..7)
+  int w_idx[3];                  // tap index inside the weight matrix
+};
+
 struct FwdParams {
-  CUtensorMap tmA0, tmA1, tmB;
-  int chunks0, chunks1;          // 64-channel K chunks per A source (source 1 = concat partner)
+  CUtensorMap tmA0_hi, tmA0_lo, tmA1_hi, tmA1_lo;  // activation slabs: boxes of 136 + 128 rows x 64 ch
+  CUtensorMap tmW;               // weights: box 128 rows (output channels) x 64 K
+  int chunks0, chunks1;          // 64-channel K chunks per activation source (source 1 = concat partner)
+  int c0_valid, c1_valid;        // physical channels per source (the last chunk issues fewer K=16 steps)
   int kofs1;                     // weight-matrix K offset of source 1
-  int ntaps;
-  int tap_a_off[kMaxTaps];       // row offset added to the anchor row for this tap
-  int tap_w[kMaxTaps];           // tap index inside the weight matrix
+  int ngroups;
+  TapGroup groups[kMaxTaps];
   int w_rows_per_tap;            // rows (output channels, physical) per tap in the weight matrix
-  int M_rows;                    // total anchor rows
+  int M_rows;                    // total anchor rows (pixels)
   int n_valid;                   // physical output channels to store
-  int BN;                        // N tile (multiple of 16, <= 256)
-  int m_tiles, n_tiles;
+  int m_tiles, n_tiles;          // 256-pixel tiles x 128-channel tiles
   RowMap map;
   __nv_bfloat16* out;            // [out rows][ldo]
   int ldo;
@@ -44,22 +54,40 @@ struct FwdParams {
   const __nv_bfloat16* mask;     // same indexing as out; keep value only where mask > 0 (ReLU bwd)
   int ldm;
   int relu;
-  int stages;
+  double* stats;                 // optional [2][n_valid]: per-channel sum / sum of squares of the stored
+                                 // (bf16-rounded) outputs over valid pixels (BatchNorm statistics, bias grads)
+  int a_slots, w_slots;
+  long long* dbg;                // optional [8] cycle counters written by CTA 0 (bring-up profiling)
 };
 
+// Host-side description of one forward-type GEMM; fwd_setup builds tensor maps + tap groups from it.
+struct FwdDesc {
+  const void* A0; long long rowsA0; int C0, ldA0;
+  const void* A1; long long rowsA1; int C1, ldA1;   // optional concat partner
+  const void* W; int w_taps, n_phys, k_total;       // bf16 [w_taps][n_phys][k_total]
+  int ntaps; const int* tap_a_off; const int* tap_w;
+  int M_rows;
+  int BN;                                            // ignored (kept for the bring-up API)
+  RowMap map;
+  void* out; int ldo;
+  const float* bias; const void* mask; int ldm; int relu;
+  double* stats;                                     // optional [2][n_phys]
+};
+
+// wgrad tap group: taps of one kernel row share one X slab (64+8 pixel rows) and one dY tile
 struct WgradGroup {
-  int first, count;              // range in the tap arrays
-  int dy_off;                    // row offset applied to dY for this group
+  int x_off;                     // row offset of the X slab relative to the K block start
+  int dy_off;                    // row offset applied to dY (phase plane of the upsample-conv)
+  int ntaps;                     // 1..3
+  int shift[3];                  // extra row shift of each tap inside the slab (0..7)
+  int w_idx[3];                  // tap index inside dW
 };
 
 struct WgradParams {
-  CUtensorMap tmX, tmDY;
-  int ntaps;
-  int tap_x_off[kMaxTaps];
-  int tap_w[kMaxTaps];
+  CUtensorMap tmX, tmDY;         // X box {64 ch, 72 rows}; dY box {64 ch, 64 rows}
   int ngroups;
   WgradGroup groups[kMaxTaps];
-  int BN;                        // co tile (multiple of 16, <= 256); group count * BN <= 512
+  int BN;                        // co tile (multiple of 16); 3 * BN <= 512 TMEM columns
   int ci_tiles, co_tiles, splits;
   int kblocks;                   // total 64-row K blocks
   int kblocks_per_split;
@@ -69,8 +97,16 @@ struct WgradParams {
   int dw_col0;                   // column offset (concat source 1)
   int ci_valid, co_valid;
   int stages;
-  // descriptor strides exposed for bring-up sweeps
-  int a_lbo, a_sbo, b_lbo, b_sbo, kstep_bytes;
+};
+
+struct WgradDesc {
+  const void* X; long long rowsX; int Cx, ldX;
+  const void* dY; long long rowsDY; int Cy, ldDY;
+  int ntaps; const int* tap_x_off; const int* tap_dy_off; const int* tap_w;
+  long long rows_total;          // K extent (anchor rows)
+  int BN;                        // 0 = choose
+  int splits;                    // 0 = choose
+  float* dW; int ldw, w_rows_per_tap, dw_col0;
 };
 
 // Host helpers -----------------------------------------------------------------------------------
@@ -78,7 +114,10 @@ struct WgradParams {
 int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
                  uint32_t box_cols, uint32_t box_rows);
 
+int fwd_setup(FwdParams& p, const FwdDesc& d);
 int launch_fwd(FwdParams& p, cudaStream_t stream);
+int pick_bn(int n_valid);
+int wgrad_setup(WgradParams& p, const WgradDesc& d);
 int launch_wgrad(WgradParams& p, cudaStream_t stream);
 int num_sms();
 

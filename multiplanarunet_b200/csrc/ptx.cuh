@@ -151,7 +151,9 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, uint32_t lbo
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;                              // descriptor version (Blackwell)
-  d |= (uint64_t)((saddr >> 7) & 0x7) << 49;           // base offset (non-zero only if start is not 1024B-aligned)
+  // base-offset field (bits 49-51) stays 0: measured on B200, the 128B swizzle is applied on absolute
+  // shared-memory address bits, so a start address shifted by whole 128 B rows inside a 1024B-aligned
+  // TMA tile needs no correction (a non-zero value here produced wrong results).
   d |= (uint64_t)2 << 61;                              // SWIZZLE_128B
   return d;
 }

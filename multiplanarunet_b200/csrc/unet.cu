@@ -234,12 +234,6 @@ static void layout_workspace(UNet& u, bool dry) {
 }
 
 // ---- GEMM wrappers ----------------------------------------------------------------------------------
-static int pick_bn(int n_valid) {
-  if (n_valid <= 256) return round_up(n_valid, 16);
-  const int tiles = (n_valid + 255) / 256;
-  return round_up((n_valid + tiles - 1) / tiles, 16);
-}
-
 static void taps3x3(int Wp, int* off) {
   for (int ky = 0; ky < 3; ++ky)
     for (int kx = 0; kx < 3; ++kx) off[ky * 3 + kx] = (ky - 1) * Wp + (kx - 1);
@@ -248,67 +242,50 @@ static void taps3x3(int Wp, int* off) {
 // out[rows][n_phys] = act( sum_taps A[m+off] . W[tap]^T + bias ), same-resolution (3x3 or dgrad).
 static int gemm_same(const bf16* A0, int C0, int ldA0, const bf16* A1, int C1, int ldA1, const bf16* W,
                      int ntap, int n_phys, int k_total, Geo g, bf16* out, int ldo, const float* bias,
-                     const bf16* mask, int ldm, int relu, cudaStream_t st) {
+                     const bf16* mask, int ldm, int relu, cudaStream_t st, double* stats = nullptr) {
+  int off[kMaxTaps] = {0}, widx[kMaxTaps];
+  if (ntap == 9) taps3x3(g.Wp(), off);
+  for (int t = 0; t < ntap; ++t) widx[t] = t;
+  FwdDesc d;
+  memset(&d, 0, sizeof(d));
+  d.A0 = A0; d.rowsA0 = g.rows(); d.C0 = C0; d.ldA0 = ldA0;
+  d.A1 = A1; d.rowsA1 = A1 ? g.rows() : 0; d.C1 = C1; d.ldA1 = ldA1;
+  d.W = W; d.w_taps = ntap; d.n_phys = n_phys; d.k_total = k_total;
+  d.ntaps = ntap; d.tap_a_off = off; d.tap_w = widx;
+  d.M_rows = (int)g.rows();
+  d.map = RowMap{g.Hp(), g.Wp(), g.Hp(), g.Wp(), 1, 0, 0};
+  d.out = out; d.ldo = ldo; d.bias = bias; d.mask = mask; d.ldm = ldm; d.relu = relu;
+  d.stats = stats;
   FwdParams p;
-  memset(&p, 0, sizeof(p));
-  const long long rows = g.rows();
-  MPU_TRY(make_tmap_2d(&p.tmA0, A0, rows, C0, ldA0, 64, 128));
-  p.chunks0 = (C0 + 63) / 64;
-  if (A1) {
-    MPU_TRY(make_tmap_2d(&p.tmA1, A1, rows, C1, ldA1, 64, 128));
-    p.chunks1 = (C1 + 63) / 64;
-    p.kofs1 = C0;
-  }
-  p.BN = pick_bn(n_phys);
-  MPU_TRY(make_tmap_2d(&p.tmB, W, (long long)ntap * n_phys, k_total, k_total, 64, p.BN));
-  p.ntaps = ntap;
-  if (ntap == 9) {
-    taps3x3(g.Wp(), p.tap_a_off);
-  } else {
-    p.tap_a_off[0] = 0;
-  }
-  for (int t = 0; t < ntap; ++t) p.tap_w[t] = t;
-  p.w_rows_per_tap = n_phys;
-  p.M_rows = (int)rows;
-  p.n_valid = n_phys;
-  p.map = RowMap{g.Hp(), g.Wp(), g.Hp(), g.Wp(), 1, 0, 0};
-  p.out = out;
-  p.ldo = ldo;
-  p.bias = bias;
-  p.mask = mask;
-  p.ldm = ldm;
-  p.relu = relu;
+  MPU_TRY(fwd_setup(p, d));
   return launch_fwd(p, st);
 }
 
 // nearest-2x upsample + 2x2 SAME conv + bias + ReLU as four phase GEMMs on the low-res grid.
 static int gemm_upconv(const bf16* X, int Cx, Geo glo, const ConvL& L, const float* bias, Geo ghi,
-                       bf16* out, cudaStream_t st) {
+                       bf16* out, cudaStream_t st, double* stats = nullptr) {
   for (int a = 0; a < 2; ++a)
     for (int b = 0; b < 2; ++b) {
-      FwdParams p;
-      memset(&p, 0, sizeof(p));
-      MPU_TRY(make_tmap_2d(&p.tmA0, X, glo.rows(), Cx, Cx, 64, 128));
-      p.chunks0 = (Cx + 63) / 64;
-      p.BN = pick_bn(L.co_phys);
-      MPU_TRY(make_tmap_2d(&p.tmB, L.wf, 9ll * L.co_phys, L.k_phys, L.k_phys, 64, p.BN));
-      p.ntaps = 0;
+      int off[kMaxTaps], widx[kMaxTaps], n = 0;
       for (int i = 0; i < 9; ++i) {
         const UpPair pr = up_pair(i);
         if (pr.a == a && pr.b == b) {
-          p.tap_a_off[p.ntaps] = pr.di * glo.Wp() + pr.dj;
-          p.tap_w[p.ntaps] = i;
-          ++p.ntaps;
+          off[n] = pr.di * glo.Wp() + pr.dj;
+          widx[n] = i;
+          ++n;
         }
       }
-      p.w_rows_per_tap = L.co_phys;
-      p.M_rows = (int)glo.rows();
-      p.n_valid = L.co_phys;
-      p.map = RowMap{glo.Hp(), glo.Wp(), ghi.Hp(), ghi.Wp(), 2, a, b};
-      p.out = out;
-      p.ldo = L.co_phys;
-      p.bias = bias;
-      p.relu = 1;
+      FwdDesc d;
+      memset(&d, 0, sizeof(d));
+      d.A0 = X; d.rowsA0 = glo.rows(); d.C0 = Cx; d.ldA0 = Cx;
+      d.W = L.wf; d.w_taps = 9; d.n_phys = L.co_phys; d.k_total = L.k_phys;
+      d.ntaps = n; d.tap_a_off = off; d.tap_w = widx;
+      d.M_rows = (int)glo.rows();
+      d.map = RowMap{glo.Hp(), glo.Wp(), ghi.Hp(), ghi.Wp(), 2, a, b};
+      d.out = out; d.ldo = L.co_phys; d.bias = bias; d.relu = 1;
+      d.stats = stats;
+      FwdParams p;
+      MPU_TRY(fwd_setup(p, d));
       MPU_TRY(launch_fwd(p, st));
     }
   return MPU_OK;
@@ -316,115 +293,65 @@ static int gemm_upconv(const bf16* X, int Cx, Geo glo, const ConvL& L, const flo
 
 // dIn[m_lo] = sum over the 9 (phase, tap) pairs of dZ[phase][m_lo - off] . Wc[pair]  (dZ phase-major)
 static int gemm_upconv_dgrad(const bf16* dzu, const ConvL& L, Geo glo, bf16* out, cudaStream_t st) {
-  FwdParams p;
-  memset(&p, 0, sizeof(p));
   const long long rows_lo = glo.rows();
-  MPU_TRY(make_tmap_2d(&p.tmA0, dzu, 4 * rows_lo, L.co_phys, L.co_phys, 64, 128));
-  p.chunks0 = (L.co_phys + 63) / 64;
-  p.BN = pick_bn(L.k_phys);
-  MPU_TRY(make_tmap_2d(&p.tmB, L.wd, 9ll * L.k_phys, L.co_phys, L.co_phys, 64, p.BN));
-  p.ntaps = 9;
+  int off[kMaxTaps], widx[kMaxTaps];
   for (int i = 0; i < 9; ++i) {
     const UpPair pr = up_pair(i);
-    p.tap_a_off[i] = (int)((pr.a * 2 + pr.b) * rows_lo) - (pr.di * glo.Wp() + pr.dj);
-    p.tap_w[i] = i;
+    off[i] = (int)((pr.a * 2 + pr.b) * rows_lo) - (pr.di * glo.Wp() + pr.dj);
+    widx[i] = i;
   }
-  p.w_rows_per_tap = L.k_phys;
-  p.M_rows = (int)rows_lo;
-  p.n_valid = L.k_phys;
-  p.map = RowMap{glo.Hp(), glo.Wp(), glo.Hp(), glo.Wp(), 1, 0, 0};
-  p.out = out;
-  p.ldo = L.k_phys;
+  FwdDesc d;
+  memset(&d, 0, sizeof(d));
+  d.A0 = dzu; d.rowsA0 = 4 * rows_lo; d.C0 = L.co_phys; d.ldA0 = L.co_phys;
+  d.W = L.wd; d.w_taps = 9; d.n_phys = L.k_phys; d.k_total = L.co_phys;
+  d.ntaps = 9; d.tap_a_off = off; d.tap_w = widx;
+  d.M_rows = (int)rows_lo;
+  d.map = RowMap{glo.Hp(), glo.Wp(), glo.Hp(), glo.Wp(), 1, 0, 0};
+  d.out = out; d.ldo = L.k_phys;
+  FwdParams p;
+  MPU_TRY(fwd_setup(p, d));
   return launch_fwd(p, st);
-}
-
-// taps per wgrad CTA: bounded by TMEM (G*BN <= 512 columns) and by shared memory (>= 3 stages of
-// G x 16 KB of X tiles + the dY tile)
-static int wgrad_group(int BN) {
-  int G = 512 / BN;
-  return G > 3 ? 3 : G;
-}
-
-static int wgrad_common(WgradParams& p, int ci_valid, int co_valid, long long rows, cudaStream_t st) {
-  p.ci_valid = ci_valid;
-  p.co_valid = co_valid;
-  p.ci_tiles = (ci_valid + 127) / 128;
-  p.co_tiles = (co_valid + p.BN - 1) / p.BN;
-  p.kblocks = (int)((rows + 63) / 64);
-  const int base = p.ci_tiles * p.co_tiles * p.ngroups;
-  int splits = (2 * num_sms() + base - 1) / base;
-  if (splits < 1) splits = 1;
-  if (splits > p.kblocks) splits = p.kblocks;
-  p.kblocks_per_split = (p.kblocks + splits - 1) / splits;
-  p.splits = (p.kblocks + p.kblocks_per_split - 1) / p.kblocks_per_split;
-  p.a_lbo = 8192;
-  p.a_sbo = 1024;
-  p.b_lbo = 8192;
-  p.b_sbo = 1024;
-  p.kstep_bytes = 2048;
-  return launch_wgrad(p, st);
 }
 
 // dW[tap][co][col0 + ci] += sum_m X[m+off_tap][ci] * dZ[m][co]   (3x3 / 1-tap, same resolution)
 static int wgrad_same(const bf16* X, int Cx, int ldX, const bf16* dZ, int Cz, int ntap, Geo g,
                       float* dW, int ldw, int co_phys, int col0, cudaStream_t st) {
+  int off[kMaxTaps] = {0}, widx[kMaxTaps];
+  if (ntap == 9) taps3x3(g.Wp(), off);
+  for (int t = 0; t < ntap; ++t) widx[t] = t;
+  WgradDesc d;
+  memset(&d, 0, sizeof(d));
+  d.X = X; d.rowsX = g.rows(); d.Cx = Cx; d.ldX = ldX;
+  d.dY = dZ; d.rowsDY = g.rows(); d.Cy = Cz; d.ldDY = Cz;
+  d.ntaps = ntap; d.tap_x_off = off; d.tap_dy_off = nullptr; d.tap_w = widx;
+  d.rows_total = g.rows();
+  d.dW = dW; d.ldw = ldw; d.w_rows_per_tap = co_phys; d.dw_col0 = col0;
   WgradParams p;
-  memset(&p, 0, sizeof(p));
-  const long long rows = g.rows();
-  MPU_TRY(make_tmap_2d(&p.tmX, X, rows, Cx, ldX, 64, 64));
-  MPU_TRY(make_tmap_2d(&p.tmDY, dZ, rows, Cz, Cz, 64, 64));
-  p.ntaps = ntap;
-  if (ntap == 9) taps3x3(g.Wp(), p.tap_x_off);
-  for (int t = 0; t < ntap; ++t) p.tap_w[t] = t;
-  p.BN = pick_bn(Cz);
-  const int G = wgrad_group(p.BN);
-  p.ngroups = 0;
-  for (int t = 0; t < ntap; t += G) {
-    p.groups[p.ngroups] = WgradGroup{t, (ntap - t) < G ? (ntap - t) : G, 0};
-    ++p.ngroups;
-  }
-  p.dW = dW;
-  p.ldw = ldw;
-  p.w_rows_per_tap = co_phys;
-  p.dw_col0 = col0;
-  return wgrad_common(p, Cx, Cz, rows, st);
+  MPU_TRY(wgrad_setup(p, d));
+  return launch_wgrad(p, st);
 }
 
 // collapsed upsample-conv weight gradient: dWc[pair][co][ci] = sum_m X[m + off][ci] * dZ[phase][m][co]
 static int wgrad_upconv(const bf16* X, int Cx, const bf16* dzu, const ConvL& L, Geo glo, float* dwc,
                         cudaStream_t st) {
-  WgradParams p;
-  memset(&p, 0, sizeof(p));
   const long long rows_lo = glo.rows();
-  MPU_TRY(make_tmap_2d(&p.tmX, X, rows_lo, Cx, Cx, 64, 64));
-  MPU_TRY(make_tmap_2d(&p.tmDY, dzu, 4 * rows_lo, L.co_phys, L.co_phys, 64, 64));
-  p.ntaps = 9;
-  p.BN = pick_bn(L.co_phys);
-  const int G = wgrad_group(p.BN);
-  p.ngroups = 0;
-  int i = 0;
-  while (i < 9) {
-    const UpPair pr = up_pair(i);
-    int n = 0;
-    while (i + n < 9 && n < G) {
-      const UpPair q = up_pair(i + n);
-      if (q.a != pr.a || q.b != pr.b) break;
-      ++n;
-    }
-    p.groups[p.ngroups] = WgradGroup{i, n, (int)((pr.a * 2 + pr.b) * rows_lo)};
-    ++p.ngroups;
-    i += n;
-  }
+  int xoff[kMaxTaps], dyoff[kMaxTaps], widx[kMaxTaps];
   for (int t = 0; t < 9; ++t) {
     const UpPair pr = up_pair(t);
-    p.tap_x_off[t] = pr.di * glo.Wp() + pr.dj;
-    p.tap_w[t] = t;
+    xoff[t] = pr.di * glo.Wp() + pr.dj;
+    dyoff[t] = (int)((pr.a * 2 + pr.b) * rows_lo);
+    widx[t] = t;
   }
-  p.dW = dwc;
-  p.ldw = L.k_phys;
-  p.w_rows_per_tap = L.co_phys;
-  p.dw_col0 = 0;
-  return wgrad_common(p, Cx, L.co_phys, rows_lo, st);
+  WgradDesc d;
+  memset(&d, 0, sizeof(d));
+  d.X = X; d.rowsX = rows_lo; d.Cx = Cx; d.ldX = Cx;
+  d.dY = dzu; d.rowsDY = 4 * rows_lo; d.Cy = L.co_phys; d.ldDY = L.co_phys;
+  d.ntaps = 9; d.tap_x_off = xoff; d.tap_dy_off = dyoff; d.tap_w = widx;
+  d.rows_total = rows_lo;
+  d.dW = dwc; d.ldw = L.k_phys; d.w_rows_per_tap = L.co_phys; d.dw_col0 = 0;
+  WgradParams p;
+  MPU_TRY(wgrad_setup(p, d));
+  return launch_wgrad(p, st);
 }
 
 // ---- schedule -------------------------------------------------------------------------------------
@@ -434,10 +361,12 @@ static Geo geo_b(const UNet& u, int l, int B) {
   return g;
 }
 
+// `stats_fused`: the producing GEMM's epilogue already accumulated sum / sum-of-squares into bn.sums
 static int bn_forward(UNet& u, BnL& bn, const bf16* y, Geo g, bf16* b, bf16* pooled, int training,
-                      cudaStream_t st) {
+                      cudaStream_t st, bool stats_fused = false) {
   const float* P = u.params;
-  if (training) MPU_TRY(launch_channel_stats(y, g.rows(), bn.c_phys, bn.c_phys, bn.sums, st));
+  if (training && !stats_fused)
+    MPU_TRY(launch_channel_stats(y, g.rows(), bn.c_phys, bn.c_phys, bn.sums, st));
   MPU_TRY(launch_bn_finalize(bn.sums, (double)g.pixels(), P + bn.g_off, P + bn.b_off,
                              u.bn_state + bn.m_off, u.bn_state + bn.v_off, u.cfg.bn_eps,
                              u.cfg.bn_momentum, training, bn.c_phys, bn.scale, bn.shift, bn.mean, bn.rstd,
@@ -470,9 +399,11 @@ static int forward(UNet& u, int B, int training, cudaStream_t st) {
     ConvL& c2 = u.enc_conv(l, 1);
     MPU_TRY(gemm_same(x, cx, cx, nullptr, 0, 0, c1.wf, 9, c1.co_phys, c1.k_phys, g, L.a1, L.C,
                       P + c1.b_off, nullptr, 0, 1, st));
+    double* st2 = training ? u.enc_bn(l).sums : nullptr;
+    if (st2) MPU_CUDA(cudaMemsetAsync(st2, 0, sizeof(double) * 2 * L.C, st));
     MPU_TRY(gemm_same(L.a1, L.C, L.C, nullptr, 0, 0, c2.wf, 9, c2.co_phys, c2.k_phys, g, L.a2, L.C,
-                      P + c2.b_off, nullptr, 0, 1, st));
-    MPU_TRY(bn_forward(u, u.enc_bn(l), L.a2, g, L.b, l < d ? L.pooled : nullptr, training, st));
+                      P + c2.b_off, nullptr, 0, 1, st, st2));
+    MPU_TRY(bn_forward(u, u.enc_bn(l), L.a2, g, L.b, l < d ? L.pooled : nullptr, training, st, st2 != nullptr));
     x = l < d ? L.pooled : L.b;
     cx = L.C;
   }
@@ -483,13 +414,17 @@ static int forward(UNet& u, int B, int training, cudaStream_t st) {
     ConvL& c1 = u.up_conv(i, 0);
     ConvL& c2 = u.up_conv(i, 1);
     ConvL& c3 = u.up_conv(i, 2);
-    MPU_TRY(gemm_upconv(x, cx, glo, c1, P + c1.b_off, g, L.u, st));
-    MPU_TRY(bn_forward(u, u.up_bn(i, 0), L.u, g, L.bn1, nullptr, training, st));
+    double* st1 = training ? u.up_bn(i, 0).sums : nullptr;
+    double* st3 = training ? u.up_bn(i, 1).sums : nullptr;
+    if (st1) MPU_CUDA(cudaMemsetAsync(st1, 0, sizeof(double) * 2 * L.C, st));
+    if (st3) MPU_CUDA(cudaMemsetAsync(st3, 0, sizeof(double) * 2 * L.C, st));
+    MPU_TRY(gemm_upconv(x, cx, glo, c1, P + c1.b_off, g, L.u, st, st1));
+    MPU_TRY(bn_forward(u, u.up_bn(i, 0), L.u, g, L.bn1, nullptr, training, st, st1 != nullptr));
     MPU_TRY(gemm_same(L.b, L.C, L.C, L.bn1, L.C, L.C, c2.wf, 9, c2.co_phys, c2.k_phys, g, L.c2, L.C,
                       P + c2.b_off, nullptr, 0, 1, st));
     MPU_TRY(gemm_same(L.c2, L.C, L.C, nullptr, 0, 0, c3.wf, 9, c3.co_phys, c3.k_phys, g, L.c3, L.C,
-                      P + c3.b_off, nullptr, 0, 1, st));
-    MPU_TRY(bn_forward(u, u.up_bn(i, 1), L.c3, g, L.bn2, nullptr, training, st));
+                      P + c3.b_off, nullptr, 0, 1, st, st3));
+    MPU_TRY(bn_forward(u, u.up_bn(i, 1), L.c3, g, L.bn2, nullptr, training, st, st3 != nullptr));
     x = L.bn2;
     cx = L.C;
   }

@@ -98,6 +98,91 @@ def conv_case(B, H, W, Cin, Cout, BN, cin_phys=None, cout_phys=None, relu=True, 
     return bad == 0 and border.item() == 0
 
 
+def perf_case(B, H, W, Cin, Cout, iters=10, two_src=False):
+    """Device-timed 3x3 conv at U-Net-like sizes; prints TFLOP/s on algorithmic (unpadded) FLOPs."""
+    import torch
+    from multiplanarunet_b200._C import lib, check, ptr, int_array
+    dev = "cuda"
+    cin_phys = (Cin + 7) // 8 * 8
+    cout_phys = (Cout + 7) // 8 * 8
+    Hp, Wp = H + 2, W + 2
+    nsrc = 2 if two_src else 1
+    xs = [pad_nhwc(torch.randn(B, H, W, Cin, device=dev), cin_phys) for _ in range(nsrc)]
+    wk = (torch.randn(9, cout_phys, nsrc * cin_phys, device=dev) * 0.05).to(torch.bfloat16)
+    out = torch.zeros(B, Hp, Wp, cout_phys, dtype=torch.bfloat16, device=dev)
+    taps_off = [(ky - 1) * Wp + (kx - 1) for ky in range(3) for kx in range(3)]
+
+    def run():
+        rc = lib.mpu_mtgemm_fwd(
+            ptr(xs[0]), ctypes.c_longlong(B * Hp * Wp), cin_phys, cin_phys,
+            ptr(xs[1] if two_src else None), ctypes.c_longlong(B * Hp * Wp if two_src else 0),
+            cin_phys if two_src else 0, cin_phys if two_src else 0,
+            ptr(wk), 9, cout_phys, nsrc * cin_phys, 9, int_array(taps_off), int_array(list(range(9))),
+            B * Hp * Wp, 0, Hp, Wp, Hp, Wp, 1, 0, 0, ptr(out), cout_phys, ptr(None), ptr(None), 0, 1,
+            ctypes.c_void_p(0))
+        check(rc, "mpu_mtgemm_fwd")
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        run()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / iters
+    fl = 2.0 * B * H * W * 9 * nsrc * Cin * Cout
+    print("  perf B=%d %dx%d %d->%d: %.3f ms  %.1f TFLOP/s (algorithmic)" % (B, H, W, nsrc * Cin, Cout, ms, fl / ms / 1e9))
+    # role-stall profile of CTA 0
+    cnt = torch.zeros(8, dtype=torch.int64, device=dev)
+    lib.mpu_debug_set_fwd_profile(ctypes.c_void_p(cnt.data_ptr()))
+    run()
+    torch.cuda.synchronize()
+    lib.mpu_debug_set_fwd_profile(ctypes.c_void_p(0))
+    c = cnt.cpu().tolist()
+    tot = max(c[7], 1)
+    print("   CTA0 cycles %d | producer wait a_empty %.0f%% b_empty %.0f%% | mma wait a_full %.0f%% b_full %.0f%% "
+          "tmem_empty %.0f%% | epilogue wait tmem_full %.0f%% busy %.0f%%" %
+          (tot, 100 * c[0] / tot, 100 * c[1] / tot, 100 * c[2] / tot, 100 * c[3] / tot, 100 * c[4] / tot,
+           100 * c[5] / tot, 100 * c[6] / tot))
+    return True
+
+
+def perf_wgrad_case(B, H, W, Cin, Cout, iters=10):
+    import torch
+    from multiplanarunet_b200._C import lib, check, ptr, int_array
+    dev = "cuda"
+    cin_phys = (Cin + 7) // 8 * 8
+    cout_phys = (Cout + 7) // 8 * 8
+    Hp, Wp = H + 2, W + 2
+    xp = pad_nhwc(torch.randn(B, H, W, Cin, device=dev), cin_phys)
+    dyp = pad_nhwc(torch.randn(B, H, W, Cout, device=dev), cout_phys)
+    dW = torch.zeros(9, cout_phys, cin_phys, dtype=torch.float32, device=dev)
+    taps_off = [(ky - 1) * Wp + (kx - 1) for ky in range(3) for kx in range(3)]
+    rows = B * Hp * Wp
+
+    def run():
+        rc = lib.mpu_mtgemm_wgrad(
+            ptr(xp), ctypes.c_longlong(rows), cin_phys, cin_phys, ptr(dyp), ctypes.c_longlong(rows),
+            cout_phys, cout_phys, 9, int_array(taps_off), int_array(list(range(9))), 1, int_array([0]),
+            int_array([9]), int_array([0]), rows, 0, 0, ptr(dW), cin_phys, cout_phys, 0, cin_phys,
+            cout_phys, 0, 0, 0, 0, 0, ctypes.c_void_p(0))
+        check(rc, "mpu_mtgemm_wgrad")
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        run()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / iters
+    fl = 2.0 * B * H * W * 9 * Cin * Cout
+    print("  wgrad perf B=%d %dx%d %d->%d: %.3f ms  %.1f TFLOP/s (algorithmic)" % (B, H, W, Cin, Cout, ms, fl / ms / 1e9))
+    return True
+
+
 def upconv_case(B, h, w_, Cin, Cout, BN, seed=0):
     """nearest-2x upsample + 2x2 SAME conv via 4 phase-collapsed multi-tap GEMMs."""
     import torch
@@ -217,6 +302,17 @@ def wgrad_case(B, H, W, Cin, Cout, BN, G=3, splits=4, variant=None, seed=0):
 
 
 CASES = {
+    "perf_L0": (perf_case, dict(B=32, H=256, W=256, Cin=90, Cout=90)),
+    "perf_L0cat": (perf_case, dict(B=32, H=256, W=256, Cin=90, Cout=90, two_src=True)),
+    "perf_L1": (perf_case, dict(B=32, H=128, W=128, Cin=181, Cout=181)),
+    "perf_L2": (perf_case, dict(B=32, H=64, W=64, Cin=362, Cout=362)),
+    "perf_L3": (perf_case, dict(B=32, H=32, W=32, Cin=724, Cout=724)),
+    "wperf_L0": (perf_wgrad_case, dict(B=32, H=256, W=256, Cin=90, Cout=90)),
+    "wperf_L1": (perf_wgrad_case, dict(B=32, H=128, W=128, Cin=181, Cout=181)),
+    "wperf_L2": (perf_wgrad_case, dict(B=32, H=64, W=64, Cin=362, Cout=362)),
+    "wperf_L3": (perf_wgrad_case, dict(B=32, H=32, W=32, Cin=724, Cout=724)),
+    "wperf_L4": (perf_wgrad_case, dict(B=32, H=16, W=16, Cin=1448, Cout=1448)),
+    "perf_L4": (perf_case, dict(B=32, H=16, W=16, Cin=1448, Cout=1448)),
     # name: (fn, kwargs)
     "fwd_small_64": (conv_case, dict(B=1, H=16, W=16, Cin=64, Cout=64, BN=64, relu=False, bias=False)),
     "fwd_small_64_relu_bias": (conv_case, dict(B=2, H=16, W=16, Cin=64, Cout=64, BN=64)),
@@ -231,8 +327,6 @@ CASES = {
     "upconv": (upconv_case, dict(B=2, h=8, w_=8, Cin=128, Cout=64, BN=64)),
     "upconv_odd": (upconv_case, dict(B=2, h=16, w_=16, Cin=181, Cout=90, BN=96)),
     "wgrad_small": (wgrad_case, dict(B=1, H=16, W=16, Cin=128, Cout=64, BN=64, G=3, splits=1)),
-    "wgrad_small_v_swap": (wgrad_case, dict(B=1, H=16, W=16, Cin=128, Cout=64, BN=64, G=3, splits=1,
-                                            variant=(1024, 8192, 1024, 8192, 2048))),
     "wgrad_split": (wgrad_case, dict(B=2, H=32, W=32, Cin=128, Cout=128, BN=128, G=3, splits=8)),
     "wgrad_c96": (wgrad_case, dict(B=2, H=32, W=32, Cin=90, Cout=90, BN=96, G=3, splits=4)),
     "wgrad_n256": (wgrad_case, dict(B=2, H=16, W=16, Cin=362, Cout=362, BN=256, G=2, splits=2)),
