@@ -26,6 +26,12 @@ extern "C" {
 
 const char* mpu_last_error(void);
 int mpu_version(void);
+/* number of CUDA kernels this library has launched so far in this process */
+long long mpu_launch_count(void);
+/* live CUDA-event timing of the tensor-core GEMM launches (bench.py roofline): enable, run a step,
+ * then read the summed device time and launch count (read also resets) */
+int mpu_profile_gemm(int enable);
+int mpu_profile_gemm_read(double* total_ms, int* launches);
 
 /* ---- kernel-level surface: multi-tap GEMM on tcgen05 (bring-up + kernel parity tests) ------------
  * The contraction inside tf.keras Conv2D / its gradients, reference call sites

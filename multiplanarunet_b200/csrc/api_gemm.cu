@@ -2,6 +2,8 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <utility>
+#include <vector>
 
 #include "../../include/mpunet_b200.h"
 #include "common.h"
@@ -16,6 +18,29 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 const char* last_error() { return g_err; }
+
+long long g_launch_count = 0;
+
+// GEMM event timer: when enabled, every tensor-core GEMM launch is bracketed by a CUDA event pair on
+// its own stream; mpu_profile_gemm_read() synchronises and sums the elapsed times.
+static bool g_timer_on = false;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_events;
+static size_t g_events_used = 0;
+void gemm_timer_begin(cudaStream_t st) {
+  if (!g_timer_on) return;
+  if (g_events_used == g_events.size()) {
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    g_events.push_back({a, b});
+  }
+  cudaEventRecord(g_events[g_events_used].first, st);
+}
+void gemm_timer_end(cudaStream_t st) {
+  if (!g_timer_on) return;
+  cudaEventRecord(g_events[g_events_used].second, st);
+  ++g_events_used;
+}
 }  // namespace mpu
 
 using namespace mpu;
@@ -25,6 +50,32 @@ extern "C" {
 const char* mpu_last_error(void) { return mpu::last_error(); }
 
 int mpu_version(void) { return 100; }
+
+long long mpu_launch_count(void) { return mpu::g_launch_count; }
+
+int mpu_profile_gemm(int enable) {
+  mpu::g_timer_on = enable != 0;
+  mpu::g_events_used = 0;
+  return MPU_OK;
+}
+
+int mpu_profile_gemm_read(double* total_ms, int* launches) {
+  double tot = 0;
+  for (size_t i = 0; i < mpu::g_events_used; ++i) {
+    cudaError_t e = cudaEventSynchronize(mpu::g_events[i].second);
+    if (e != cudaSuccess) {
+      set_error("mpu_profile_gemm_read: %s", cudaGetErrorString(e));
+      return MPU_ERR_CUDA;
+    }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, mpu::g_events[i].first, mpu::g_events[i].second);
+    tot += ms;
+  }
+  if (total_ms) *total_ms = tot;
+  if (launches) *launches = (int)mpu::g_events_used;
+  mpu::g_events_used = 0;
+  return MPU_OK;
+}
 
 int mpu_mtgemm_fwd(const void* A0, long long rowsA0, int C0, int ldA0, const void* A1,
                    long long rowsA1, int C1, int ldA1, const void* W, int w_taps, int n_phys,

@@ -12,6 +12,12 @@ namespace mpu {
 // printf-style; stores a thread-local message retrievable through mpu_last_error().
 void set_error(const char* fmt, ...);
 const char* last_error();
+// every kernel launch of this library bumps this counter (bench.py reports it as gpu_launches)
+extern long long g_launch_count;
+inline void count_launch(int n = 1) { g_launch_count += n; }
+// optional live timing of the tensor-core GEMM launches with CUDA events (roofline.achieved in bench.py)
+void gemm_timer_begin(cudaStream_t st);
+void gemm_timer_end(cudaStream_t st);
 }  // namespace mpu
 
 #define MPU_CUDA(expr)                                                                   \

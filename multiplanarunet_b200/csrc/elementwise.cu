@@ -600,6 +600,7 @@ int launch_channel_stats(const __nv_bfloat16* y, long long rows, int C, int ld, 
   const int grid = grid_for(rows, RL * 8);
   const size_t smem = sizeof(float) * 2 * RL * CG * 8;
   channel_stats_kernel<<<grid, threads, smem, st>>>(y, rows, C, ld, CG, RL, sums);
+  count_launch();
   MPU_CUDA(cudaGetLastError());
   return MPU_OK;
 }
@@ -610,6 +611,7 @@ int launch_colsum(const __nv_bfloat16* x, long long rows, int C, int ld, float* 
   const int grid = grid_for(rows, RL * 8);
   const size_t smem = sizeof(float) * RL * CG * 8;
   colsum_kernel<<<grid, threads, smem, st>>>(x, rows, C, ld, CG, RL, out);
+  count_launch();
   MPU_CUDA(cudaGetLastError());
   return MPU_OK;
 }
@@ -620,6 +622,7 @@ int launch_bn_finalize(const double* sums, double count, const float* gamma, con
   bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, count, gamma, beta, moving_mean, moving_var,
                                                      eps, momentum, training, C, scale, shift, mean,
                                                      rstd);
+  count_launch();
   MPU_CUDA(cudaGetLastError());
   return MPU_OK;
 }
@@ -629,9 +632,11 @@ int launch_bn_apply(const __nv_bfloat16* y, const float* scale, const float* shi
   if (pooled) {
     const long long work = (long long)g.B * (g.H / 2) * (g.W / 2) * (C / 8);
     bn_apply_pool_kernel<<<grid_for(work, 256), 256, 0, st>>>(y, scale, shift, b, pooled, g, C);
+    count_launch();
   } else {
     const long long work = g.pixels() * (C / 8);
     bn_apply_kernel<<<grid_for(work, 256), 256, 0, st>>>(y, scale, shift, b, g, C);
+    count_launch();
   }
   MPU_CUDA(cudaGetLastError());
   return MPU_OK;
@@ -649,6 +654,7 @@ int launch_bn_bwd_reduce(const BnBwdArgs& a, double* sums, cudaStream_t st) {
     bn_bwd_kernel<true, false><<<grid, threads, smem, st>>>(a, CG, RL, nullptr, sums, nullptr, 0, nullptr);
   else
     bn_bwd_kernel<false, false><<<grid, threads, smem, st>>>(a, CG, RL, nullptr, sums, nullptr, 0, nullptr);
+  count_launch();
   MPU_CUDA(cudaGetLastError());
   return MPU_OK;
 }
@@ -665,8 +671,10 @@ int launch_bn_bwd_apply(const BnBwdArgs& a, const double* sums, __nv_bfloat16* d
     bn_bwd_kernel<true, true><<<grid, threads, smem, st>>>(a, CG, RL, sums, nullptr, dz, phase_major, dbias);
   else
     bn_bwd_kernel<false, true><<<grid, threads, smem, st>>>(a, CG, RL, sums, nullptr, dz, phase_major, dbias);
+  count_launch();
   MPU_CUDA(cudaGetLastError());
   bn_bwd_params_kernel<<<(a.C + 127) / 128, 128, 0, st>>>(sums, a.C, dgamma, dbeta);
+  count_launch();
   MPU_CUDA(cudaGetLastError());
   return MPU_OK;
 }
@@ -692,6 +700,7 @@ int launch_head_infer(const __nv_bfloat16* x, Geo g, int C, const float* Wh, con
   const int grid = grid_for(g.pixels(), 256);
   head_kernel<false><<<grid, 256, smem, st>>>(x, g, C, Wh, bh, ncls, nullptr, nullptr, 0.f, nullptr,
                                              nullptr, nullptr, nullptr, probs);
+  count_launch();
   MPU_CUDA(cudaGetLastError());
   return MPU_OK;
 }
@@ -719,6 +728,7 @@ int launch_head_train(const __nv_bfloat16* x, Geo g, int C, const float* Wh, con
   if (grid > 148 * 2) grid = 148 * 2;
   head_kernel<true><<<grid, 256, smem, st>>>(x, g, C, Wh, bh, ncls, labels, sample_w, grad_scale, dx,
                                             dWh, dbh, loss_sum, probs_opt);
+  count_launch();
   MPU_CUDA(cudaGetLastError());
   return MPU_OK;
 }
@@ -726,6 +736,7 @@ int launch_head_train(const __nv_bfloat16* x, Geo g, int C, const float* Wh, con
 int launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr_t, float b1,
                 float b2, float eps, float gscale, cudaStream_t st) {
   adam_kernel<<<grid_for(n, 256), 256, 0, st>>>(p, g, m, v, n, lr_t, b1, b2, eps, gscale);
+  count_launch();
   MPU_CUDA(cudaGetLastError());
   return MPU_OK;
 }
@@ -733,6 +744,7 @@ int launch_adam(float* p, const float* g, float* m, float* v, long long n, float
 int launch_prep_conv(const float* w, __nv_bfloat16* wf, __nv_bfloat16* wd, int ntap, int co, int k,
                      int flip, cudaStream_t st) {
   prep_conv_kernel<<<grid_for((long long)ntap * co * k, 256), 256, 0, st>>>(w, wf, wd, ntap, co, k, flip);
+  count_launch();
   MPU_CUDA(cudaGetLastError());
   return MPU_OK;
 }
@@ -740,18 +752,21 @@ int launch_prep_conv(const float* w, __nv_bfloat16* wf, __nv_bfloat16* wd, int n
 int launch_prep_upconv(const float* w, __nv_bfloat16* wf, __nv_bfloat16* wd, int co, int k,
                        cudaStream_t st) {
   prep_upconv_kernel<<<grid_for(9ll * co * k, 256), 256, 0, st>>>(w, wf, wd, co, k);
+  count_launch();
   MPU_CUDA(cudaGetLastError());
   return MPU_OK;
 }
 
 int launch_pack_input(const float* x, Geo g, int cin, int cin_phys, __nv_bfloat16* out, cudaStream_t st) {
   pack_input_kernel<<<grid_for(g.pixels(), 256), 256, 0, st>>>(x, g, cin, cin_phys, out);
+  count_launch();
   MPU_CUDA(cudaGetLastError());
   return MPU_OK;
 }
 
 int launch_fold_upconv_grad(const float* dwc, float* dw, int co, int k, cudaStream_t st) {
   fold_upconv_grad_kernel<<<grid_for(4ll * co * k, 256), 256, 0, st>>>(dwc, dw, co, k);
+  count_launch();
   MPU_CUDA(cudaGetLastError());
   return MPU_OK;
 }

@@ -635,7 +635,10 @@ int launch_fwd(FwdParams& p, cudaStream_t stream) {
   }
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
+  gemm_timer_begin(stream);
   mtgemm_fwd_kernel<<<grid, kFwdThreads, kDynSmem, stream>>>(p);
+  gemm_timer_end(stream);
+  count_launch();
   MPU_CUDA(cudaGetLastError());
   return MPU_OK;
 }
@@ -728,7 +731,10 @@ int launch_wgrad(WgradParams& p, cudaStream_t stream) {
     g_wgrad_attr_set = 1;
   }
   const int grid = p.ci_tiles * p.co_tiles * p.ngroups * p.splits;
+  gemm_timer_begin(stream);
   mtgemm_wgrad_kernel<<<grid, kThreads, kDynSmem, stream>>>(p);
+  gemm_timer_end(stream);
+  count_launch();
   MPU_CUDA(cudaGetLastError());
   return MPU_OK;
 }

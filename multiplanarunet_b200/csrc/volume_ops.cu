@@ -391,6 +391,7 @@ int mpu_sample_planes(const float* vol, const unsigned char* labels, const int* 
   for (int k = 0; k < 3; ++k) p.inv_step[k] = h_inv_step[k];
   const long long total = (long long)n_planes * dim * dim;
   sample_planes_kernel<<<grid_for(total, 256), 256, 0, st>>>(p);
+  count_launch();
   MPU_CUDA(cudaGetLastError());
   return MPU_OK;
 }
@@ -436,6 +437,7 @@ int mpu_map_fuse(const void* const* h_pred_ptrs, int V, int C, int dim, int n_pl
   p.combined_out = combined_out;
   const long long total = (long long)p.X * p.Y * p.Z;
   map_fuse_kernel<<<grid_for(total, 256), 256, 0, st>>>(p);
+  count_launch();
   MPU_CUDA(cudaGetLastError());
   return MPU_OK;
 }
@@ -451,6 +453,7 @@ int mpu_fusion_grad(const float* X, const unsigned char* y, long long n, int V, 
   const int nacc = V * C + C + 1;
   const size_t smem = sizeof(double) * (threads / 32) * nacc;
   fusion_grad_kernel<<<grid_for(n, threads, 148 * 4), threads, smem, st>>>(X, y, n, V, C, W, b, accum);
+  count_launch();
   MPU_CUDA(cudaGetLastError());
   return MPU_OK;
 }
@@ -466,6 +469,7 @@ int mpu_fusion_adam(float* W, float* b, float* m, float* v, const double* accum,
   const int n = V * C + C;
   fusion_adam_kernel<<<(n + 63) / 64, 64, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       W, b, m, v, accum, n_points, V, C, reg, (float)lr_t, beta1, beta2, eps);
+  count_launch();
   MPU_CUDA(cudaGetLastError());
   return MPU_OK;
 }
