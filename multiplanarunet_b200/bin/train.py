@@ -1,0 +1,215 @@
+"""`mp train` on the B200 engine (mirror of mpunet/bin/train.py:18-416 for MultiPlanar projects).
+
+Keeps the reference's flags, project-dir layout (train_hparams.yaml, views.npz, model/, logs/) and
+training semantics (Adam, sparse CE x sample weight, FG-balanced random oblique slices, per-epoch
+validation dice driving ReduceLROnPlateau / best-checkpoint / early stopping with the YAML presets);
+the Keras fit loop is replaced by a thin step loop over the device sampler and the CUDA train step.
+Launch under torchrun for multi-GPU (one process per GPU, NCCL gradient all-reduce)."""
+import csv
+import math
+import os
+import shutil
+from argparse import ArgumentParser
+
+import numpy as np
+
+
+def get_argparser():
+    p = ArgumentParser(description='Fit a mpunet model defined in a project folder. '
+                                   'Invoke "init_project" to start a new project.')
+    p.add_argument("--project_dir", type=str, default="./")
+    p.add_argument("--num_GPUs", type=int, default=1)
+    p.add_argument("--force_GPU", type=str, default="")
+    p.add_argument("--continue_training", action="store_true")
+    p.add_argument("--overwrite", action="store_true")
+    p.add_argument("--just_one", action="store_true")
+    p.add_argument("--no_val", action="store_true")
+    p.add_argument("--no_images", action="store_true")
+    p.add_argument("--debug", action="store_true")
+    p.add_argument("--wait_for", type=str, default="")
+    p.add_argument("--train_images_per_epoch", type=int, default=2500)
+    p.add_argument("--val_images_per_epoch", type=int, default=3500)
+    p.add_argument("--max_loaded_images", type=int, default=None)
+    p.add_argument("--epochs", type=int, default=None)
+    p.add_argument("--num_access", type=int, default=50)
+    return p
+
+
+def validate_project_dir(project_dir):
+    if not os.path.exists(project_dir) or not os.path.exists(os.path.join(project_dir, "train_hparams.yaml")):
+        raise RuntimeError("The script was launched from directory:\n'%s'\n... but this is not a valid project "
+                           "folder.\n\n* Make sure to launch the script from within a MultiPlanarNet project "
+                           "directory\n* Make sure that the directory contains a 'train_hparams.yaml' file."
+                           % project_dir)
+
+
+def remove_previous_session(project_folder):
+    for p in ("images", "logs", "model", "tensorboard", "views.npz", "views.png"):
+        p = os.path.join(project_folder, p)
+        if os.path.isdir(p):
+            shutil.rmtree(p)
+        elif os.path.exists(p):
+            os.remove(p)
+
+
+def load_or_create_views(project_dir, n_views, continue_training):
+    from ..interpolation import sample_random_views_with_angle_restriction
+    path = os.path.join(project_dir, "views.npz")
+    if continue_training and os.path.exists(path):
+        return np.load(path)["arr_0"]
+    views = sample_random_views_with_angle_restriction(n_views, 60)
+    np.savez(path, views)
+    return views
+
+
+def validation_dice(model, seq, n_images, n_classes):
+    """Epoch-end validation like callbacks/validation.py:91-230: sample validation batches, accumulate
+    TP / relevant / selected per class, return mean foreground dice."""
+    tp = np.zeros(n_classes)
+    rel = np.zeros(n_classes)
+    sel = np.zeros(n_classes)
+    steps = max(1, int(math.ceil(n_images / seq.batch_size)))
+    for _ in range(steps):
+        x, y, _ = seq.sample_batch_device()
+        pred = model.predict_on_batch(x, as_numpy=False).argmax(-1).reshape(-1)
+        yy = y.reshape(-1).long()
+        k = n_classes
+        cm = np.bincount((yy * k + pred).cpu().numpy(), minlength=k * k).reshape(k, k)
+        tp += np.diag(cm)
+        rel += cm.sum(1)
+        sel += cm.sum(0)
+    dice = (2 * tp) / np.maximum(rel + sel, 1)
+    return float(np.mean(dice[1:])) if n_classes > 1 else float(dice[0])
+
+
+def run(project_dir, args):
+    import torch
+    from .. import distributed as D
+    from ..hyperparameters import YAMLHParams
+    from ..image import Auditor, ImagePairLoader
+    from .. import models
+    from ..sequences import IsotrophicLiveViewSequence2D
+    from ..utils.utils import get_last_model
+
+    hp = YAMLHParams(os.path.join(project_dir, "train_hparams.yaml"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    world = D.init_from_env(device=torch.device("cuda", local))
+    rank = D.rank()
+    log = print if rank == 0 else (lambda *a, **k: None)
+
+    bg_value = hp.get_from_anywhere("bg_value") or 0.0
+    train = ImagePairLoader(bg_value=bg_value, **hp["train_data"])
+    val = None if args.no_val else ImagePairLoader(bg_value=bg_value, **hp["val_data"])
+    if len(train) == 0:
+        raise OSError("No training images found under %s" % hp["train_data"]["base_dir"])
+    if args.just_one:
+        train.image_paths = train.image_paths[:1]
+        if val:
+            val.image_paths = val.image_paths[:1]
+    if rank == 0:
+        paths = train.image_paths + (val.image_paths if val else [])
+        labs = [train.label_path_for(p) for p in train.image_paths]
+        Auditor(paths, [l for l in labs if l], hparams=hp).fill(hp, "2d")
+    if world > 1:
+        torch.distributed.barrier()
+        hp = YAMLHParams(os.path.join(project_dir, "train_hparams.yaml"))
+    build, fit = dict(hp["build"]), dict(hp["fit"])
+    views = load_or_create_views(project_dir, fit["views"], args.continue_training) if rank == 0 else None
+    if world > 1:
+        torch.distributed.barrier()
+    if views is None:
+        views = np.load(os.path.join(project_dir, "views.npz"))["arr_0"]
+
+    # volumes shard across ranks (one or more resident volumes per GPU); every rank keeps >= 1
+    my_train = D.shard(list(range(len(train)))) or [rank % len(train)]
+    train_images = [train.get(i) for i in my_train]
+    val_images = [val.get(i) for i in range(len(val))] if val else []
+    bs = int(fit["batch_size"])
+    common = dict(views=views, sample_dim=build["dim"], real_space_span=fit["real_space_span"],
+                  n_classes=build["n_classes"], batch_size=bs, fg_batch_fraction=fit.get("fg_batch_fraction", 0.5))
+    tr_seq = IsotrophicLiveViewSequence2D(train_images, noise_sd=fit.get("noise_sd", 0.1), **common)
+    va_seq = IsotrophicLiveViewSequence2D(val_images, is_validation=True, **common) if val_images else None
+    if fit.get("augmenters"):
+        log("[NOTE] augmenters %s are not applied on the B200 path yet (elastic deformation is a 'next' "
+            "row)" % [a.get("cls_name") for a in fit["augmenters"]])
+
+    cls = models.__dict__[build["model_class_name"]]
+    model = cls(max_batch=bs, training=True, **build)
+    okw = fit.get("optimizer_kwargs", {})
+    model.optimizer.lr = float(okw.get("lr", 5e-5))
+    model.optimizer.beta_1, model.optimizer.beta_2 = float(okw.get("beta_1", 0.9)), float(okw.get("beta_2", 0.999))
+    model.optimizer.epsilon = float(okw.get("epsilon", 1e-7))
+    os.makedirs(os.path.join(project_dir, "model"), exist_ok=True)
+    os.makedirs(os.path.join(project_dir, "logs"), exist_ok=True)
+    init_epoch = 0
+    if args.continue_training:
+        last, init_epoch = get_last_model(os.path.join(project_dir, "model"))
+        if last:
+            model.load_weights(last)
+            log("[NOTICE] Continuing from %s (epoch %d)" % (last, init_epoch))
+    dp = D.DataParallel(model)
+
+    n_epochs = args.epochs or int(fit["n_epochs"])
+    steps = int(math.ceil(args.train_images_per_epoch / (bs * world)))
+    cbs = {c["nickname"]: c.get("kwargs", {}) for c in fit.get("callbacks", []) if isinstance(c, dict)}
+    rlop, es = cbs.get("rlop"), cbs.get("es")
+    best, wait_lr, wait_es, best_path = -1.0, 0, 0, None
+    csv_path = os.path.join(project_dir, "logs", "training.csv")
+    try:
+        for epoch in range(init_epoch, n_epochs):
+            losses = []
+            for _ in range(steps):
+                x, y, w = tr_seq.sample_batch_device()
+                losses.append(dp.train_on_batch(x, y, torch.as_tensor(w)))
+            logs = {"epoch": epoch, "loss": float(np.mean(losses)), "lr": model.optimizer.lr}
+            if va_seq is not None:
+                vd = validation_dice(model, va_seq, args.val_images_per_epoch, build["n_classes"])
+                logs["val_dice"] = vd
+                if vd > best:
+                    best, wait_lr, wait_es = vd, 0, 0
+                    if rank == 0:
+                        if best_path and os.path.exists(best_path):
+                            os.remove(best_path)
+                        best_path = os.path.join(project_dir, "model",
+                                                 "@epoch_%02d_val_dice_%.5f.npz" % (epoch + 1, vd))
+                        model.save_weights(best_path)
+                else:
+                    wait_lr += 1
+                    wait_es += 1
+                    if rlop and wait_lr > int(rlop.get("patience", 2)):
+                        model.optimizer.lr *= float(rlop.get("factor", 0.9))
+                        wait_lr = 0
+            if rank == 0:
+                new = not os.path.exists(csv_path)
+                with open(csv_path, "a", newline="") as f:
+                    wtr = csv.DictWriter(f, fieldnames=sorted(logs))
+                    if new:
+                        wtr.writeheader()
+                    wtr.writerow(logs)
+            log("Epoch %d/%d - %s" % (epoch + 1, n_epochs, " - ".join("%s: %.5g" % kv for kv in sorted(logs.items()))))
+            if es and va_seq is not None and wait_es > int(es.get("patience", 15)):
+                log("Early stopping")
+                break
+    except KeyboardInterrupt:
+        pass
+    finally:
+        if rank == 0:
+            model.save_weights(os.path.join(project_dir, "model", "model_weights.npz"))
+
+
+def entry_func(args=None):
+    a = get_argparser().parse_args(args)
+    project_dir = os.path.abspath(a.project_dir)
+    validate_project_dir(project_dir)
+    if a.overwrite and a.continue_training:
+        raise ValueError("Cannot both continue training and overwrite the previous training session.")
+    if a.overwrite and int(os.environ.get("RANK", "0")) == 0:
+        remove_previous_session(project_dir)
+    elif not a.continue_training and os.path.exists(os.path.join(project_dir, "model")) and \
+            os.listdir(os.path.join(project_dir, "model")):
+        raise OSError("There seems to be a previous training session at '%s'. Use --overwrite or "
+                      "--continue_training." % project_dir)
+    if a.force_GPU:
+        os.environ["CUDA_VISIBLE_DEVICES"] = a.force_GPU
+    run(project_dir, a)

@@ -1,0 +1,74 @@
+"""Project-directory helpers mirroring mpunet/utils/utils.py (best/last model selection :88-130,
+output-bias initialisation :205-242, folder creation)."""
+import glob
+import os
+import re
+
+import numpy as np
+
+WEIGHT_EXTS = (".npz", ".h5")
+
+
+def _models_in(model_dir):
+    out = []
+    for ext in WEIGHT_EXTS:
+        out += glob.glob(os.path.join(model_dir, "@epoch*" + ext))
+    return out
+
+
+def get_best_model(model_dir):
+    """Highest val_dice in `@epoch_XX_val_dice_Y` names, else model_weights (utils.py:88-110)."""
+    models = _models_in(model_dir)
+    if models:
+        scores = [float(re.findall(r"val_dice_(\d+\.\d+)", os.path.basename(m))[0]) for m in models]
+        return os.path.abspath(models[int(np.argmax(scores))])
+    for ext in WEIGHT_EXTS:
+        p = os.path.join(model_dir, "model_weights" + ext)
+        if os.path.exists(p):
+            return os.path.abspath(p)
+    raise OSError("Did not find any model files in directory {}".format(model_dir))
+
+
+def get_last_model(model_dir):
+    """(path, epoch) of the checkpoint with the largest epoch number (utils.py:113-130)."""
+    models = _models_in(model_dir)
+    if not models:
+        for ext in WEIGHT_EXTS:
+            p = os.path.join(model_dir, "model_weights" + ext)
+            if os.path.exists(p):
+                return p, 0
+        return None, 0
+    epochs = [int(re.findall(r"@epoch_(\d+)", os.path.basename(m))[0]) for m in models]
+    i = int(np.argmax(epochs))
+    return os.path.abspath(models[i]), epochs[i]
+
+
+def create_folders(folders, create_deep=False):
+    folders = [folders] if isinstance(folders, str) else folders
+    for f in folders:
+        os.makedirs(f, exist_ok=True) if create_deep else (os.path.isdir(f) or os.mkdir(f))
+
+
+def set_bias_weights(layer, class_counts, logger=None):
+    """Initialise the softmax layer's bias from class frequencies (utils.py:205-242):
+    b = log(freq * sum(exp(freq))) normalised to unit length."""
+    counts = np.asarray(class_counts, dtype=np.float64)
+    freq = counts / counts.sum()
+    bias = np.log(freq * np.sum(np.exp(freq)))
+    bias /= np.linalg.norm(bias)
+    ws = layer.get_weights()
+    ws[-1] = bias.reshape(ws[-1].shape).astype(np.float32)
+    layer.set_weights(ws)
+    return bias
+
+
+def pred_to_class(tensor, img_dims=3, threshold=0.5, has_batch_dim=False):
+    """utils.py:311-328: soft-max volume -> uint8 class map."""
+    tensor = np.asarray(tensor)
+    tensor_dim = img_dims + int(has_batch_dim)
+    dims = len(tensor.shape)
+    if dims == tensor_dim:
+        return tensor
+    if tensor.shape[-1] == 1:
+        return (tensor.squeeze(-1) > threshold).astype(np.uint8)
+    return tensor.argmax(-1).astype(np.uint8)
