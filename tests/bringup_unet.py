@@ -31,7 +31,9 @@ def fetch(model, level, which, B, C_logical):
     off = ptr.value - model.workspace.data_ptr()
     src = model.workspace[off:off + 2 * n].view(torch.bfloat16)
     arr = src.float().cpu().numpy().reshape(B, H + 2, W + 2, C.value)
-    border = np.abs(arr).sum() - np.abs(arr[:, 1:-1, 1:-1]).sum()
+    bm = np.ones(arr.shape[:3], dtype=bool)
+    bm[:, 1:-1, 1:-1] = False
+    border = float(np.abs(arr[bm]).sum())
     padc = np.abs(arr[..., C_logical:]).sum()
     return arr[:, 1:-1, 1:-1, :C_logical], border, padc
 
