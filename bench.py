@@ -307,6 +307,46 @@ def main():
                         n_l.value, gemm_ms.value),
                     "algorithmic_flops_per_step": flops, "peak_source": src}
 
+    # ---- BASELINE.json's secondary figures (config 3): 6-view predict + fusion on the resident volume
+    extras = None
+    if rank == 0 and world == 1:
+        from multiplanarunet_b200.sequences import IsotrophicLiveViewSequence2D
+        from multiplanarunet_b200.utils.fusion.fuse_and_predict import _map_fuse, predict_stack_device
+        seq = IsotrophicLiveViewSequence2D([image], views=views, sample_dim=dim, real_space_span=span,
+                                           n_classes=args.classes, is_validation=True)
+        Wf = np.random.RandomState(0).uniform(0.5, 1.5, (6, args.classes)).astype(np.float32)
+        bf = np.zeros(args.classes, np.float32)
+
+        def predict_volume():
+            preds, grids, ibs = [], [], []
+            for v in views:
+                p_, g_, ib_ = predict_stack_device(model, seq, image, v, "same+20", B)
+                preds.append(p_)
+                grids.append(g_)
+                ibs.append(ib_)
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            ev[0].record()
+            lab, _, _ = _map_fuse(preds, grids, ibs, image.shape[:3], image.affine[:3, :3], Wf, bf)
+            ev[1].record()
+            return lab, ev
+        predict_volume()  # warm-up
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        lab, ev = predict_volume()
+        b.record()
+        torch.cuda.synchronize()
+        ms_vol, ms_fuse = a.elapsed_time(b), ev[0].elapsed_time(ev[1])
+        nvox = float(dim) ** 3
+        fuse_bytes = nvox * (6 * args.classes * 4 + 1)  # reference-shaped traffic: read V*C fp32, write 1 label
+        hbm = peaks.get("hbm_gbs")
+        extras = {"predict_volumes_per_sec": 1e3 / ms_vol, "predict_ms_per_volume": ms_vol,
+                  "predict_config": "6 views x %d planes of %dx%d, U-Net inference (moving-stat BN) + map + fuse + argmax, "
+                                    "one %d^3 volume resident in HBM" % (dim + 20, dim, dim, dim),
+                  "fusion_ms": ms_fuse, "fusion_algorithmic_gbs": fuse_bytes / ms_fuse / 1e6,
+                  "fusion_frac_of_measured_hbm": (fuse_bytes / ms_fuse / 1e6 / hbm) if hbm else None,
+                  "foreground_fraction": float((lab > 0).float().mean().item())}
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         step, cores = cpu_reference_step_factory(args.cf, dim, args.classes)
@@ -330,6 +370,7 @@ def main():
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
+            "extras": extras,
         }
         print(json.dumps(out))
     if world > 1:
