@@ -337,22 +337,31 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mtgemm_fwd_kernel(const __grid
 }
 
 // ------------------------------------------------------------------------------------------------
-// Wgrad kernel: one CTA = (ci tile of 128, co tile of BN, tap group = one kernel row, K split).
-// MN-major operands straight from the NHWC tensors (pixels are the contraction dim): per 64-pixel K
-// block one X slab of 72 rows serves the group's taps through row-shifted descriptors, one dY tile
-// feeds all of them; fp32 accumulators in TMEM (one per tap), fp32 atomics into dW at the end.
+// Wgrad kernel.  dW_t[co, ci] = sum_m dY[m, co] * X[m + x_off + j_t, ci]  with pixels m as the
+// contraction dim; both operands are read MN-major straight from the NHWC tensors.
+//   * A = dY^T tile (M = 128 output channels, two 64-channel atoms);
+//   * B = X slab of 72 rows x 64 input channels.  The kx taps of one kernel row are STACKED ALONG N of a
+//     single MMA: the B descriptor's atom stride (LBO) is one 128-byte row, so N-atom j is the slab
+//     shifted by j rows - one MMA of N = 64*ntaps computes all taps of the row at once;
+//   * one CTA = (co tile of 128) x (CA ci atoms) x (tap row) x (K split); fp32 accumulators in TMEM
+//     (CA x 64*ntaps columns); `red.global.add.v4.f32` into the flat gradient at the end.
 // ------------------------------------------------------------------------------------------------
 static constexpr uint32_t kWgSlabRows = 72;
-static constexpr uint32_t kWgAtomBytes = kWgSlabRows * 128u;  // 9216: one 64-channel atom of the slab
+static constexpr uint32_t kWgAtomBytes = kWgSlabRows * 128u;  // 9216: one 64-channel X slab
+static constexpr uint32_t kWgABytes = 2u * 8192u;             // dY tile: 2 atoms x 64 rows x 128 B
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
 
 __global__ void __launch_bounds__(kThreads, 1)
     mtgemm_wgrad_kernel(const __grid_constant__ WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int S = p.stages;
-  const int nb = (p.BN + 63) / 64;
-  const uint32_t a_bytes = 2u * kWgAtomBytes;  // two 64-channel atoms (M = 128 input channels)
-  const uint32_t stage_bytes = a_bytes + (uint32_t)nb * 8192u;
+  const int CA = p.CA;
+  const uint32_t stage_bytes = kWgABytes + (uint32_t)CA * kWgAtomBytes;
   const uint32_t bar_base = smem_base + (uint32_t)S * stage_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
@@ -371,10 +380,11 @@ __global__ void __launch_bounds__(kThreads, 1)
   const int co_t = w % p.co_tiles; w /= p.co_tiles;
   const int ci_t = w;
   const WgradGroup& grp = p.groups[gi];
-  const int ci0 = ci_t * 128, co0 = co_t * p.BN;
+  const int ci0 = ci_t * CA * 64, co0 = co_t * 128;
   const int kb0 = split * p.kblocks_per_split;
   const int kb1 = min(p.kblocks, kb0 + p.kblocks_per_split);
   const int nkb = max(0, kb1 - kb0);
+  const int ncol = 64 * grp.ntaps;  // accumulator columns per ci atom (MMA N)
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.tmX);
@@ -406,17 +416,17 @@ __global__ void __launch_bounds__(kThreads, 1)
       const uint32_t st = smem_base + (uint32_t)s * stage_bytes;
       if (elect_one()) {
         mbar_expect_tx(full_bar(s), stage_bytes);
-        tma_load_2d(&p.tmX, full_bar(s), st, ci0, r0 + grp.x_off);
-        tma_load_2d(&p.tmX, full_bar(s), st + kWgAtomBytes, ci0 + 64, r0 + grp.x_off);
-        for (int j = 0; j < nb; ++j)
-          tma_load_2d(&p.tmDY, full_bar(s), st + a_bytes + (uint32_t)j * 8192u, co0 + j * 64,
-                      r0 + grp.dy_off);
+        tma_load_2d(&p.tmDY, full_bar(s), st, co0, r0 + grp.dy_off);
+        tma_load_2d(&p.tmDY, full_bar(s), st + 8192u, co0 + 64, r0 + grp.dy_off);
+        for (int a = 0; a < CA; ++a)
+          tma_load_2d(&p.tmX, full_bar(s), st + kWgABytes + (uint32_t)a * kWgAtomBytes, ci0 + a * 64,
+                      r0 + grp.x_off);
       }
       __syncwarp();
       if (++s == S) { s = 0; ph ^= 1u; }
     }
   } else if (warp == 1) {
-    const uint32_t idesc = make_idesc_bf16(128, p.BN, 1, 1);
+    const uint32_t idesc = make_idesc_bf16(128, ncol, 1, 1);
     int s = 0;
     uint32_t ph = 0;
     for (int kb = 0; kb < nkb; ++kb) {
@@ -424,15 +434,16 @@ __global__ void __launch_bounds__(kThreads, 1)
       tc_fence_after();
       if (elect_one()) {
         const uint32_t st = smem_base + (uint32_t)s * stage_bytes;
-        const uint32_t bst = st + a_bytes;
-        for (int g = 0; g < grp.ntaps; ++g) {
-          const uint32_t d_tmem = tmem_base + (uint32_t)(g * p.BN);
-          const uint32_t a0 = st + (uint32_t)grp.shift[g] * 128u;
+        const uint32_t bst = st + kWgABytes;
+        for (int a = 0; a < CA; ++a) {
+          const uint32_t d_tmem = tmem_base + (uint32_t)(a * ncol);
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
-            // K step = 16 pixel rows = 2048 B; M atoms (64 channels) kWgAtomBytes apart; N atoms 8192 B
-            const uint64_t a_desc = make_desc_sw128(a0 + (uint32_t)kk * 2048u, kWgAtomBytes, 1024);
-            const uint64_t b_desc = make_desc_sw128(bst + (uint32_t)kk * 2048u, 8192, 1024);
+            // K step = 16 pixel rows = 2048 B.  A: co atoms 8192 B apart.  B: "atom" j = slab shifted by
+            // j rows (LBO = 128 B) -> the taps of this kernel row side by side along N.
+            const uint64_t a_desc = make_desc_sw128(st + (uint32_t)kk * 2048u, 8192, 1024);
+            const uint64_t b_desc =
+                make_desc_sw128(bst + (uint32_t)a * kWgAtomBytes + (uint32_t)kk * 2048u, 128, 1024);
             mma_bf16_ss(d_tmem, a_desc, b_desc, idesc, (kb | kk) != 0 ? 1u : 0u);
           }
         }
@@ -448,21 +459,25 @@ __global__ void __launch_bounds__(kThreads, 1)
     mbar_wait(done_bar, 0);
     tc_fence_after();
     if (nkb > 0) {
-      const int ci = ci0 + q * 32 + lane;
-      for (int g = 0; g < grp.ntaps; ++g) {
-        const int tw = grp.w_idx[g];
-        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * p.BN);
-        for (int c0 = 0; c0 < p.BN; c0 += 16) {
-          uint32_t r[16];
-          tmem_ld16(t_row + (uint32_t)c0, r);
-          tmem_ld_wait();
-          if (ci < p.ci_valid) {
+      const int co = co0 + q * 32 + lane;
+      for (int a = 0; a < CA; ++a) {
+        for (int j = 0; j < grp.ntaps; ++j) {
+          // tap j sits at slab shift grp.shift[j] (shifts are consecutive 0..ntaps-1 by construction)
+          const int tw = grp.w_idx[j];
+          const uint32_t t_row =
+              tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * ncol + grp.shift[j] * 64);
+          float* row = p.dW + ((size_t)tw * p.w_rows_per_tap + co) * p.ldw + p.dw_col0 + ci0 + a * 64;
+          for (int c0 = 0; c0 < 64; c0 += 16) {
+            uint32_t r[16];
+            tmem_ld16(t_row + (uint32_t)c0, r);
+            tmem_ld_wait();
+            if (co < p.co_valid) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int co = co0 + c0 + j;
-              if (co < p.co_valid) {
-                float* dst = p.dW + ((size_t)tw * p.w_rows_per_tap + co) * p.ldw + p.dw_col0 + ci;
-                atomicAdd(dst, __uint_as_float(r[j]));
+              for (int v4 = 0; v4 < 4; ++v4) {
+                const int ci = ci0 + a * 64 + c0 + v4 * 4;
+                if (ci < p.ci_valid)  // ci_valid is a multiple of 8
+                  red_add_v4(row + c0 + v4 * 4, __uint_as_float(r[v4 * 4 + 0]), __uint_as_float(r[v4 * 4 + 1]),
+                             __uint_as_float(r[v4 * 4 + 2]), __uint_as_float(r[v4 * 4 + 3]));
               }
             }
           }
@@ -643,36 +658,20 @@ int launch_fwd(FwdParams& p, cudaStream_t stream) {
   return MPU_OK;
 }
 
-// co tile for wgrad: multiple of 16, at most 160 (3 tap accumulators x BN <= 512 TMEM columns),
-// chosen to minimise padding
-static int pick_bn_wgrad(int co) {
-  int best = 160, best_pad = 1 << 30;
-  for (int tiles = (co + 159) / 160; tiles <= (co + 159) / 160 + 2; ++tiles) {
-    const int bn = ((co + tiles - 1) / tiles + 15) / 16 * 16;
-    if (bn > 160 || bn < 16) continue;
-    const int pad = bn * tiles - co;
-    if (pad < best_pad) {
-      best_pad = pad;
-      best = bn;
-    }
-  }
-  return best;
-}
-
 int wgrad_setup(WgradParams& p, const WgradDesc& d) {
   memset(&p, 0, sizeof(p));
   if (!d.X || !d.dY || !d.dW || d.ntaps < 1 || d.ntaps > kMaxTaps) {
     set_error("wgrad_setup: bad arguments");
     return MPU_ERR_ARG;
   }
-  p.BN = d.BN > 0 ? d.BN : pick_bn_wgrad(d.Cy);
-  if (p.BN % 16 != 0 || p.BN < 16 || 3 * p.BN > 512) {
-    set_error("wgrad_setup: BN=%d must be a multiple of 16 and <= 160", p.BN);
+  if ((d.ldw % 4) || (d.dw_col0 % 4)) {
+    set_error("wgrad_setup: dW row stride / column offset must be multiples of 4 floats");
     return MPU_ERR_ARG;
   }
   MPU_TRY(make_tmap_2d(&p.tmX, d.X, (uint64_t)d.rowsX, (uint64_t)d.Cx, (uint64_t)d.ldX, 64, kWgSlabRows));
   MPU_TRY(make_tmap_2d(&p.tmDY, d.dY, (uint64_t)d.rowsDY, (uint64_t)d.Cy, (uint64_t)d.ldDY, 64, 64));
-  // sort taps by (dy_off, x_off); group taps of one dY plane whose X rows are < 8 apart
+  // sort taps by (dy_off, x_off); a group = taps of one dY plane at CONSECUTIVE rows (shift 0,1,2):
+  // they become the N atoms of one MMA
   int order[kMaxTaps];
   for (int i = 0; i < d.ntaps; ++i) order[i] = i;
   auto less = [&](int a, int b) {
@@ -693,9 +692,9 @@ int wgrad_setup(WgradParams& p, const WgradDesc& d) {
     G.x_off = d.tap_x_off[order[i]];
     G.dy_off = d.tap_dy_off ? d.tap_dy_off[order[i]] : 0;
     G.ntaps = 0;
-    while (i < d.ntaps && G.ntaps < 3 && d.tap_x_off[order[i]] - G.x_off < 8 &&
+    while (i < d.ntaps && G.ntaps < 3 && d.tap_x_off[order[i]] - G.x_off == G.ntaps &&
            (d.tap_dy_off ? d.tap_dy_off[order[i]] : 0) == G.dy_off) {
-      G.shift[G.ntaps] = d.tap_x_off[order[i]] - G.x_off;
+      G.shift[G.ntaps] = G.ntaps;
       G.w_idx[G.ntaps] = d.tap_w[order[i]];
       ++G.ntaps;
       ++i;
@@ -703,8 +702,10 @@ int wgrad_setup(WgradParams& p, const WgradDesc& d) {
   }
   p.ci_valid = d.Cx;
   p.co_valid = d.Cy;
-  p.ci_tiles = (d.Cx + 127) / 128;
-  p.co_tiles = (d.Cy + p.BN - 1) / p.BN;
+  const int atoms = (d.Cx + 63) / 64;
+  p.CA = atoms >= 2 ? 2 : 1;
+  p.ci_tiles = (atoms + p.CA - 1) / p.CA;
+  p.co_tiles = (d.Cy + 127) / 128;
   p.kblocks = (int)((d.rows_total + 63) / 64);
   const int base = p.ci_tiles * p.co_tiles * p.ngroups;
   int splits = d.splits > 0 ? d.splits : (2 * num_sms() + base - 1) / base;
@@ -720,8 +721,7 @@ int wgrad_setup(WgradParams& p, const WgradDesc& d) {
 }
 
 int launch_wgrad(WgradParams& p, cudaStream_t stream) {
-  const int nb = (p.BN + 63) / 64;
-  const int stage_bytes = 2 * (int)kWgAtomBytes + nb * 8192;
+  const int stage_bytes = (int)kWgABytes + p.CA * (int)kWgAtomBytes;
   int S = kSmemBudget / stage_bytes;
   if (S > 8) S = 8;
   p.stages = S;

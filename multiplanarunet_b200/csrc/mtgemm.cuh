@@ -87,16 +87,17 @@ struct WgradParams {
   CUtensorMap tmX, tmDY;         // X box {64 ch, 72 rows}; dY box {64 ch, 64 rows}
   int ngroups;
   WgradGroup groups[kMaxTaps];
-  int BN;                        // co tile (multiple of 16); 3 * BN <= 512 TMEM columns
-  int ci_tiles, co_tiles, splits;
+  int CA;                        // 64-channel ci atoms per CTA (1 or 2)
+  int ci_tiles, co_tiles, splits;  // ci tiles of CA*64 channels, co tiles of 128 channels
   int kblocks;                   // total 64-row K blocks
   int kblocks_per_split;
-  float* dW;                     // [tap][co][ldw] fp32, accumulated with atomics
+  float* dW;                     // [tap][co][ldw] fp32, accumulated with vector reductions
   int ldw;
   int w_rows_per_tap;
   int dw_col0;                   // column offset (concat source 1)
   int ci_valid, co_valid;
   int stages;
+  int BN;                        // unused (kept for the bring-up API)
 };
 
 struct WgradDesc {
