@@ -204,10 +204,15 @@ __global__ void bn_apply_pool_kernel(const __nv_bfloat16* __restrict__ y,
 // Work item = (pixel or 2x2 window, channel group).  g(p,c) = gA[p] + (p is the first arg-max of its
 // window ? gP[window] : 0).  Window arg-max is recomputed from the bf16-rounded BN outputs, scanning
 // row-major so the first maximum wins (the forward max-pool kept no index).
+// Pass 1 accumulates sum(g) and sum(g*y); with xhat = (y-mu)*rstd the BN backward is then the per-channel
+// affine map dz = relu'(y) * (a*g + b*y + c):  a = gamma*rstd, b = -a*rstd*mgx, c = -a*mg - b*mu  where
+// mg = mean(g), mgx = mean(g*xhat) = rstd*(mean(g*y) - mu*mg).  Few per-thread coefficients keep the
+// register count low enough for 4+ resident blocks per SM (these kernels are pure HBM streams).
 template <bool POOL, bool APPLY>
-__global__ void bn_bwd_kernel(BnBwdArgs a, int CG, int RL, const double* __restrict__ sums_in,
-                              double* __restrict__ sums_out, __nv_bfloat16* __restrict__ dz,
-                              int phase_major, float* __restrict__ dbias) {
+__global__ void __launch_bounds__(256, POOL ? 2 : 3)
+    bn_bwd_kernel(BnBwdArgs a, int CG, int RL, const double* __restrict__ sums_in,
+                  double* __restrict__ sums_out, __nv_bfloat16* __restrict__ dz, int phase_major,
+                  float* __restrict__ dbias) {
   const int tid = threadIdx.x;
   const int cg = tid % CG, rl = tid / CG;
   const int C = a.C;
@@ -215,19 +220,25 @@ __global__ void bn_bwd_kernel(BnBwdArgs a, int CG, int RL, const double* __restr
   const int Wp = g.W + 2;
   const int hh = g.H / 2, wh = g.W / 2;
   const long long items = POOL ? (long long)g.B * hh * wh : g.pixels();
-  float sc[8], sh[8], mu[8], rs[8], k1[8], mg[8], mgx[8];
+  float sc[POOL ? 8 : 1], sh[POOL ? 8 : 1];
+  float ca[APPLY ? 8 : 1], cb[APPLY ? 8 : 1], cc[APPLY ? 8 : 1];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = cg * 8 + j;
-    sc[j] = a.scale[c];
-    sh[j] = a.shift[c];
-    mu[j] = a.mean[c];
-    rs[j] = a.rstd[c];
+    if (POOL) {
+      sc[j] = a.scale[c];
+      sh[j] = a.shift[c];
+    }
     if (APPLY) {
       const double cnt = (double)g.pixels();
-      k1[j] = a.gamma[c] * rs[j];
-      mg[j] = (float)(sums_in[c] / cnt);
-      mgx[j] = (float)(sums_in[C + c] / cnt);
+      const float mu = a.mean[c], rs = a.rstd[c];
+      const float mg = (float)(sums_in[c] / cnt);
+      const float mgy = (float)(sums_in[C + c] / cnt);
+      const float mgx = rs * (mgy - mu * mg);
+      const float k1 = a.gamma[c] * rs;
+      ca[j] = k1;
+      cb[j] = -k1 * rs * mgx;
+      cc[j] = -k1 * mg - cb[j] * mu;
     }
   }
   float acc[2][8];
@@ -255,7 +266,7 @@ __global__ void bn_bwd_kernel(BnBwdArgs a, int CG, int RL, const double* __restr
       rows4[0] = padded_row(g, it);
       nsub = 1;
     }
-    Vec8 yv[4];
+    Vec8 yv[POOL ? 4 : 1];
     int amax[8];
     if (POOL) {
       float best[8];
@@ -281,50 +292,51 @@ __global__ void bn_bwd_kernel(BnBwdArgs a, int CG, int RL, const double* __restr
     }
     Vec8 gp;
     if (POOL && a.gP) gp = load8(a.gP + prow * C + cg * 8);
-    for (int d = 0; d < nsub; ++d) {
-      Vec8 gv;
-      if (a.gA) {
-        gv = load8(a.gA + rows4[d] * (long long)a.ldA + cg * 8);
-      } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) gv.v[j] = 0.f;
-      }
-      if (POOL && a.gP) {
+    for (int d = 0; d < (POOL ? 4 : 1); ++d) {
+      if (d < nsub) {
+        Vec8 gv;
+        if (a.gA) {
+          gv = load8(a.gA + rows4[d] * (long long)a.ldA + cg * 8);
+        } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (amax[j] == d) gv.v[j] += gp.v[j];
-      }
-      if (!APPLY) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float xh = (yv[d].v[j] - mu[j]) * rs[j];
-          acc[0][j] += gv.v[j];
-          acc[1][j] += gv.v[j] * xh;
+          for (int j = 0; j < 8; ++j) gv.v[j] = 0.f;
         }
-      } else {
-        Vec8 o;
+        if (POOL && a.gP) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float xh = (yv[d].v[j] - mu[j]) * rs[j];
-          float v = k1[j] * (gv.v[j] - mg[j] - xh * mgx[j]);
-          if (!(yv[d].v[j] > 0.f)) v = 0.f;
-          v = bf16_round(v);
-          o.v[j] = v;
-          acc[0][j] += v;
+          for (int j = 0; j < 8; ++j)
+            if (amax[j] == d) gv.v[j] += gp.v[j];
         }
-        long long orow = rows4[d];
-        if (phase_major) {
-          // pixel (n, y, x) of this level -> [phase][rows of the half-resolution level]
-          const long long plane = (long long)(g.H + 2) * Wp;
-          const long long n = orow / plane;
-          const long long rem = orow - n * plane;
-          const int yy = (int)(rem / Wp) - 1, xx = (int)(rem % Wp) - 1;
-          const int ph = (yy & 1) * 2 + (xx & 1);
-          const long long rows_lo = (long long)g.B * (hh + 2) * (wh + 2);
-          orow = ph * rows_lo + n * (long long)(hh + 2) * (wh + 2) +
-                 (long long)((yy >> 1) + 1) * (wh + 2) + ((xx >> 1) + 1);
+        if (!APPLY) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            acc[0][j] += gv.v[j];
+            acc[1][j] = fmaf(gv.v[j], yv[d].v[j], acc[1][j]);
+          }
+        } else {
+          Vec8 o;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float v = fmaf(ca[j], gv.v[j], fmaf(cb[j], yv[d].v[j], cc[j]));
+            if (!(yv[d].v[j] > 0.f)) v = 0.f;
+            v = bf16_round(v);
+            o.v[j] = v;
+            acc[0][j] += v;
+          }
+          long long orow = rows4[d];
+          if (phase_major) {
+            // pixel (n, y, x) of this level -> [phase][rows of the half-resolution level]
+            const long long plane = (long long)(g.H + 2) * Wp;
+            const long long n = orow / plane;
+            const long long rem = orow - n * plane;
+            const int yy = (int)(rem / Wp) - 1, xx = (int)(rem % Wp) - 1;
+            const int ph = (yy & 1) * 2 + (xx & 1);
+            const long long rows_lo = (long long)g.B * (hh + 2) * (wh + 2);
+            orow = ph * rows_lo + n * (long long)(hh + 2) * (wh + 2) +
+                   (long long)((yy >> 1) + 1) * (wh + 2) + ((xx >> 1) + 1);
+          }
+          store8(dz + orow * C + cg * 8, o);
         }
-        store8(dz + orow * C + cg * 8, o);
       }
     }
   }
@@ -338,11 +350,13 @@ __global__ void bn_bwd_kernel(BnBwdArgs a, int CG, int RL, const double* __restr
   }
 }
 
-__global__ void bn_bwd_params_kernel(const double* __restrict__ sums, int C, float* dgamma, float* dbeta) {
+// sums = [sum g | sum g*y]  ->  dbeta += sum g ; dgamma += sum g*xhat = rstd * (sum g*y - mu * sum g)
+__global__ void bn_bwd_params_kernel(const double* __restrict__ sums, const float* __restrict__ mean,
+                                     const float* __restrict__ rstd, int C, float* dgamma, float* dbeta) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   dbeta[c] += (float)sums[c];
-  dgamma[c] += (float)sums[C + c];
+  dgamma[c] += (float)((double)rstd[c] * (sums[C + c] - (double)mean[c] * sums[c]));
 }
 
 // ---- head ----------------------------------------------------------------------------------------
@@ -673,7 +687,7 @@ int launch_bn_bwd_apply(const BnBwdArgs& a, const double* sums, __nv_bfloat16* d
     bn_bwd_kernel<false, true><<<grid, threads, smem, st>>>(a, CG, RL, sums, nullptr, dz, phase_major, dbias);
   count_launch();
   MPU_CUDA(cudaGetLastError());
-  bn_bwd_params_kernel<<<(a.C + 127) / 128, 128, 0, st>>>(sums, a.C, dgamma, dbeta);
+  bn_bwd_params_kernel<<<(a.C + 127) / 128, 128, 0, st>>>(sums, a.mean, a.rstd, a.C, dgamma, dbeta);
   count_launch();
   MPU_CUDA(cudaGetLastError());
   return MPU_OK;
