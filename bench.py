@@ -175,7 +175,9 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # a short collective timeout: a rank-asymmetric bug must abort in minutes, not hang the box
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
 
     from multiplanarunet_b200 import _C
     from multiplanarunet_b200._C import lib, check
@@ -283,13 +285,14 @@ def main():
     d2h = 8
 
     # ---- roofline of the dominant kernels (tensor-core GEMMs), timed live with CUDA events
+    # (every rank runs the extra step - it contains the gradient all-reduce - only rank 0 reads the timer)
     roofline = None
+    check(lib.mpu_profile_gemm(1))
+    step_value(W + K + 1)
+    gemm_ms, n_l = ctypes.c_double(), ctypes.c_int()
+    check(lib.mpu_profile_gemm_read(ctypes.byref(gemm_ms), ctypes.byref(n_l)))
+    check(lib.mpu_profile_gemm(0))
     if rank == 0:
-        check(lib.mpu_profile_gemm(1))
-        step_value(W + K + 1)
-        gemm_ms, n_l = ctypes.c_double(), ctypes.c_int()
-        check(lib.mpu_profile_gemm_read(ctypes.byref(gemm_ms), ctypes.byref(n_l)))
-        check(lib.mpu_profile_gemm(0))
         flops = 3.0 * FWD_GFLOP_PER_SLICE.get(args.cf, 0.0) * 1e9 * (dim / 256.0) ** 2 * B
         peaks = {}
         try:

@@ -36,6 +36,17 @@ __device__ __forceinline__ int find_cell(const T* __restrict__ g, int n, double 
   return i;
 }
 
+// (x - g0) / (g1 - g0) <= 0.5 evaluated exactly as numpy does (division rounded to nearest, then the
+// comparison) but without the division in all but a vanishing sliver of cases: with a = x - g0 and
+// b = g1 - g0 > 0, fl(a/b) <= 0.5 holds iff a/b <= 0.5*(1 + 2^-53); 2a <= b decides "yes" and
+// 2a > b*(1 + 2^-51) decides "no"; only values in between take the division.
+__device__ __forceinline__ bool lower_half(double a, double b) {
+  const double d = __dsub_rn(__dadd_rn(a, a), b);
+  if (d <= 0.0) return true;
+  if (d > b * 4.5e-16) return false;
+  return __ddiv_rn(a, b) <= 0.5;
+}
+
 __device__ __forceinline__ double dot3(const double* m, double a, double b, double c) {
   // BLAS-style accumulate: ((m0*a) + m1*b) + m2*c with fused multiply-adds
   return fma(m[2], c, fma(m[1], b, __dmul_rn(m[0], a)));
@@ -188,8 +199,7 @@ __global__ void map_fuse_kernel(const MapFuseParams p) {
         const int n = a < 2 ? p.dim : p.n_planes;
         const double inv = a < 2 ? p.inv_step_ax : p.inv_step_off[v];
         const int c = find_cell(g, n, q[a], inv);
-        const double t = __ddiv_rn(__dsub_rn(q[a], g[c]), __dsub_rn(g[c + 1], g[c]));
-        sel[a] = t <= 0.5 ? c : c + 1;
+        sel[a] = lower_half(__dsub_rn(q[a], g[c]), __dsub_rn(g[c + 1], g[c])) ? c : c + 1;
         oob = oob || q[a] < g[0] || q[a] > g[n - 1];
       }
       const float* src = p.pred[v] + (((long long)sel[2] * p.dim + sel[0]) * p.dim + sel[1]) * p.C;
