@@ -380,11 +380,11 @@ __global__ void head_kernel(const __nv_bfloat16* __restrict__ x, Geo g, int C,
   __syncthreads();
 
   const long long npix = g.pixels();
-  const int npairs = ncls * C;
-  constexpr int kPairsPerThread = 8;  // supports ncls*C <= 2048 with 256 threads
-  float wacc[kPairsPerThread];
+  const int nseg = max(1, 256 / C);                  // pixel segments for the weight-gradient pass
+  const int rows_per_seg = (256 + nseg - 1) / nseg;
+  float wacc[kMaxCls];
 #pragma unroll
-  for (int k = 0; k < kPairsPerThread; ++k) wacc[k] = 0.f;
+  for (int c = 0; c < kMaxCls; ++c) wacc[c] = 0.f;
   float bacc = 0.f;
   double lacc = 0.0;
 
@@ -468,15 +468,17 @@ __global__ void head_kernel(const __nv_bfloat16* __restrict__ x, Geo g, int C,
     }
     if (TRAIN) {
       __syncthreads();
+      // dWh[c][ci] += sum_p dl[p][c] * x[p][ci]: thread = (input channel ci, pixel segment); all classes
+      // accumulate in registers, one x read + ncls broadcast reads per pixel
       const int nrows = (int)min((long long)256, npix - p0);
+      if (threadIdx.x < nseg * C) {
+        const int ci = threadIdx.x % C, seg = threadIdx.x / C;
+        const int r_lo = seg * rows_per_seg, r_hi = min(nrows, r_lo + rows_per_seg);
+        for (int r = r_lo; r < r_hi; ++r) {
+          const float xv = __bfloat162float(xs[r * C + ci]);
 #pragma unroll
-      for (int k = 0; k < kPairsPerThread; ++k) {
-        const int pr = threadIdx.x + k * 256;
-        if (pr < npairs) {
-          const int c = pr / C, ci = pr % C;
-          float s = 0.f;
-          for (int r = 0; r < nrows; ++r) s = fmaf(dl[r * ncls + c], __bfloat162float(xs[r * C + ci]), s);
-          wacc[k] += s;
+          for (int c = 0; c < kMaxCls; ++c)
+            if (c < ncls) wacc[c] = fmaf(dl[r * ncls + c], xv, wacc[c]);
         }
       }
       if (threadIdx.x < ncls) {
@@ -488,10 +490,11 @@ __global__ void head_kernel(const __nv_bfloat16* __restrict__ x, Geo g, int C,
     }
   }
   if (TRAIN) {
+    if (threadIdx.x < nseg * C) {
+      const int ci = threadIdx.x % C;
 #pragma unroll
-    for (int k = 0; k < kPairsPerThread; ++k) {
-      const int pr = threadIdx.x + k * 256;
-      if (pr < npairs) atomicAdd(dWh + pr, wacc[k]);
+      for (int c = 0; c < kMaxCls; ++c)
+        if (c < ncls) atomicAdd(dWh + c * C + ci, wacc[c]);
     }
     if (threadIdx.x < ncls) atomicAdd(dbh + threadIdx.x, bacc);
     // block reduce loss
@@ -509,7 +512,7 @@ __global__ void head_kernel(const __nv_bfloat16* __restrict__ x, Geo g, int C,
 // ---- optimizer / weight layout ---------------------------------------------------------------------
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, long long n, float lr_t, float b1, float b2, float eps,
-                            float gscale) {
+                            float gscale, __nv_bfloat16* __restrict__ shadow) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     const float gi = g[i] * gscale;
@@ -517,8 +520,16 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
     m[i] = mi;
     v[i] = vi;
-    p[i] = p[i] - lr_t * mi / (sqrtf(vi) + eps);
+    const float pn = p[i] - lr_t * mi / (sqrtf(vi) + eps);
+    p[i] = pn;
+    if (shadow) shadow[i] = __float2bfloat16_rn(pn);
   }
+}
+
+__global__ void cast_bf16_kernel(const float* __restrict__ p, __nv_bfloat16* __restrict__ shadow, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    shadow[i] = __float2bfloat16_rn(p[i]);
 }
 
 __global__ void prep_conv_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
@@ -531,7 +542,7 @@ __global__ void prep_conv_kernel(const float* __restrict__ w, __nv_bfloat16* __r
     const int c = (int)(t % co);
     const int tap = (int)(t / co);
     const __nv_bfloat16 b = __float2bfloat16_rn(w[i]);
-    wf[i] = b;
+    if (wf) wf[i] = b;
     if (wd) {
       const int td = flip ? ntap - 1 - tap : tap;
       wd[((long long)td * k + kk) * co + c] = b;
@@ -562,7 +573,7 @@ __global__ void prep_upconv_kernel(const float* __restrict__ w, __nv_bfloat16* _
     const int pair = (int)(t / co);
     const __nv_bfloat16 b = __float2bfloat16_rn(collapsed_weight(w, pair, c, kk, co, k));
     wf[i] = b;
-    wd[((long long)pair * k + kk) * co + c] = b;
+    if (wd) wd[((long long)pair * k + kk) * co + c] = b;
   }
 }
 
@@ -723,9 +734,8 @@ int launch_head_train(const __nv_bfloat16* x, Geo g, int C, const float* Wh, con
                       const uint8_t* labels, const float* sample_w, float grad_scale,
                       __nv_bfloat16* dx, float* dWh, float* dbh, double* loss_sum, float* probs_opt,
                       cudaStream_t st) {
-  if (ncls > kMaxCls || ncls * C > 8 * 256) {
-    set_error("head(train): n_classes=%d x C=%d not supported (max %d classes, ncls*C<=2048)", ncls, C,
-              kMaxCls);
+  if (ncls > kMaxCls || C > 256) {
+    set_error("head(train): n_classes=%d, C=%d not supported (max %d classes, C <= 256)", ncls, C, kMaxCls);
     return MPU_ERR_ARG;
   }
   const size_t smem = head_smem(C, ncls, true);
@@ -748,8 +758,15 @@ int launch_head_train(const __nv_bfloat16* x, Geo g, int C, const float* Wh, con
 }
 
 int launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr_t, float b1,
-                float b2, float eps, float gscale, cudaStream_t st) {
-  adam_kernel<<<grid_for(n, 256), 256, 0, st>>>(p, g, m, v, n, lr_t, b1, b2, eps, gscale);
+                float b2, float eps, float gscale, __nv_bfloat16* shadow, cudaStream_t st) {
+  adam_kernel<<<grid_for(n, 256), 256, 0, st>>>(p, g, m, v, n, lr_t, b1, b2, eps, gscale, shadow);
+  count_launch();
+  MPU_CUDA(cudaGetLastError());
+  return MPU_OK;
+}
+
+int launch_cast_bf16(const float* p, __nv_bfloat16* shadow, long long n, cudaStream_t st) {
+  cast_bf16_kernel<<<grid_for(n, 256), 256, 0, st>>>(p, shadow, n);
   count_launch();
   MPU_CUDA(cudaGetLastError());
   return MPU_OK;

@@ -60,8 +60,10 @@ int launch_head_train(const __nv_bfloat16* x, Geo g, int C, const float* Wh, con
                       float grad_scale, __nv_bfloat16* dx, float* dWh, float* dbh,
                       double* loss_sum, float* probs_opt, cudaStream_t st);
 
+// Adam on the flat parameter buffer; also writes the bf16 shadow copy (same indexing) the GEMMs read.
 int launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr_t, float b1,
-                float b2, float eps, float gscale, cudaStream_t st);
+                float b2, float eps, float gscale, __nv_bfloat16* shadow, cudaStream_t st);
+int launch_cast_bf16(const float* p, __nv_bfloat16* shadow, long long n, cudaStream_t st);
 
 // master fp32 [ntap][co][k] -> bf16 forward copy (same layout) and dgrad copy [ntap][k][co].
 // flip: dgrad tap index = ntap-1-t (3x3 spatial flip).

@@ -159,8 +159,14 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mtgemm_fwd_kernel(const __grid
             timed_wait(w_empty(ws), wph ^ 1u, prof ? &w1 : nullptr);
             if (elect_one()) {
               mbar_expect_tx(w_full(ws), kWTileBytes);
-              tma_load_2d(&p.tmW, w_full(ws), w_base + (uint32_t)ws * kWTileBytes, kcol,
-                          G.w_idx[t] * p.w_rows_per_tap + n0);
+              const uint32_t w_dst = w_base + (uint32_t)ws * kWTileBytes;
+              if (!p.w_mn) {
+                tma_load_2d(&p.tmW, w_full(ws), w_dst, kcol, G.w_idx[t] * p.w_rows_per_tap + n0);
+              } else {  // two 64-channel atoms of [64 K rows][64 channels]
+                const int wrow = G.w_idx[t] * p.w_rows_per_tap + kcol;
+                tma_load_2d(&p.tmW, w_full(ws), w_dst, n0, wrow);
+                tma_load_2d(&p.tmW, w_full(ws), w_dst + 8192u, n0 + 64, wrow);
+              }
             }
             __syncwarp();
             if (++ws == NW) { ws = 0; wph ^= 1u; }
@@ -174,7 +180,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mtgemm_fwd_kernel(const __grid
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    const uint32_t idesc = make_idesc_bf16(128, kPT, 0, 0);
+    const uint32_t idesc = make_idesc_bf16(128, kPT, p.w_mn, 0);
     int as = 0, ws = 0;
     uint32_t aph = 0, wph = 0;
     int acs = 0;
@@ -196,12 +202,17 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mtgemm_fwd_kernel(const __grid
             timed_wait(w_full(ws), wph, prof ? &w1 : nullptr);
             tc_fence_after();
             if (elect_one()) {
-              const uint64_t w_desc = make_desc_sw128(w_base + (uint32_t)ws * kWTileBytes, 16, 1024);
+              // K-major weights: K step = +32 B inside the 128 B row.  MN-major weights (w_mn): K step =
+              // 16 rows = +2048 B, channel atoms 8192 B apart.
+              const uint64_t w_desc = p.w_mn
+                                          ? make_desc_sw128(w_base + (uint32_t)ws * kWTileBytes, 8192, 1024)
+                                          : make_desc_sw128(w_base + (uint32_t)ws * kWTileBytes, 16, 1024);
+              const uint64_t w_step = p.w_mn ? 128u : 2u;  // in 16-byte units
               const uint64_t x_desc = make_desc_sw128(a_addr + (uint32_t)G.shift[t] * 128u, 16, 1024);
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk) {
                 if (kk < ksteps)
-                  mma_bf16_ss(d_tmem, w_desc + (uint64_t)(kk * 2), x_desc + (uint64_t)(kk * 2), idesc,
+                  mma_bf16_ss(d_tmem, w_desc + (uint64_t)kk * w_step, x_desc + (uint64_t)(kk * 2), idesc,
                               (first && kk == 0) ? 0u : 1u);
               }
               mma_commit(w_empty(ws));
@@ -581,8 +592,14 @@ int fwd_setup(FwdParams& p, const FwdDesc& d) {
     p.chunks1 = (d.C1 + 63) / 64;
     p.kofs1 = d.C0;
   }
-  MPU_TRY(make_tmap_2d(&p.tmW, d.W, (uint64_t)d.w_taps * d.n_phys, (uint64_t)d.k_total,
-                       (uint64_t)d.k_total, 64, 128));
+  p.w_mn = d.w_mn ? 1 : 0;
+  if (!d.w_mn) {
+    MPU_TRY(make_tmap_2d(&p.tmW, d.W, (uint64_t)d.w_taps * d.n_phys, (uint64_t)d.k_total,
+                         (uint64_t)d.k_total, 64, 128));
+  } else {
+    MPU_TRY(make_tmap_2d(&p.tmW, d.W, (uint64_t)d.w_taps * d.w_rows, (uint64_t)d.n_phys,
+                         (uint64_t)d.n_phys, 64, 64));
+  }
   // group taps that are < 8 rows apart (sorted by offset) into slabs of up to 3 taps
   int order[kMaxTaps];
   for (int i = 0; i < d.ntaps; ++i) order[i] = i;
@@ -606,7 +623,7 @@ int fwd_setup(FwdParams& p, const FwdDesc& d) {
       ++i;
     }
   }
-  p.w_rows_per_tap = d.n_phys;
+  p.w_rows_per_tap = d.w_mn ? d.w_rows : d.n_phys;
   p.M_rows = d.M_rows;
   p.n_valid = d.n_phys;
   p.map = d.map;

@@ -37,7 +37,9 @@ struct TapGroup {
 
 struct FwdParams {
   CUtensorMap tmA0_hi, tmA0_lo, tmA1_hi, tmA1_lo;  // activation slabs: boxes of 136 + 128 rows x 64 ch
-  CUtensorMap tmW;               // weights: box 128 rows (output channels) x 64 K
+  CUtensorMap tmW;               // weights: box 128 rows (output channels) x 64 K; or, w_mn, 64 K rows x 64 channels
+  int w_mn;                      // 1: weights read MN-major from the FORWARD layout [tap][K rows][channels]
+                                 //    (dgrad reuses the forward weights: no transposed copy)
   int chunks0, chunks1;          // 64-channel K chunks per activation source (source 1 = concat partner)
   int c0_valid, c1_valid;        // physical channels per source (the last chunk issues fewer K=16 steps)
   int kofs1;                     // weight-matrix K offset of source 1
@@ -65,6 +67,7 @@ struct FwdDesc {
   const void* A0; long long rowsA0; int C0, ldA0;
   const void* A1; long long rowsA1; int C1, ldA1;   // optional concat partner
   const void* W; int w_taps, n_phys, k_total;       // bf16 [w_taps][n_phys][k_total]
+  int w_mn, w_rows;                                  // w_mn: W is [w_taps][w_rows = K][n_phys] (forward layout)
   int ntaps; const int* tap_a_off; const int* tap_w;
   int M_rows;
   int BN;                                            // ignored (kept for the bring-up API)

@@ -8,6 +8,7 @@
 // HBM-bound kernels of elementwise.cu.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -69,6 +70,9 @@ struct UNet {
   char* ws = nullptr;
   long long ws_bytes = 0, ws_used = 0;
   bf16* x_in = nullptr;      // [rows0][cin_phys]
+  bf16* shadow = nullptr;    // bf16 copy of the whole flat parameter buffer (written by Adam); the forward
+                             // GEMM operand of every 3x3 conv is a view into it
+  bool dgrad_mn = true;      // dgrad reads the forward weights MN-major (no transposed copies)
   float* dwc = nullptr;      // scratch for collapsed upsample-conv weight gradients
   long long dwc_floats = 0;
   bool training_buffers = false;
@@ -215,12 +219,17 @@ static void layout_workspace(UNet& u, bool dry) {
     }
   }
   long long dwc = 0;
+  u.shadow = bump<bf16>(u, u.n_params, dry);
   for (ConvL& L : u.convs) {
     const long long n = (long long)L.ntap_gemm * L.co_phys * L.k_phys;
     if (L.ksize == 1) continue;  // head runs on CUDA cores from the fp32 master
-    L.wf = bump<bf16>(u, n, dry);
-    L.wd = bump<bf16>(u, n, dry);
-    if (L.ksize == 2 && n > dwc) dwc = n;
+    if (L.ksize == 3) {
+      L.wf = dry ? nullptr : u.shadow + L.w_off;  // same [tap][co][k] indexing as the master
+    } else {
+      L.wf = bump<bf16>(u, n, dry);               // collapsed 9-pair weights of the upsample-conv
+      if (n > dwc) dwc = n;
+    }
+    L.wd = u.dgrad_mn ? nullptr : bump<bf16>(u, n, dry);
   }
   u.dwc_floats = dwc;
   u.dwc = tr ? bump<float>(u, dwc, dry) : nullptr;
@@ -242,10 +251,11 @@ static void taps3x3(int Wp, int* off) {
 // out[rows][n_phys] = act( sum_taps A[m+off] . W[tap]^T + bias ), same-resolution (3x3 or dgrad).
 static int gemm_same(const bf16* A0, int C0, int ldA0, const bf16* A1, int C1, int ldA1, const bf16* W,
                      int ntap, int n_phys, int k_total, Geo g, bf16* out, int ldo, const float* bias,
-                     const bf16* mask, int ldm, int relu, cudaStream_t st, double* stats = nullptr) {
+                     const bf16* mask, int ldm, int relu, cudaStream_t st, double* stats = nullptr,
+                     int w_mn = 0, int w_rows = 0, bool flip = false) {
   int off[kMaxTaps] = {0}, widx[kMaxTaps];
   if (ntap == 9) taps3x3(g.Wp(), off);
-  for (int t = 0; t < ntap; ++t) widx[t] = t;
+  for (int t = 0; t < ntap; ++t) widx[t] = flip ? ntap - 1 - t : t;
   FwdDesc d;
   memset(&d, 0, sizeof(d));
   d.A0 = A0; d.rowsA0 = g.rows(); d.C0 = C0; d.ldA0 = ldA0;
@@ -256,10 +266,16 @@ static int gemm_same(const bf16* A0, int C0, int ldA0, const bf16* A1, int C1, i
   d.map = RowMap{g.Hp(), g.Wp(), g.Hp(), g.Wp(), 1, 0, 0};
   d.out = out; d.ldo = ldo; d.bias = bias; d.mask = mask; d.ldm = ldm; d.relu = relu;
   d.stats = stats;
+  d.w_mn = w_mn; d.w_rows = w_rows;
   FwdParams p;
   MPU_TRY(fwd_setup(p, d));
   return launch_fwd(p, st);
 }
+
+// dX = sum_taps dZ[m - off] . W[tap]  for a 3x3 conv layer L (K = L.co_phys, outputs = L.k_phys channels):
+// either from the forward weights read MN-major with flipped tap index, or from the transposed copy
+static int gemm_dgrad3x3(UNet& u, const bf16* dz, const ConvL& L, Geo g, bf16* out, const bf16* mask, int ldm,
+                         cudaStream_t st);
 
 // nearest-2x upsample + 2x2 SAME conv + bias + ReLU as four phase GEMMs on the low-res grid.
 static int gemm_upconv(const bf16* X, int Cx, Geo glo, const ConvL& L, const float* bias, Geo ghi,
@@ -292,7 +308,7 @@ static int gemm_upconv(const bf16* X, int Cx, Geo glo, const ConvL& L, const flo
 }
 
 // dIn[m_lo] = sum over the 9 (phase, tap) pairs of dZ[phase][m_lo - off] . Wc[pair]  (dZ phase-major)
-static int gemm_upconv_dgrad(const bf16* dzu, const ConvL& L, Geo glo, bf16* out, cudaStream_t st) {
+static int gemm_upconv_dgrad(UNet& u, const bf16* dzu, const ConvL& L, Geo glo, bf16* out, cudaStream_t st) {
   const long long rows_lo = glo.rows();
   int off[kMaxTaps], widx[kMaxTaps];
   for (int i = 0; i < 9; ++i) {
@@ -303,7 +319,12 @@ static int gemm_upconv_dgrad(const bf16* dzu, const ConvL& L, Geo glo, bf16* out
   FwdDesc d;
   memset(&d, 0, sizeof(d));
   d.A0 = dzu; d.rowsA0 = 4 * rows_lo; d.C0 = L.co_phys; d.ldA0 = L.co_phys;
-  d.W = L.wd; d.w_taps = 9; d.n_phys = L.k_phys; d.k_total = L.co_phys;
+  d.w_taps = 9; d.n_phys = L.k_phys; d.k_total = L.co_phys;
+  if (u.dgrad_mn) {
+    d.W = L.wf; d.w_mn = 1; d.w_rows = L.co_phys;
+  } else {
+    d.W = L.wd;
+  }
   d.ntaps = 9; d.tap_a_off = off; d.tap_w = widx;
   d.M_rows = (int)rows_lo;
   d.map = RowMap{glo.Hp(), glo.Wp(), glo.Hp(), glo.Wp(), 1, 0, 0};
@@ -311,6 +332,15 @@ static int gemm_upconv_dgrad(const bf16* dzu, const ConvL& L, Geo glo, bf16* out
   FwdParams p;
   MPU_TRY(fwd_setup(p, d));
   return launch_fwd(p, st);
+}
+
+static int gemm_dgrad3x3(UNet& u, const bf16* dz, const ConvL& L, Geo g, bf16* out, const bf16* mask, int ldm,
+                         cudaStream_t st) {
+  if (u.dgrad_mn)
+    return gemm_same(dz, L.co_phys, L.co_phys, nullptr, 0, 0, L.wf, 9, L.k_phys, L.co_phys, g, out, L.k_phys,
+                     nullptr, mask, ldm, 0, st, nullptr, 1, L.co_phys, true);
+  return gemm_same(dz, L.co_phys, L.co_phys, nullptr, 0, 0, L.wd, 9, L.k_phys, L.co_phys, g, out, L.k_phys,
+                   nullptr, mask, ldm, 0, st);
 }
 
 // dW[tap][co][col0 + ci] += sum_m X[m+off_tap][ci] * dZ[m][co]   (3x3 / 1-tap, same resolution)
@@ -374,14 +404,21 @@ static int bn_forward(UNet& u, BnL& bn, const bf16* y, Geo g, bf16* b, bf16* poo
   return launch_bn_apply(y, bn.scale, bn.shift, b, pooled, g, bn.c_phys, st);
 }
 
-static int sync_weights(UNet& u, cudaStream_t st) {
+// bf16 operand copies that are NOT plain views of the shadow buffer: collapsed upsample-conv weights,
+// and (only without MN-major dgrad) the transposed 3x3 copies
+static int derive_weights(UNet& u, cudaStream_t st) {
   for (ConvL& L : u.convs) {
-    if (L.ksize == 1) continue;
-    if (L.ksize == 3)
-      MPU_TRY(launch_prep_conv(u.params + L.w_off, L.wf, L.wd, 9, L.co_phys, L.k_phys, 1, st));
-    else
+    if (L.ksize == 2)
       MPU_TRY(launch_prep_upconv(u.params + L.w_off, L.wf, L.wd, L.co_phys, L.k_phys, st));
+    else if (L.ksize == 3 && L.wd)
+      MPU_TRY(launch_prep_conv(u.params + L.w_off, nullptr, L.wd, 9, L.co_phys, L.k_phys, 1, st));
   }
+  return MPU_OK;
+}
+
+static int sync_weights(UNet& u, cudaStream_t st) {
+  MPU_TRY(launch_cast_bf16(u.params, u.shadow, u.n_params, st));
+  MPU_TRY(derive_weights(u, st));
   u.weights_synced = true;
   return MPU_OK;
 }
@@ -457,15 +494,12 @@ static int block_tail_backward(UNet& u, ConvL& c1, ConvL& c2, const bf16* xin0, 
                                Geo g, cudaStream_t st) {
   float* G = u.grads;
   MPU_TRY(wgrad_same(a1, C, C, dz2, C, 9, g, G + c2.w_off, c2.k_phys, c2.co_phys, 0, st));
-  MPU_TRY(gemm_same(dz2, C, C, nullptr, 0, 0, c2.wd, 9, c2.k_phys, c2.co_phys, g, dz1, C, nullptr, a1,
-                    C, 0, st));
+  MPU_TRY(gemm_dgrad3x3(u, dz2, c2, g, dz1, a1, C, st));
   MPU_TRY(launch_colsum(dz1, g.rows(), C, C, G + c1.b_off, st));
   MPU_TRY(wgrad_same(xin0, cx0, cx0, dz1, C, 9, g, G + c1.w_off, c1.k_phys, c1.co_phys, 0, st));
   if (xin1)
     MPU_TRY(wgrad_same(xin1, cx1, cx1, dz1, C, 9, g, G + c1.w_off, c1.k_phys, c1.co_phys, cx0, st));
-  if (dxin)
-    MPU_TRY(gemm_same(dz1, C, C, nullptr, 0, 0, c1.wd, 9, c1.k_phys, c1.co_phys, g, dxin, c1.k_phys,
-                      nullptr, nullptr, 0, 0, st));
+  if (dxin) MPU_TRY(gemm_dgrad3x3(u, dz1, c1, g, dxin, nullptr, 0, st));
   return MPU_OK;
 }
 
@@ -493,7 +527,7 @@ static int backward(UNet& u, int B, cudaStream_t st) {
     MPU_CUDA(cudaMemsetAsync(u.dwc, 0, sizeof(float) * 9 * c1.co_phys * c1.k_phys, st));
     MPU_TRY(wgrad_upconv(xin, Lo.C, L.dzu, c1, glo, u.dwc, st));
     MPU_TRY(launch_fold_upconv_grad(u.dwc, G + c1.w_off, c1.co_phys, c1.k_phys, st));
-    MPU_TRY(gemm_upconv_dgrad(L.dzu, c1, glo, Lo.gout, st));
+    MPU_TRY(gemm_upconv_dgrad(u, L.dzu, c1, glo, Lo.gout, st));
   }
   // bottom + encoder
   for (int l = d; l >= 0; --l) {
@@ -540,6 +574,7 @@ int mpu_unet_sizes(const MpuUNetConfig* cfg, long long* n_params, long long* n_b
   MPU_TRY(check_cfg(cfg));
   UNet u;
   u.cfg = *cfg;
+  if (const char* e = getenv("MPU_DGRAD_MN")) u.dgrad_mn = atoi(e) != 0;
   MPU_TRY(build_tables(u));
   layout_workspace(u, true);
   if (n_params) *n_params = u.n_params;
@@ -567,6 +602,7 @@ int mpu_unet_create(const MpuUNetConfig* cfg, float* params, float* grads, float
   }
   UNet* u = new UNet();
   u->cfg = *cfg;
+  if (const char* e = getenv("MPU_DGRAD_MN")) u->dgrad_mn = atoi(e) != 0;
   int rc = build_tables(*u);
   if (rc != MPU_OK) {
     delete u;
@@ -710,8 +746,8 @@ int mpu_unet_adam(void* handle, float lr, float beta1, float beta2, float eps, i
   }
   const double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, step)) / (1.0 - pow((double)beta1, step));
   MPU_TRY(launch_adam(u->params, u->grads, u->adam_m, u->adam_v, u->n_params, (float)lr_t, beta1, beta2,
-                      eps, grad_scale, st));
-  return sync_weights(*u, st);
+                      eps, grad_scale, u->shadow, st));
+  return derive_weights(*u, st);
 }
 
 // debug / test access to internal activations: which = 0:a1 1:a2 2:b 3:pooled 4:u 5:bn1 6:c2 7:c3 8:bn2
