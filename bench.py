@@ -222,15 +222,11 @@ def main():
                                     cen, scl, None, in_ptr, cpad.value, _C.ptr(y_dev), _C.current_stream()),
               "mpu_sample_planes")
 
-    def reduce_and_update():
-        if world > 1:
-            dist.all_reduce(model.grads)  # SUM, like MirroredStrategy's gradient aggregation
-        model.apply_gradients()
-
     def step_value(s):
         sample_into_unet(s)
-        model.forward_backward(None, y_dev, None, input_packed=True, batch=B)
-        reduce_and_update()
+        # SUM all-reduce of the gradients (MirroredStrategy's aggregation) overlapped with backward
+        model.forward_backward_overlapped(None, y_dev, None, input_packed=True, batch=B)
+        model.apply_gradients()
 
     def timed(fn, nwarm, nsteps, first):
         for i in range(nwarm):
@@ -276,8 +272,8 @@ def main():
         xd = x_host.to(dev, non_blocking=True)
         yd = y_host.to(dev, non_blocking=True)
         wd = w_host.to(dev, non_blocking=True)
-        loss = model.forward_backward(xd, yd, wd)
-        reduce_and_update()
+        loss = model.forward_backward_overlapped(xd, yd, wd)
+        model.apply_gradients()
         losses.append(float(loss.item()) / (B * dim * dim))  # D2H read of the step's loss
 
     ms_e2e, _ = timed(step_e2e, 2, K, 0)

@@ -100,7 +100,15 @@ int mpu_unet_forward(void* handle, int B, int bn_training, float* probs_out, voi
  * grad_scale multiplies dlogits (1 = Keras' sum-of-unreduced-losses semantics). */
 int mpu_unet_train_step(void* handle, int B, const unsigned char* labels, const float* sample_w,
                         float grad_scale, double* loss_sum, float* probs_opt, void* stream);
-/* Keras Adam step t (1-based) over the whole parameter buffer, then mpu_unet_sync_weights */
+/* The same step split for data-parallel overlap: forward + loss, then backward stage 0 (up path),
+ * 1 (bottom block), 2 (encoder).  mpu_unet_grad_ranges fills 4 [begin,end) float ranges of `grads`:
+ * [0] complete after stage 0, [1] after stage 1, [2] and [3] after stage 2 - each can be all-reduced
+ * (replacing MirroredStrategy's aggregation, bin/train.py:349) while the next stage runs. */
+int mpu_unet_train_forward(void* handle, int B, const unsigned char* labels, const float* sample_w,
+                           float grad_scale, double* loss_sum, float* probs_opt, void* stream);
+int mpu_unet_backward_stage(void* handle, int B, int stage, void* stream);
+int mpu_unet_grad_ranges(void* handle, long long* h_out8);
+/* Keras Adam step t (1-based) over the whole parameter buffer; refreshes the bf16 GEMM operand copies */
 int mpu_unet_adam(void* handle, float lr, float beta1, float beta2, float eps, int step,
                   float grad_scale, void* stream);
 int mpu_unet_debug_buffer(void* handle, int level, int which, void** ptr, long long* rows, int* C);

@@ -359,6 +359,49 @@ __global__ void bn_bwd_params_kernel(const double* __restrict__ sums, const floa
   dgamma[c] += (float)((double)rstd[c] * (sums[C + c] - (double)mean[c] * sums[c]));
 }
 
+// ---- first conv (CUDA cores) -------------------------------------------------------------------------
+// thread = (pixel, 8-channel output group); the 9 x cin inputs of the pixel sit in registers, weights in
+// shared memory as fp32 [9][cin][co_phys]
+__global__ void conv_first_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
+                                  const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, Geo g,
+                                  int cin, int co_phys) {
+  extern __shared__ float cw[];  // [9][cin][co_phys] + bias[co_phys]
+  for (int i = threadIdx.x; i < 9 * cin * co_phys; i += blockDim.x) {
+    const int co = i % co_phys;
+    const int t2 = i / co_phys;
+    const int ci = t2 % cin, tap = t2 / cin;
+    cw[i] = __bfloat162float(w[((long long)tap * co_phys + co) * 8 + ci]);
+  }
+  float* sb = cw + 9 * cin * co_phys;
+  for (int i = threadIdx.x; i < co_phys; i += blockDim.x) sb[i] = bias[i];
+  __syncthreads();
+  const int CG = co_phys / 8;
+  const int Wp = g.W + 2;
+  const long long total = g.pixels() * CG;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % CG);
+    const long long row = padded_row(g, i / CG);
+    Vec8 acc;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc.v[j] = sb[cg * 8 + j];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const long long r = row + (tap / 3 - 1) * Wp + (tap % 3 - 1);
+      const Vec8 xv = load8(x + r * 8);
+      for (int ci = 0; ci < cin; ++ci) {
+        const float xs = xv.v[ci];
+        const float* wr = cw + (tap * cin + ci) * co_phys + cg * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc.v[j] = fmaf(xs, wr[j], acc.v[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc.v[j] = fmaxf(acc.v[j], 0.f);
+    store8(out + row * co_phys + cg * 8, acc);
+  }
+}
+
 // ---- head ----------------------------------------------------------------------------------------
 constexpr int kMaxCls = 16;
 
@@ -708,6 +751,24 @@ static size_t head_smem(int C, int ncls, bool train) {
   size_t s = sizeof(float) * ((size_t)ncls * C + ((ncls + 3) & ~3));
   if (train) s += (size_t)256 * C * 2 + sizeof(float) * 256 * ncls;
   return s;
+}
+
+int launch_conv_first(const __nv_bfloat16* x, const __nv_bfloat16* w, const float* bias, __nv_bfloat16* out,
+                      Geo g, int cin, int co_phys, cudaStream_t st) {
+  if (cin < 1 || cin > 8 || co_phys % 8) {
+    set_error("conv_first: cin=%d co_phys=%d unsupported", cin, co_phys);
+    return MPU_ERR_ARG;
+  }
+  const size_t smem = sizeof(float) * (9 * cin * co_phys + co_phys);
+  if (smem > 48 * 1024) {
+    set_error("conv_first: weights do not fit in shared memory");
+    return MPU_ERR_ARG;
+  }
+  const long long work = g.pixels() * (co_phys / 8);
+  conv_first_kernel<<<grid_for(work, 256), 256, smem, st>>>(x, w, bias, out, g, cin, co_phys);
+  count_launch();
+  MPU_CUDA(cudaGetLastError());
+  return MPU_OK;
 }
 
 int launch_head_infer(const __nv_bfloat16* x, Geo g, int C, const float* Wh, const float* bh, int ncls,

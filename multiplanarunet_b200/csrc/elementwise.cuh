@@ -51,6 +51,13 @@ int launch_bn_bwd_apply(const BnBwdArgs& a, const double* sums, __nv_bfloat16* d
 // Per-channel column sum of a bf16 matrix, accumulated into fp32 out[C] (bias gradients).
 int launch_colsum(const __nv_bfloat16* x, long long rows, int C, int ld, float* out, cudaStream_t st);
 
+// First conv of the network (tiny K = 9 * n_channels): CUDA-core 3x3 conv + bias + ReLU from the
+// zero-bordered bf16 input [rows][cin_phys] (cin_phys == 8) with the bf16 forward weights
+// [9][co_phys][8]; writes the zero-bordered bf16 output.  The tensor-core path would spend its time on
+// zero-filled TMA tiles here.
+int launch_conv_first(const __nv_bfloat16* x, const __nv_bfloat16* w, const float* bias, __nv_bfloat16* out,
+                      Geo g, int cin, int co_phys, cudaStream_t st);
+
 // 1x1 conv + softmax head.  x = BN2 output of the last up block.
 int launch_head_infer(const __nv_bfloat16* x, Geo g, int C, const float* Wh /*[ncls][C]*/,
                       const float* bh, int ncls, float* probs /*[B,H,W,ncls]*/, cudaStream_t st);

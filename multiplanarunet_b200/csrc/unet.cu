@@ -434,8 +434,13 @@ static int forward(UNet& u, int B, int training, cudaStream_t st) {
     const Geo g = geo_b(u, l, B);
     ConvL& c1 = u.enc_conv(l, 0);
     ConvL& c2 = u.enc_conv(l, 1);
-    MPU_TRY(gemm_same(x, cx, cx, nullptr, 0, 0, c1.wf, 9, c1.co_phys, c1.k_phys, g, L.a1, L.C,
-                      P + c1.b_off, nullptr, 0, 1, st));
+    if (l == 0 && u.cin_phys == 8 && 9 * u.cfg.n_channels * c1.co_phys * 4 + c1.co_phys * 4 <= 48 * 1024) {
+      // K = 9 * n_channels is too thin for the tensor cores: CUDA-core kernel, HBM-write bound
+      MPU_TRY(launch_conv_first(x, c1.wf, P + c1.b_off, L.a1, g, u.cfg.n_channels, c1.co_phys, st));
+    } else {
+      MPU_TRY(gemm_same(x, cx, cx, nullptr, 0, 0, c1.wf, 9, c1.co_phys, c1.k_phys, g, L.a1, L.C,
+                        P + c1.b_off, nullptr, 0, 1, st));
+    }
     double* st2 = training ? u.enc_bn(l).sums : nullptr;
     if (st2) MPU_CUDA(cudaMemsetAsync(st2, 0, sizeof(double) * 2 * L.C, st));
     MPU_TRY(gemm_same(L.a1, L.C, L.C, nullptr, 0, 0, c2.wf, 9, c2.co_phys, c2.k_phys, g, L.a2, L.C,
@@ -503,10 +508,12 @@ static int block_tail_backward(UNet& u, ConvL& c1, ConvL& c2, const bf16* xin0, 
   return MPU_OK;
 }
 
-static int backward(UNet& u, int B, cudaStream_t st) {
+// Backward in three stages so the caller can start the gradient all-reduce of finished parameter ranges
+// while the rest of backward still runs:  0 = up path (+ head, already done by the loss kernel),
+// 1 = bottom block, 2 = encoder levels depth-1 .. 0.
+static int backward_up(UNet& u, int B, cudaStream_t st) {
   const int d = u.depth;
   float* G = u.grads;
-  // up path, from the output resolution down
   for (int l = 0; l < d; ++l) {
     const int i = d - 1 - l;
     Level& L = u.lv[l];
@@ -529,23 +536,41 @@ static int backward(UNet& u, int B, cudaStream_t st) {
     MPU_TRY(launch_fold_upconv_grad(u.dwc, G + c1.w_off, c1.co_phys, c1.k_phys, st));
     MPU_TRY(gemm_upconv_dgrad(u, L.dzu, c1, glo, Lo.gout, st));
   }
-  // bottom + encoder
-  for (int l = d; l >= 0; --l) {
-    Level& L = u.lv[l];
-    const Geo g = geo_b(u, l, B);
-    ConvL& c1 = u.enc_conv(l, 0);
-    ConvL& c2 = u.enc_conv(l, 1);
-    if (l == d) {
-      MPU_TRY(bn_backward(u, u.enc_bn(l), L.a2, L.gout, L.C, nullptr, g, L.s1, 0, G + c2.b_off, st));
-    } else {
-      // skip gradient = first half of dcat_l; pooled gradient = dpool_l (from level l+1's conv1 dgrad)
-      MPU_TRY(bn_backward(u, u.enc_bn(l), L.a2, L.dcat, 2 * L.C, L.dpool, g, L.s1, 0, G + c2.b_off, st));
-    }
-    const bf16* xin = l == 0 ? u.x_in : u.lv[l - 1].pooled;
-    const int cx = l == 0 ? u.cin_phys : u.lv[l - 1].C;
-    bf16* dxin = l == 0 ? nullptr : u.lv[l - 1].dpool;
-    MPU_TRY(block_tail_backward(u, c1, c2, xin, cx, nullptr, 0, L.a1, L.s1, L.s2, dxin, L.C, g, st));
+  return MPU_OK;
+}
+
+static int backward_enc_level(UNet& u, int B, int l, cudaStream_t st) {
+  const int d = u.depth;
+  float* G = u.grads;
+  Level& L = u.lv[l];
+  const Geo g = geo_b(u, l, B);
+  ConvL& c1 = u.enc_conv(l, 0);
+  ConvL& c2 = u.enc_conv(l, 1);
+  if (l == d) {
+    MPU_TRY(bn_backward(u, u.enc_bn(l), L.a2, L.gout, L.C, nullptr, g, L.s1, 0, G + c2.b_off, st));
+  } else {
+    // skip gradient = first half of dcat_l; pooled gradient = dpool_l (from level l+1's conv1 dgrad)
+    MPU_TRY(bn_backward(u, u.enc_bn(l), L.a2, L.dcat, 2 * L.C, L.dpool, g, L.s1, 0, G + c2.b_off, st));
   }
+  const bf16* xin = l == 0 ? u.x_in : u.lv[l - 1].pooled;
+  const int cx = l == 0 ? u.cin_phys : u.lv[l - 1].C;
+  bf16* dxin = l == 0 ? nullptr : u.lv[l - 1].dpool;
+  return block_tail_backward(u, c1, c2, xin, cx, nullptr, 0, L.a1, L.s1, L.s2, dxin, L.C, g, st);
+}
+
+static int backward_stage(UNet& u, int B, int stage, cudaStream_t st) {
+  if (stage == 0) return backward_up(u, B, st);
+  if (stage == 1) return backward_enc_level(u, B, u.depth, st);
+  if (stage == 2) {
+    for (int l = u.depth - 1; l >= 0; --l) MPU_TRY(backward_enc_level(u, B, l, st));
+    return MPU_OK;
+  }
+  set_error("backward_stage: stage %d out of range", stage);
+  return MPU_ERR_ARG;
+}
+
+static int backward(UNet& u, int B, cudaStream_t st) {
+  for (int s = 0; s < 3; ++s) MPU_TRY(backward_stage(u, B, s, st));
   return MPU_OK;
 }
 
@@ -713,10 +738,8 @@ int mpu_unet_forward(void* handle, int B, int bn_training, float* probs_out, voi
                            u->params + H.b_off, u->cfg.n_classes, probs_out, st);
 }
 
-int mpu_unet_train_step(void* handle, int B, const unsigned char* labels, const float* sample_w,
-                        float grad_scale, double* loss_sum, float* probs_opt, void* stream) {
-  UNet* u = reinterpret_cast<UNet*>(handle);
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+static int train_forward(UNet* u, int B, const unsigned char* labels, const float* sample_w,
+                         float grad_scale, double* loss_sum, float* probs_opt, cudaStream_t st) {
   if (!u->cfg.training) {
     set_error("train_step: handle was created with training=0");
     return MPU_ERR_STATE;
@@ -729,11 +752,46 @@ int mpu_unet_train_step(void* handle, int B, const unsigned char* labels, const 
   MPU_CUDA(cudaMemsetAsync(loss_sum, 0, sizeof(double), st));
   MPU_TRY(forward(*u, B, 1, st));
   const ConvL& H = u->head();
-  MPU_TRY(launch_head_train(u->lv[0].bn2, geo_b(*u, 0, B), u->lv[0].C, u->params + H.w_off,
-                            u->params + H.b_off, u->cfg.n_classes, labels, sample_w, grad_scale,
-                            u->lv[0].gout, u->grads + H.w_off, u->grads + H.b_off, loss_sum, probs_opt,
-                            st));
+  return launch_head_train(u->lv[0].bn2, geo_b(*u, 0, B), u->lv[0].C, u->params + H.w_off,
+                           u->params + H.b_off, u->cfg.n_classes, labels, sample_w, grad_scale,
+                           u->lv[0].gout, u->grads + H.w_off, u->grads + H.b_off, loss_sum, probs_opt, st);
+}
+
+int mpu_unet_train_step(void* handle, int B, const unsigned char* labels, const float* sample_w,
+                        float grad_scale, double* loss_sum, float* probs_opt, void* stream) {
+  UNet* u = reinterpret_cast<UNet*>(handle);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  MPU_TRY(train_forward(u, B, labels, sample_w, grad_scale, loss_sum, probs_opt, st));
   return backward(*u, B, st);
+}
+
+int mpu_unet_train_forward(void* handle, int B, const unsigned char* labels, const float* sample_w,
+                           float grad_scale, double* loss_sum, float* probs_opt, void* stream) {
+  return train_forward(reinterpret_cast<UNet*>(handle), B, labels, sample_w, grad_scale, loss_sum, probs_opt,
+                       reinterpret_cast<cudaStream_t>(stream));
+}
+
+int mpu_unet_backward_stage(void* handle, int B, int stage, void* stream) {
+  UNet* u = reinterpret_cast<UNet*>(handle);
+  if (!u->cfg.training || B < 1 || B > u->cfg.max_batch) {
+    set_error("backward_stage: bad handle state or batch");
+    return MPU_ERR_ARG;
+  }
+  return backward_stage(*u, B, stage, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int mpu_unet_grad_ranges(void* handle, long long* out8) {
+  UNet* u = reinterpret_cast<UNet*>(handle);
+  if (!u || !out8) {
+    set_error("grad_ranges: null argument");
+    return MPU_ERR_ARG;
+  }
+  const long long up0 = u->up_conv(0, 0).w_off, bot0 = u->enc_conv(u->depth, 0).w_off, bn0 = u->bns[0].g_off;
+  out8[0] = up0;  out8[1] = u->n_params;  // complete after stage 0 (up path + head)
+  out8[2] = bot0; out8[3] = bn0;          // complete after stage 1 (bottom convs)
+  out8[4] = 0;    out8[5] = bot0;         // complete after stage 2 (encoder convs)
+  out8[6] = bn0;  out8[7] = up0;          // complete after stage 2 (encoder + bottom BatchNorm)
+  return MPU_OK;
 }
 
 int mpu_unet_adam(void* handle, float lr, float beta1, float beta2, float eps, int step,

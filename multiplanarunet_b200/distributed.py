@@ -82,8 +82,8 @@ class DataParallel(object):
         model._sync()
 
     def train_on_batch(self, x, y, sample_weight=None):
-        loss = self.model.forward_backward(x, y, sample_weight)
-        all_reduce_flat(self.model.grads)
+        # gradients are SUM-reduced range by range while backward is still running
+        loss = self.model.forward_backward_overlapped(x, y, sample_weight)
         self.model.apply_gradients()
         H, W, _ = self.model.img_shape
         return float(loss.item()) / (self.model._last_B * H * W)

@@ -342,6 +342,42 @@ class UNet(object):
         self._last_B = B
         return self._loss_dev
 
+    def forward_backward_overlapped(self, x, y, sample_weight=None, input_packed=False, batch=None):
+        """forward_backward with the gradient all-reduce overlapped with backward: parameter ranges whose
+        gradients are final after each backward stage are all-reduced asynchronously (NCCL stream) while
+        the next stage computes.  Falls back to forward_backward when no process group is initialised."""
+        import torch
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return self.forward_backward(x, y, sample_weight, input_packed, batch)
+        B = batch if input_packed else self._pack(x)
+        H, W, _ = self.img_shape
+        yy = y if torch.is_tensor(y) else torch.as_tensor(np.ascontiguousarray(y).reshape(B, H, W).astype(np.uint8))
+        yy = yy.to(self.device, dtype=torch.uint8, non_blocking=True).contiguous()
+        sw = None
+        if sample_weight is not None:
+            sw = sample_weight if torch.is_tensor(sample_weight) else torch.as_tensor(
+                np.asarray(sample_weight, dtype=np.float32))
+            sw = sw.to(self.device, dtype=torch.float32).contiguous()
+        gscale = 1.0 if self.loss_scale_mode == "sum" else 1.0 / (B * H * W)
+        st = _C.current_stream()
+        check(lib.mpu_unet_train_forward(self._h, B, _C.ptr(yy), _C.ptr(sw), ctypes.c_float(gscale),
+                                         _C.ptr(self._loss_dev), _C.ptr(None), st), "mpu_unet_train_forward")
+        if not hasattr(self, "_ranges"):
+            r = (ctypes.c_longlong * 8)()
+            check(lib.mpu_unet_grad_ranges(self._h, r), "mpu_unet_grad_ranges")
+            self._ranges = [(r[2 * i], r[2 * i + 1]) for i in range(4)]
+        works = []
+        for stage in range(3):
+            check(lib.mpu_unet_backward_stage(self._h, B, stage, st), "mpu_unet_backward_stage")
+            for (a, b) in ([self._ranges[stage]] if stage < 2 else self._ranges[2:]):
+                if b > a:
+                    works.append(dist.all_reduce(self.grads[a:b], async_op=True))
+        for w in works:
+            w.wait()
+        self._last_B = B
+        return self._loss_dev
+
     def apply_gradients(self, grad_scale=1.0):
         o = self.optimizer
         o.iterations += 1

@@ -1,8 +1,9 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -x -q -m gpu 2>&1 | tail -8
-echo "##### perf"
-timeout 300 python tests/perf_unet.py 2>&1 | tail -6
-echo "##### perf with MPU_DGRAD_MN=0"
-MPU_DGRAD_MN=0 timeout 300 python tests/perf_unet.py 2>&1 | tail -5
+timeout 600 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1
+echo "pytest rc=$?"
+tail -n 8 gpurun_out/pytest_gpu.log
+timeout 200 python tests/perf_unet.py > gpurun_out/perf.log 2>&1
+echo "perf rc=$?"
+tail -n 12 gpurun_out/perf.log

@@ -123,3 +123,36 @@ def test_training_reduces_loss():
     y = (x[..., 0] > 0).astype(np.uint8) + (x[..., 1] > 1).astype(np.uint8)
     losses = [m.train_on_batch(x, y) for _ in range(30)]
     assert losses[-1] < 0.6 * losses[0], losses[::5]
+
+
+def test_staged_backward_equals_single_call(setup):
+    """mpu_unet_train_forward + mpu_unet_backward_stage(0..2) (the data-parallel overlap entry points)
+    produce the gradients of mpu_unet_train_step; the four all-reduce ranges tile the gradient buffer."""
+    import ctypes
+    import torch
+    from multiplanarunet_b200 import _C
+    m = setup["model"]
+    m.forward_backward(setup["x"], setup["y"], setup["sw"])
+    g_ref = m.grads.clone()
+    loss_ref = float(m._loss_dev.item())
+    B = m._pack(setup["x"])
+    y = torch.as_tensor(setup["y"]).cuda()
+    sw = torch.as_tensor(setup["sw"]).cuda()
+    st = _C.current_stream()
+    H, W, _ = m.img_shape
+    gscale = 1.0 if m.loss_scale_mode == "sum" else 1.0 / (B * H * W)
+    _C.check(_C.lib.mpu_unet_train_forward(m._h, B, _C.ptr(y), _C.ptr(sw), ctypes.c_float(gscale),
+                                           _C.ptr(m._loss_dev), _C.ptr(None), st), "train_forward")
+    for stage in range(3):
+        _C.check(_C.lib.mpu_unet_backward_stage(m._h, B, stage, st), "backward_stage")
+    torch.cuda.synchronize()
+    assert abs(float(m._loss_dev.item()) - loss_ref) <= 1e-6 * abs(loss_ref)
+    # fp32 atomics in the weight-gradient kernels reorder sums between runs
+    err = (m.grads - g_ref).abs().max().item()
+    assert err <= 1e-4 * g_ref.abs().max().item(), err
+    r = (ctypes.c_longlong * 8)()
+    _C.check(_C.lib.mpu_unet_grad_ranges(m._h, r), "grad_ranges")
+    spans = sorted((r[2 * i], r[2 * i + 1]) for i in range(4))
+    assert spans[0][0] == 0 and spans[-1][1] == m.grads.numel()
+    assert all(spans[i][1] == spans[i + 1][0] for i in range(3))
+    assert _C.lib.mpu_unet_backward_stage(m._h, B, 3, st) != 0
