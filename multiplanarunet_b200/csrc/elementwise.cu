@@ -69,6 +69,8 @@ __device__ __forceinline__ void block_reduce_store(float (&acc)[NV][8], int CG, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Row loops of the pure reductions keep 4 independent 16-byte loads in flight per thread (these kernels
+// are latency-bound HBM streams: bytes in flight per SM, not instruction count, sets their speed).
 __global__ void channel_stats_kernel(const __nv_bfloat16* __restrict__ y, long long rows, int C, int ld,
                                      int CG, int RL, double* __restrict__ sums) {
   const int tid = threadIdx.x;
@@ -76,13 +78,26 @@ __global__ void channel_stats_kernel(const __nv_bfloat16* __restrict__ y, long l
   float acc[2][8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
-  for (long long r = (long long)blockIdx.x * RL + rl; r < rows; r += (long long)gridDim.x * RL) {
-    const Vec8 x = load8(y + r * ld + cg * 8);
+  const long long stride = (long long)gridDim.x * RL;
+  for (long long r = (long long)blockIdx.x * RL + rl; r < rows; r += 4 * stride) {
+    Vec8 x[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      acc[0][j] += x.v[j];
-      acc[1][j] += x.v[j] * x.v[j];
+    for (int u = 0; u < 4; ++u) {
+      const long long rr = r + u * stride;
+      if (rr < rows) {
+        x[u] = load8(y + rr * ld + cg * 8);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[u].v[j] = 0.f;
+      }
     }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[0][j] += x[u].v[j];
+        acc[1][j] = fmaf(x[u].v[j], x[u].v[j], acc[1][j]);
+      }
   }
   block_reduce_store<2, double>(acc, CG, RL, C, sums);
 }
@@ -94,10 +109,23 @@ __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ x, long long row
   float acc[1][8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[0][j] = 0.f;
-  for (long long r = (long long)blockIdx.x * RL + rl; r < rows; r += (long long)gridDim.x * RL) {
-    const Vec8 v = load8(x + r * ld + cg * 8);
+  const long long stride = (long long)gridDim.x * RL;
+  for (long long r = (long long)blockIdx.x * RL + rl; r < rows; r += 4 * stride) {
+    Vec8 v[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[0][j] += v.v[j];
+    for (int u = 0; u < 4; ++u) {
+      const long long rr = r + u * stride;
+      if (rr < rows) {
+        v[u] = load8(x + rr * ld + cg * 8);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[u].v[j] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[0][j] += v[u].v[j];
   }
   block_reduce_store<1, float>(acc, CG, RL, C, out);
 }
@@ -141,19 +169,70 @@ __device__ __forceinline__ long long padded_row(const Geo& g, long long pix) {
   return n * (long long)(g.H + 2) * (g.W + 2) + (long long)(yy + 1) * (g.W + 2) + (x + 1);
 }
 
+// Work distribution of the per-pixel kernels: a work item is a segment of one image line - U*RL consecutive
+// pixels (or 2x2 windows) handled by the RL row lanes of a block, every thread keeping its channel group.
+// Items are walked with a mixed-radix counter (image, line, segment), so the hot loops contain no integer
+// division (the padded-row arithmetic used to cost more instructions than the BN math itself).
+struct SegIter {
+  int n, yy, seg;
+  int dn, dy, ds;
+  int H, nseg;
+  __device__ __forceinline__ void init(int start, int stride, int H_, int nseg_) {
+    H = H_;
+    nseg = nseg_;
+    seg = start % nseg;
+    int t = start / nseg;
+    yy = t % H;
+    n = t / H;
+    ds = stride % nseg;
+    t = stride / nseg;
+    dy = t % H;
+    dn = t / H;
+  }
+  __device__ __forceinline__ void next() {
+    seg += ds;
+    yy += dy;
+    n += dn;
+    if (seg >= nseg) {
+      seg -= nseg;
+      ++yy;
+    }
+    if (yy >= H) {
+      yy -= H;
+      ++n;
+    }
+  }
+};
+
 __global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
                                 const float* __restrict__ shift, __nv_bfloat16* __restrict__ b, Geo g,
-                                int C) {
-  const int CG = C / 8;
-  const long long total = g.pixels() * CG;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % CG);
-    const long long row = padded_row(g, i / CG);
-    Vec8 v = load8(y + row * C + cg * 8);
+                                int C, int CG, int RL) {
+  constexpr int U = 4;  // independent 16-byte loads in flight per thread
+  const int tid = threadIdx.x;
+  const int cg = tid % CG, rl = tid / CG;
+  float sc[8], sh[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v.v[j] = fmaf(v.v[j], scale[cg * 8 + j], shift[cg * 8 + j]);
-    store8(b + row * C + cg * 8, v);
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = scale[cg * 8 + j];
+    sh[j] = shift[cg * 8 + j];
+  }
+  const int Wp = g.W + 2;
+  SegIter it;
+  it.init(blockIdx.x, gridDim.x, g.H, (g.W + U * RL - 1) / (U * RL));
+  for (; it.n < g.B; it.next()) {
+    const long long base = ((long long)it.n * (g.H + 2) + it.yy + 1) * Wp + 1;
+    const int x0 = it.seg * (U * RL) + rl;
+    Vec8 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (x0 + u * RL < g.W) v[u] = load8(y + (base + x0 + u * RL) * C + cg * 8);
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (x0 + u * RL < g.W) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[u].v[j] = fmaf(v[u].v[j], sc[j], sh[j]);
+        store8(b + (base + x0 + u * RL) * C + cg * 8, v[u]);
+      }
   }
 }
 
@@ -161,65 +240,63 @@ __global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float
 __global__ void bn_apply_pool_kernel(const __nv_bfloat16* __restrict__ y,
                                      const float* __restrict__ scale, const float* __restrict__ shift,
                                      __nv_bfloat16* __restrict__ b, __nv_bfloat16* __restrict__ pooled,
-                                     Geo g, int C) {
-  const int CG = C / 8;
+                                     Geo g, int C, int CG, int RL) {
+  const int tid = threadIdx.x;
+  const int cg = tid % CG, rl = tid / CG;
   const int h = g.H / 2, w = g.W / 2;
-  const long long total = (long long)g.B * h * w * CG;
   const int Wp = g.W + 2;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % CG);
-    long long t = i / CG;
-    const int jx = (int)(t % w);
-    t /= w;
-    const int iy = (int)(t % h);
-    const long long n = t / h;
-    const long long base = n * (long long)(g.H + 2) * Wp + (long long)(2 * iy + 1) * Wp + (2 * jx + 1);
-    float sc[8], sh[8];
+  float sc[8], sh[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      sc[j] = scale[cg * 8 + j];
-      sh[j] = shift[cg * 8 + j];
-    }
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = scale[cg * 8 + j];
+    sh[j] = shift[cg * 8 + j];
+  }
+  SegIter it;
+  it.init(blockIdx.x, gridDim.x, h, (w + RL - 1) / RL);
+  for (; it.n < g.B; it.next()) {
+    const int jx = it.seg * RL + rl, iy = it.yy;
+    if (jx >= w) continue;
+    const long long base = ((long long)it.n * (g.H + 2) + 2 * iy + 1) * Wp + (2 * jx + 1);
+    Vec8 v[4];
+#pragma unroll
+    for (int d = 0; d < 4; ++d) v[d] = load8(y + (base + (d >> 1) * Wp + (d & 1)) * C + cg * 8);
     Vec8 mx;
 #pragma unroll
     for (int j = 0; j < 8; ++j) mx.v[j] = -INFINITY;
 #pragma unroll
     for (int d = 0; d < 4; ++d) {
-      const long long row = base + (d >> 1) * Wp + (d & 1);
-      Vec8 v = load8(y + row * C + cg * 8);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        v.v[j] = bf16_round(fmaf(v.v[j], sc[j], sh[j]));
-        mx.v[j] = fmaxf(mx.v[j], v.v[j]);
+        v[d].v[j] = bf16_round(fmaf(v[d].v[j], sc[j], sh[j]));
+        mx.v[j] = fmaxf(mx.v[j], v[d].v[j]);
       }
-      store8(b + row * C + cg * 8, v);
+      store8(b + (base + (d >> 1) * Wp + (d & 1)) * C + cg * 8, v[d]);
     }
-    const long long prow = n * (long long)(h + 2) * (w + 2) + (long long)(iy + 1) * (w + 2) + (jx + 1);
+    const long long prow = ((long long)it.n * (h + 2) + iy + 1) * (w + 2) + (jx + 1);
     store8(pooled + prow * C + cg * 8, mx);
   }
 }
 
 // ---- BN backward ---------------------------------------------------------------------------------
-// Work item = (pixel or 2x2 window, channel group).  g(p,c) = gA[p] + (p is the first arg-max of its
-// window ? gP[window] : 0).  Window arg-max is recomputed from the bf16-rounded BN outputs, scanning
+// Work item = segment of pixels (or 2x2 windows) x channel group.  g(p,c) = gA[p] + (p is the first arg-max
+// of its window ? gP[window] : 0).  Window arg-max is recomputed from the bf16-rounded BN outputs, scanning
 // row-major so the first maximum wins (the forward max-pool kept no index).
 // Pass 1 accumulates sum(g) and sum(g*y); with xhat = (y-mu)*rstd the BN backward is then the per-channel
 // affine map dz = relu'(y) * (a*g + b*y + c):  a = gamma*rstd, b = -a*rstd*mgx, c = -a*mg - b*mu  where
 // mg = mean(g), mgx = mean(g*xhat) = rstd*(mean(g*y) - mu*mg).  Few per-thread coefficients keep the
-// register count low enough for 4+ resident blocks per SM (these kernels are pure HBM streams).
+// register count low enough for 3 resident blocks per SM (these kernels are pure HBM streams).
 template <bool POOL, bool APPLY>
 __global__ void __launch_bounds__(256, POOL ? 2 : 3)
     bn_bwd_kernel(BnBwdArgs a, int CG, int RL, const double* __restrict__ sums_in,
                   double* __restrict__ sums_out, __nv_bfloat16* __restrict__ dz, int phase_major,
                   float* __restrict__ dbias) {
+  constexpr int U = POOL ? 1 : 2;
   const int tid = threadIdx.x;
   const int cg = tid % CG, rl = tid / CG;
   const int C = a.C;
   const Geo g = a.g;
   const int Wp = g.W + 2;
   const int hh = g.H / 2, wh = g.W / 2;
-  const long long items = POOL ? (long long)g.B * hh * wh : g.pixels();
   float sc[POOL ? 8 : 1], sh[POOL ? 8 : 1];
   float ca[APPLY ? 8 : 1], cb[APPLY ? 8 : 1], cc[APPLY ? 8 : 1];
 #pragma unroll
@@ -244,100 +321,96 @@ __global__ void __launch_bounds__(256, POOL ? 2 : 3)
   float acc[2][8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
+  const long long rows_lo = (long long)g.B * (hh + 2) * (wh + 2);
 
-  for (long long it = (long long)blockIdx.x * RL + rl; it < items; it += (long long)gridDim.x * RL) {
-    long long rows4[4];
-    int nsub;
-    long long prow = 0;
-    if (POOL) {
-      long long t = it;
-      const int jx = (int)(t % wh);
-      t /= wh;
-      const int iy = (int)(t % hh);
-      const long long n = t / hh;
-      const long long base = n * (long long)(g.H + 2) * Wp + (long long)(2 * iy + 1) * Wp + (2 * jx + 1);
-      rows4[0] = base;
-      rows4[1] = base + 1;
-      rows4[2] = base + Wp;
-      rows4[3] = base + Wp + 1;
-      nsub = 4;
-      prow = n * (long long)(hh + 2) * (wh + 2) + (long long)(iy + 1) * (wh + 2) + (jx + 1);
-    } else {
-      rows4[0] = padded_row(g, it);
-      nsub = 1;
-    }
-    Vec8 yv[POOL ? 4 : 1];
-    int amax[8];
-    if (POOL) {
-      float best[8];
+  // one pixel: accumulate the reduction terms (pass 1) or write dz (pass 2)
+  auto emit = [&](const Vec8& gv, const Vec8& yv, int n, int yy, int xx, long long row) {
+    if (!APPLY) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        best[j] = -INFINITY;
-        amax[j] = 0;
-      }
-#pragma unroll
-      for (int d = 0; d < 4; ++d) {
-        yv[d] = load8(a.y + rows4[d] * C + cg * 8);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float bv = bf16_round(fmaf(yv[d].v[j], sc[j], sh[j]));
-          if (bv > best[j]) {
-            best[j] = bv;
-            amax[j] = d;
-          }
-        }
+        acc[0][j] += gv.v[j];
+        acc[1][j] = fmaf(gv.v[j], yv.v[j], acc[1][j]);
       }
     } else {
-      yv[0] = load8(a.y + rows4[0] * C + cg * 8);
+      Vec8 o;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float v = fmaf(ca[j], gv.v[j], fmaf(cb[j], yv.v[j], cc[j]));
+        if (!(yv.v[j] > 0.f)) v = 0.f;
+        v = bf16_round(v);
+        o.v[j] = v;
+        acc[0][j] += v;
+      }
+      long long orow = row;
+      if (phase_major)  // pixel (n, yy, xx) of this level -> [phase][rows of the half-resolution level]
+        orow = ((yy & 1) * 2 + (xx & 1)) * rows_lo + ((long long)n * (hh + 2) + (yy >> 1) + 1) * (wh + 2) +
+               ((xx >> 1) + 1);
+      store8(dz + orow * C + cg * 8, o);
     }
-    Vec8 gp;
-    if (POOL && a.gP) gp = load8(a.gP + prow * C + cg * 8);
+  };
+
+  SegIter it;
+  it.init(blockIdx.x, gridDim.x, POOL ? hh : g.H, ((POOL ? wh : g.W) + U * RL - 1) / (U * RL));
+  for (; it.n < g.B; it.next()) {
+    if (POOL) {
+      const int jx = it.seg * RL + rl, iy = it.yy;
+      if (jx >= wh) continue;
+      const long long base = ((long long)it.n * (g.H + 2) + 2 * iy + 1) * Wp + (2 * jx + 1);
+      Vec8 yv[4], gv[4];
 #pragma unroll
-    for (int d = 0; d < (POOL ? 4 : 1); ++d) {
-      if (d < nsub) {
-        Vec8 gv;
+      for (int d = 0; d < 4; ++d) {
+        const long long row = base + (d >> 1) * Wp + (d & 1);
+        yv[d] = load8(a.y + row * C + cg * 8);
         if (a.gA) {
-          gv = load8(a.gA + rows4[d] * (long long)a.ldA + cg * 8);
+          gv[d] = load8(a.gA + row * (long long)a.ldA + cg * 8);
         } else {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) gv.v[j] = 0.f;
-        }
-        if (POOL && a.gP) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (amax[j] == d) gv.v[j] += gp.v[j];
-        }
-        if (!APPLY) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            acc[0][j] += gv.v[j];
-            acc[1][j] = fmaf(gv.v[j], yv[d].v[j], acc[1][j]);
-          }
-        } else {
-          Vec8 o;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float v = fmaf(ca[j], gv.v[j], fmaf(cb[j], yv[d].v[j], cc[j]));
-            if (!(yv[d].v[j] > 0.f)) v = 0.f;
-            v = bf16_round(v);
-            o.v[j] = v;
-            acc[0][j] += v;
-          }
-          long long orow = rows4[d];
-          if (phase_major) {
-            // pixel (n, y, x) of this level -> [phase][rows of the half-resolution level]
-            const long long plane = (long long)(g.H + 2) * Wp;
-            const long long n = orow / plane;
-            const long long rem = orow - n * plane;
-            const int yy = (int)(rem / Wp) - 1, xx = (int)(rem % Wp) - 1;
-            const int ph = (yy & 1) * 2 + (xx & 1);
-            const long long rows_lo = (long long)g.B * (hh + 2) * (wh + 2);
-            orow = ph * rows_lo + n * (long long)(hh + 2) * (wh + 2) +
-                   (long long)((yy >> 1) + 1) * (wh + 2) + ((xx >> 1) + 1);
-          }
-          store8(dz + orow * C + cg * 8, o);
+          for (int j = 0; j < 8; ++j) gv[d].v[j] = 0.f;
         }
       }
+      if (a.gP) {
+        const long long prow = ((long long)it.n * (hh + 2) + iy + 1) * (wh + 2) + (jx + 1);
+        const Vec8 gp = load8(a.gP + prow * C + cg * 8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float best = -INFINITY;
+          int am = 0;
+#pragma unroll
+          for (int d = 0; d < 4; ++d) {
+            const float bv = bf16_round(fmaf(yv[d].v[j], sc[j], sh[j]));
+            if (bv > best) {
+              best = bv;
+              am = d;
+            }
+          }
+#pragma unroll
+          for (int d = 0; d < 4; ++d)
+            if (am == d) gv[d].v[j] += gp.v[j];
+        }
+      }
+#pragma unroll
+      for (int d = 0; d < 4; ++d)
+        emit(gv[d], yv[d], it.n, 2 * iy + (d >> 1), 2 * jx + (d & 1), base + (d >> 1) * Wp + (d & 1));
+    } else {
+      const long long base = ((long long)it.n * (g.H + 2) + it.yy + 1) * Wp + 1;
+      const int x0 = it.seg * (U * RL) + rl;
+      Vec8 yv[U], gv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (x0 + u * RL < g.W) {
+          const long long row = base + x0 + u * RL;
+          yv[u] = load8(a.y + row * C + cg * 8);
+          if (a.gA) {
+            gv[u] = load8(a.gA + row * (long long)a.ldA + cg * 8);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) gv[u].v[j] = 0.f;
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (x0 + u * RL < g.W) emit(gv[u], yv[u], it.n, it.yy, x0 + u * RL, base + x0 + u * RL);
     }
   }
   if (!APPLY) {
@@ -360,89 +433,128 @@ __global__ void bn_bwd_params_kernel(const double* __restrict__ sums, const floa
 }
 
 // ---- first conv (CUDA cores) -------------------------------------------------------------------------
-// thread = (pixel, 8-channel output group); the 9 x cin inputs of the pixel sit in registers, weights in
-// shared memory as fp32 [9][cin][co_phys]
+// thread = pixel: the 9 x CIN inputs sit in registers, the weights in shared memory as fp32
+// [9*CIN][co_phys] and are read as warp-wide broadcasts; all output channels of the pixel are produced
+// 8 at a time (one 16-byte store each).
+template <int CIN>
 __global__ void conv_first_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
                                   const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, Geo g,
-                                  int cin, int co_phys) {
-  extern __shared__ float cw[];  // [9][cin][co_phys] + bias[co_phys]
-  for (int i = threadIdx.x; i < 9 * cin * co_phys; i += blockDim.x) {
+                                  int co_phys) {
+  extern __shared__ float4 cw4[];  // [9*CIN][co_phys] + bias[co_phys]
+  float* cw = reinterpret_cast<float*>(cw4);
+  for (int i = threadIdx.x; i < 9 * CIN * co_phys; i += blockDim.x) {
     const int co = i % co_phys;
     const int t2 = i / co_phys;
-    const int ci = t2 % cin, tap = t2 / cin;
+    const int ci = t2 % CIN, tap = t2 / CIN;
     cw[i] = __bfloat162float(w[((long long)tap * co_phys + co) * 8 + ci]);
   }
-  float* sb = cw + 9 * cin * co_phys;
+  float* sb = cw + 9 * CIN * co_phys;
   for (int i = threadIdx.x; i < co_phys; i += blockDim.x) sb[i] = bias[i];
   __syncthreads();
   const int CG = co_phys / 8;
   const int Wp = g.W + 2;
-  const long long total = g.pixels() * CG;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % CG);
-    const long long row = padded_row(g, i / CG);
-    Vec8 acc;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc.v[j] = sb[cg * 8 + j];
+  SegIter it;
+  it.init(blockIdx.x, gridDim.x, g.H, (g.W + blockDim.x - 1) / blockDim.x);
+  for (; it.n < g.B; it.next()) {
+    const int xx = it.seg * blockDim.x + threadIdx.x;
+    if (xx >= g.W) continue;
+    const long long row = ((long long)it.n * (g.H + 2) + it.yy + 1) * Wp + xx + 1;
+    float xs[9 * CIN];
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) {
       const long long r = row + (tap / 3 - 1) * Wp + (tap % 3 - 1);
-      const Vec8 xv = load8(x + r * 8);
-      for (int ci = 0; ci < cin; ++ci) {
-        const float xs = xv.v[ci];
-        const float* wr = cw + (tap * cin + ci) * co_phys + cg * 8;
+      if (CIN == 1) {
+        xs[tap] = __bfloat162float(x[r * 8]);
+      } else {
+        const Vec8 xv = load8(x + r * 8);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc.v[j] = fmaf(xs, wr[j], acc.v[j]);
+        for (int ci = 0; ci < CIN; ++ci) xs[tap * CIN + ci] = xv.v[ci];
       }
     }
+    for (int cg = 0; cg < CG; ++cg) {
+      Vec8 acc;
+      {
+        const float4 b0 = *reinterpret_cast<const float4*>(sb + cg * 8);
+        const float4 b1 = *reinterpret_cast<const float4*>(sb + cg * 8 + 4);
+        acc.v[0] = b0.x; acc.v[1] = b0.y; acc.v[2] = b0.z; acc.v[3] = b0.w;
+        acc.v[4] = b1.x; acc.v[5] = b1.y; acc.v[6] = b1.z; acc.v[7] = b1.w;
+      }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc.v[j] = fmaxf(acc.v[j], 0.f);
-    store8(out + row * co_phys + cg * 8, acc);
+      for (int k = 0; k < 9 * CIN; ++k) {
+        const float4 w0 = *reinterpret_cast<const float4*>(cw + k * co_phys + cg * 8);
+        const float4 w1 = *reinterpret_cast<const float4*>(cw + k * co_phys + cg * 8 + 4);
+        acc.v[0] = fmaf(xs[k], w0.x, acc.v[0]);
+        acc.v[1] = fmaf(xs[k], w0.y, acc.v[1]);
+        acc.v[2] = fmaf(xs[k], w0.z, acc.v[2]);
+        acc.v[3] = fmaf(xs[k], w0.w, acc.v[3]);
+        acc.v[4] = fmaf(xs[k], w1.x, acc.v[4]);
+        acc.v[5] = fmaf(xs[k], w1.y, acc.v[5]);
+        acc.v[6] = fmaf(xs[k], w1.z, acc.v[6]);
+        acc.v[7] = fmaf(xs[k], w1.w, acc.v[7]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc.v[j] = fmaxf(acc.v[j], 0.f);
+      store8(out + row * co_phys + cg * 8, acc);
+    }
   }
 }
 
 // ---- head ----------------------------------------------------------------------------------------
 constexpr int kMaxCls = 16;
+constexpr int kHeadTile = 256;  // pixels per block iteration (= blockDim)
 
-template <bool TRAIN>
-__global__ void head_kernel(const __nv_bfloat16* __restrict__ x, Geo g, int C,
-                            const float* __restrict__ Wh, const float* __restrict__ bh, int ncls,
-                            const uint8_t* __restrict__ labels, const float* __restrict__ sample_w,
-                            float grad_scale, __nv_bfloat16* __restrict__ dx, float* __restrict__ dWh,
-                            float* __restrict__ dbh, double* __restrict__ loss_sum,
-                            float* __restrict__ probs) {
-  extern __shared__ unsigned char hsm[];
-  // smem: Wh [ncls][C] f32 | bh [ncls] | (TRAIN) xs [256][C] bf16 | dl [256][ncls] f32
-  float* sW = reinterpret_cast<float*>(hsm);
-  float* sB = sW + ncls * C;
-  __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(sB + ((ncls + 3) & ~3));
-  float* dl = reinterpret_cast<float*>(xs + (TRAIN ? 256 * C : 0));
+// NC > 0: number of classes known at compile time (class loops fully unrolled, no predication);
+// NC == 0: generic path for up to kMaxCls classes.
+// TRAIN: phase A, thread = pixel: logits, softmax, loss, dlogits, dx; phase B, thread = (channel pair,
+// pixel segment): dWh[c][ci] += sum_p dlogit[p][c] * x[p][ci] from the tile's x (bf16, shared memory).
+template <bool TRAIN, int NC>
+__global__ void __launch_bounds__(kHeadTile)
+    head_kernel(const __nv_bfloat16* __restrict__ x, Geo g, int C, const float* __restrict__ Wh,
+                const float* __restrict__ bh, int ncls_rt, const uint8_t* __restrict__ labels,
+                const float* __restrict__ sample_w, float grad_scale, __nv_bfloat16* __restrict__ dx,
+                float* __restrict__ dWh, float* __restrict__ dbh, double* __restrict__ loss_sum,
+                float* __restrict__ probs) {
+  constexpr int MC = NC > 0 ? NC : kMaxCls;  // unrolled class loop bound
+  constexpr int DLS = (MC + 3) & ~3;         // dlogit row stride (float4 reads)
+  const int ncls = NC > 0 ? NC : ncls_rt;
+  extern __shared__ float4 hsm4[];
+  // smem: Wh [ncls][C] f32 | bh [DLS] | (TRAIN) dl [256][DLS] f32 | xs [256][C+8] bf16
+  float* sW = reinterpret_cast<float*>(hsm4);
+  float* sB = sW + ((ncls * C + 3) & ~3);
+  float* dl = sB + DLS;
+  const int XS = C + 8;  // row stride of the x tile: +16 B keeps the 16-byte row writes off the same banks
+  __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(dl + (TRAIN ? kHeadTile * DLS : 0));
   for (int i = threadIdx.x; i < ncls * C; i += blockDim.x) sW[i] = Wh[i];
-  for (int i = threadIdx.x; i < ncls; i += blockDim.x) sB[i] = bh[i];
+  for (int i = threadIdx.x; i < DLS; i += blockDim.x) sB[i] = i < ncls ? bh[i] : 0.f;
   __syncthreads();
 
   const long long npix = g.pixels();
-  const int nseg = max(1, 256 / C);                  // pixel segments for the weight-gradient pass
-  const int rows_per_seg = (256 + nseg - 1) / nseg;
-  float wacc[kMaxCls];
+  const int Wp = g.W + 2;
+  const int C2 = C / 2;                          // channel pairs
+  const int nseg = max(1, kHeadTile / C2);       // pixel segments of the weight-gradient pass
+  const int rows_per_seg = (kHeadTile + nseg - 1) / nseg;
+  float wacc[2][MC];
+  float bsum[MC];
 #pragma unroll
-  for (int c = 0; c < kMaxCls; ++c) wacc[c] = 0.f;
-  float bacc = 0.f;
+  for (int c = 0; c < MC; ++c) wacc[0][c] = wacc[1][c] = bsum[c] = 0.f;
   double lacc = 0.0;
+  const int hw = g.H * g.W;
 
-  for (long long p0 = (long long)blockIdx.x * 256; p0 < npix; p0 += (long long)gridDim.x * 256) {
+  for (long long p0 = (long long)blockIdx.x * kHeadTile; p0 < npix; p0 += (long long)gridDim.x * kHeadTile) {
     const long long pix = p0 + threadIdx.x;
     const bool valid = pix < npix;
-    float z[kMaxCls];
-    long long row = 0;
     if (valid) {
-      row = padded_row(g, pix);
+      // one division chain per tile and thread (tiles are 256x fewer than pixels)
+      const int n = (int)(pix / hw);
+      const int rem = (int)(pix - (long long)n * hw);
+      const int yy = rem / g.W, xx = rem - yy * g.W;
+      const long long row = ((long long)n * (g.H + 2) + yy + 1) * Wp + xx + 1;
+      float z[MC];
 #pragma unroll
-      for (int c = 0; c < kMaxCls; ++c) z[c] = c < ncls ? sB[c] : 0.f;
+      for (int c = 0; c < MC; ++c) z[c] = sB[c];
       for (int k8 = 0; k8 < C; k8 += 8) {
         const uint4 u = *reinterpret_cast<const uint4*>(x + row * C + k8);
-        if (TRAIN) *reinterpret_cast<uint4*>(xs + threadIdx.x * C + k8) = u;
+        if (TRAIN) *reinterpret_cast<uint4*>(xs + threadIdx.x * XS + k8) = u;
         const __nv_bfloat162* hv = reinterpret_cast<const __nv_bfloat162*>(&u);
         float xv[8];
 #pragma unroll
@@ -452,100 +564,134 @@ __global__ void head_kernel(const __nv_bfloat16* __restrict__ x, Geo g, int C,
           xv[2 * j + 1] = f.y;
         }
 #pragma unroll
-        for (int c = 0; c < kMaxCls; ++c) {
-          if (c < ncls) {
+        for (int c = 0; c < MC; ++c) {
+          if (NC > 0 || c < ncls) {
+            const float4 w0 = *reinterpret_cast<const float4*>(sW + c * C + k8);
+            const float4 w1 = *reinterpret_cast<const float4*>(sW + c * C + k8 + 4);
             float s = z[c];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) s = fmaf(xv[j], sW[c * C + k8 + j], s);
+            s = fmaf(xv[0], w0.x, s);
+            s = fmaf(xv[1], w0.y, s);
+            s = fmaf(xv[2], w0.z, s);
+            s = fmaf(xv[3], w0.w, s);
+            s = fmaf(xv[4], w1.x, s);
+            s = fmaf(xv[5], w1.y, s);
+            s = fmaf(xv[6], w1.z, s);
+            s = fmaf(xv[7], w1.w, s);
             z[c] = s;
           }
         }
       }
       float mx = z[0];
 #pragma unroll
-      for (int c = 1; c < kMaxCls; ++c)
-        if (c < ncls) mx = fmaxf(mx, z[c]);
-      float e[kMaxCls];
+      for (int c = 1; c < MC; ++c)
+        if (NC > 0 || c < ncls) mx = fmaxf(mx, z[c]);
+      float e[MC];
       float se = 0.f;
 #pragma unroll
-      for (int c = 0; c < kMaxCls; ++c) {
-        e[c] = c < ncls ? expf(z[c] - mx) : 0.f;
+      for (int c = 0; c < MC; ++c) {
+        e[c] = (NC > 0 || c < ncls) ? expf(z[c] - mx) : 0.f;
         se += e[c];
       }
       const float inv = 1.f / se;
       if (probs) {
 #pragma unroll
-        for (int c = 0; c < kMaxCls; ++c)
-          if (c < ncls) probs[pix * ncls + c] = e[c] * inv;
+        for (int c = 0; c < MC; ++c)
+          if (NC > 0 || c < ncls) probs[pix * ncls + c] = e[c] * inv;
       }
       if (TRAIN) {
         const int lab = labels[pix];
-        const int n = (int)(pix / ((long long)g.H * g.W));
         const float w = sample_w ? sample_w[n] : 1.f;
         float zy = 0.f;
 #pragma unroll
-        for (int c = 0; c < kMaxCls; ++c)
+        for (int c = 0; c < MC; ++c)
           if (c == lab) zy = z[c];
         lacc += (double)((logf(se) + mx - zy) * w);
+        float d[MC];
 #pragma unroll
-        for (int c = 0; c < kMaxCls; ++c)
-          if (c < ncls) dl[threadIdx.x * ncls + c] = (e[c] * inv - (c == lab ? 1.f : 0.f)) * w * grad_scale;
+        for (int c = 0; c < MC; ++c) {
+          d[c] = (NC > 0 || c < ncls) ? (e[c] * inv - (c == lab ? 1.f : 0.f)) * w * grad_scale : 0.f;
+          bsum[c] += d[c];
+          dl[threadIdx.x * DLS + c] = d[c];
+        }
+#pragma unroll
+        for (int c = MC; c < DLS; ++c) dl[threadIdx.x * DLS + c] = 0.f;
         // dx[ci] = sum_c dlogit_c * Wh[c][ci]
         for (int k8 = 0; k8 < C; k8 += 8) {
           Vec8 o;
 #pragma unroll
           for (int j = 0; j < 8; ++j) o.v[j] = 0.f;
 #pragma unroll
-          for (int c = 0; c < kMaxCls; ++c) {
-            if (c < ncls) {
-              const float d = dl[threadIdx.x * ncls + c];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) o.v[j] = fmaf(d, sW[c * C + k8 + j], o.v[j]);
+          for (int c = 0; c < MC; ++c) {
+            if (NC > 0 || c < ncls) {
+              const float4 w0 = *reinterpret_cast<const float4*>(sW + c * C + k8);
+              const float4 w1 = *reinterpret_cast<const float4*>(sW + c * C + k8 + 4);
+              o.v[0] = fmaf(d[c], w0.x, o.v[0]);
+              o.v[1] = fmaf(d[c], w0.y, o.v[1]);
+              o.v[2] = fmaf(d[c], w0.z, o.v[2]);
+              o.v[3] = fmaf(d[c], w0.w, o.v[3]);
+              o.v[4] = fmaf(d[c], w1.x, o.v[4]);
+              o.v[5] = fmaf(d[c], w1.y, o.v[5]);
+              o.v[6] = fmaf(d[c], w1.z, o.v[6]);
+              o.v[7] = fmaf(d[c], w1.w, o.v[7]);
             }
           }
           store8(dx + row * C + k8, o);
         }
       }
-    } else if (TRAIN) {
-      for (int c = 0; c < ncls; ++c) dl[threadIdx.x * ncls + c] = 0.f;
     }
     if (TRAIN) {
       __syncthreads();
-      // dWh[c][ci] += sum_p dl[p][c] * x[p][ci]: thread = (input channel ci, pixel segment); all classes
-      // accumulate in registers, one x read + ncls broadcast reads per pixel
-      const int nrows = (int)min((long long)256, npix - p0);
-      if (threadIdx.x < nseg * C) {
-        const int ci = threadIdx.x % C, seg = threadIdx.x / C;
+      const int nrows = (int)min((long long)kHeadTile, npix - p0);
+      if (threadIdx.x < nseg * C2) {
+        const int cp = threadIdx.x % C2, seg = threadIdx.x / C2;
         const int r_lo = seg * rows_per_seg, r_hi = min(nrows, r_lo + rows_per_seg);
         for (int r = r_lo; r < r_hi; ++r) {
-          const float xv = __bfloat162float(xs[r * C + ci]);
+          const float2 xv =
+              __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(xs + r * XS + 2 * cp));
+          float dv[DLS];
 #pragma unroll
-          for (int c = 0; c < kMaxCls; ++c)
-            if (c < ncls) wacc[c] = fmaf(dl[r * ncls + c], xv, wacc[c]);
+          for (int q = 0; q < DLS / 4; ++q) {
+            const float4 t = *reinterpret_cast<const float4*>(dl + r * DLS + 4 * q);
+            dv[4 * q] = t.x;
+            dv[4 * q + 1] = t.y;
+            dv[4 * q + 2] = t.z;
+            dv[4 * q + 3] = t.w;
+          }
+#pragma unroll
+          for (int c = 0; c < MC; ++c) {
+            wacc[0][c] = fmaf(dv[c], xv.x, wacc[0][c]);
+            wacc[1][c] = fmaf(dv[c], xv.y, wacc[1][c]);
+          }
         }
-      }
-      if (threadIdx.x < ncls) {
-        float s = 0.f;
-        for (int r = 0; r < nrows; ++r) s += dl[r * ncls + threadIdx.x];
-        bacc += s;
       }
       __syncthreads();
     }
   }
   if (TRAIN) {
-    if (threadIdx.x < nseg * C) {
-      const int ci = threadIdx.x % C;
+    if (threadIdx.x < nseg * C2) {
+      const int cp = threadIdx.x % C2;
 #pragma unroll
-      for (int c = 0; c < kMaxCls; ++c)
-        if (c < ncls) atomicAdd(dWh + c * C + ci, wacc[c]);
+      for (int c = 0; c < MC; ++c)
+        if (NC > 0 || c < ncls) {
+          atomicAdd(dWh + c * C + 2 * cp, wacc[0][c]);
+          atomicAdd(dWh + c * C + 2 * cp + 1, wacc[1][c]);
+        }
     }
-    if (threadIdx.x < ncls) atomicAdd(dbh + threadIdx.x, bacc);
+#pragma unroll
+    for (int c = 0; c < MC; ++c) {
+      if (NC > 0 || c < ncls) {
+        float v = bsum[c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) atomicAdd(dbh + c, v);
+      }
+    }
     // block reduce loss
-    __shared__ double lred[256];
+    __shared__ double lred[kHeadTile];
     lred[threadIdx.x] = lacc;
     __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) {
-      if (threadIdx.x < s) lred[threadIdx.x] += lred[threadIdx.x + s];
+    for (int s2 = kHeadTile / 2; s2 > 0; s2 >>= 1) {
+      if (threadIdx.x < s2) lred[threadIdx.x] += lred[threadIdx.x + s2];
       __syncthreads();
     }
     if (threadIdx.x == 0) atomicAdd(loss_sum, lred[0]);
@@ -657,6 +803,31 @@ inline int grid_for(long long work, int threads) {
   return (int)b;
 }
 
+// Grid of a grid-stride kernel = the number of blocks that are resident at once (no partial last wave),
+// capped by the number of work items.
+template <typename K>
+int resident_grid(K kernel, int threads, size_t smem, long long items) {
+  int occ = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem) != cudaSuccess || occ < 1) {
+    cudaGetLastError();
+    occ = 1;
+  }
+  long long b = 148ll * occ;
+  if (b > items) b = items;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+// thread layout of the per-pixel kernels: blockDim = CG * RL with RL a power of two (row lanes), at most
+// `span` pixels (or windows) per line segment
+inline void line_layout(int C, int span, int* CG, int* RL, int* threads) {
+  *CG = C / 8;
+  int rl = 1;
+  while (2 * rl * *CG <= 256 && 2 * rl <= span) rl *= 2;
+  *RL = rl;
+  *threads = *CG * rl;
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -665,8 +836,8 @@ int launch_channel_stats(const __nv_bfloat16* y, long long rows, int C, int ld, 
   int CG, RL, threads;
   reduce_layout(C, &CG, &RL, &threads);
   MPU_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st));
-  const int grid = grid_for(rows, RL * 8);
   const size_t smem = sizeof(float) * 2 * RL * CG * 8;
+  const int grid = resident_grid(channel_stats_kernel, threads, smem, (rows + 4 * RL - 1) / (4 * RL));
   channel_stats_kernel<<<grid, threads, smem, st>>>(y, rows, C, ld, CG, RL, sums);
   count_launch();
   MPU_CUDA(cudaGetLastError());
@@ -676,8 +847,8 @@ int launch_channel_stats(const __nv_bfloat16* y, long long rows, int C, int ld, 
 int launch_colsum(const __nv_bfloat16* x, long long rows, int C, int ld, float* out, cudaStream_t st) {
   int CG, RL, threads;
   reduce_layout(C, &CG, &RL, &threads);
-  const int grid = grid_for(rows, RL * 8);
   const size_t smem = sizeof(float) * RL * CG * 8;
+  const int grid = resident_grid(colsum_kernel, threads, smem, (rows + 4 * RL - 1) / (4 * RL));
   colsum_kernel<<<grid, threads, smem, st>>>(x, rows, C, ld, CG, RL, out);
   count_launch();
   MPU_CUDA(cudaGetLastError());
@@ -697,65 +868,72 @@ int launch_bn_finalize(const double* sums, double count, const float* gamma, con
 
 int launch_bn_apply(const __nv_bfloat16* y, const float* scale, const float* shift, __nv_bfloat16* b,
                     __nv_bfloat16* pooled, Geo g, int C, cudaStream_t st) {
-  if (pooled) {
-    const long long work = (long long)g.B * (g.H / 2) * (g.W / 2) * (C / 8);
-    bn_apply_pool_kernel<<<grid_for(work, 256), 256, 0, st>>>(y, scale, shift, b, pooled, g, C);
-    count_launch();
-  } else {
-    const long long work = g.pixels() * (C / 8);
-    bn_apply_kernel<<<grid_for(work, 256), 256, 0, st>>>(y, scale, shift, b, g, C);
-    count_launch();
+  int CG, RL, threads;
+  if (C / 8 > 256) {
+    set_error("bn_apply: C=%d exceeds 2048 channels", C);
+    return MPU_ERR_ARG;
   }
+  if (pooled) {
+    line_layout(C, g.W / 2, &CG, &RL, &threads);
+    const long long items = (long long)g.B * (g.H / 2) * ((g.W / 2 + RL - 1) / RL);
+    const int grid = resident_grid(bn_apply_pool_kernel, threads, 0, items);
+    bn_apply_pool_kernel<<<grid, threads, 0, st>>>(y, scale, shift, b, pooled, g, C, CG, RL);
+  } else {
+    line_layout(C, (g.W + 3) / 4, &CG, &RL, &threads);
+    const long long items = (long long)g.B * g.H * ((g.W + 4 * RL - 1) / (4 * RL));
+    const int grid = resident_grid(bn_apply_kernel, threads, 0, items);
+    bn_apply_kernel<<<grid, threads, 0, st>>>(y, scale, shift, b, g, C, CG, RL);
+  }
+  count_launch();
   MPU_CUDA(cudaGetLastError());
   return MPU_OK;
 }
 
-int launch_bn_bwd_reduce(const BnBwdArgs& a, double* sums, cudaStream_t st) {
+namespace {
+// pass selection + launch of bn_bwd_kernel<POOL, APPLY>
+template <bool POOL, bool APPLY>
+int launch_bn_bwd(const BnBwdArgs& a, const double* sums_in, double* sums_out, __nv_bfloat16* dz,
+                  int phase_major, float* dbias, cudaStream_t st) {
   int CG, RL, threads;
-  reduce_layout(a.C, &CG, &RL, &threads);
-  MPU_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * a.C, st));
-  const bool pool = a.gP != nullptr;
-  const long long items = pool ? (long long)a.g.B * (a.g.H / 2) * (a.g.W / 2) : a.g.pixels();
-  const int grid = grid_for(items, RL * 4);
+  const int span = POOL ? a.g.W / 2 : (a.g.W + 1) / 2;
+  line_layout(a.C, span, &CG, &RL, &threads);
+  const int U = POOL ? 1 : 2;
+  const long long items =
+      (long long)a.g.B * (POOL ? a.g.H / 2 : a.g.H) * (((POOL ? a.g.W / 2 : a.g.W) + U * RL - 1) / (U * RL));
   const size_t smem = sizeof(float) * 2 * RL * CG * 8;
-  if (pool)
-    bn_bwd_kernel<true, false><<<grid, threads, smem, st>>>(a, CG, RL, nullptr, sums, nullptr, 0, nullptr);
-  else
-    bn_bwd_kernel<false, false><<<grid, threads, smem, st>>>(a, CG, RL, nullptr, sums, nullptr, 0, nullptr);
+  const int grid = resident_grid(bn_bwd_kernel<POOL, APPLY>, threads, smem, items);
+  bn_bwd_kernel<POOL, APPLY><<<grid, threads, smem, st>>>(a, CG, RL, sums_in, sums_out, dz, phase_major, dbias);
   count_launch();
   MPU_CUDA(cudaGetLastError());
   return MPU_OK;
+}
+}  // namespace
+
+int launch_bn_bwd_reduce(const BnBwdArgs& a, double* sums, cudaStream_t st) {
+  if (a.C / 8 > 256) {
+    set_error("bn_bwd: C=%d exceeds 2048 channels", a.C);
+    return MPU_ERR_ARG;
+  }
+  MPU_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * a.C, st));
+  if (a.gP != nullptr) return launch_bn_bwd<true, false>(a, nullptr, sums, nullptr, 0, nullptr, st);
+  return launch_bn_bwd<false, false>(a, nullptr, sums, nullptr, 0, nullptr, st);
 }
 
 int launch_bn_bwd_apply(const BnBwdArgs& a, const double* sums, __nv_bfloat16* dz, int phase_major,
                         float* dgamma, float* dbeta, float* dbias, cudaStream_t st) {
-  int CG, RL, threads;
-  reduce_layout(a.C, &CG, &RL, &threads);
-  const bool pool = a.gP != nullptr;
-  const long long items = pool ? (long long)a.g.B * (a.g.H / 2) * (a.g.W / 2) : a.g.pixels();
-  const int grid = grid_for(items, RL * 4);
-  const size_t smem = sizeof(float) * 2 * RL * CG * 8;
-  if (pool)
-    bn_bwd_kernel<true, true><<<grid, threads, smem, st>>>(a, CG, RL, sums, nullptr, dz, phase_major, dbias);
+  if (a.gP != nullptr)
+    MPU_TRY((launch_bn_bwd<true, true>(a, sums, nullptr, dz, phase_major, dbias, st)));
   else
-    bn_bwd_kernel<false, true><<<grid, threads, smem, st>>>(a, CG, RL, sums, nullptr, dz, phase_major, dbias);
-  count_launch();
-  MPU_CUDA(cudaGetLastError());
+    MPU_TRY((launch_bn_bwd<false, true>(a, sums, nullptr, dz, phase_major, dbias, st)));
   bn_bwd_params_kernel<<<(a.C + 127) / 128, 128, 0, st>>>(sums, a.mean, a.rstd, a.C, dgamma, dbeta);
   count_launch();
   MPU_CUDA(cudaGetLastError());
   return MPU_OK;
 }
 
-static size_t head_smem(int C, int ncls, bool train) {
-  size_t s = sizeof(float) * ((size_t)ncls * C + ((ncls + 3) & ~3));
-  if (train) s += (size_t)256 * C * 2 + sizeof(float) * 256 * ncls;
-  return s;
-}
-
 int launch_conv_first(const __nv_bfloat16* x, const __nv_bfloat16* w, const float* bias, __nv_bfloat16* out,
                       Geo g, int cin, int co_phys, cudaStream_t st) {
-  if (cin < 1 || cin > 8 || co_phys % 8) {
+  if (cin < 1 || cin > 4 || co_phys % 8) {
     set_error("conv_first: cin=%d co_phys=%d unsupported", cin, co_phys);
     return MPU_ERR_ARG;
   }
@@ -764,58 +942,96 @@ int launch_conv_first(const __nv_bfloat16* x, const __nv_bfloat16* w, const floa
     set_error("conv_first: weights do not fit in shared memory");
     return MPU_ERR_ARG;
   }
-  const long long work = g.pixels() * (co_phys / 8);
-  conv_first_kernel<<<grid_for(work, 256), 256, smem, st>>>(x, w, bias, out, g, cin, co_phys);
+  int threads = ((g.W + 31) / 32) * 32;
+  if (threads > 256) threads = 256;
+  const long long items = (long long)g.B * g.H * ((g.W + threads - 1) / threads);
+#define MPU_CONV_FIRST(CIN)                                                                        \
+  conv_first_kernel<CIN><<<resident_grid(conv_first_kernel<CIN>, threads, smem, items), threads, smem, st>>>( \
+      x, w, bias, out, g, co_phys)
+  switch (cin) {
+    case 1: MPU_CONV_FIRST(1); break;
+    case 2: MPU_CONV_FIRST(2); break;
+    case 3: MPU_CONV_FIRST(3); break;
+    default: MPU_CONV_FIRST(4); break;
+  }
+#undef MPU_CONV_FIRST
   count_launch();
   MPU_CUDA(cudaGetLastError());
   return MPU_OK;
 }
 
-int launch_head_infer(const __nv_bfloat16* x, Geo g, int C, const float* Wh, const float* bh, int ncls,
-                      float* probs, cudaStream_t st) {
-  if (ncls > kMaxCls) {
-    set_error("head: n_classes=%d exceeds the supported maximum %d", ncls, kMaxCls);
+namespace {
+size_t head_smem(int C, int ncls, int mc, bool train) {
+  const int dls = (mc + 3) & ~3;
+  size_t s = sizeof(float) * ((size_t)((ncls * C + 3) & ~3) + dls);
+  if (train) s += sizeof(float) * kHeadTile * dls + (size_t)kHeadTile * (C + 8) * 2;
+  return s;
+}
+
+template <bool TRAIN, int NC>
+int launch_head(const __nv_bfloat16* x, Geo g, int C, const float* Wh, const float* bh, int ncls,
+                const uint8_t* labels, const float* sample_w, float grad_scale, __nv_bfloat16* dx,
+                float* dWh, float* dbh, double* loss_sum, float* probs, cudaStream_t st) {
+  const size_t smem = head_smem(C, ncls, NC > 0 ? NC : kMaxCls, TRAIN);
+  if (smem > 200 * 1024) {
+    set_error("head: shared memory %zu too large (C=%d, n_classes=%d)", smem, C, ncls);
     return MPU_ERR_ARG;
   }
-  const size_t smem = head_smem(C, ncls, false);
-  static bool attr = false;
+  static bool attr = false;  // one flag per instantiation
   if (!attr) {
-    MPU_CUDA(cudaFuncSetAttribute(head_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    MPU_CUDA(cudaFuncSetAttribute(head_kernel<TRAIN, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  200 * 1024));
     attr = true;
   }
-  const int grid = grid_for(g.pixels(), 256);
-  head_kernel<false><<<grid, 256, smem, st>>>(x, g, C, Wh, bh, ncls, nullptr, nullptr, 0.f, nullptr,
-                                             nullptr, nullptr, nullptr, probs);
+  const long long tiles = (g.pixels() + kHeadTile - 1) / kHeadTile;
+  const int grid = resident_grid(head_kernel<TRAIN, NC>, kHeadTile, smem, tiles);
+  head_kernel<TRAIN, NC><<<grid, kHeadTile, smem, st>>>(x, g, C, Wh, bh, ncls, labels, sample_w, grad_scale,
+                                                       dx, dWh, dbh, loss_sum, probs);
   count_launch();
   MPU_CUDA(cudaGetLastError());
   return MPU_OK;
+}
+
+template <bool TRAIN>
+int dispatch_head(const __nv_bfloat16* x, Geo g, int C, const float* Wh, const float* bh, int ncls,
+                  const uint8_t* labels, const float* sample_w, float grad_scale, __nv_bfloat16* dx,
+                  float* dWh, float* dbh, double* loss_sum, float* probs, cudaStream_t st) {
+#define MPU_HEAD(NC) \
+  return launch_head<TRAIN, NC>(x, g, C, Wh, bh, ncls, labels, sample_w, grad_scale, dx, dWh, dbh, loss_sum, probs, st)
+  switch (ncls) {
+    case 2: MPU_HEAD(2);
+    case 3: MPU_HEAD(3);
+    case 4: MPU_HEAD(4);
+    case 5: MPU_HEAD(5);
+    case 6: MPU_HEAD(6);
+    case 7: MPU_HEAD(7);
+    case 8: MPU_HEAD(8);
+    default: MPU_HEAD(0);
+  }
+#undef MPU_HEAD
+}
+}  // namespace
+
+int launch_head_infer(const __nv_bfloat16* x, Geo g, int C, const float* Wh, const float* bh, int ncls,
+                      float* probs, cudaStream_t st) {
+  if (ncls < 1 || ncls > kMaxCls) {
+    set_error("head: n_classes=%d outside [1,%d]", ncls, kMaxCls);
+    return MPU_ERR_ARG;
+  }
+  return dispatch_head<false>(x, g, C, Wh, bh, ncls, nullptr, nullptr, 0.f, nullptr, nullptr, nullptr, nullptr,
+                              probs, st);
 }
 
 int launch_head_train(const __nv_bfloat16* x, Geo g, int C, const float* Wh, const float* bh, int ncls,
                       const uint8_t* labels, const float* sample_w, float grad_scale,
                       __nv_bfloat16* dx, float* dWh, float* dbh, double* loss_sum, float* probs_opt,
                       cudaStream_t st) {
-  if (ncls > kMaxCls || C > 256) {
+  if (ncls < 1 || ncls > kMaxCls || C > 256) {
     set_error("head(train): n_classes=%d, C=%d not supported (max %d classes, C <= 256)", ncls, C, kMaxCls);
     return MPU_ERR_ARG;
   }
-  const size_t smem = head_smem(C, ncls, true);
-  static bool attr = false;
-  if (!attr) {
-    MPU_CUDA(cudaFuncSetAttribute(head_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr = true;
-  }
-  if (smem > 200 * 1024) {
-    set_error("head(train): shared memory %zu too large", smem);
-    return MPU_ERR_ARG;
-  }
-  int grid = grid_for(g.pixels(), 256);
-  if (grid > 148 * 2) grid = 148 * 2;
-  head_kernel<true><<<grid, 256, smem, st>>>(x, g, C, Wh, bh, ncls, labels, sample_w, grad_scale, dx,
-                                            dWh, dbh, loss_sum, probs_opt);
-  count_launch();
-  MPU_CUDA(cudaGetLastError());
-  return MPU_OK;
+  return dispatch_head<true>(x, g, C, Wh, bh, ncls, labels, sample_w, grad_scale, dx, dWh, dbh, loss_sum,
+                             probs_opt, st);
 }
 
 int launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr_t, float b1,

@@ -434,7 +434,7 @@ static int forward(UNet& u, int B, int training, cudaStream_t st) {
     const Geo g = geo_b(u, l, B);
     ConvL& c1 = u.enc_conv(l, 0);
     ConvL& c2 = u.enc_conv(l, 1);
-    if (l == 0 && u.cin_phys == 8 && 9 * u.cfg.n_channels * c1.co_phys * 4 + c1.co_phys * 4 <= 48 * 1024) {
+    if (l == 0 && u.cin_phys == 8 && u.cfg.n_channels <= 4 && 9 * u.cfg.n_channels * c1.co_phys * 4 + c1.co_phys * 4 <= 48 * 1024) {
       // K = 9 * n_channels is too thin for the tensor cores: CUDA-core kernel, HBM-write bound
       MPU_TRY(launch_conv_first(x, c1.wf, P + c1.b_off, L.a1, g, u.cfg.n_channels, c1.co_phys, st));
     } else {

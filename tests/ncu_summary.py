@@ -45,12 +45,13 @@ KEYS = [
 def main(path):
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
-    h, units, v = rows[0], rows[1], rows[2]
-    d = {n: (v[i], units[i]) for i, n in enumerate(h)}
-    print("== %s  kernel=%s" % (path, d.get("Kernel Name", ("?",))[0][:60]))
-    for k in KEYS:
-        if k in d:
-            print("   %-95s %s %s" % (k, d[k][0], d[k][1]))
+    h, units = rows[0], rows[1]
+    for v in rows[2:]:  # one block per profiled launch
+        d = {n: (v[i], units[i]) for i, n in enumerate(h)}
+        print("== %s  kernel=%s" % (path, d.get("Kernel Name", ("?",))[0][:60]))
+        for k in KEYS:
+            if k in d:
+                print("   %-95s %s %s" % (k, d[k][0], d[k][1]))
 
 
 if __name__ == "__main__":
