@@ -26,6 +26,7 @@ long long g_launch_count = 0;
 static bool g_timer_on = false;
 static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_events;
 static size_t g_events_used = 0;
+bool gemm_timer_on() { return g_timer_on; }
 void gemm_timer_begin(cudaStream_t st) {
   if (!g_timer_on) return;
   if (g_events_used == g_events.size()) {

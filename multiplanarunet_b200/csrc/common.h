@@ -18,6 +18,7 @@ inline void count_launch(int n = 1) { g_launch_count += n; }
 // optional live timing of the tensor-core GEMM launches with CUDA events (roofline.achieved in bench.py)
 void gemm_timer_begin(cudaStream_t st);
 void gemm_timer_end(cudaStream_t st);
+bool gemm_timer_on();
 }  // namespace mpu
 
 #define MPU_CUDA(expr)                                                                   \

@@ -499,6 +499,50 @@ __global__ void conv_first_kernel(const __nv_bfloat16* __restrict__ x, const __n
   }
 }
 
+// Weight gradient of the first conv: dW[tap][co][ci] += sum_p dz[p][co] * x[p + tap][ci] for one input channel
+// ci = blockIdx.y.  Thread = (8-channel group of dz, row lane); the 9 x 8 partial sums live in registers and are
+// reduced over the block's row lanes through shared memory, then added with one atomic per value.
+__global__ void __launch_bounds__(256)
+    conv_first_wgrad_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dz, Geo g,
+                            int co_phys, int CG, int RL, float* __restrict__ dW, int ldw) {
+  extern __shared__ float wred[];  // [RL][CG*8]
+  const int tid = threadIdx.x;
+  const int cg = tid % CG, rl = tid / CG;
+  const int ci = blockIdx.y;
+  const int Wp = g.W + 2;
+  float acc[9][8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
+  SegIter it;
+  it.init(blockIdx.x, gridDim.x, g.H, (g.W + RL - 1) / RL);
+  for (; it.n < g.B; it.next()) {
+    const int xx = it.seg * RL + rl;
+    if (xx >= g.W) continue;
+    const long long row = ((long long)it.n * (g.H + 2) + it.yy + 1) * Wp + xx + 1;
+    const Vec8 d = load8(dz + row * co_phys + cg * 8);
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const float xv = __bfloat162float(x[(row + (t / 3 - 1) * Wp + (t % 3 - 1)) * 8 + ci]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[t][j] = fmaf(d.v[j], xv, acc[t][j]);
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wred[tid * 8 + j] = acc[t][j];
+    __syncthreads();
+    for (int c = tid; c < CG * 8; c += blockDim.x) {
+      float sum = 0.f;
+      for (int r = 0; r < RL; ++r) sum += wred[r * (CG * 8) + c];
+      atomicAdd(dW + ((long long)t * co_phys + c) * ldw + ci, sum);
+    }
+    __syncthreads();
+  }
+}
+
 // ---- head ----------------------------------------------------------------------------------------
 constexpr int kMaxCls = 16;
 constexpr int kHeadTile = 256;  // pixels per block iteration (= blockDim)
@@ -955,6 +999,23 @@ int launch_conv_first(const __nv_bfloat16* x, const __nv_bfloat16* w, const floa
     default: MPU_CONV_FIRST(4); break;
   }
 #undef MPU_CONV_FIRST
+  count_launch();
+  MPU_CUDA(cudaGetLastError());
+  return MPU_OK;
+}
+
+int launch_conv_first_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dz, Geo g, int cin, int co_phys,
+                            float* dW, int ldw, cudaStream_t st) {
+  if (cin < 1 || cin > 8 || co_phys % 8 || co_phys / 8 > 256) {
+    set_error("conv_first_wgrad: cin=%d co_phys=%d unsupported", cin, co_phys);
+    return MPU_ERR_ARG;
+  }
+  int CG, RL, threads;
+  line_layout(co_phys, g.W, &CG, &RL, &threads);
+  const size_t smem = sizeof(float) * threads * 8;
+  const long long items = (long long)g.B * g.H * ((g.W + RL - 1) / RL);
+  const int grid = resident_grid(conv_first_wgrad_kernel, threads, smem, items);
+  conv_first_wgrad_kernel<<<dim3(grid, cin), threads, smem, st>>>(x, dz, g, co_phys, CG, RL, dW, ldw);
   count_launch();
   MPU_CUDA(cudaGetLastError());
   return MPU_OK;

@@ -77,6 +77,21 @@ struct UNet {
   long long dwc_floats = 0;
   bool training_buffers = false;
   bool weights_synced = false;
+  // Second stream for work that is off the critical path (weight gradients, two of the four upsample-conv
+  // phases): its CTAs fill the SMs that the tail of the kernel on the main stream leaves idle.
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+  bool overlap = true;
+  int blk = 0;  // backward block counter within a stage (ring index of ev_join)
+
+  ~UNet() {
+    if (side) cudaStreamDestroy(side);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    for (cudaEvent_t e : ev_join)
+      if (e) cudaEventDestroy(e);
+  }
+  // side stream to use for this call (the main stream itself when overlap is off or GEMMs are being timed)
+  cudaStream_t side_for(cudaStream_t st) const { return (overlap && side && !gemm_timer_on()) ? side : st; }
 
   ConvL& enc_conv(int l, int j) { return convs[2 * l + j]; }
   ConvL& up_conv(int i, int j) { return convs[2 * (depth + 1) + 3 * i + j]; }
@@ -278,8 +293,31 @@ static int gemm_dgrad3x3(UNet& u, const bf16* dz, const ConvL& L, Geo g, bf16* o
                          cudaStream_t st);
 
 // nearest-2x upsample + 2x2 SAME conv + bias + ReLU as four phase GEMMs on the low-res grid.
-static int gemm_upconv(const bf16* X, int Cx, Geo glo, const ConvL& L, const float* bias, Geo ghi,
+// side stream starts after everything enqueued on st so far
+static int fork_side(UNet& u, cudaStream_t st, cudaStream_t sb) {
+  if (sb == st) return MPU_OK;
+  MPU_CUDA(cudaEventRecord(u.ev_fork, st));
+  MPU_CUDA(cudaStreamWaitEvent(sb, u.ev_fork, 0));
+  return MPU_OK;
+}
+// mark the side stream's position in ring slot `slot`
+static int mark_side(UNet& u, cudaStream_t st, cudaStream_t sb, int slot) {
+  if (sb == st) return MPU_OK;
+  MPU_CUDA(cudaEventRecord(u.ev_join[slot], sb));
+  return MPU_OK;
+}
+// st waits for the side-stream position marked in `slot`
+static int wait_side(UNet& u, cudaStream_t st, cudaStream_t sb, int slot) {
+  if (sb == st) return MPU_OK;
+  MPU_CUDA(cudaStreamWaitEvent(st, u.ev_join[slot], 0));
+  return MPU_OK;
+}
+
+static int gemm_upconv(UNet& u, const bf16* X, int Cx, Geo glo, const ConvL& L, const float* bias, Geo ghi,
                        bf16* out, cudaStream_t st, double* stats = nullptr) {
+  // the four output phases are independent launches: phases (0,1) and (1,0) go to the side stream
+  cudaStream_t sb = u.side_for(st);
+  MPU_TRY(fork_side(u, st, sb));
   for (int a = 0; a < 2; ++a)
     for (int b = 0; b < 2; ++b) {
       int off[kMaxTaps], widx[kMaxTaps], n = 0;
@@ -302,9 +340,10 @@ static int gemm_upconv(const bf16* X, int Cx, Geo glo, const ConvL& L, const flo
       d.stats = stats;
       FwdParams p;
       MPU_TRY(fwd_setup(p, d));
-      MPU_TRY(launch_fwd(p, st));
+      MPU_TRY(launch_fwd(p, a != b ? sb : st));
     }
-  return MPU_OK;
+  MPU_TRY(mark_side(u, st, sb, 0));
+  return wait_side(u, st, sb, 0);
 }
 
 // dIn[m_lo] = sum over the 9 (phase, tap) pairs of dZ[phase][m_lo - off] . Wc[pair]  (dZ phase-major)
@@ -460,7 +499,7 @@ static int forward(UNet& u, int B, int training, cudaStream_t st) {
     double* st3 = training ? u.up_bn(i, 1).sums : nullptr;
     if (st1) MPU_CUDA(cudaMemsetAsync(st1, 0, sizeof(double) * 2 * L.C, st));
     if (st3) MPU_CUDA(cudaMemsetAsync(st3, 0, sizeof(double) * 2 * L.C, st));
-    MPU_TRY(gemm_upconv(x, cx, glo, c1, P + c1.b_off, g, L.u, st, st1));
+    MPU_TRY(gemm_upconv(u, x, cx, glo, c1, P + c1.b_off, g, L.u, st, st1));
     MPU_TRY(bn_forward(u, u.up_bn(i, 0), L.u, g, L.bn1, nullptr, training, st, st1 != nullptr));
     MPU_TRY(gemm_same(L.b, L.C, L.C, L.bn1, L.C, L.C, c2.wf, 9, c2.co_phys, c2.k_phys, g, L.c2, L.C,
                       P + c2.b_off, nullptr, 0, 1, st));
@@ -496,25 +535,51 @@ static int bn_backward(UNet& u, BnL& bn, const bf16* y, const bf16* gA, int ldA,
 // wgrad conv2, dgrad conv2 (masked by a1 -> dz1), bias1, wgrad conv1, optional dgrad conv1.
 static int block_tail_backward(UNet& u, ConvL& c1, ConvL& c2, const bf16* xin0, int cx0, const bf16* xin1,
                                int cx1, const bf16* a1, const bf16* dz2, bf16* dz1, bf16* dxin, int C,
-                               Geo g, cudaStream_t st) {
+                               Geo g, cudaStream_t st, cudaStream_t sb) {
   float* G = u.grads;
-  MPU_TRY(wgrad_same(a1, C, C, dz2, C, 9, g, G + c2.w_off, c2.k_phys, c2.co_phys, 0, st));
+  // weight / bias gradients run on the side stream sb; the dgrad chain (critical path) stays on st
+  MPU_TRY(fork_side(u, st, sb));  // dz2 is ready
+  MPU_TRY(wgrad_same(a1, C, C, dz2, C, 9, g, G + c2.w_off, c2.k_phys, c2.co_phys, 0, sb));
   MPU_TRY(gemm_dgrad3x3(u, dz2, c2, g, dz1, a1, C, st));
-  MPU_TRY(launch_colsum(dz1, g.rows(), C, C, G + c1.b_off, st));
-  MPU_TRY(wgrad_same(xin0, cx0, cx0, dz1, C, 9, g, G + c1.w_off, c1.k_phys, c1.co_phys, 0, st));
+  MPU_TRY(fork_side(u, st, sb));  // dz1 is ready
+  MPU_TRY(launch_colsum(dz1, g.rows(), C, C, G + c1.b_off, sb));
+  if (!xin1 && cx0 == 8 && c1.k_phys == 8 && u.cfg.n_channels <= 4 && xin0 == u.x_in)
+    // first conv of the network: K = 9 * n_channels is too thin for the tensor cores
+    MPU_TRY(launch_conv_first_wgrad(xin0, dz1, g, u.cfg.n_channels, c1.co_phys, G + c1.w_off, c1.k_phys, sb));
+  else
+    MPU_TRY(wgrad_same(xin0, cx0, cx0, dz1, C, 9, g, G + c1.w_off, c1.k_phys, c1.co_phys, 0, sb));
   if (xin1)
-    MPU_TRY(wgrad_same(xin1, cx1, cx1, dz1, C, 9, g, G + c1.w_off, c1.k_phys, c1.co_phys, cx0, st));
+    MPU_TRY(wgrad_same(xin1, cx1, cx1, dz1, C, 9, g, G + c1.w_off, c1.k_phys, c1.co_phys, cx0, sb));
   if (dxin) MPU_TRY(gemm_dgrad3x3(u, dz1, c1, g, dxin, nullptr, 0, st));
+  return MPU_OK;
+}
+
+// Buffers the side stream reads (dz tensors of a level) are rewritten by the main stream at the earliest two
+// blocks later (up block of level l -> encoder block of level l), so each block first waits for the side
+// work of the block before the previous one; stages end with a full join.
+static int block_begin(UNet& u, cudaStream_t st, cudaStream_t sb) {
+  if (u.blk >= 2) MPU_TRY(wait_side(u, st, sb, (u.blk - 2) % 3));
+  return MPU_OK;
+}
+static int block_end(UNet& u, cudaStream_t st, cudaStream_t sb) {
+  MPU_TRY(mark_side(u, st, sb, u.blk % 3));
+  ++u.blk;
+  return MPU_OK;
+}
+static int stage_join(UNet& u, cudaStream_t st, cudaStream_t sb) {
+  if (u.blk > 0) MPU_TRY(wait_side(u, st, sb, (u.blk - 1) % 3));
+  u.blk = 0;
   return MPU_OK;
 }
 
 // Backward in three stages so the caller can start the gradient all-reduce of finished parameter ranges
 // while the rest of backward still runs:  0 = up path (+ head, already done by the loss kernel),
 // 1 = bottom block, 2 = encoder levels depth-1 .. 0.
-static int backward_up(UNet& u, int B, cudaStream_t st) {
+static int backward_up(UNet& u, int B, cudaStream_t st, cudaStream_t sb) {
   const int d = u.depth;
   float* G = u.grads;
   for (int l = 0; l < d; ++l) {
+    MPU_TRY(block_begin(u, st, sb));
     const int i = d - 1 - l;
     Level& L = u.lv[l];
     Level& Lo = u.lv[l + 1];
@@ -525,23 +590,26 @@ static int backward_up(UNet& u, int B, cudaStream_t st) {
     // BN2 backward: gradient wrt bn2_l is in L.gout
     MPU_TRY(bn_backward(u, u.up_bn(i, 1), L.c3, L.gout, L.C, nullptr, g, L.s1, 0, G + c3.b_off, st));
     // conv3 / conv2 ([skip | bn1] concat input) backward; dgrad of conv2 -> dcat [rows][2C]
-    MPU_TRY(block_tail_backward(u, c2, c3, L.b, L.C, L.bn1, L.C, L.c2, L.s1, L.s2, L.dcat, L.C, g, st));
+    MPU_TRY(block_tail_backward(u, c2, c3, L.b, L.C, L.bn1, L.C, L.c2, L.s1, L.s2, L.dcat, L.C, g, st, sb));
     // BN1 backward on the second half of dcat -> dz of the upsample-conv, phase-major
     MPU_TRY(bn_backward(u, u.up_bn(i, 0), L.u, L.dcat + L.C, 2 * L.C, nullptr, g, L.dzu, 1,
                         G + c1.b_off, st));
     // upsample-conv backward
     const bf16* xin = (l + 1 == d) ? Lo.b : Lo.bn2;
-    MPU_CUDA(cudaMemsetAsync(u.dwc, 0, sizeof(float) * 9 * c1.co_phys * c1.k_phys, st));
-    MPU_TRY(wgrad_upconv(xin, Lo.C, L.dzu, c1, glo, u.dwc, st));
-    MPU_TRY(launch_fold_upconv_grad(u.dwc, G + c1.w_off, c1.co_phys, c1.k_phys, st));
+    MPU_TRY(fork_side(u, st, sb));  // dzu is ready
+    MPU_CUDA(cudaMemsetAsync(u.dwc, 0, sizeof(float) * 9 * c1.co_phys * c1.k_phys, sb));
+    MPU_TRY(wgrad_upconv(xin, Lo.C, L.dzu, c1, glo, u.dwc, sb));
+    MPU_TRY(launch_fold_upconv_grad(u.dwc, G + c1.w_off, c1.co_phys, c1.k_phys, sb));
     MPU_TRY(gemm_upconv_dgrad(u, L.dzu, c1, glo, Lo.gout, st));
+    MPU_TRY(block_end(u, st, sb));
   }
   return MPU_OK;
 }
 
-static int backward_enc_level(UNet& u, int B, int l, cudaStream_t st) {
+static int backward_enc_level(UNet& u, int B, int l, cudaStream_t st, cudaStream_t sb) {
   const int d = u.depth;
   float* G = u.grads;
+  MPU_TRY(block_begin(u, st, sb));
   Level& L = u.lv[l];
   const Geo g = geo_b(u, l, B);
   ConvL& c1 = u.enc_conv(l, 0);
@@ -555,18 +623,24 @@ static int backward_enc_level(UNet& u, int B, int l, cudaStream_t st) {
   const bf16* xin = l == 0 ? u.x_in : u.lv[l - 1].pooled;
   const int cx = l == 0 ? u.cin_phys : u.lv[l - 1].C;
   bf16* dxin = l == 0 ? nullptr : u.lv[l - 1].dpool;
-  return block_tail_backward(u, c1, c2, xin, cx, nullptr, 0, L.a1, L.s1, L.s2, dxin, L.C, g, st);
+  MPU_TRY(block_tail_backward(u, c1, c2, xin, cx, nullptr, 0, L.a1, L.s1, L.s2, dxin, L.C, g, st, sb));
+  return block_end(u, st, sb);
 }
 
 static int backward_stage(UNet& u, int B, int stage, cudaStream_t st) {
-  if (stage == 0) return backward_up(u, B, st);
-  if (stage == 1) return backward_enc_level(u, B, u.depth, st);
-  if (stage == 2) {
-    for (int l = u.depth - 1; l >= 0; --l) MPU_TRY(backward_enc_level(u, B, l, st));
-    return MPU_OK;
+  cudaStream_t sb = u.side_for(st);
+  u.blk = 0;
+  if (stage == 0) {
+    MPU_TRY(backward_up(u, B, st, sb));
+  } else if (stage == 1) {
+    MPU_TRY(backward_enc_level(u, B, u.depth, st, sb));
+  } else if (stage == 2) {
+    for (int l = u.depth - 1; l >= 0; --l) MPU_TRY(backward_enc_level(u, B, l, st, sb));
+  } else {
+    set_error("backward_stage: stage %d out of range", stage);
+    return MPU_ERR_ARG;
   }
-  set_error("backward_stage: stage %d out of range", stage);
-  return MPU_ERR_ARG;
+  return stage_join(u, st, sb);  // all gradients of the stage are complete on st
 }
 
 static int backward(UNet& u, int B, cudaStream_t st) {
@@ -628,6 +702,17 @@ int mpu_unet_create(const MpuUNetConfig* cfg, float* params, float* grads, float
   UNet* u = new UNet();
   u->cfg = *cfg;
   if (const char* e = getenv("MPU_DGRAD_MN")) u->dgrad_mn = atoi(e) != 0;
+  if (const char* e = getenv("MPU_OVERLAP")) u->overlap = atoi(e) != 0;
+  if (u->overlap) {
+    bool ok = cudaStreamCreateWithFlags(&u->side, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&u->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+    for (cudaEvent_t& ev : u->ev_join) ok = ok && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+      set_error("unet_create: could not create the side stream / events: %s", cudaGetErrorString(cudaGetLastError()));
+      delete u;
+      return MPU_ERR_CUDA;
+    }
+  }
   int rc = build_tables(*u);
   if (rc != MPU_OK) {
     delete u;
