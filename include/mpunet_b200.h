@@ -158,6 +158,13 @@ int mpu_fusion_adam(float* W, float* b, float* m, float* v, const double* accum,
                     int V, int C, float reg, float lr, float beta1, float beta2, float eps, int step,
                     void* stream);
 
+/* Confusion-matrix counts for the validation callback and dice_all: ADDS into counts [3][n_classes] int64
+ * (device): [0] true == c & pred == c (TP), [1] true == c (relevant), [2] pred == c (selected).
+ * pred is either y_pred (u8 labels) or, when scores != NULL, the first arg-max of scores [n][n_classes] f32.
+ * Replaces callbacks/validation.py:117-131 (np.bincount x3) and the sums of evaluate/metrics.py:12-52. */
+int mpu_label_counts(const unsigned char* y_true, const unsigned char* y_pred, const float* scores,
+                     long long n, int n_classes, long long* counts, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -56,3 +56,10 @@ def double_array(vals):
 def current_stream():
     import torch
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda():
+    """There is no CPU path: every compute entry point needs a CUDA device."""
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("multiplanarunet_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")

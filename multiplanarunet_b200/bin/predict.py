@@ -91,12 +91,8 @@ def entry_func(args=None):
         out = probs.cpu().numpy() if a.no_argmax else labels.cpu().numpy()
         write_nifti(os.path.join(nii_dir, image.identifier + "_PRED.nii.gz"), out, image.affine)
         if image.labels is not None and not a.no_eval:
-            pred = labels.cpu().numpy()
-            dices = []
-            for c in range(1, build["n_classes"]):
-                s1, s2 = image.labels == c, pred == c
-                dices.append((1.0 + 2 * np.logical_and(s1, s2).sum()) / (1.0 + s1.sum() + s2.sum())
-                             if (s1.any() or s2.any()) else np.nan)
+            from ..evaluate import dice_all
+            dices = list(dice_all(image.labels, labels, n_classes=build["n_classes"], ignore_zero=True))
             rows.append([image.identifier] + dices)
             print("%s  mean dice %.4f" % (image.identifier, np.nanmean(dices)))
     if rows and D.rank() == 0:

@@ -64,22 +64,19 @@ def load_or_create_views(project_dir, n_views, continue_training):
 
 def validation_dice(model, seq, n_images, n_classes):
     """Epoch-end validation like callbacks/validation.py:91-230: sample validation batches, accumulate
-    TP / relevant / selected per class, return mean foreground dice."""
-    tp = np.zeros(n_classes)
-    rel = np.zeros(n_classes)
-    sel = np.zeros(n_classes)
+    TP / relevant / selected per class on the device (mpu_label_counts), return the mean foreground dice
+    (background ignored, `ignore_class_zero`)."""
+    from ..evaluate import compute_dice, label_counts
+    counts = None
     steps = max(1, int(math.ceil(n_images / seq.batch_size)))
     for _ in range(steps):
         x, y, _ = seq.sample_batch_device()
-        pred = model.predict_on_batch(x, as_numpy=False).argmax(-1).reshape(-1)
-        yy = y.reshape(-1).long()
-        k = n_classes
-        cm = np.bincount((yy * k + pred).cpu().numpy(), minlength=k * k).reshape(k, k)
-        tp += np.diag(cm)
-        rel += cm.sum(1)
-        sel += cm.sum(0)
-    dice = (2 * tp) / np.maximum(rel + sel, 1)
-    return float(np.mean(dice[1:])) if n_classes > 1 else float(dice[0])
+        probs = model.predict_on_batch(x, as_numpy=False)
+        counts = label_counts(y, probs, n_classes, counts=counts)
+    c = counts.cpu().numpy()
+    # validation.py:213-215 passes sel=relevant, rel=selected; dice is symmetric in the two
+    _, _, dices = compute_dice(tp=c[0], rel=c[2], sel=c[1])
+    return float(np.mean(dices[1:])) if n_classes > 1 else float(dices[0])
 
 
 def run(project_dir, args):

@@ -339,6 +339,48 @@ inline int grid_for(long long work, int threads, int cap = 148 * 16) {
   return (int)g;
 }
 
+
+// ---- confusion-matrix counts ---------------------------------------------------------------------------
+// counts[0][c] = #(true == c & pred == c), counts[1][c] = #(true == c), counts[2][c] = #(pred == c)
+// (TP / relevant / selected of callbacks/validation.py:117-131; the three sums of evaluate/metrics.py:12-23).
+// pred comes either as labels (u8) or as per-class scores [n][ncls] f32 whose first maximum is the label
+// (numpy argmax).  Integer work: exact.
+__global__ void label_counts_kernel(const unsigned char* __restrict__ yt, const unsigned char* __restrict__ yp,
+                                    const float* __restrict__ scores, long long n, int ncls,
+                                    unsigned long long* __restrict__ counts) {
+  __shared__ unsigned int h[3 * 256];
+  for (int i = threadIdx.x; i < 3 * 256; i += blockDim.x) h[i] = 0;
+  __syncthreads();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int t = yt[i];
+    int p;
+    if (scores) {
+      const float* s = scores + i * ncls;
+      float best = s[0];
+      p = 0;
+      for (int c = 1; c < ncls; ++c) {
+        const float v = s[c];
+        if (v > best) {
+          best = v;
+          p = c;
+        }
+      }
+    } else {
+      p = yp[i];
+    }
+    if (t < ncls) {
+      atomicAdd(&h[256 + t], 1u);
+      if (t == p) atomicAdd(&h[t], 1u);
+    }
+    if (p < ncls) atomicAdd(&h[512 + p], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * ncls; i += blockDim.x) {
+    const unsigned int v = h[(i / ncls) * 256 + i % ncls];
+    if (v) atomicAdd(counts + i, (unsigned long long)v);
+  }
+}
 }  // namespace
 }  // namespace mpu
 
@@ -479,6 +521,23 @@ int mpu_fusion_adam(float* W, float* b, float* m, float* v, const double* accum,
   const int n = V * C + C;
   fusion_adam_kernel<<<(n + 63) / 64, 64, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       W, b, m, v, accum, n_points, V, C, reg, (float)lr_t, beta1, beta2, eps);
+  count_launch();
+  MPU_CUDA(cudaGetLastError());
+  return MPU_OK;
+}
+
+int mpu_label_counts(const unsigned char* y_true, const unsigned char* y_pred, const float* scores,
+                     long long n, int n_classes, long long* counts, void* stream) {
+  if (!y_true || (!y_pred && !scores) || !counts || n < 0 || n_classes < 1 || n_classes > 256) {
+    set_error("label_counts: bad argument (n=%lld, n_classes=%d)", n, n_classes);
+    return MPU_ERR_ARG;
+  }
+  if (n == 0) return MPU_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  long long blocks = (n + 256 * 16 - 1) / (256 * 16);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  label_counts_kernel<<<(int)blocks, 256, 0, st>>>(y_true, scores ? nullptr : y_pred, scores, n, n_classes,
+                                                   reinterpret_cast<unsigned long long*>(counts));
   count_launch();
   MPU_CUDA(cudaGetLastError());
   return MPU_OK;

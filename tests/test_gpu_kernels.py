@@ -102,3 +102,40 @@ def test_map_fuse_full_size_properties():
     # the volume centre is inside every view's stack; the far corner is outside all of them
     assert int(lab4[128, 128, 128]) == 3 and int(lab4[0, 0, 0]) == 0
     assert set(torch.unique(lab4).tolist()) <= {0, 3}
+
+
+def test_label_counts_and_dice_all_exact():
+    """mpu_label_counts (integer work: bit-exact) against oracle/metrics.py, labels and score inputs, an
+    unaligned odd length, accumulation over calls, and dice_all on a 256^3-sized volume via the invariant
+    sum(relevant) == sum(selected) == n."""
+    import torch
+    from multiplanarunet_b200.evaluate import compute_dice, dice, dice_all, label_counts
+    from oracle import metrics as om
+    rng = np.random.RandomState(11)
+    k = 5
+    n = 100003
+    y = rng.randint(0, k, size=n).astype(np.uint8)
+    p = rng.randint(0, k, size=n).astype(np.uint8)
+    c = label_counts(y, p, k).cpu().numpy()
+    tp, rel, sel = om.cm_counts(y, p, k)
+    assert np.array_equal(c[0], tp.astype(np.int64)) and np.array_equal(c[1], rel.astype(np.int64))
+    assert np.array_equal(c[2], sel.astype(np.int64))
+    scores = rng.rand(n, k).astype(np.float32)
+    scores[:1000] = 0.5
+    acc = label_counts(y, scores, k)
+    acc = label_counts(y, scores, k, counts=acc)  # accumulates
+    tp, rel, sel = om.cm_counts(y, scores, k)
+    assert np.array_equal(acc.cpu().numpy(), 2 * np.stack([tp, rel, sel]).astype(np.int64))
+    for kw in [dict(n_classes=k), dict(n_classes=k, ignore_zero=False), dict(n_classes=None),
+               dict(n_classes=7, skip_if_no_y=True)]:
+        assert np.array_equal(dice_all(y, p, **kw), om.dice_all(y, p, **kw), equal_nan=True)
+    assert dice(y > 1, p > 2) == om.dice(y > 1, p > 2)
+    pr, rc, dc = compute_dice(tp, rel, sel)
+    pr2, rc2, dc2 = om.compute_dice(tp, rel, sel)
+    assert np.array_equal(dc, dc2) and np.array_equal(pr, pr2) and np.array_equal(rc, rc2)
+    # full-size volume (BASELINE config 3): device-resident labels
+    big_t = torch.randint(0, k, (256 ** 3,), dtype=torch.uint8, device="cuda")
+    big_p = torch.randint(0, k, (256 ** 3,), dtype=torch.uint8, device="cuda")
+    cb = label_counts(big_t, big_p, k)
+    assert int(cb[1].sum()) == 256 ** 3 and int(cb[2].sum()) == 256 ** 3
+    assert torch.equal(cb[0], torch.stack([((big_t == i) & (big_p == i)).sum() for i in range(k)]))

@@ -84,3 +84,26 @@ def test_dice_all():
     b = np.array([0, 1, 2, 2, 2, 0])
     d = fusion.dice_all(a, b, 3)
     assert np.allclose(d, [(1 + 2 * 1) / (1 + 2 + 1), (1 + 2 * 2) / (1 + 3 + 3)])
+
+
+def test_validation_counts_and_dice():
+    """oracle/metrics.py: the bincount rule of callbacks/validation.py:117-131 against brute force, and
+    _compute_dice's zero-fill convention."""
+    from oracle import metrics as om
+    rng = np.random.RandomState(2)
+    k = 4
+    y = rng.randint(0, k, size=500)
+    scores = rng.rand(500, k).astype(np.float32)
+    scores[:50] = 0.25  # ties: first maximum wins
+    p = scores.argmax(-1)
+    tp, rel, sel = om.cm_counts(y, scores, k)
+    for c in range(k):
+        assert tp[c] == np.sum((y == c) & (p == c))
+        assert rel[c] == np.sum(y == c)
+        assert sel[c] == np.sum(p == c)
+    assert np.all(p[:50] == 0)
+    pr, rc, dc = om.compute_dice(tp, rel, sel)
+    for c in range(k):
+        assert abs(dc[c] - 2 * tp[c] / float(rel[c] + sel[c])) < 1e-6
+    pr, rc, dc = om.compute_dice(np.array([0, 3]), np.array([0, 4]), np.array([0, 3]))
+    assert pr[0] == rc[0] == dc[0] == 0 and abs(dc[1] - 2 * 1.0 * 0.75 / 1.75) < 1e-6

@@ -75,3 +75,27 @@ def test_host_geometry_mirror_equals_reference(ref):
         grid, g_r, inv_r = ref.sample_grid.sample_plane_at(view, 32, 30, 2.5, 0., test_mode=True)
         assert np.array_equal(inv, inv_r) and np.array_equal(g, g_r) and off == 2.5
     assert np.array_equal(view_offsets(64, 64.0, "same+20"), sampler.view_offsets(64, 64.0, "same+20"))
+
+
+def test_dice_all_equals_reference():
+    """evaluate/metrics.py imports tensorflow at module level; the shim's stub satisfies the import and
+    dice/dice_all themselves are plain numpy."""
+    from oracle import metrics as om, ref_shim
+    ref_shim.install()
+    import importlib.util
+    import os
+    path = os.path.join(ref_shim.REF_ROOT, "mpunet", "evaluate", "metrics.py")
+    spec = importlib.util.spec_from_file_location("_ref_metrics", path)
+    rm = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(rm)
+    rng = np.random.RandomState(5)
+    for n_classes, kw in [(5, {}), (5, dict(ignore_zero=False)), (None, {}), (4, dict(skip_if_no_y=True)),
+                          (3, dict(smooth=0.5))]:
+        k = n_classes or 6
+        a = rng.randint(0, k, size=(9, 10, 11)).astype(np.uint8)
+        b = rng.randint(0, k, size=(9, 10, 11)).astype(np.uint8)
+        a[a == 2] = 0  # a class missing from y_true
+        want = rm.dice_all(a, b, n_classes=n_classes, **kw)
+        got = om.dice_all(a, b, n_classes=n_classes, **kw)
+        assert np.array_equal(want, got, equal_nan=True)
+    assert rm.dice(a > 1, b > 2) == om.dice(a > 1, b > 2)
