@@ -165,6 +165,20 @@ int mpu_fusion_adam(float* W, float* b, float* m, float* v, const double* accum,
 int mpu_label_counts(const unsigned char* y_true, const unsigned char* y_pred, const float* scores,
                      long long n, int n_classes, long long* counts, void* stream);
 
+/* Elastic2D augmentation of n slices (augmentation/elastic_deformation.py:6-69, called from
+ * augmentation/augmenters.py:87-109 after scaling).  All pointers are device pointers.
+ *   x_in [n][H][W][C] f32, y_in [n][H][W] u8 or NULL -> x_out, y_out (not in place)
+ *   fields [n][2][H][W] f64: in = the uniform(-1,1) noise images (dx, dy) drawn by the caller's RNG;
+ *                            out = gaussian_filter(noise, sigma, mode="constant") (before the alpha factor)
+ *   scratch: same size as fields
+ *   d_weights [n][weight_stride] f64: normalised Gaussian taps of each slice, 2*radius+1 values from index 0
+ *   d_radius [n] int (= int(4*sigma + 0.5)), d_alpha [n] f64, d_bg [n][C] f32 (fill value per channel)
+ * Image: bilinear with float64 weights -> f32; labels: nearest, out-of-bounds -> 0. */
+int mpu_elastic_2d(const float* x_in, const unsigned char* y_in, double* fields, double* scratch,
+                   const double* d_weights, int weight_stride, const int* d_radius, const double* d_alpha,
+                   const float* d_bg, int n, int H, int W, int C, float* x_out, unsigned char* y_out,
+                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif

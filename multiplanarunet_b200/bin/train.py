@@ -125,11 +125,19 @@ def run(project_dir, args):
     bs = int(fit["batch_size"])
     common = dict(views=views, sample_dim=build["dim"], real_space_span=fit["real_space_span"],
                   n_classes=build["n_classes"], batch_size=bs, fg_batch_fraction=fit.get("fg_batch_fraction", 0.5))
-    tr_seq = IsotrophicLiveViewSequence2D(train_images, noise_sd=fit.get("noise_sd", 0.1), **common)
-    va_seq = IsotrophicLiveViewSequence2D(val_images, is_validation=True, **common) if val_images else None
+    aug_list = []
     if fit.get("augmenters"):
-        log("[NOTE] augmenters %s are not applied on the B200 path yet (elastic deformation is a 'next' "
-            "row)" % [a.get("cls_name") for a in fit["augmenters"]])
+        # sequences/utils.py:38-47: classes looked up by name, kwargs from the YAML
+        from .. import augmentation
+        for aug in fit["augmenters"]:
+            if aug["cls_name"] not in augmentation.__dict__:
+                raise NotImplementedError("augmenter %r is not available on the B200 path (2D pipeline: "
+                                          "Elastic2D)" % aug["cls_name"])
+            aug_list.append(augmentation.__dict__[aug["cls_name"]](**aug["kwargs"]))
+        log("Using on-the-fly augmenters: %s" % aug_list)
+    tr_seq = IsotrophicLiveViewSequence2D(train_images, noise_sd=fit.get("noise_sd", 0.1),
+                                          list_of_augmenters=aug_list, **common)
+    va_seq = IsotrophicLiveViewSequence2D(val_images, is_validation=True, **common) if val_images else None
 
     cls = models.__dict__[build["model_class_name"]]
     model = cls(max_batch=bs, training=True, **build)

@@ -381,6 +381,97 @@ __global__ void label_counts_kernel(const unsigned char* __restrict__ yt, const 
     if (v) atomicAdd(counts + i, (unsigned long long)v);
   }
 }
+
+// ---- Elastic2D augmentation ------------------------------------------------------------------------------
+// (mpunet/augmentation/elastic_deformation.py:6-69.)  The displacement fields are scipy's
+// gaussian_filter(noise, sigma, mode="constant") - two separable float64 passes, axis 0 then axis 1 - whose
+// inner loop (scipy/ndimage/src/ni_filters.c, NI_Correlate1D, symmetric branch) is
+//     out = in[p]*w[0];  for j = -r .. -1:  out += (in[p+j] + in[p-j]) * w[j]
+// evaluated here in the same order with explicitly rounded double operations (no FMA contraction).
+__global__ void gauss1d_kernel(const double* __restrict__ in, double* __restrict__ out, int H, int W, int axis,
+                               const double* __restrict__ weights, int wstride, const int* __restrict__ radius) {
+  const int field = blockIdx.y;          // slice * 2 + {dx, dy}
+  const int slice = field >> 1;
+  const int r = radius[slice];
+  const double* fw = weights + (long long)slice * wstride + r;  // centre tap
+  const double* src = in + (long long)field * H * W;
+  double* dst = out + (long long)field * H * W;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < H * W; p += gridDim.x * blockDim.x) {
+    const int y = p / W, x = p - y * W;
+    const int pos = axis == 0 ? y : x, len = axis == 0 ? H : W, step = axis == 0 ? W : 1;
+    double acc = __dmul_rn(src[p], fw[0]);
+    for (int j = -r; j < 0; ++j) {
+      const int a = pos + j, b = pos - j;
+      const double va = a >= 0 ? src[p + j * step] : 0.0;
+      const double vb = b < len ? src[p - j * step] : 0.0;
+      acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(va, vb), fw[j]));
+    }
+    dst[p] = acc;
+  }
+}
+
+// one axis of the reference's RegularGridInterpolator on the integer grid arange(n)
+// (regular_grid_interpolator.py:252-270): i = searchsorted(grid, x) - 1 clamped to [0, n-2], t = x - i
+__device__ __forceinline__ void find_index_arange(double x, int n, int* i, double* t, bool* oob) {
+  int k = (int)ceil(fmin(fmax(x, -1.0e9), 1.0e9)) - 1;
+  k = k < 0 ? 0 : (k > n - 2 ? n - 2 : k);
+  *i = k;
+  *t = __dsub_rn(x, (double)k);
+  *oob = (x < 0.0) || (x > (double)(n - 1));
+}
+
+__global__ void elastic_resample_kernel(const float* __restrict__ xin, const unsigned char* __restrict__ yin,
+                                        const double* __restrict__ fields, const double* __restrict__ alpha,
+                                        const float* __restrict__ bg, int H, int W, int C,
+                                        float* __restrict__ xout, unsigned char* __restrict__ yout) {
+  const int slice = blockIdx.y;
+  const double al = alpha[slice];
+  const double* dxf = fields + (long long)(2 * slice) * H * W;
+  const double* dyf = dxf + (long long)H * W;
+  const float* xi = xin + (long long)slice * H * W * C;
+  float* xo = xout + (long long)slice * H * W * C;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < H * W; p += gridDim.x * blockDim.x) {
+    const int r = p / W, c = p - r * W;
+    const double px = __dadd_rn((double)r, __dmul_rn(dxf[p], al));
+    const double py = __dadd_rn((double)c, __dmul_rn(dyf[p], al));
+    int i0, i1;
+    double t0, t1;
+    bool o0, o1;
+    find_index_arange(px, H, &i0, &t0, &o0);
+    find_index_arange(py, W, &i1, &t1, &o1);
+    const bool oob = o0 || o1;
+    // corner weights in itertools.product order, weight = (1. * w_axis0) * w_axis1
+    const double w0[2] = {__dsub_rn(1.0, t0), t0};
+    const double w1[2] = {__dsub_rn(1.0, t1), t1};
+    for (int ch = 0; ch < C; ++ch) {
+      float outv;
+      if (oob) {
+        outv = bg[slice * C + ch];
+      } else {
+        double acc = 0.0;
+#pragma unroll
+        for (int e0 = 0; e0 < 2; ++e0)
+#pragma unroll
+          for (int e1 = 0; e1 < 2; ++e1) {
+            const double w = __dmul_rn(w0[e0], w1[e1]);
+            const double v = (double)xi[((long long)(i0 + e0) * W + (i1 + e1)) * C + ch];
+            acc = __dadd_rn(acc, __dmul_rn(v, w));
+          }
+        outv = __double2float_rn(acc);
+      }
+      xo[(long long)p * C + ch] = outv;
+    }
+    if (yin) {
+      unsigned char lab = 0;
+      if (!oob) {
+        const int j0 = t0 <= 0.5 ? i0 : i0 + 1;
+        const int j1 = t1 <= 0.5 ? i1 : i1 + 1;
+        lab = yin[(long long)slice * H * W + (long long)j0 * W + j1];
+      }
+      yout[(long long)slice * H * W + p] = lab;
+    }
+  }
+}
 }  // namespace
 }  // namespace mpu
 
@@ -539,6 +630,32 @@ int mpu_label_counts(const unsigned char* y_true, const unsigned char* y_pred, c
   label_counts_kernel<<<(int)blocks, 256, 0, st>>>(y_true, scores ? nullptr : y_pred, scores, n, n_classes,
                                                    reinterpret_cast<unsigned long long*>(counts));
   count_launch();
+  MPU_CUDA(cudaGetLastError());
+  return MPU_OK;
+}
+
+int mpu_elastic_2d(const float* x_in, const unsigned char* y_in, double* fields, double* scratch,
+                   const double* d_weights, int weight_stride, const int* d_radius, const double* d_alpha,
+                   const float* d_bg, int n, int H, int W, int C, float* x_out, unsigned char* y_out,
+                   void* stream) {
+  if (!x_in || !fields || !scratch || !d_weights || !d_radius || !d_alpha || !d_bg || !x_out || n < 0 ||
+      H < 2 || W < 2 || C < 1 || (y_in && !y_out)) {
+    set_error("elastic_2d: bad argument (n=%d, H=%d, W=%d, C=%d)", n, H, W, C);
+    return MPU_ERR_ARG;
+  }
+  if (n == 0) return MPU_OK;
+  if (x_in == x_out || (y_in && y_in == y_out)) {
+    set_error("elastic_2d: in-place operation is not supported");
+    return MPU_ERR_ARG;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int bx = (H * W + 255) / 256;
+  if (bx > 148 * 4) bx = 148 * 4;
+  const dim3 gf(bx, 2 * n), gs(bx, n);
+  gauss1d_kernel<<<gf, 256, 0, st>>>(fields, scratch, H, W, 0, d_weights, weight_stride, d_radius);
+  gauss1d_kernel<<<gf, 256, 0, st>>>(scratch, fields, H, W, 1, d_weights, weight_stride, d_radius);
+  elastic_resample_kernel<<<gs, 256, 0, st>>>(x_in, y_in, fields, d_alpha, d_bg, H, W, C, x_out, y_out);
+  count_launch(3);
   MPU_CUDA(cudaGetLastError());
   return MPU_OK;
 }

@@ -53,7 +53,7 @@ class SyntheticImage(object):
 class IsotrophicLiveViewSequence2D(object):
     def __init__(self, images, views, sample_dim, real_space_span, n_classes, batch_size=16,
                  noise_sd=0.1, fg_batch_fraction=0.5, force_all_fg="auto", is_validation=False,
-                 label_crop=None, logger=None, **kwargs):
+                 label_crop=None, logger=None, list_of_augmenters=None, **kwargs):
         self.images = list(images) if isinstance(images, (list, tuple)) else [images]
         self.views = np.asarray(views, dtype=np.float64)
         self.sample_dim = int(sample_dim)
@@ -67,6 +67,17 @@ class IsotrophicLiveViewSequence2D(object):
         self.fg_classes = np.arange(1, self.n_classes)
         self.label_crop = np.zeros((2, 2), dtype=int) if label_crop is None else label_crop
         self.logger = logger or (lambda *a, **k: None)
+        # on-the-fly augmenters (sequences/utils.py:38-47); never applied to validation batches
+        self.list_of_augmenters = None if is_validation else (list(list_of_augmenters or []) or None)
+
+    def augment(self, batch_x, batch_y, batch_w, bg_values):
+        """isotrophic_live_view_sequence.py:130-139: every augmenter sees the scaled batch and the UNSCALED
+        per-image background values (reference behaviour, …_2d.py:195-208)."""
+        if self.list_of_augmenters:
+            for aug in self.list_of_augmenters:
+                batch_x, batch_y, batch_w = aug(batch_x=batch_x, batch_y=batch_y, batch_w=batch_w,
+                                                bg_values=bg_values)
+        return batch_x, batch_y, batch_w
 
     # -- reference properties (isotrophic_live_view_sequence.py:70-90)
     @property
@@ -167,6 +178,9 @@ class IsotrophicLiveViewSequence2D(object):
                     pick = t
                     break
             chosen_bases[s], chosen_offs[s] = cand_bases[s, pick], cand_offs[s, pick]
+        if self.list_of_augmenters and out_padded is not None:
+            raise NotImplementedError("augmenters need the float32 batch: call sample_batch_device() without "
+                                      "out_padded and pack the augmented batch")
         x = torch.empty(B, dim, dim, self.images[0].n_channels, dtype=torch.float32,
                         device=self.images[0].interpolator.device) if out_padded is None else None
         y = torch.empty(B, dim, dim, dtype=torch.uint8, device=self.images[0].interpolator.device)
@@ -186,6 +200,11 @@ class IsotrophicLiveViewSequence2D(object):
                 raise NotImplementedError("direct U-Net input writes need a single resident image per rank")
             y[torch.as_tensor(slots, device=y.device)] = yi
             w[slots] = image.sample_weight
+        if self.list_of_augmenters:
+            bg_values = [self.images[i].interpolator.bg_value for i in im_idx]
+            wl = list(w)
+            x, y, wl = self.augment(x, y, wl, bg_values)
+            w = np.asarray(wl, dtype=np.float32)
         return x, y, w
 
     def __getitem__(self, idx):

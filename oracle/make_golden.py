@@ -62,6 +62,20 @@ def main():
                             vgrid_corner=vgrid[:, :2, :2, :2])
         print("mapping_%s: %s" % (case["name"], np.stack(mapped).shape))
 
+    # ---- Elastic2D: the reference function with numpy's global RNG seeded per case
+    import importlib
+    ed = importlib.import_module("mpunet.augmentation.elastic_deformation")
+    outs = {}
+    for case in gi.ELASTIC_CASES:
+        im, lab = gi.elastic_inputs(case)
+        np.random.seed(case["seed"])
+        o, l = ed.elastic_transform_2d(im.copy(), lab.copy(), case["alpha"], case["sigma"], case["bg"])
+        outs["im_" + case["name"]] = o
+        outs["lab_" + case["name"]] = l
+        print("elastic_%s: mean |delta| %.4f, %d labels moved" % (case["name"], np.abs(o - im).mean(),
+                                                                 int((l != lab).sum())))
+    np.savez_compressed(os.path.join(out_dir, "elastic.npz"), **outs)
+
 
 if __name__ == "__main__":
     main()

@@ -39,3 +39,17 @@ def mapping_inputs(case):
         inv_bases.append(np.linalg.inv(sampler.plane_basis(v)))
     affine = np.diag(list(case["pix"]) + [1.0])
     return preds, grids, inv_bases, case["shape"], affine
+
+
+# ---- Elastic2D (augmentation/elastic_deformation.py) -------------------------------------------------------
+ELASTIC_CASES = [
+    dict(name="mild", H=40, W=48, C=2, alpha=40.0, sigma=3.0, bg=[0.25, -1.0], seed=11),
+    dict(name="strong", H=64, W=56, C=1, alpha=300.0, sigma=6.5, bg=[0.5], seed=12),   # pushes points out of bounds
+]
+
+
+def elastic_inputs(case):
+    rng = np.random.RandomState(100 + case["seed"])
+    im = rng.randn(case["H"], case["W"], case["C"]).astype(np.float32)
+    lab = rng.randint(0, 5, size=(case["H"], case["W"])).astype(np.uint8)
+    return im, lab

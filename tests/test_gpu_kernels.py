@@ -139,3 +139,39 @@ def test_label_counts_and_dice_all_exact():
     cb = label_counts(big_t, big_p, k)
     assert int(cb[1].sum()) == 256 ** 3 and int(cb[2].sum()) == 256 ** 3
     assert torch.equal(cb[0], torch.stack([((big_t == i) & (big_p == i)).sum() for i in range(k)]))
+
+
+def test_elastic_2d_against_reference_goldens_and_oracle():
+    """mpu_elastic_2d: the float64 Gaussian filter / displaced bilinear + nearest resampling against the
+    reference's own outputs (tests/golden/elastic.npz) and the oracle on a 256x256 batch.
+    Bar: labels bit-exact, image within 1 float32 ulp-scale (2e-6 abs on O(1) data) - the device evaluates the
+    same float64 expression order, so equality is expected; the bound only allows for libm/FMA differences in
+    scipy's build."""
+    import os
+    import torch
+    import golden_inputs as gi
+    from multiplanarunet_b200.augmentation import Elastic2D, elastic_transform_2d
+    from oracle import elastic as oe
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "elastic.npz"))
+    for case in gi.ELASTIC_CASES:
+        im, lab = gi.elastic_inputs(case)
+        np.random.seed(case["seed"])
+        o, l = elastic_transform_2d(im, lab, case["alpha"], case["sigma"], case["bg"])
+        assert o.dtype == np.float32 and l.dtype == np.uint8
+        assert np.abs(o - z["im_" + case["name"]]).max() <= 2e-6, case["name"]
+        assert np.array_equal(l, z["lab_" + case["name"]]), case["name"]
+        print("elastic %s: image bit-exact=%s" % (case["name"], np.array_equal(o, z["im_" + case["name"]])))
+    # batch call at the benchmark slice size, YAML default parameter ranges
+    rng = np.random.RandomState(4)
+    B, H, W = 6, 256, 256
+    xs = rng.randn(B, H, W, 1).astype(np.float32)
+    ys = rng.randint(0, 5, size=(B, H, W)).astype(np.uint8)
+    bgs = [[-0.5]] * B
+    np.random.seed(9)
+    ox, oy, ow = oe.Elastic2D([0, 450], [20, 30], 0.5)(list(xs), list(ys), bgs, [1.0] * B, rng=np.random)
+    np.random.seed(9)
+    gx, gy, gw = Elastic2D([0, 450], [20, 30], 0.5)(torch.as_tensor(xs).cuda(), torch.as_tensor(ys).cuda(), bgs,
+                                                   [1.0] * B)
+    assert gw == ow and 0.33 in gw
+    assert np.abs(gx.cpu().numpy() - np.stack(ox)).max() <= 2e-6
+    assert np.array_equal(gy.cpu().numpy(), np.stack(oy))

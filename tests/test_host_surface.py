@@ -95,3 +95,24 @@ def test_unet_filter_rule_and_param_count():
     assert unet_filters(4, 2) == [90, 181, 362, 724, 1448]   # int(64 * 2**i * sqrt(2)), unet.py:91,120
     assert unet_filters(4, 1) == [64, 128, 256, 512, 1024]
     assert count_params(init_params(5, 1, 4, 2.0)) == 62050512  # 62.05 M trainable at cf=2
+
+
+def test_augmenter_registry_and_argument_errors():
+    """Elastic2D is looked up by name from the YAML (sequences/utils.py:38-47) and validates its arguments like
+    the reference (augmentation/augmenters.py:41-55); without a GPU the call itself fails loudly."""
+    import pytest
+    from multiplanarunet_b200 import augmentation
+    aug = augmentation.__dict__["Elastic2D"](alpha=[0, 450], sigma=[20, 30], apply_prob=0.333)
+    assert str(aug) == "Elastic2D(alpha=[0, 450], sigma=[20, 30], apply_prob=0.333)"
+    assert aug.weight == 0.33
+    for bad in (dict(alpha=[1, 2, 3], sigma=1, apply_prob=0.5), dict(alpha=[5, 1], sigma=1, apply_prob=0.5),
+                dict(alpha=1, sigma=[3, 3], apply_prob=0.5), dict(alpha=1, sigma=2, apply_prob=1.5)):
+        with pytest.raises(ValueError):
+            augmentation.Elastic2D(**bad)
+    from multiplanarunet_b200.augmentation.elastic_deformation import gaussian_taps
+    w, r = gaussian_taps(25.0)
+    assert r == 100 and len(w) == 201 and abs(w.sum() - 1) < 1e-12 and np.array_equal(w, w[::-1])
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            augmentation.elastic_transform_2d(np.zeros((8, 8), np.float32), None, 1.0, 1.0)

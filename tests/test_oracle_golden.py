@@ -107,3 +107,19 @@ def test_validation_counts_and_dice():
         assert abs(dc[c] - 2 * tp[c] / float(rel[c] + sel[c])) < 1e-6
     pr, rc, dc = om.compute_dice(np.array([0, 3]), np.array([0, 4]), np.array([0, 3]))
     assert pr[0] == rc[0] == dc[0] == 0 and abs(dc[1] - 2 * 1.0 * 0.75 / 1.75) < 1e-6
+
+
+def test_elastic_matches_reference_goldens():
+    """oracle/elastic.py against tests/golden/elastic.npz (outputs of the unmodified reference function with
+    numpy's global generator seeded): image bit-exact, labels bit-exact."""
+    import golden_inputs as gi
+    from oracle import elastic
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "elastic.npz"))
+    for case in gi.ELASTIC_CASES:
+        im, lab = gi.elastic_inputs(case)
+        np.random.seed(case["seed"])
+        o, l = elastic.elastic_transform_2d(im, lab, case["alpha"], case["sigma"], case["bg"], rng=np.random)
+        assert np.array_equal(o, z["im_" + case["name"]]), case["name"]
+        assert np.array_equal(l, z["lab_" + case["name"]]), case["name"]
+    # the strong case must exercise the out-of-bounds fill
+    assert np.any(z["im_strong"] == np.float32(0.5))

@@ -99,3 +99,31 @@ def test_dice_all_equals_reference():
         got = om.dice_all(a, b, n_classes=n_classes, **kw)
         assert np.array_equal(want, got, equal_nan=True)
     assert rm.dice(a > 1, b > 2) == om.dice(a > 1, b > 2)
+
+
+def test_elastic_augmenter_equals_reference():
+    """Elastic2D batch call: same mask / alpha / sigma / noise draw order as augmentation/augmenters.py:87-109."""
+    from oracle import elastic, ref_shim
+    ref_shim.install()
+    import importlib
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ra = importlib.import_module("mpunet.augmentation.augmenters")
+    rng = np.random.RandomState(7)
+    xs = [rng.randn(24, 20, 1).astype(np.float32) for _ in range(6)]
+    ys = [rng.randint(0, 3, size=(24, 20)).astype(np.uint8) for _ in range(6)]
+    bgs = [[0.1 * i] for i in range(6)]
+    np.random.seed(3)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        rx, ry, rw = ra.Elastic2D(alpha=[0, 60], sigma=[2, 4], apply_prob=0.5)(
+            batch_x=[x.copy() for x in xs], batch_y=[y.copy() for y in ys], bg_values=bgs, batch_w=[1.0] * 6)
+    np.random.seed(3)
+    ox, oy, ow = elastic.Elastic2D(alpha=[0, 60], sigma=[2, 4], apply_prob=0.5)(
+        [x.copy() for x in xs], [y.copy() for y in ys], bgs, [1.0] * 6, rng=np.random)
+    assert rw == ow and 0.33 in ow and 1.0 in ow
+    for a, b in zip(rx, ox):
+        assert np.array_equal(a, b)
+    for a, b in zip(ry, oy):
+        assert np.array_equal(a, b)
