@@ -289,7 +289,18 @@ def main():
     check(lib.mpu_profile_gemm_read(ctypes.byref(gemm_ms), ctypes.byref(n_l)))
     check(lib.mpu_profile_gemm(0))
     if rank == 0:
-        flops = 3.0 * FWD_GFLOP_PER_SLICE.get(args.cf, 0.0) * 1e9 * (dim / 256.0) ** 2 * B
+        # algorithmic FLOPs executed by the tensor-core GEMM kernels: 3x forward minus the first conv
+        # (CUDA-core kernels, no input gradient) and the 1x1 head (fused softmax/CE kernel)
+        non_gemm = {2.0: 0.106 + 0.059, 1.0: 0.075 + 0.042}.get(args.cf, 0.0)
+        flops = 3.0 * (FWD_GFLOP_PER_SLICE.get(args.cf, 0.0) - non_gemm) * 1e9 * (dim / 256.0) ** 2 * B
+        # DRAM bytes per GEMM launch from the committed ncu pass over one train step (profiles/)
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")))
+            if args.cf == 2.0 and dim == 256 and B == 32:
+                traffic = tr["gemm_dram_bytes_per_launch"]
+        except Exception:
+            pass
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -301,7 +312,9 @@ def main():
             peak, src = 1400.0, "fallback (B200_PROFILING.md sustained figure)"
         ach = flops / (gemm_ms.value * 1e-3) / 1e12 if gemm_ms.value > 0 else None
         roofline = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                    "frac": (ach / peak) if ach else None, "traffic": None,
+                    "frac": (ach / peak) if ach else None, "traffic": traffic,
+                    "traffic_note": "mean dram__bytes_read+write per GEMM launch, ncu pass over one train step "
+                                    "(profiles/r01_gemm_traffic.json)" if traffic else None,
                     "kernels": "mtgemm_fwd_kernel + mtgemm_wgrad_kernel (%d launches/step, %.2f ms/step)" % (
                         n_l.value, gemm_ms.value),
                     "algorithmic_flops_per_step": flops, "peak_source": src}

@@ -1,6 +1,6 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-timeout 600 python -W ignore -m pytest tests -x -q -m gpu -s > gpurun_out/pytest_gpu.log 2>&1
-echo "pytest rc=$?"
-grep -E "elastic|passed|failed|Error|error|assert" gpurun_out/pytest_gpu.log | tail -n 25
+timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 3 > gpurun_out/bench_n2.log 2>&1
+echo "rc=$?"
+tail -n 1 gpurun_out/bench_n2.log | cut -c1-1500
