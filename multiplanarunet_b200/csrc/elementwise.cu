@@ -433,13 +433,17 @@ __global__ void bn_bwd_params_kernel(const double* __restrict__ sums, const floa
 }
 
 // ---- first conv (CUDA cores) -------------------------------------------------------------------------
-// thread = pixel: the 9 x CIN inputs sit in registers, the weights in shared memory as fp32
-// [9*CIN][co_phys] and are read as warp-wide broadcasts; all output channels of the pixel are produced
-// 8 at a time (one 16-byte store each).
+// thread = a column of kRows vertically adjacent pixels: their (kRows+2) x 3 x CIN inputs sit in registers, the
+// weights in shared memory as fp32 [9*CIN][co_phys] and are read as warp-wide broadcasts - one pair of 16-byte
+// weight reads now feeds kRows x 8 FMAs (the one-pixel version was bound by the shared-memory pipe); output
+// channels are produced 8 at a time (one 16-byte store per pixel).
+constexpr int kFirstRows = 4;
+
 template <int CIN>
 __global__ void conv_first_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
                                   const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, Geo g,
                                   int co_phys) {
+  constexpr int R = kFirstRows;
   extern __shared__ float4 cw4[];  // [9*CIN][co_phys] + bias[co_phys]
   float* cw = reinterpret_cast<float*>(cw4);
   for (int i = threadIdx.x; i < 9 * CIN * co_phys; i += blockDim.x) {
@@ -453,48 +457,72 @@ __global__ void conv_first_kernel(const __nv_bfloat16* __restrict__ x, const __n
   __syncthreads();
   const int CG = co_phys / 8;
   const int Wp = g.W + 2;
+  const int bands = (g.H + R - 1) / R;
   SegIter it;
-  it.init(blockIdx.x, gridDim.x, g.H, (g.W + blockDim.x - 1) / blockDim.x);
+  it.init(blockIdx.x, gridDim.x, bands, (g.W + blockDim.x - 1) / blockDim.x);
   for (; it.n < g.B; it.next()) {
     const int xx = it.seg * blockDim.x + threadIdx.x;
     if (xx >= g.W) continue;
-    const long long row = ((long long)it.n * (g.H + 2) + it.yy + 1) * Wp + xx + 1;
-    float xs[9 * CIN];
+    const int y0 = it.yy * R;  // first image row of the band
+    // padded row of pixel (y0 - 1, xx - 1): top-left input of the band's first pixel
+    const long long row0 = ((long long)it.n * (g.H + 2) + y0) * Wp + xx;
+    float xs[R + 2][3 * CIN];
 #pragma unroll
-    for (int tap = 0; tap < 9; ++tap) {
-      const long long r = row + (tap / 3 - 1) * Wp + (tap % 3 - 1);
-      if (CIN == 1) {
-        xs[tap] = __bfloat162float(x[r * 8]);
-      } else {
-        const Vec8 xv = load8(x + r * 8);
+    for (int r = 0; r < R + 2; ++r) {
+      const bool live = y0 + r - 1 <= g.H;  // rows past the bottom border belong to the next image
 #pragma unroll
-        for (int ci = 0; ci < CIN; ++ci) xs[tap * CIN + ci] = xv.v[ci];
+      for (int dx = 0; dx < 3; ++dx) {
+        const long long rr = row0 + (long long)r * Wp + dx;
+        if (CIN == 1) {
+          xs[r][dx] = live ? __bfloat162float(x[rr * 8]) : 0.f;
+        } else {
+          Vec8 xv;
+          if (live) xv = load8(x + rr * 8);
+#pragma unroll
+          for (int ci = 0; ci < CIN; ++ci) xs[r][dx * CIN + ci] = live ? xv.v[ci] : 0.f;
+        }
       }
     }
     for (int cg = 0; cg < CG; ++cg) {
-      Vec8 acc;
+      float acc[R][8];
       {
         const float4 b0 = *reinterpret_cast<const float4*>(sb + cg * 8);
         const float4 b1 = *reinterpret_cast<const float4*>(sb + cg * 8 + 4);
-        acc.v[0] = b0.x; acc.v[1] = b0.y; acc.v[2] = b0.z; acc.v[3] = b0.w;
-        acc.v[4] = b1.x; acc.v[5] = b1.y; acc.v[6] = b1.z; acc.v[7] = b1.w;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          acc[r][0] = b0.x; acc[r][1] = b0.y; acc[r][2] = b0.z; acc[r][3] = b0.w;
+          acc[r][4] = b1.x; acc[r][5] = b1.y; acc[r][6] = b1.z; acc[r][7] = b1.w;
+        }
       }
 #pragma unroll
-      for (int k = 0; k < 9 * CIN; ++k) {
-        const float4 w0 = *reinterpret_cast<const float4*>(cw + k * co_phys + cg * 8);
-        const float4 w1 = *reinterpret_cast<const float4*>(cw + k * co_phys + cg * 8 + 4);
-        acc.v[0] = fmaf(xs[k], w0.x, acc.v[0]);
-        acc.v[1] = fmaf(xs[k], w0.y, acc.v[1]);
-        acc.v[2] = fmaf(xs[k], w0.z, acc.v[2]);
-        acc.v[3] = fmaf(xs[k], w0.w, acc.v[3]);
-        acc.v[4] = fmaf(xs[k], w1.x, acc.v[4]);
-        acc.v[5] = fmaf(xs[k], w1.y, acc.v[5]);
-        acc.v[6] = fmaf(xs[k], w1.z, acc.v[6]);
-        acc.v[7] = fmaf(xs[k], w1.w, acc.v[7]);
-      }
+      for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc.v[j] = fmaxf(acc.v[j], 0.f);
-      store8(out + row * co_phys + cg * 8, acc);
+        for (int k = 0; k < 3 * CIN; ++k) {
+          const float* wr = cw + ((ky * 3) * CIN + k) * co_phys + cg * 8;  // tap (ky, k / CIN), channel k % CIN
+          const float4 w0 = *reinterpret_cast<const float4*>(wr);
+          const float4 w1 = *reinterpret_cast<const float4*>(wr + 4);
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const float xv = xs[r + ky][k];
+            acc[r][0] = fmaf(xv, w0.x, acc[r][0]);
+            acc[r][1] = fmaf(xv, w0.y, acc[r][1]);
+            acc[r][2] = fmaf(xv, w0.z, acc[r][2]);
+            acc[r][3] = fmaf(xv, w0.w, acc[r][3]);
+            acc[r][4] = fmaf(xv, w1.x, acc[r][4]);
+            acc[r][5] = fmaf(xv, w1.y, acc[r][5]);
+            acc[r][6] = fmaf(xv, w1.z, acc[r][6]);
+            acc[r][7] = fmaf(xv, w1.w, acc[r][7]);
+          }
+        }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        if (y0 + r < g.H) {
+          Vec8 o;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o.v[j] = fmaxf(acc[r][j], 0.f);
+          store8(out + (row0 + (long long)(r + 1) * Wp + 1) * co_phys + cg * 8, o);
+        }
+      }
     }
   }
 }
@@ -988,7 +1016,7 @@ int launch_conv_first(const __nv_bfloat16* x, const __nv_bfloat16* w, const floa
   }
   int threads = ((g.W + 31) / 32) * 32;
   if (threads > 256) threads = 256;
-  const long long items = (long long)g.B * g.H * ((g.W + threads - 1) / threads);
+  const long long items = (long long)g.B * ((g.H + kFirstRows - 1) / kFirstRows) * ((g.W + threads - 1) / threads);
 #define MPU_CONV_FIRST(CIN)                                                                        \
   conv_first_kernel<CIN><<<resident_grid(conv_first_kernel<CIN>, threads, smem, items), threads, smem, st>>>( \
       x, w, bias, out, g, co_phys)

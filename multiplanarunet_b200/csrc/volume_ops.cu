@@ -7,6 +7,7 @@
 //   * fusion-layer training step (evaluate/loss_functions.py:207-246, models/fusion_model.py:9-11)
 // Index math is float64 in the reference's operation order (explicit _rn intrinsics: no FMA
 // contraction) so gathers are bit-exact; see oracle/sampler.py and oracle/fusion.py.
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -170,87 +171,133 @@ struct MapFuseParams {
   float* combined_out;               // [V][X][Y][Z][C] or null
 };
 
-__global__ void map_fuse_kernel(const MapFuseParams p) {
-  const long long total = (long long)p.X * p.Y * p.Z;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int k = (int)(idx % p.Z);
-    const long long t0 = idx / p.Z;
-    const int j = (int)(t0 % p.Y);
-    const int i = (int)(t0 / p.Y);
-    double xr[3];
-    xr[0] = __dsub_rn(dot3(p.affine + 0, (double)i, (double)j, (double)k), p.mean[0]);
-    xr[1] = __dsub_rn(dot3(p.affine + 3, (double)i, (double)j, (double)k), p.mean[1]);
-    xr[2] = __dsub_rn(dot3(p.affine + 6, (double)i, (double)j, (double)k), p.mean[2]);
-    float z[kMaxClasses];
+// Persistent blocks walk (i, j) lines of the voxel grid, threads walk k: no per-voxel integer division.  The
+// axis tables every lookup reads (in-plane axis, per-view plane offsets) and the fusion weights are staged in
+// shared memory once per block when they fit (SMEM), else read through L1.  NC > 0: class count known at
+// compile time (loops fully unrolled without predication); NC == 0: generic, up to kMaxClasses.
+template <int NC, bool SMEM>
+__global__ void __launch_bounds__(256) map_fuse_kernel(const MapFuseParams p) {
+  constexpr int MC = NC > 0 ? NC : kMaxClasses;
+  const int C = NC > 0 ? NC : p.C;
+  extern __shared__ double mf_sm[];
+  const double* ax = p.ax;
+  const double* offs = p.offsets;
+  const double* ibv = p.inv_basis;
+  if (SMEM) {
+    double* s_ax = mf_sm;
+    double* s_off = s_ax + p.dim;
+    double* s_ib = s_off + p.V * p.n_planes;
+    for (int t = threadIdx.x; t < p.dim; t += blockDim.x) s_ax[t] = p.ax[t];
+    for (int t = threadIdx.x; t < p.V * p.n_planes; t += blockDim.x) s_off[t] = p.offsets[t];
+    for (int t = threadIdx.x; t < p.V * 9; t += blockDim.x) s_ib[t] = p.inv_basis[t];
+    __syncthreads();
+    ax = s_ax;
+    offs = s_off;
+    ibv = s_ib;
+  }
+  const long long plane = (long long)p.Y * p.Z;
+  const long long total = (long long)p.X * plane;
+  const int lines = p.X * p.Y;
+  for (int line = blockIdx.x; line < lines; line += gridDim.x) {
+    const int i = line / p.Y, j = line - i * p.Y;
+    for (int k = threadIdx.x; k < p.Z; k += blockDim.x) {
+      const long long idx = (long long)line * p.Z + k;
+      double xr[3];
+      xr[0] = __dsub_rn(dot3(p.affine + 0, (double)i, (double)j, (double)k), p.mean[0]);
+      xr[1] = __dsub_rn(dot3(p.affine + 3, (double)i, (double)j, (double)k), p.mean[1]);
+      xr[2] = __dsub_rn(dot3(p.affine + 6, (double)i, (double)j, (double)k), p.mean[2]);
+      float z[MC];
 #pragma unroll
-    for (int c = 0; c < kMaxClasses; ++c) z[c] = 0.f;
-    for (int v = 0; v < p.V; ++v) {
-      const double* ib = p.inv_basis + v * 9;
-      double q[3];
-      q[0] = dot3(ib + 0, xr[0], xr[1], xr[2]);
-      q[1] = dot3(ib + 3, xr[0], xr[1], xr[2]);
-      q[2] = dot3(ib + 6, xr[0], xr[1], xr[2]);
-      const double* off = p.offsets + (size_t)v * p.n_planes;
-      int sel[3];
-      bool oob = false;
-      for (int a = 0; a < 3; ++a) {
-        const double* g = a < 2 ? p.ax : off;
-        const int n = a < 2 ? p.dim : p.n_planes;
-        const double inv = a < 2 ? p.inv_step_ax : p.inv_step_off[v];
-        const int c = find_cell(g, n, q[a], inv);
-        sel[a] = lower_half(__dsub_rn(q[a], g[c]), __dsub_rn(g[c + 1], g[c])) ? c : c + 1;
-        oob = oob || q[a] < g[0] || q[a] > g[n - 1];
-      }
-      const float* src = p.pred[v] + (((long long)sel[2] * p.dim + sel[0]) * p.dim + sel[1]) * p.C;
+      for (int c = 0; c < MC; ++c) z[c] = 0.f;
+      for (int v = 0; v < p.V; ++v) {
+        const double* ib = ibv + v * 9;
+        double q[3];
+        q[0] = dot3(ib + 0, xr[0], xr[1], xr[2]);
+        q[1] = dot3(ib + 3, xr[0], xr[1], xr[2]);
+        q[2] = dot3(ib + 6, xr[0], xr[1], xr[2]);
+        const double* off = offs + (size_t)v * p.n_planes;
+        int sel[3];
+        bool oob = false;
 #pragma unroll
-      for (int c = 0; c < kMaxClasses; ++c) {
-        if (c < p.C) {
-          const float x = oob ? (c == 0 ? 1.f : 0.f) : __ldg(src + c);
-          if (p.combined_out) p.combined_out[((long long)v * total + idx) * p.C + c] = x;
-          if (p.sum_fusion) z[c] = __fadd_rn(z[c], x);
-          else z[c] = __fadd_rn(z[c], __fmul_rn(p.W[v * p.C + c], x));
+        for (int a = 0; a < 3; ++a) {
+          const double* g = a < 2 ? ax : off;
+          const int n = a < 2 ? p.dim : p.n_planes;
+          const double inv = a < 2 ? p.inv_step_ax : p.inv_step_off[v];
+          const int c = find_cell(g, n, q[a], inv);
+          sel[a] = lower_half(__dsub_rn(q[a], g[c]), __dsub_rn(g[c + 1], g[c])) ? c : c + 1;
+          oob = oob || q[a] < g[0] || q[a] > g[n - 1];
+        }
+        const float* src = p.pred[v] + (((long long)sel[2] * p.dim + sel[0]) * p.dim + sel[1]) * C;
+#pragma unroll
+        for (int c = 0; c < MC; ++c) {
+          if (NC > 0 || c < C) {
+            const float x = oob ? (c == 0 ? 1.f : 0.f) : __ldg(src + c);
+            if (p.combined_out) p.combined_out[((long long)v * total + idx) * C + c] = x;
+            if (p.sum_fusion) z[c] = __fadd_rn(z[c], x);
+            else z[c] = __fadd_rn(z[c], __fmul_rn(__ldg(p.W + v * C + c), x));
+          }
         }
       }
-    }
-    float pr[kMaxClasses];
-    if (p.sum_fusion) {
+      float pr[MC];
+      if (p.sum_fusion) {
 #pragma unroll
-      for (int c = 0; c < kMaxClasses; ++c) pr[c] = z[c];
-    } else {
-      float m = -INFINITY;
+        for (int c = 0; c < MC; ++c) pr[c] = z[c];
+      } else {
+        float m = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < kMaxClasses; ++c)
-        if (c < p.C) {
-          z[c] = __fadd_rn(z[c], p.b[c]);
-          m = fmaxf(m, z[c]);
-        }
-      float s = 0.f;
+        for (int c = 0; c < MC; ++c)
+          if (NC > 0 || c < C) {
+            z[c] = __fadd_rn(z[c], __ldg(p.b + c));
+            m = fmaxf(m, z[c]);
+          }
+        float sum = 0.f;
 #pragma unroll
-      for (int c = 0; c < kMaxClasses; ++c)
-        if (c < p.C) {
-          pr[c] = expf(__fsub_rn(z[c], m));
-          s = __fadd_rn(s, pr[c]);
-        }
+        for (int c = 0; c < MC; ++c)
+          if (NC > 0 || c < C) {
+            pr[c] = expf(__fsub_rn(z[c], m));
+            sum = __fadd_rn(sum, pr[c]);
+          }
 #pragma unroll
-      for (int c = 0; c < kMaxClasses; ++c)
-        if (c < p.C) pr[c] = __fdiv_rn(pr[c], s);
-    }
-    int best = 0;
-    float bv = pr[0];
-#pragma unroll
-    for (int c = 1; c < kMaxClasses; ++c)
-      if (c < p.C && pr[c] > bv) {
-        bv = pr[c];
-        best = c;
+        for (int c = 0; c < MC; ++c)
+          if (NC > 0 || c < C) pr[c] = __fdiv_rn(pr[c], sum);
       }
-    if (p.labels_out) p.labels_out[idx] = (uint8_t)best;
-    if (p.probs_out) {
+      int best = 0;
+      float bv = pr[0];
 #pragma unroll
-      for (int c = 0; c < kMaxClasses; ++c)
-        if (c < p.C) p.probs_out[idx * p.C + c] = pr[c];
+      for (int c = 1; c < MC; ++c)
+        if ((NC > 0 || c < C) && pr[c] > bv) {
+          bv = pr[c];
+          best = c;
+        }
+      if (p.labels_out) p.labels_out[idx] = (uint8_t)best;
+      if (p.probs_out) {
+#pragma unroll
+        for (int c = 0; c < MC; ++c)
+          if (NC > 0 || c < C) p.probs_out[idx * C + c] = pr[c];
+      }
     }
   }
+}
+
+template <int NC>
+int launch_map_fuse(const MapFuseParams& p, cudaStream_t st) {
+  const size_t smem = sizeof(double) * ((size_t)p.dim + (size_t)p.V * p.n_planes + (size_t)p.V * 9);
+  const int lines = p.X * p.Y;
+  int occ = 1;
+  if (smem <= 40 * 1024) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, map_fuse_kernel<NC, true>, 256, smem) != cudaSuccess)
+      occ = 1;
+    const int grid = std::max(1, std::min(lines, 148 * std::max(occ, 1)));
+    map_fuse_kernel<NC, true><<<grid, 256, smem, st>>>(p);
+  } else {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, map_fuse_kernel<NC, false>, 256, 0) != cudaSuccess)
+      occ = 1;
+    const int grid = std::max(1, std::min(lines, 148 * std::max(occ, 1)));
+    map_fuse_kernel<NC, false><<<grid, 256, 0, st>>>(p);
+  }
+  count_launch();
+  MPU_CUDA(cudaGetLastError());
+  return MPU_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -578,11 +625,20 @@ int mpu_map_fuse(const void* const* h_pred_ptrs, int V, int C, int dim, int n_pl
   p.labels_out = labels_out;
   p.probs_out = probs_out;
   p.combined_out = combined_out;
-  const long long total = (long long)p.X * p.Y * p.Z;
-  map_fuse_kernel<<<grid_for(total, 256), 256, 0, st>>>(p);
-  count_launch();
-  MPU_CUDA(cudaGetLastError());
-  return MPU_OK;
+  if ((long long)p.X * p.Y > 0x7fffffffLL) {
+    set_error("mpu_map_fuse: volume too large");
+    return MPU_ERR_ARG;
+  }
+  switch (C) {
+    case 2: return launch_map_fuse<2>(p, st);
+    case 3: return launch_map_fuse<3>(p, st);
+    case 4: return launch_map_fuse<4>(p, st);
+    case 5: return launch_map_fuse<5>(p, st);
+    case 6: return launch_map_fuse<6>(p, st);
+    case 7: return launch_map_fuse<7>(p, st);
+    case 8: return launch_map_fuse<8>(p, st);
+    default: return launch_map_fuse<0>(p, st);
+  }
 }
 
 int mpu_fusion_grad(const float* X, const unsigned char* y, long long n, int V, int C, const float* W,
