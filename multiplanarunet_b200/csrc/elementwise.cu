@@ -972,7 +972,7 @@ int launch_bn_bwd(const BnBwdArgs& a, const double* sums_in, double* sums_out, _
   const int U = POOL ? 1 : 2;
   const long long items =
       (long long)a.g.B * (POOL ? a.g.H / 2 : a.g.H) * (((POOL ? a.g.W / 2 : a.g.W) + U * RL - 1) / (U * RL));
-  const size_t smem = sizeof(float) * 2 * RL * CG * 8;
+  const size_t smem = sizeof(float) * (APPLY ? 1 : 2) * RL * CG * 8;
   const int grid = resident_grid(bn_bwd_kernel<POOL, APPLY>, threads, smem, items);
   bn_bwd_kernel<POOL, APPLY><<<grid, threads, smem, st>>>(a, CG, RL, sums_in, sums_out, dz, phase_major, dbias);
   count_launch();

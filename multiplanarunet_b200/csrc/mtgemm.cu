@@ -559,6 +559,7 @@ int num_sms() {
 }
 
 static int g_fwd_attr_set = 0, g_wgrad_attr_set = 0;
+static constexpr int kDefaultSmemReserveKB = 0;
 static constexpr int kDynSmem = 232448 - 1024;  // leave room for static smem (none) and the driver
 
 int pick_bn(int n_valid) { return (n_valid + 15) / 16 * 16 > 256 ? 256 : (n_valid + 15) / 16 * 16; }
@@ -643,13 +644,27 @@ int fwd_setup(FwdParams& p, const FwdDesc& d) {
   return MPU_OK;
 }
 
+// Shared memory the GEMM CTAs leave free on their SM so that blocks of the HBM-bound elementwise kernels running
+// on the other stream can be co-resident (tensor pipe and LSU then work at the same time).
+static int smem_reserve() {
+  static int r = -1;
+  if (r < 0) {
+    const char* e = getenv("MPU_SMEM_RESERVE_KB");
+    r = (e ? atoi(e) : kDefaultSmemReserveKB) * 1024;
+    if (r < 0) r = 0;
+    if (r > 96 * 1024) r = 96 * 1024;
+  }
+  return r;
+}
+
 int launch_fwd(FwdParams& p, cudaStream_t stream) {
   const int fixed = 2 * (int)kStageHalfBytes + 1024;  // epilogue staging + row table
+  const int budget = kSmemBudget - smem_reserve();
   int NA = 2;
-  int NW = (kSmemBudget - fixed - NA * (int)kSlabBytes) / (int)kWTileBytes;
+  int NW = (budget - fixed - NA * (int)kSlabBytes) / (int)kWTileBytes;
   if (const char* e = getenv("MPU_FWD_NA")) {  // bring-up overrides
     NA = atoi(e);
-    NW = (kSmemBudget - fixed - NA * (int)kSlabBytes) / (int)kWTileBytes;
+    NW = (budget - fixed - NA * (int)kSlabBytes) / (int)kWTileBytes;
   }
   if (NW > 8) NW = 8;
   if (NA < 1 || NW < 2) {
@@ -668,7 +683,7 @@ int launch_fwd(FwdParams& p, cudaStream_t stream) {
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   gemm_timer_begin(stream);
-  mtgemm_fwd_kernel<<<grid, kFwdThreads, kDynSmem, stream>>>(p);
+  mtgemm_fwd_kernel<<<grid, kFwdThreads, kDynSmem - smem_reserve(), stream>>>(p);
   gemm_timer_end(stream);
   count_launch();
   MPU_CUDA(cudaGetLastError());
@@ -739,8 +754,12 @@ int wgrad_setup(WgradParams& p, const WgradDesc& d) {
 
 int launch_wgrad(WgradParams& p, cudaStream_t stream) {
   const int stage_bytes = (int)kWgABytes + p.CA * (int)kWgAtomBytes;
-  int S = kSmemBudget / stage_bytes;
+  int S = (kSmemBudget - smem_reserve()) / stage_bytes;
   if (S > 8) S = 8;
+  if (S < 2) {
+    set_error("launch_wgrad: not enough shared memory for 2 stages");
+    return MPU_ERR_ARG;
+  }
   p.stages = S;
   if (!g_wgrad_attr_set) {
     MPU_CUDA(cudaFuncSetAttribute(mtgemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -749,7 +768,7 @@ int launch_wgrad(WgradParams& p, cudaStream_t stream) {
   }
   const int grid = p.ci_tiles * p.co_tiles * p.ngroups * p.splits;
   gemm_timer_begin(stream);
-  mtgemm_wgrad_kernel<<<grid, kThreads, kDynSmem, stream>>>(p);
+  mtgemm_wgrad_kernel<<<grid, kThreads, kDynSmem - smem_reserve(), stream>>>(p);
   gemm_timer_end(stream);
   count_launch();
   MPU_CUDA(cudaGetLastError());
