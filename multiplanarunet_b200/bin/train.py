@@ -5,7 +5,6 @@ training semantics (Adam, sparse CE x sample weight, FG-balanced random oblique 
 validation dice driving ReduceLROnPlateau / best-checkpoint / early stopping with the YAML presets);
 the Keras fit loop is replaced by a thin step loop over the device sampler and the CUDA train step.
 Launch under torchrun for multi-GPU (one process per GPU, NCCL gradient all-reduce)."""
-import csv
 import math
 import os
 import shutil
@@ -60,23 +59,6 @@ def load_or_create_views(project_dir, n_views, continue_training):
     views = sample_random_views_with_angle_restriction(n_views, 60)
     np.savez(path, views)
     return views
-
-
-def validation_dice(model, seq, n_images, n_classes):
-    """Epoch-end validation like callbacks/validation.py:91-230: sample validation batches, accumulate
-    TP / relevant / selected per class on the device (mpu_label_counts), return the mean foreground dice
-    (background ignored, `ignore_class_zero`)."""
-    from ..evaluate import compute_dice, label_counts
-    counts = None
-    steps = max(1, int(math.ceil(n_images / seq.batch_size)))
-    for _ in range(steps):
-        x, y, _ = seq.sample_batch_device()
-        probs = model.predict_on_batch(x, as_numpy=False)
-        counts = label_counts(y, probs, n_classes, counts=counts)
-    c = counts.cpu().numpy()
-    # validation.py:213-215 passes sel=relevant, rel=selected; dice is symmetric in the two
-    _, _, dices = compute_dice(tp=c[0], rel=c[2], sel=c[1])
-    return float(np.mean(dices[1:])) if n_classes > 1 else float(dices[0])
 
 
 def run(project_dir, args):
@@ -149,56 +131,80 @@ def run(project_dir, args):
     os.makedirs(os.path.join(project_dir, "logs"), exist_ok=True)
     init_epoch = 0
     if args.continue_training:
-        last, init_epoch = get_last_model(os.path.join(project_dir, "model"))
+        # models/model_init.py:25-51: last checkpoint, its epoch (or the CSV's last epoch), the LR logged there
+        from ..utils.utils import clear_csv_after_epoch, get_last_epoch, get_lr_at_epoch
+        last, epoch = get_last_model(os.path.join(project_dir, "model"))
         if last:
             model.load_weights(last)
-            log("[NOTICE] Continuing from %s (epoch %d)" % (last, init_epoch))
+        csv_file = os.path.join(project_dir, "logs", "training.csv")
+        if epoch == 0:
+            epoch = get_last_epoch(csv_file)
+        elif rank == 0:
+            clear_csv_after_epoch(epoch, csv_file)
+        if world > 1:
+            torch.distributed.barrier()
+        init_epoch = epoch + 1
+        lr, _ = get_lr_at_epoch(epoch, os.path.join(project_dir, "logs"))
+        if lr:
+            model.optimizer.lr = lr
+        log("[NOTICE] Training continues from:\nModel: %s\nEpoch: %i\nLR:    %s"
+            % (os.path.split(last)[-1] if last else "<No model found>", epoch, lr))
     dp = D.DataParallel(model)
 
     n_epochs = args.epochs or int(fit["n_epochs"])
     steps = int(math.ceil(args.train_images_per_epoch / (bs * world)))
-    cbs = {c["nickname"]: c.get("kwargs", {}) for c in fit.get("callbacks", []) if isinstance(c, dict)}
-    rlop, es = cbs.get("rlop"), cbs.get("es")
-    best, wait_lr, wait_es, best_path = -1.0, 0, 0, None
-    csv_path = os.path.join(project_dir, "logs", "training.csv")
+
+    # ---- callbacks (train/trainer.py:180-232): Validation first, then the YAML list, FGBatchBalancer, divider
+    from ..callbacks import (DividerLine, FGBatchBalancer, Validation, init_callback_objects,
+                             remove_validation_callbacks)
+    cb_descr = [dict(c) for c in fit.get("callbacks", []) if isinstance(c, dict)]
+    if rank != 0:  # files are written by rank 0 only
+        cb_descr = [c for c in cb_descr if c["class_name"] not in ("ModelCheckPointClean", "CSVLogger",
+                                                                     "TensorBoard")]
+    if va_seq is None:
+        remove_validation_callbacks(cb_descr, log)
+        callbacks = list(cb_descr)
+    else:
+        val_steps = max(1, int(math.ceil(args.val_images_per_epoch / bs)))
+        callbacks = [Validation(va_seq, steps=val_steps, logger=log, verbose=bool(fit.get("verbose", True)),
+                                ignore_class_zero=bool(fit.get("val_ignore_class_zero", True)))] + cb_descr
+    callbacks.append(FGBatchBalancer(tr_seq, logger=log))
+    callbacks.append(DividerLine(log))
+    cwd = os.getcwd()
+    os.chdir(project_dir)  # the YAML's callback paths are relative to the project (bin/train.py:398)
+    callbacks, cb_dict = init_callback_objects(callbacks, log)
+    if "CSVLogger" in cb_dict and args.continue_training:
+        cb_dict["CSVLogger"].append = True
+    for cb in callbacks:
+        cb.set_model(model)
+    model.stop_training = False
     try:
+        for cb in callbacks:
+            cb.on_train_begin()
         for epoch in range(init_epoch, n_epochs):
+            for cb in callbacks:
+                cb.on_epoch_begin(epoch)
             losses = []
             for _ in range(steps):
                 x, y, w = tr_seq.sample_batch_device()
                 losses.append(dp.train_on_batch(x, y, torch.as_tensor(w)))
-            logs = {"epoch": epoch, "loss": float(np.mean(losses)), "lr": model.optimizer.lr}
-            if va_seq is not None:
-                vd = validation_dice(model, va_seq, args.val_images_per_epoch, build["n_classes"])
-                logs["val_dice"] = vd
-                if vd > best:
-                    best, wait_lr, wait_es = vd, 0, 0
-                    if rank == 0:
-                        if best_path and os.path.exists(best_path):
-                            os.remove(best_path)
-                        best_path = os.path.join(project_dir, "model",
-                                                 "@epoch_%02d_val_dice_%.5f.npz" % (epoch + 1, vd))
-                        model.save_weights(best_path)
-                else:
-                    wait_lr += 1
-                    wait_es += 1
-                    if rlop and wait_lr > int(rlop.get("patience", 2)):
-                        model.optimizer.lr *= float(rlop.get("factor", 0.9))
-                        wait_lr = 0
-            if rank == 0:
-                new = not os.path.exists(csv_path)
-                with open(csv_path, "a", newline="") as f:
-                    wtr = csv.DictWriter(f, fieldnames=sorted(logs))
-                    if new:
-                        wtr.writeheader()
-                    wtr.writerow(logs)
-            log("Epoch %d/%d - %s" % (epoch + 1, n_epochs, " - ".join("%s: %.5g" % kv for kv in sorted(logs.items()))))
-            if es and va_seq is not None and wait_es > int(es.get("patience", 15)):
-                log("Early stopping")
+            logs = {"loss": float(np.mean(losses))}
+            for cb in callbacks:
+                cb.on_epoch_end(epoch, logs)
+            log("Epoch %d/%d - %s" % (epoch + 1, n_epochs, " - ".join(
+                "%s: %.5g" % kv for kv in sorted(logs.items()) if np.isscalar(kv[1]))))
+            if world > 1:  # every rank takes the same stop decision
+                flag = torch.tensor([1.0 if model.stop_training else 0.0], device="cuda")
+                torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MAX)
+                model.stop_training = bool(flag.item() > 0)
+            if model.stop_training:
                 break
     except KeyboardInterrupt:
         pass
     finally:
+        for cb in callbacks:
+            cb.on_train_end()
+        os.chdir(cwd)
         if rank == 0:
             model.save_weights(os.path.join(project_dir, "model", "model_weights.npz"))
 

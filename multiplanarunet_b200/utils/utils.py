@@ -43,6 +43,61 @@ def get_last_model(model_dir):
     return os.path.abspath(models[i]), epochs[i]
 
 
+def _read_csv(csv_file):
+    import csv
+    with open(csv_file, newline="") as f:
+        rows = list(csv.reader(f))
+    return (rows[0], rows[1:]) if rows else ([], [])
+
+
+def get_last_epoch(csv_file):
+    """Last value of the `epoch` column of logs/training.csv, 0 if there is none (utils.py:171-177)."""
+    if not os.path.exists(csv_file):
+        return 0
+    header, rows = _read_csv(csv_file)
+    if "epoch" not in header or not rows:
+        return 0
+    return int(float(rows[-1][header.index("epoch")]))
+
+
+def get_lr_at_epoch(epoch, log_dir):
+    """(lr, column name) logged for `epoch` in logs/training.csv, (None, None) if unavailable (utils.py:133-147)."""
+    log_path = os.path.join(log_dir, "training.csv")
+    if not os.path.exists(log_path):
+        print("No training.csv file found at %s. Continuing with default learning rate found in parameter file."
+              % log_dir)
+        return None, None
+    header, rows = _read_csv(log_path)
+    for name in ("lr", "LR", "learning_rate", "LearningRate"):
+        if name in header:
+            if int(epoch) >= len(rows):
+                return None, None
+            return float(rows[int(epoch)][header.index(name)]), name
+    return None, None
+
+
+def clear_csv_after_epoch(epoch, csv_file):
+    """Keeps the last run in the file (from its last `epoch == 0` row) up to and including `epoch`
+    (utils.py:150-168)."""
+    if not os.path.exists(csv_file):
+        return
+    header, rows = _read_csv(csv_file)
+    if not header:
+        os.remove(csv_file)
+        return
+    if "epoch" in header:
+        col = header.index("epoch")
+        zeros = [i for i, r in enumerate(rows) if int(float(r[col])) == 0]
+        if zeros:
+            rows = rows[zeros[-1]:]
+    rows = rows[:epoch + 1]
+    import csv
+    with open(csv_file, "w", newline="") as f:
+        w = csv.writer(f)
+        w.writerow(header)
+        w.writerows(rows)
+
+
 def create_folders(folders, create_deep=False):
     folders = [folders] if isinstance(folders, str) else folders
     for f in folders:

@@ -50,6 +50,17 @@ def test_cli_round_trip(tmp_path):
     assert os.path.exists(os.path.join(proj, "views.npz")) and np.load(os.path.join(proj, "views.npz"))["arr_0"].shape == (6, 3)
     assert os.path.exists(os.path.join(proj, "model", "model_weights.npz"))
     assert os.path.exists(os.path.join(proj, "logs", "training.csv"))
+    import csv
+    rows = list(csv.DictReader(open(os.path.join(proj, "logs", "training.csv"))))
+    assert [r["epoch"] for r in rows] == ["0", "1"]
+    assert {"loss", "lr", "val_dice", "val_precision", "val_recall", "epoch_minutes", "train_hours"} <= set(rows[0])
+    ckpts = [f for f in os.listdir(os.path.join(proj, "model")) if f.startswith("@epoch_")]
+    assert len(ckpts) == 1 and ckpts[0].endswith(".npz") and "_val_dice_" in ckpts[0]   # ModelCheckPointClean
+    # --continue_training resumes after the last checkpoint's epoch with the logged LR (models/model_init.py:25-51)
+    mp.entry_func(["train", "--project_dir", proj, "--continue_training", "--epochs", "3",
+                   "--train_images_per_epoch", "48", "--val_images_per_epoch", "16"])
+    rows = list(csv.DictReader(open(os.path.join(proj, "logs", "training.csv"))))
+    assert [r["epoch"] for r in rows] == ["0", "1", "2"]
     mp.entry_func(["train_fusion", "--project_dir", proj, "--epochs", "2", "--batch_size", "65536"])
     fdir = os.path.join(proj, "model", "fusion_weights")
     assert len(os.listdir(fdir)) == 1
