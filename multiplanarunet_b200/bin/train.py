@@ -122,7 +122,7 @@ def run(project_dir, args):
     va_seq = IsotrophicLiveViewSequence2D(val_images, is_validation=True, **common) if val_images else None
 
     cls = models.__dict__[build["model_class_name"]]
-    model = cls(max_batch=bs, training=True, **build)
+    model = cls(max_batch=bs, training=True, logger=log, **{k: v for k, v in build.items() if k != "logger"})
     okw = fit.get("optimizer_kwargs", {})
     model.optimizer.lr = float(okw.get("lr", 5e-5))
     model.optimizer.beta_1, model.optimizer.beta_2 = float(okw.get("beta_1", 0.9)), float(okw.get("beta_2", 0.999))
@@ -175,35 +175,25 @@ def run(project_dir, args):
     callbacks, cb_dict = init_callback_objects(callbacks, log)
     if "CSVLogger" in cb_dict and args.continue_training:
         cb_dict["CSVLogger"].append = True
-    for cb in callbacks:
-        cb.set_model(model)
-    model.stop_training = False
+
+    def batches():
+        while True:
+            x, y, w = tr_seq.sample_batch_device()
+            yield x, y, torch.as_tensor(w)
+
+    def sync_stop(flag):  # every rank takes the same stop decision
+        if world == 1:
+            return flag
+        t = torch.tensor([1.0 if flag else 0.0], device="cuda")
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return bool(t.item() > 0)
+
     try:
-        for cb in callbacks:
-            cb.on_train_begin()
-        for epoch in range(init_epoch, n_epochs):
-            for cb in callbacks:
-                cb.on_epoch_begin(epoch)
-            losses = []
-            for _ in range(steps):
-                x, y, w = tr_seq.sample_batch_device()
-                losses.append(dp.train_on_batch(x, y, torch.as_tensor(w)))
-            logs = {"loss": float(np.mean(losses))}
-            for cb in callbacks:
-                cb.on_epoch_end(epoch, logs)
-            log("Epoch %d/%d - %s" % (epoch + 1, n_epochs, " - ".join(
-                "%s: %.5g" % kv for kv in sorted(logs.items()) if np.isscalar(kv[1]))))
-            if world > 1:  # every rank takes the same stop decision
-                flag = torch.tensor([1.0 if model.stop_training else 0.0], device="cuda")
-                torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MAX)
-                model.stop_training = bool(flag.item() > 0)
-            if model.stop_training:
-                break
+        model.fit(batches(), steps_per_epoch=steps, epochs=n_epochs, callbacks=callbacks,
+                  initial_epoch=init_epoch, verbose=1, train_on_batch=dp.train_on_batch, sync_stop=sync_stop)
     except KeyboardInterrupt:
         pass
     finally:
-        for cb in callbacks:
-            cb.on_train_end()
         os.chdir(cwd)
         if rank == 0:
             model.save_weights(os.path.join(project_dir, "model", "model_weights.npz"))

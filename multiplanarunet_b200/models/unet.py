@@ -391,21 +391,13 @@ class UNet(object):
         H, W, _ = self.img_shape
         return float(loss.item()) / (self._last_B * H * W)
 
-    def fit(self, x, steps_per_epoch=None, epochs=1, callbacks=None, initial_epoch=0, verbose=1, **kw):
-        """Thin step loop over a generator of (x, y, w) batches (train/trainer.py:246-257)."""
-        history = []
-        it = iter(x)
-        for epoch in range(initial_epoch, epochs):
-            losses = []
-            for _ in range(steps_per_epoch or 1):
-                bx, by, bw = next(it)
-                losses.append(self.train_on_batch(bx, by, bw))
-            history.append(float(np.mean(losses)))
-            if verbose:
-                self.logger("Epoch %d/%d - loss: %.5f" % (epoch + 1, epochs, history[-1]))
-            if self.stop_training:
-                break
-        return history
+    def fit(self, x, steps_per_epoch=None, epochs=1, callbacks=None, initial_epoch=0, verbose=1,
+            train_on_batch=None, sync_stop=None, **kw):
+        """Keras-style fit over a generator of (x, y, w) batches with epoch callbacks
+        (train/trainer.py:246-257); returns History.history-like {"loss": [...], ...}."""
+        from ..train import fit_loop
+        return fit_loop(self, x, steps_per_epoch, epochs, callbacks=callbacks, initial_epoch=initial_epoch,
+                        train_on_batch=train_on_batch, verbose=verbose, logger=self.logger, sync_stop=sync_stop)
 
     def reset_metrics(self):
         pass

@@ -144,3 +144,45 @@ def test_continue_training_csv_helpers(tmp_path):
     assert [r["epoch"] for r in rows] == ["0", "1", "2"] and rows[0]["lr"] == "0.002"
     assert U.get_lr_at_epoch(2, str(logs)) == (0.0018, "lr")
     assert U.get_lr_at_epoch(7, str(logs)) == (None, None)
+
+
+def test_fit_loop_drives_callbacks_and_stops():
+    """train.fit_loop (the loop Keras' model.fit runs for the reference, train/trainer.py:246-257) with a fake
+    model: callback order, logs/history, early stop, stop-flag synchronisation hook."""
+    from multiplanarunet_b200.train import fit_loop
+    m = _Model()
+    seen = []
+    m.train_on_batch = lambda x, y, w: seen.append(x) or 1.0 / (len(seen))
+
+    class Val(C.Callback):
+        def on_epoch_end(self, epoch, logs=None):
+            logs["val_dice"] = [0.2, 0.3, 0.3, 0.3, 0.9][epoch]
+    order = []
+
+    class Probe(C.Callback):
+        def on_train_begin(self, logs=None):
+            order.append("begin")
+
+        def on_epoch_begin(self, epoch, logs=None):
+            order.append("eb%d" % epoch)
+
+        def on_epoch_end(self, epoch, logs=None):
+            order.append("ee%d" % epoch)
+            assert "val_dice" in logs and "loss" in logs       # Validation ran first
+
+        def on_train_end(self, logs=None):
+            order.append("end")
+    es = C.EarlyStopping(monitor="val_dice", patience=2, mode="max")
+    batches = ((i, None, None) for i in range(1000))
+    msgs = []
+    hist = fit_loop(m, batches, steps_per_epoch=3, epochs=10, callbacks=[Val(), Probe(), es], initial_epoch=0,
+                    logger=msgs.append, sync_stop=lambda f: f)
+    assert hist["val_dice"] == [0.2, 0.3, 0.3, 0.3] and len(hist["loss"]) == 4       # stopped after epoch 3
+    assert seen == list(range(12))
+    assert order == ["begin", "eb0", "ee0", "eb1", "ee1", "eb2", "ee2", "eb3", "ee3", "end"]
+    assert m.stop_training and len(msgs) == 4
+    # initial_epoch resumes the numbering
+    order.clear()
+    fit_loop(m, ((i, None, None) for i in range(10)), steps_per_epoch=1, epochs=4, callbacks=[Val(), Probe()],
+             initial_epoch=2, verbose=0)
+    assert order == ["begin", "eb2", "ee2", "eb3", "ee3", "end"]
