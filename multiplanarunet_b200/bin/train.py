@@ -149,6 +149,23 @@ def run(project_dir, args):
             model.optimizer.lr = lr
         log("[NOTICE] Training continues from:\nModel: %s\nEpoch: %i\nLR:    %s"
             % (os.path.split(last)[-1] if last else "<No model found>", epoch, lr))
+    elif build.get("biased_output_layer"):
+        # bin/train.py:294-299: output bias from the training set's class frequencies (summed over all ranks'
+        # shards so that every replica starts from identical weights)
+        from ..utils.utils import set_bias_weights_on_all_outputs
+        k = int(build["n_classes"])
+        counts = np.zeros(k, dtype=np.int64)
+        for image in train_images:
+            if image.labels is not None:
+                counts += np.bincount(np.asarray(image.labels).ravel(), minlength=k)[:k]
+        if world > 1:
+            t = torch.as_tensor(counts, device="cuda")
+            torch.distributed.all_reduce(t)
+            counts = t.cpu().numpy()
+        if counts.sum() > 0 and np.all(counts > 0):
+            set_bias_weights_on_all_outputs(model, train_images, {"class_counts": counts}, log)
+        else:
+            log("[NOTE] output bias not initialised from class frequencies (classes missing: %s)" % counts)
     dp = D.DataParallel(model)
 
     n_epochs = args.epochs or int(fit["n_epochs"])

@@ -104,17 +104,43 @@ def create_folders(folders, create_deep=False):
         os.makedirs(f, exist_ok=True) if create_deep else (os.path.isdir(f) or os.mkdir(f))
 
 
-def set_bias_weights(layer, class_counts, logger=None):
-    """Initialise the softmax layer's bias from class frequencies (utils.py:205-242):
-    b = log(freq * sum(exp(freq))) normalised to unit length."""
+def set_bias_weights(layer, data_queue=None, class_counts=None, logger=None):
+    """Initialise the softmax layer's bias so that a zero input gives the class frequencies
+    (utils.py:205-242): b = log(freq * sum(exp(freq))) normalised to unit length.  `data_queue`: iterable of
+    images with `.labels` (counted when `class_counts` is None)."""
+    if getattr(layer.activation, "__name__", None) != "softmax":
+        raise ValueError("Setting output layer bias currently only supported with softmax activation functions. "
+                         "Output layer has '%s'" % getattr(layer.activation, "__name__", layer.activation))
+    weights = layer.get_weights()
+    if len(weights) != 2:
+        raise ValueError("Output layer does not have bias weights.")
+    bias_shape = weights[-1].shape
+    n_classes = weights[-1].size
+    if class_counts is None:
+        class_counts = np.zeros(shape=[n_classes], dtype=np.int64)
+        images = list(data_queue)
+        (logger or print)("OBS: Estimating class counts from {} images".format(len(images)))
+        for image in images:
+            class_counts += np.bincount(np.asarray(image.labels).ravel(), minlength=n_classes)[:n_classes]
     counts = np.asarray(class_counts, dtype=np.float64)
-    freq = counts / counts.sum()
+    freq = counts / np.sum(counts)
     bias = np.log(freq * np.sum(np.exp(freq)))
     bias /= np.linalg.norm(bias)
-    ws = layer.get_weights()
-    ws[-1] = bias.reshape(ws[-1].shape).astype(np.float32)
-    layer.set_weights(ws)
+    weights[-1] = bias.reshape(bias_shape).astype(np.float32)
+    layer.set_weights(weights)
+    (logger or print)("Setting bias weights on output layer to:\n%s" % bias)
     return bias
+
+
+def set_bias_weights_on_all_outputs(model, data_queue, hparams, logger=None):
+    """utils.py:179-202: the last layer that has an activation is the output layer."""
+    layer = None
+    for lay in model.layers[::-1]:
+        if hasattr(lay, "activation"):
+            layer = lay
+            break
+    class_counts = hparams.get("class_counts") if hasattr(hparams, "get") else None
+    return set_bias_weights(layer=layer, data_queue=data_queue, class_counts=class_counts, logger=logger)
 
 
 def pred_to_class(tensor, img_dims=3, threshold=0.5, has_batch_dim=False):

@@ -186,3 +186,43 @@ def test_fit_loop_drives_callbacks_and_stops():
     fit_loop(m, ((i, None, None) for i in range(10)), steps_per_epoch=1, epochs=4, callbacks=[Val(), Probe()],
              initial_epoch=2, verbose=0)
     assert order == ["begin", "eb2", "ee2", "eb3", "ee3", "end"]
+
+
+def test_output_bias_from_class_frequencies():
+    """utils.set_bias_weights(_on_all_outputs) (mpunet/utils/utils.py:179-242): softmax(bias) is proportional to the
+    class frequencies before the unit-norm scaling, only softmax output layers are accepted."""
+    from multiplanarunet_b200.utils import utils as U
+
+    class Layer:
+        def __init__(self, act):
+            self.activation = act
+            self.w = [np.zeros((1, 1, 4, 3), np.float32), np.zeros(3, np.float32)]
+
+        def get_weights(self):
+            return [w.copy() for w in self.w]
+
+        def set_weights(self, ws):
+            self.w = ws
+
+    def softmax(x):
+        return x
+
+    def relu(x):
+        return x
+
+    class Img:
+        labels = np.array([0] * 70 + [1] * 20 + [2] * 10, dtype=np.uint8).reshape(10, 10)
+
+    class M:
+        layers = [Layer(relu), Layer(softmax)]
+    msgs = []
+    b = U.set_bias_weights_on_all_outputs(M, [Img, Img], {}, msgs.append)
+    freq = np.array([0.7, 0.2, 0.1])
+    raw = np.log(freq * np.exp(freq).sum())
+    assert np.allclose(b, raw / np.linalg.norm(raw)) and np.allclose(M.layers[-1].w[-1], b.astype(np.float32))
+    assert np.allclose(np.exp(raw) / np.exp(raw).sum(), freq)
+    assert M.layers[0].w[-1].sum() == 0 and any("Estimating class counts from 2 images" in s for s in msgs)
+    b2 = U.set_bias_weights(M.layers[-1], class_counts=[7, 2, 1], logger=msgs.append)
+    assert np.allclose(b, b2)
+    with pytest.raises(ValueError):
+        U.set_bias_weights(M.layers[0], class_counts=[7, 2, 1])
