@@ -84,19 +84,47 @@ def entry_func(args=None):
     nii_dir = os.path.join(out_dir, "nii_files")
     os.makedirs(nii_dir, exist_ok=True)
     os.makedirs(os.path.join(out_dir, "csv"), exist_ok=True)
+    if a.continue_:
+        # remove_already_predicted (bin/predict.py:120-131)
+        done = set(f.replace("_PRED", "").split(".")[0] for f in os.listdir(nii_dir))
+        if done:
+            print("[OBS] Not predicting on images: {} (--continue mode)".format(sorted(done)))
+        images = [im for im in images if im.identifier not in done]
     rows = []
     for image in images:
         labels, probs, _ = predict_multi_view(model, seq, image, views, W, b, sum_fusion=a.sum_fusion,
                                               want_probs=a.no_argmax)
         out = probs.cpu().numpy() if a.no_argmax else labels.cpu().numpy()
-        write_nifti(os.path.join(nii_dir, image.identifier + "_PRED.nii.gz"), out, image.affine)
+        # save_nii_files (bin/predict.py:88-117): with --save_input_files everything goes to a per-image folder
+        dst = os.path.join(nii_dir, image.identifier) if a.save_input_files else nii_dir
+        os.makedirs(dst, exist_ok=True)
+        write_nifti(os.path.join(dst, image.identifier + "_PRED.nii.gz"), out, image.affine)
+        if a.save_input_files:
+            write_nifti(os.path.join(dst, image.identifier + "_IMAGE.nii.gz"), np.asarray(image.image), image.affine)
+            if image.labels is not None:
+                write_nifti(os.path.join(dst, image.identifier + "_LABELS.nii.gz"), np.asarray(image.labels),
+                            image.affine)
         if image.labels is not None and not a.no_eval:
+            if np.random.rand() > a.eval_prob:
+                print("Skipping evaluation for %s... (eval_prob=%.3f)" % (image.identifier, a.eval_prob))
+                continue
             from ..evaluate import dice_all
             dices = list(dice_all(image.labels, labels, n_classes=build["n_classes"], ignore_zero=True))
-            rows.append([image.identifier] + dices)
-            print("%s  mean dice %.4f" % (image.identifier, np.nanmean(dices)))
+            rows.append([image.identifier] + [float(d) for d in dices])
+            print("%s  combined dices %s  mean dice %.4f" % (image.identifier, np.round(dices, 4),
+                                                             np.nanmean(dices)))
+    if D.world_size() > 1:  # volumes were sharded: collect every rank's rows on rank 0
+        gathered = [None] * D.world_size()
+        torch.distributed.all_gather_object(gathered, rows)
+        rows = [r for part in gathered for r in part]
     if rows and D.rank() == 0:
-        with open(os.path.join(out_dir, "csv", "results.csv"), "w", newline="") as f:
+        path = os.path.join(out_dir, "csv", "results.csv")
+        header = ["id"] + ["class_%d" % c for c in range(1, build["n_classes"])]
+        old = []
+        if a.continue_ and os.path.exists(path):
+            with open(path, newline="") as f:
+                old = [r for r in csv.reader(f)][1:]
+        with open(path, "w", newline="") as f:
             w = csv.writer(f)
-            w.writerow(["id"] + ["class_%d" % c for c in range(1, build["n_classes"])])
-            w.writerows(rows)
+            w.writerow(header)
+            w.writerows(old + rows)

@@ -69,6 +69,13 @@ def test_cli_round_trip(tmp_path):
     pred, aff, _ = read_nifti(os.path.join(out, "nii_files", "im0_PRED.nii.gz"))
     assert pred.shape == (48, 48, 48) and pred.dtype == np.uint8 and pred.max() <= 2
     assert os.path.exists(os.path.join(out, "csv", "results.csv"))
+    # --continue skips what is already there; --save_input_files writes per-image folders
+    mp.entry_func(["predict", "--project_dir", proj, "--out_dir", out, "--continue"])
+    assert len(open(os.path.join(out, "csv", "results.csv")).read().strip().splitlines()) == 2
+    out3 = str(tmp_path / "preds_inputs")
+    mp.entry_func(["predict", "--project_dir", proj, "--out_dir", out3, "--sum_fusion", "--save_input_files"])
+    sub = os.path.join(out3, "nii_files", "im0")
+    assert sorted(os.listdir(sub)) == ["im0_IMAGE.nii.gz", "im0_LABELS.nii.gz", "im0_PRED.nii.gz"]
     out2 = str(tmp_path / "preds_sum")
     mp.entry_func(["predict", "--project_dir", proj, "--out_dir", out2, "--sum_fusion", "--no_eval"])
     pred2, _, _ = read_nifti(os.path.join(out2, "nii_files", "im0_PRED.nii.gz"))
