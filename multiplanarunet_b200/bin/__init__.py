@@ -1,0 +1,1 @@
+"""multiplanarunet_b200.bin package."""
