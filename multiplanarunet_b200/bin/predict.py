@@ -73,11 +73,19 @@ def entry_func(args=None):
     W = b = None
     if not a.sum_fusion:
         stem = os.path.splitext(os.path.basename(weights))[0]
-        fpath = os.path.join(base_dir, "model", "fusion_weights", "%s_fusion_weights.npz" % stem)
-        if not os.path.exists(fpath):
-            raise OSError("Fusion weights not found at %s; run `mp train_fusion` or pass --sum_fusion" % fpath)
-        with np.load(fpath) as z:
-            W, b = z["W"], z["b"]
+        fbase = os.path.join(base_dir, "model", "fusion_weights", "%s_fusion_weights" % stem)
+        if os.path.exists(fbase + ".npz"):
+            with np.load(fbase + ".npz") as z:
+                W, b = z["W"], z["b"]
+        elif os.path.exists(fbase + ".h5"):  # fusion weights trained with the reference (bin/predict.py:227-233)
+            from ..utils.keras_h5 import load_keras_weights
+            layers = [d for d in load_keras_weights(fbase + ".h5").values() if "W" in d and "b" in d]
+            if len(layers) != 1:
+                raise OSError("%s.h5 does not hold exactly one fusion layer" % fbase)
+            W, b = layers[0]["W"], layers[0]["b"]
+        else:
+            raise OSError("Fusion weights not found at %s.{npz,h5}; run `mp train_fusion` or pass --sum_fusion"
+                          % fbase)
     seq = IsotrophicLiveViewSequence2D(images, views=views, sample_dim=build["dim"],
                                        real_space_span=fit["real_space_span"], n_classes=build["n_classes"],
                                        is_validation=True)

@@ -46,10 +46,21 @@ class FusionModel(object):
 
     def save_weights(self, path, overwrite=True):
         W, b = self.get_weights()
+        if path.endswith((".h5", ".hdf5")):  # Keras layout of the reference's FusionLayer (fusion_model.py:14-43)
+            from ..utils.keras_h5 import save_keras_weights
+            save_keras_weights(path, {"fusion_layer": {"W": W, "b": b}})
+            return
         with open(path, "wb") as f:
             np.savez(f, W=W, b=b)
 
     def load_weights(self, path, by_name=True):
+        if path.endswith((".h5", ".hdf5")):
+            from ..utils.keras_h5 import load_keras_weights
+            layers = [d for d in load_keras_weights(path).values() if "W" in d and "b" in d]
+            if len(layers) != 1:
+                raise ValueError("%s does not hold exactly one fusion layer" % path)
+            self.set_weights([layers[0]["W"], layers[0]["b"]])
+            return
         with np.load(path) as z:
             self.set_weights([z["W"], z["b"]])
 

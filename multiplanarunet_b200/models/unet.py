@@ -270,23 +270,37 @@ class UNet(object):
         return n
 
     def save_weights(self, path, overwrite=True):
-        """Weights only, by Keras layer name (as model.save_weights does, bin/train.py:303-317).
-        Stored as .npz (h5py is not a dependency of this path); `path` is used verbatim."""
-        flat = {}
-        for name, d in self.get_keras_weights().items():
-            for k, v in d.items():
-                flat["%s/%s" % (name, k)] = v
+        """Weights only, by Keras layer name (as model.save_weights does, bin/train.py:303-317).  `*.h5` / `*.hdf5`
+        paths are written in Keras' HDF5 layout by utils/keras_h5.py (no h5py needed), anything else as `.npz`."""
         if not overwrite and os.path.exists(path):
             raise OSError("%s exists" % path)
+        weights = self.get_keras_weights()
+        if path.endswith((".h5", ".hdf5")):
+            from ..utils.keras_h5 import save_keras_weights
+            save_keras_weights(path, weights, layer_order=[i["name"] for i in self._ordered_infos()])
+            return
+        flat = {}
+        for name, d in weights.items():
+            for k, v in d.items():
+                flat["%s/%s" % (name, k)] = v
         with open(path, "wb") as f:
             np.savez(f, **flat)
 
     def load_weights(self, path, by_name=True):
-        with np.load(path) as z:
-            weights = {}
-            for key in z.files:
-                name, k = key.rsplit("/", 1)
-                weights.setdefault(name, {})[k] = z[key]
+        """`.npz` archives of this package or Keras HDF5 weight files (load_weights(path, by_name=True),
+        models/model_init.py:31,56): layers are matched by name, shapes must agree."""
+        if path.endswith((".h5", ".hdf5")):
+            from ..utils.keras_h5 import load_keras_weights
+            weights = load_keras_weights(path)
+        else:
+            with np.load(path) as z:
+                weights = {}
+                for key in z.files:
+                    name, k = key.rsplit("/", 1)
+                    weights.setdefault(name, {})[k] = z[key]
+        known = set(i["name"] for i in self._infos)
+        if not known & set(weights):
+            raise ValueError("%s holds no layer of this model (found %s)" % (path, sorted(weights)[:5]))
         self.set_keras_weights(weights)
 
     # ------------------------------------------------------------------ inference
