@@ -158,6 +158,16 @@ int mpu_fusion_adam(float* W, float* b, float* m, float* v, const double* accum,
                     int V, int C, float reg, float lr, float beta1, float beta2, float eps, int step,
                     void* stream);
 
+/* Interpolation of the resident volume at explicit real-space coordinates: ViewInterpolator.__call__ /
+ * intrp_image / intrp_labels on an arbitrary grid (interpolation/view_interpolator.py:62-101, after the optional
+ * apply_rotation, which the caller does on the host).  coords: device [3][n] float64 (x | y | z).  out_f32 [n][C]
+ * (trilinear, float64 weights, cast to f32, out-of-bounds -> h_bg_value) and/or out_labels [n] (nearest,
+ * out-of-bounds -> bg_class); no scaling is applied (the reference scales after interpolation). */
+int mpu_interp_points(const float* vol, const unsigned char* labels, const int* h_dims, int C,
+                      const float* gx, const float* gy, const float* gz, const double* h_inv_step,
+                      const double* coords, long long n, const float* h_bg_value, int bg_class,
+                      float* out_f32, unsigned char* out_labels, void* stream);
+
 /* Confusion-matrix counts for the validation callback and dice_all: ADDS into counts [3][n_classes] int64
  * (device): [0] true == c & pred == c (TP), [1] true == c (relevant), [2] pred == c (selected).
  * pred is either y_pred (u8 labels) or, when scores != NULL, the first arg-max of scores [n][n_classes] f32.

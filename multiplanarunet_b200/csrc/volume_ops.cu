@@ -387,6 +387,77 @@ inline int grid_for(long long work, int threads, int cap = 148 * 16) {
 }
 
 
+// ---- interpolation at explicit coordinates ------------------------------------------------------------------
+// ViewInterpolator.__call__ / intrp_image / intrp_labels on an arbitrary grid (view_interpolator.py:62-101): the
+// same per-point arithmetic as sample_planes_kernel (index search on the float32 voxel axes, float64 trilinear
+// weights in itertools.product order, nearest labels, whole-point out-of-bounds fill), with the real-space
+// coordinates supplied by the caller as [3][n] float64 instead of derived from a plane description.
+struct PointsParams {
+  const float* vol;
+  const uint8_t* labels;
+  int X, Y, Z, C;
+  const float *gx, *gy, *gz;
+  double inv_step[3];
+  const double* coords;  // [3][n]
+  long long n;
+  float bg_value[kMaxCh];
+  int bg_class;
+  float* out_f32;    // [n][C] or null
+  uint8_t* out_lab;  // [n] or null
+};
+
+__global__ void sample_points_kernel(const PointsParams p) {
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < p.n;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const double q[3] = {p.coords[idx], p.coords[p.n + idx], p.coords[2 * p.n + idx]};
+    const float* gs[3] = {p.gx, p.gy, p.gz};
+    const int ns[3] = {p.X, p.Y, p.Z};
+    int ci[3];
+    double tt[3];
+    bool oob = false;
+    for (int k = 0; k < 3; ++k) {
+      const float* g = gs[k];
+      const int n = ns[k];
+      const int c = find_cell(g, n, q[k], p.inv_step[k]);
+      ci[k] = c;
+      const float den = __fsub_rn(g[c + 1], g[c]);
+      tt[k] = __ddiv_rn(__dsub_rn(q[k], (double)g[c]), (double)den);
+      oob = oob || q[k] < (double)g[0] || q[k] > (double)g[n - 1];
+    }
+    const long long sY = (long long)p.Z * p.C, sX = (long long)p.Y * sY;
+    const long long base = (long long)ci[0] * sX + (long long)ci[1] * sY + (long long)ci[2] * p.C;
+    if (p.out_f32) {
+      for (int c = 0; c < p.C; ++c) {
+        double acc = 0.0;
+        if (!oob) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int dx = (e >> 2) & 1, dy = (e >> 1) & 1, dz = e & 1;
+            double w = dx ? tt[0] : __dsub_rn(1.0, tt[0]);
+            w = __dmul_rn(w, dy ? tt[1] : __dsub_rn(1.0, tt[1]));
+            w = __dmul_rn(w, dz ? tt[2] : __dsub_rn(1.0, tt[2]));
+            const float v = __ldg(p.vol + base + dx * sX + dy * sY + dz * p.C + c);
+            acc = __dadd_rn(acc, __dmul_rn((double)v, w));
+          }
+        } else {
+          acc = (double)p.bg_value[c];
+        }
+        p.out_f32[idx * p.C + c] = (float)acc;
+      }
+    }
+    if (p.out_lab) {
+      int lab = p.bg_class;
+      if (!oob && p.labels) {
+        const int s0 = tt[0] <= 0.5 ? ci[0] : ci[0] + 1;
+        const int s1 = tt[1] <= 0.5 ? ci[1] : ci[1] + 1;
+        const int s2 = tt[2] <= 0.5 ? ci[2] : ci[2] + 1;
+        lab = p.labels[((long long)s0 * p.Y + s1) * p.Z + s2];
+      }
+      p.out_lab[idx] = (uint8_t)lab;
+    }
+  }
+}
+
 // ---- confusion-matrix counts ---------------------------------------------------------------------------
 // counts[0][c] = #(true == c & pred == c), counts[1][c] = #(true == c), counts[2][c] = #(pred == c)
 // (TP / relevant / selected of callbacks/validation.py:117-131; the three sums of evaluate/metrics.py:12-23).
@@ -712,6 +783,48 @@ int mpu_elastic_2d(const float* x_in, const unsigned char* y_in, double* fields,
   gauss1d_kernel<<<gf, 256, 0, st>>>(scratch, fields, H, W, 1, d_weights, weight_stride, d_radius);
   elastic_resample_kernel<<<gs, 256, 0, st>>>(x_in, y_in, fields, d_alpha, d_bg, H, W, C, x_out, y_out);
   count_launch(3);
+  MPU_CUDA(cudaGetLastError());
+  return MPU_OK;
+}
+
+int mpu_interp_points(const float* vol, const unsigned char* labels, const int* h_dims, int C,
+                      const float* gx, const float* gy, const float* gz, const double* h_inv_step,
+                      const double* coords, long long n, const float* h_bg_value, int bg_class,
+                      float* out_f32, unsigned char* out_labels, void* stream) {
+  if (!vol || !h_dims || !gx || !gy || !gz || !h_inv_step || !coords || n < 0 || (!out_f32 && !out_labels)) {
+    set_error("mpu_interp_points: bad arguments");
+    return MPU_ERR_ARG;
+  }
+  if (C < 1 || C > kMaxCh) {
+    set_error("mpu_interp_points: %d channels unsupported (max %d)", C, kMaxCh);
+    return MPU_ERR_ARG;
+  }
+  if (h_dims[0] < 2 || h_dims[1] < 2 || h_dims[2] < 2) {
+    set_error("mpu_interp_points: every volume axis needs at least 2 voxels");
+    return MPU_ERR_ARG;
+  }
+  if (n == 0) return MPU_OK;
+  PointsParams p;
+  memset(&p, 0, sizeof(p));
+  p.vol = vol;
+  p.labels = labels;
+  p.X = h_dims[0];
+  p.Y = h_dims[1];
+  p.Z = h_dims[2];
+  p.C = C;
+  p.gx = gx;
+  p.gy = gy;
+  p.gz = gz;
+  for (int k = 0; k < 3; ++k) p.inv_step[k] = h_inv_step[k];
+  p.coords = coords;
+  p.n = n;
+  for (int c = 0; c < C; ++c) p.bg_value[c] = h_bg_value ? h_bg_value[c] : 0.f;
+  p.bg_class = bg_class;
+  p.out_f32 = out_f32;
+  p.out_lab = out_labels;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  sample_points_kernel<<<grid_for(n, 256), 256, 0, st>>>(p);
+  count_launch();
   MPU_CUDA(cudaGetLastError());
   return MPU_OK;
 }

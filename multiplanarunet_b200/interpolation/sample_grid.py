@@ -56,6 +56,35 @@ def sample_plane_at(norm_vector, sample_dim, real_space_span, offset_from_center
     return basis, float(offset_from_center)
 
 
+def plane_mgrid(basis, sample_dim, real_space_span, offset_from_center):
+    """The dense float64 grid [3, dim, dim, 1] the reference's sample_plane_at returns (sample_grid.py:227-239):
+    `basis . (a, b, offset)` over np.mgrid[-hd:hd:dim*1j] with hd = span // 2.  Only needed to feed
+    ViewInterpolator.__call__ / intrp_* (the sampler kernel builds these coordinates itself)."""
+    hd = real_space_span // 2
+    g = np.linspace(-hd, hd, sample_dim)
+    j = complex(sample_dim)
+    grid = np.mgrid[-hd:hd:j, -hd:hd:j, offset_from_center:offset_from_center:1j]
+    points = mgrid_to_points(grid)
+    real = basis.dot(points.T).T
+    return points_to_mgrid(real, grid.shape[1:]), g
+
+
+def mgrid_to_points(mgrid):
+    """[N, D1, D2, D3] mesh grid (or tuple) -> [D1*D2*D3, N] points (interpolation/linalg.py:5-14)."""
+    pts = np.empty(shape=(int(np.prod(mgrid[0].shape)), len(mgrid)), dtype=mgrid[0].dtype)
+    for k in range(len(mgrid)):
+        pts[:, k] = mgrid[k].ravel()
+    return pts
+
+
+def points_to_mgrid(points, grid_shape):
+    """Inverse of mgrid_to_points (interpolation/linalg.py:17-24)."""
+    mgrid = np.empty(shape=(points.shape[1],) + tuple(grid_shape), dtype=points.dtype)
+    for k in range(points.shape[1]):
+        mgrid[k] = points[:, k].reshape(grid_shape)
+    return mgrid
+
+
 def view_offsets(sample_dim, real_space_span, n_planes="same+20", bounding_radius=None):
     """Plane offsets of an inference stack (sequences/isotrophic_live_view_sequence_2d.py:47-62)."""
     sample_res = real_space_span / (sample_dim - 1)

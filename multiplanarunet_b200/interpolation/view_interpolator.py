@@ -78,3 +78,55 @@ class ViewInterpolator(object):
                                     _C.ptr(out_f32), _C.ptr(out_padded), int(cpad), _C.ptr(out_labels),
                                     _C.current_stream()), "mpu_sample_planes")
         return out_f32, out_labels
+
+    # -- reference call surface on explicit grids (view_interpolator.py:54-101) --------------------------
+    def apply_rotation(self, mgrid):
+        """Grid [3, ...] float64 -> grid aligned with the voxel axes (`rot_mat . points`), host numpy like the
+        reference (3 x N doubles)."""
+        if self.rot_mat is None:
+            return mgrid
+        from .sample_grid import mgrid_to_points, points_to_mgrid
+        shape = mgrid[0].shape
+        rotated = np.asarray(self.rot_mat).dot(mgrid_to_points(mgrid).T).T
+        return points_to_mgrid(rotated, shape)
+
+    def _interp_points(self, mgrid, want_image, want_labels):
+        import torch
+        _C.require_cuda()
+        grid = np.asarray(mgrid if not isinstance(mgrid, tuple) else np.stack(mgrid), dtype=np.float64)
+        if grid.shape[0] != 3:
+            raise ValueError("grid must be [3, ...] (x, y, z coordinates); got shape %s" % (grid.shape,))
+        out_shape = np.squeeze(grid[0]).shape
+        n = int(np.prod(grid.shape[1:]))
+        coords = torch.from_numpy(np.ascontiguousarray(grid.reshape(3, n))).to(self.device)
+        im = torch.empty(n, self.n_channels, dtype=torch.float32, device=self.device) if want_image else None
+        lab = torch.empty(n, dtype=torch.uint8, device=self.device) if want_labels else None
+        check(lib.mpu_interp_points(_C.ptr(self.vol), _C.ptr(self.labels), _C.int_array(self.im_shape[:3]),
+                                    self.n_channels, _C.ptr(self._g[0]), _C.ptr(self._g[1]), _C.ptr(self._g[2]),
+                                    self._inv_step, _C.ptr(coords), ctypes.c_longlong(n),
+                                    _C.float_array(self.bg_value), self.bg_class, _C.ptr(im), _C.ptr(lab),
+                                    _C.current_stream()), "mpu_interp_points")
+        im_np = im.cpu().numpy().reshape(out_shape + (self.n_channels,)) if want_image else None
+        lab_np = lab.cpu().numpy().reshape(out_shape) if want_labels else None
+        return im_np, lab_np
+
+    def intrp_image(self, mgrid, apply_rot=True):
+        """-> image [h, w, C] float32 at the grid points (trilinear, out-of-bounds = bg_value)."""
+        if apply_rot:
+            mgrid = self.apply_rotation(mgrid)
+        return self._interp_points(mgrid, True, False)[0]
+
+    def intrp_labels(self, mgrid, apply_rot=True):
+        """-> labels [h, w] uint8 (nearest, out-of-bounds = bg_class), None without a label volume."""
+        if self.labels is None:
+            return None
+        if apply_rot:
+            mgrid = self.apply_rotation(mgrid)
+        return self._interp_points(mgrid, False, True)[1]
+
+    def __call__(self, rgrid_mgrid):
+        """(image, labels) on one grid, as `image.interpolator(mgrid)` returns them in the reference."""
+        grid = self.apply_rotation(rgrid_mgrid)
+        im, lab = self._interp_points(grid, True, self.labels is not None)
+        return im, lab
+

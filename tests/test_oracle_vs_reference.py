@@ -74,6 +74,9 @@ def test_host_geometry_mirror_equals_reference(ref):
         (basis, off), g, inv = sample_plane_at(view, 32, 30, 2.5, 0., test_mode=True)
         grid, g_r, inv_r = ref.sample_grid.sample_plane_at(view, 32, 30, 2.5, 0., test_mode=True)
         assert np.array_equal(inv, inv_r) and np.array_equal(g, g_r) and off == 2.5
+        from multiplanarunet_b200.interpolation import plane_mgrid
+        dense, g_d = plane_mgrid(basis, 32, 30, 2.5)          # the grid ViewInterpolator.__call__ consumes
+        assert dense.shape == grid.shape == (3, 32, 32, 1) and np.array_equal(dense, grid) and np.array_equal(g_d, g_r)
     assert np.array_equal(view_offsets(64, 64.0, "same+20"), sampler.view_offsets(64, 64.0, "same+20"))
 
 
