@@ -116,3 +116,26 @@ def test_augmenter_registry_and_argument_errors():
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError):
             augmentation.elastic_transform_2d(np.zeros((8, 8), np.float32), None, 1.0, 1.0)
+
+
+def test_get_sequence_registry():
+    """sequences.get_sequence (mpunet/sequences/utils.py:5-79): iso_live -> 2D live-view sequence with augmenter
+    objects for training only; 3D styles refused by name; unknown styles are a ValueError like the reference."""
+    import pytest
+    from multiplanarunet_b200.sequences import IsotrophicLiveViewSequence2D, get_sequence
+    views = np.eye(3)
+    kw = dict(views=views, sample_dim=32, real_space_span=30.0, n_classes=3, batch_size=4, intrp_style="iso_live")
+    aug = [dict(cls_name="Elastic2D", kwargs=dict(alpha=[0, 450], sigma=[20, 30], apply_prob=0.333))]
+    msgs = []
+    tr = get_sequence([object()], is_validation=False, logger=msgs.append, augmenters=aug, **kw)
+    va = get_sequence([object()], is_validation=True, logger=msgs.append, augmenters=aug, **kw)
+    assert isinstance(tr, IsotrophicLiveViewSequence2D) and len(tr.list_of_augmenters) == 1
+    assert va.list_of_augmenters is None and va.noise_sd == 0.0 and tr.noise_sd == 0.1
+    assert tr.n_fg_slices == 2 and tr.force_all_fg            # batch 4 > 2 foreground classes
+    assert any("augmenters" in str(m) for m in msgs)
+    with pytest.raises(NotImplementedError):
+        get_sequence([object()], False, **dict(kw, intrp_style="iso_live_3d"))
+    with pytest.raises(ValueError):
+        get_sequence([object()], False, **dict(kw, intrp_style="bogus"))
+    with pytest.raises(NotImplementedError):
+        get_sequence([object()], False, augmenters=[dict(cls_name="Elastic3D", kwargs={})], **kw)
