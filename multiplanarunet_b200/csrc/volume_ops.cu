@@ -791,6 +791,7 @@ int mpu_interp_points(const float* vol, const unsigned char* labels, const int* 
                       const float* gx, const float* gy, const float* gz, const double* h_inv_step,
                       const double* coords, long long n, const float* h_bg_value, int bg_class,
                       float* out_f32, unsigned char* out_labels, void* stream) {
+  if (n == 0) return MPU_OK;
   if (!vol || !h_dims || !gx || !gy || !gz || !h_inv_step || !coords || n < 0 || (!out_f32 && !out_labels)) {
     set_error("mpu_interp_points: bad arguments");
     return MPU_ERR_ARG;
@@ -803,7 +804,6 @@ int mpu_interp_points(const float* vol, const unsigned char* labels, const int* 
     set_error("mpu_interp_points: every volume axis needs at least 2 voxels");
     return MPU_ERR_ARG;
   }
-  if (n == 0) return MPU_OK;
   PointsParams p;
   memset(&p, 0, sizeof(p));
   p.vol = vol;

@@ -98,6 +98,9 @@ class ViewInterpolator(object):
             raise ValueError("grid must be [3, ...] (x, y, z coordinates); got shape %s" % (grid.shape,))
         out_shape = np.squeeze(grid[0]).shape
         n = int(np.prod(grid.shape[1:]))
+        if n == 0:
+            return (np.empty(out_shape + (self.n_channels,), np.float32) if want_image else None,
+                    np.empty(out_shape, np.uint8) if want_labels else None)
         coords = torch.from_numpy(np.ascontiguousarray(grid.reshape(3, n))).to(self.device)
         im = torch.empty(n, self.n_channels, dtype=torch.float32, device=self.device) if want_image else None
         lab = torch.empty(n, dtype=torch.uint8, device=self.device) if want_labels else None
