@@ -355,7 +355,7 @@ class _Writer(object):
 
     # ---- objects ------------------------------------------------------------------------------------
     def dataset(self, arr, attrs=None):
-        arr = np.ascontiguousarray(arr)
+        arr = np.asarray(arr)  # (np.ascontiguousarray would turn a scalar into shape (1,))
         data_addr = self.alloc(arr.tobytes()) if arr.size else UNDEF
         msgs = [(0x0001, self.dataspace(arr.shape)), (0x0003, self.datatype(arr.dtype)),
                 (0x0005, struct.pack("<BBBB", 2, 2, 2, 0)),                    # fill value v2: late alloc, undefined
