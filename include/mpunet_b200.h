@@ -131,6 +131,18 @@ int mpu_sample_planes(const float* vol, const unsigned char* labels, const int* 
                       const double* h_scale, float* out_f32, void* out_padded_bf16, int cpad,
                       unsigned char* out_labels, void* stream);
 
+/* Candidate probe of the training-batch rejection sampler (sequences/isotrophic_live_view_sequence_2d.py:119-161):
+ * same plane description as mpu_sample_planes, nothing is materialised.  Per candidate plane (device uint32 [n],
+ * overwritten):  class_mask = OR over pixels of (1u << nearest label), out-of-bounds pixels = bg_class - the
+ * np.isin(fg_classes, lab) of validate_lab / validate_lab_vec (isotrophic_live_view_sequence.py:98-128);
+ * valid = 1 iff some pixel of some channel of the UNSCALED trilinear image is not np.isclose(bg_value) - is_valid_im
+ * (isotrophic_live_view_sequence.py:91-96).  Either output may be NULL.  Labels above 31 share bit 31. */
+int mpu_probe_planes(const float* vol, const unsigned char* labels, const int* h_dims, int C,
+                     const float* gx, const float* gy, const float* gz, const double* h_inv_step,
+                     const double* h_rot, const double* planes, int n_planes, int dim, double span,
+                     const float* h_bg_value, int bg_class, unsigned int* class_mask, unsigned int* valid,
+                     void* stream);
+
 /* ---- multi-view mapping + fusion ---------------------------------------------------------------------
  * Replaces map_real_space_pred per view (mpunet/utils/fusion/fuse_and_predict.py:92-137) fused with
  * FusionLayer.call + argmax (models/fusion_model.py:38-39, bin/predict.py:349-366, utils/utils.py:311-328).

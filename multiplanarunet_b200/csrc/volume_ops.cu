@@ -74,6 +74,66 @@ struct SamplerParams {
   uint8_t* out_lab;        // [n][dim][dim] or null
 };
 
+// real-space coordinates of pixel (i, j) of plane pl (sample_grid.py:227-239 + optional view_interpolator.py:54-60)
+__device__ __forceinline__ void plane_point(const SamplerParams& p, int pl, int i, int j, double* q) {
+  const double* P = p.planes + (size_t)pl * 10;
+  const double a = __dadd_rn(__dmul_rn((double)i, p.ax_step), p.ax_start);
+  const double b = __dadd_rn(__dmul_rn((double)j, p.ax_step), p.ax_start);
+  const double off = P[9];
+  q[0] = dot3(P + 0, a, b, off);
+  q[1] = dot3(P + 3, a, b, off);
+  q[2] = dot3(P + 6, a, b, off);
+  if (p.has_rot) {
+    const double r0 = dot3(p.rot + 0, q[0], q[1], q[2]);
+    const double r1 = dot3(p.rot + 3, q[0], q[1], q[2]);
+    const double r2 = dot3(p.rot + 6, q[0], q[1], q[2]);
+    q[0] = r0; q[1] = r1; q[2] = r2;
+  }
+}
+
+// regular_grid_interpolator.py:252-270 on the three float32 voxel axes: cell index, float64 weight, OOB flag
+__device__ __forceinline__ bool locate(const SamplerParams& p, const double* q, int* ci, double* tt) {
+  const float* gs[3] = {p.gx, p.gy, p.gz};
+  const int ns[3] = {p.X, p.Y, p.Z};
+  bool oob = false;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float* g = gs[k];
+    const int n = ns[k];
+    const int c = find_cell(g, n, q[k], p.inv_step[k]);
+    ci[k] = c;
+    const float den = __fsub_rn(g[c + 1], g[c]);  // float32 axis difference, as numpy computes it
+    tt[k] = __ddiv_rn(__dsub_rn(q[k], (double)g[c]), (double)den);
+    oob = oob || q[k] < (double)g[0] || q[k] > (double)g[n - 1];
+  }
+  return oob;
+}
+
+// regular_grid_interpolator.py:204-217: 8 corners in itertools.product order, float64 weights and accumulation
+__device__ __forceinline__ double trilinear(const SamplerParams& p, const int* ci, const double* tt, int c) {
+  const long long sY = (long long)p.Z * p.C, sX = (long long)p.Y * sY;
+  const long long base = (long long)ci[0] * sX + (long long)ci[1] * sY + (long long)ci[2] * p.C;
+  double acc = 0.0;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int dx = (e >> 2) & 1, dy = (e >> 1) & 1, dz = e & 1;
+    double w = dx ? tt[0] : __dsub_rn(1.0, tt[0]);
+    w = __dmul_rn(w, dy ? tt[1] : __dsub_rn(1.0, tt[1]));
+    w = __dmul_rn(w, dz ? tt[2] : __dsub_rn(1.0, tt[2]));
+    const float v = __ldg(p.vol + base + dx * sX + dy * sY + dz * p.C + c);
+    acc = __dadd_rn(acc, __dmul_rn((double)v, w));
+  }
+  return acc;
+}
+
+// regular_grid_interpolator.py:219-223: per axis t <= .5 -> i else i + 1
+__device__ __forceinline__ int nearest_label(const SamplerParams& p, const int* ci, const double* tt) {
+  const int s0 = tt[0] <= 0.5 ? ci[0] : ci[0] + 1;
+  const int s1 = tt[1] <= 0.5 ? ci[1] : ci[1] + 1;
+  const int s2 = tt[2] <= 0.5 ? ci[2] : ci[2] + 1;
+  return p.labels[((long long)s0 * p.Y + s1) * p.Z + s2];
+}
+
 __global__ void sample_planes_kernel(const SamplerParams p) {
   const long long total = (long long)p.n_planes * p.dim * p.dim;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -82,51 +142,12 @@ __global__ void sample_planes_kernel(const SamplerParams p) {
     const long long t0 = idx / p.dim;
     const int i = (int)(t0 % p.dim);
     const int pl = (int)(t0 / p.dim);
-    const double* P = p.planes + (size_t)pl * 10;
-    const double a = __dadd_rn(__dmul_rn((double)i, p.ax_step), p.ax_start);
-    const double b = __dadd_rn(__dmul_rn((double)j, p.ax_step), p.ax_start);
-    const double off = P[9];
-    double q[3];
-    q[0] = dot3(P + 0, a, b, off);
-    q[1] = dot3(P + 3, a, b, off);
-    q[2] = dot3(P + 6, a, b, off);
-    if (p.has_rot) {
-      const double r0 = dot3(p.rot + 0, q[0], q[1], q[2]);
-      const double r1 = dot3(p.rot + 3, q[0], q[1], q[2]);
-      const double r2 = dot3(p.rot + 6, q[0], q[1], q[2]);
-      q[0] = r0; q[1] = r1; q[2] = r2;
-    }
-    const float* gs[3] = {p.gx, p.gy, p.gz};
-    const int ns[3] = {p.X, p.Y, p.Z};
+    double q[3], tt[3];
     int ci[3];
-    double tt[3];
-    bool oob = false;
-    for (int k = 0; k < 3; ++k) {
-      const float* g = gs[k];
-      const int n = ns[k];
-      const int c = find_cell(g, n, q[k], p.inv_step[k]);
-      ci[k] = c;
-      const float den = __fsub_rn(g[c + 1], g[c]);  // float32 axis difference, as numpy computes it
-      tt[k] = __ddiv_rn(__dsub_rn(q[k], (double)g[c]), (double)den);
-      oob = oob || q[k] < (double)g[0] || q[k] > (double)g[n - 1];
-    }
-    const long long sY = (long long)p.Z * p.C, sX = (long long)p.Y * sY;
-    const long long base = (long long)ci[0] * sX + (long long)ci[1] * sY + (long long)ci[2] * p.C;
+    plane_point(p, pl, i, j, q);
+    const bool oob = locate(p, q, ci, tt);
     for (int c = 0; c < p.C; ++c) {
-      double acc = 0.0;
-      if (!oob) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int dx = (e >> 2) & 1, dy = (e >> 1) & 1, dz = e & 1;
-          double w = dx ? tt[0] : __dsub_rn(1.0, tt[0]);
-          w = __dmul_rn(w, dy ? tt[1] : __dsub_rn(1.0, tt[1]));
-          w = __dmul_rn(w, dz ? tt[2] : __dsub_rn(1.0, tt[2]));
-          const float v = __ldg(p.vol + base + dx * sX + dy * sY + dz * p.C + c);
-          acc = __dadd_rn(acc, __dmul_rn((double)v, w));
-        }
-      } else {
-        acc = (double)p.bg_value[c];
-      }
+      const double acc = oob ? (double)p.bg_value[c] : trilinear(p, ci, tt, c);
       float val = (float)acc;
       if (p.apply_scaler) {
         const float t = (float)__dsub_rn((double)val, p.center[c]);
@@ -140,14 +161,56 @@ __global__ void sample_planes_kernel(const SamplerParams p) {
     }
     if (p.out_lab) {
       int lab = p.bg_class;
-      if (!oob && p.labels) {
-        const int s0 = tt[0] <= 0.5 ? ci[0] : ci[0] + 1;
-        const int s1 = tt[1] <= 0.5 ? ci[1] : ci[1] + 1;
-        const int s2 = tt[2] <= 0.5 ? ci[2] : ci[2] + 1;
-        lab = p.labels[((long long)s0 * p.Y + s1) * p.Z + s2];
-      }
+      if (!oob && p.labels) lab = nearest_label(p, ci, tt);
       p.out_lab[idx] = (uint8_t)lab;
     }
+  }
+}
+
+// Candidate probe of the training-batch rejection sampler: what validate_lab / validate_lab_vec
+// (sequences/isotrophic_live_view_sequence.py:98-128) and is_valid_im (:91-96) need to know about a candidate
+// plane, without materialising it.  grid = (blocks per plane, planes).
+//   class_mask[pl] |= 1u << nearest label of every pixel (out-of-bounds pixels carry bg_class)
+//   valid[pl]       = 1 once any pixel of any channel of the UNSCALED trilinear image is not
+//                     np.isclose(value, bg_value) (|v - bg| <= 1e-8 + 1e-5 |bg|); threads skip the image work
+//                     as soon as the plane's flag is up, so the pass costs little more than the label gather.
+__global__ void __launch_bounds__(256) probe_planes_kernel(const SamplerParams p, unsigned int* __restrict__ class_mask,
+                                                           unsigned int* __restrict__ valid) {
+  const int pl = blockIdx.y;
+  __shared__ unsigned int s_mask, s_valid;
+  if (threadIdx.x == 0) {
+    s_mask = 0u;
+    s_valid = 0u;
+  }
+  __syncthreads();
+  unsigned int mask = 0u;
+  volatile unsigned int* gvalid = valid + pl;
+  const int npix = p.dim * p.dim;
+  for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += gridDim.x * blockDim.x) {
+    const int i = pix / p.dim, j = pix - i * p.dim;
+    double q[3], tt[3];
+    int ci[3];
+    plane_point(p, pl, i, j, q);
+    const bool oob = locate(p, q, ci, tt);
+    int lab = p.bg_class;
+    if (!oob && p.labels) lab = nearest_label(p, ci, tt);
+    mask |= 1u << (lab > 31 ? 31 : lab);
+    if (valid && !oob && !s_valid && !*gvalid) {
+      bool differs = false;
+      for (int c = 0; c < p.C; ++c) {
+        const float v = (float)trilinear(p, ci, tt, c);
+        const double bg = (double)p.bg_value[c];
+        differs = differs || !(fabs((double)v - bg) <= 1e-8 + 1e-5 * fabs(bg));
+      }
+      if (differs) s_valid = 1u;
+    }
+  }
+  mask = __reduce_or_sync(0xffffffffu, mask);
+  if ((threadIdx.x & 31) == 0 && mask) atomicOr(&s_mask, mask);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (class_mask && s_mask) atomicOr(class_mask + pl, s_mask);
+    if (valid && s_valid) atomicOr(valid + pl, 1u);
   }
 }
 
@@ -597,26 +660,18 @@ using namespace mpu;
 
 extern "C" {
 
-int mpu_sample_planes(const float* vol, const unsigned char* labels, const int* h_dims, int C,
-                      const float* gx, const float* gy, const float* gz, const double* h_inv_step,
-                      const double* h_rot,
-                      const double* planes, int n_planes, int dim, double span,
-                      const float* h_bg_value, int bg_class, const double* h_center,
-                      const double* h_scale, float* out_f32, void* out_padded_bf16, int cpad,
-                      unsigned char* out_labels, void* stream) {
+static int fill_sampler_params(SamplerParams& p, const char* who, const float* vol, const unsigned char* labels,
+                               const int* h_dims, int C, const float* gx, const float* gy, const float* gz,
+                               const double* h_inv_step, const double* h_rot, const double* planes, int n_planes,
+                               int dim, double span, const float* h_bg_value, int bg_class) {
   if (!vol || !h_dims || !gx || !gy || !gz || !h_inv_step || !planes || n_planes < 1 || dim < 2) {
-    set_error("mpu_sample_planes: bad arguments");
+    set_error("%s: bad arguments", who);
     return MPU_ERR_ARG;
   }
   if (C < 1 || C > kMaxCh) {
-    set_error("mpu_sample_planes: %d channels unsupported (max %d)", C, kMaxCh);
+    set_error("%s: %d channels unsupported (max %d)", who, C, kMaxCh);
     return MPU_ERR_ARG;
   }
-  if (out_padded_bf16 && cpad < C) {
-    set_error("mpu_sample_planes: padded channel count %d < C=%d", cpad, C);
-    return MPU_ERR_ARG;
-  }
-  SamplerParams p;
   memset(&p, 0, sizeof(p));
   p.vol = vol;
   p.labels = labels;
@@ -638,6 +693,25 @@ int mpu_sample_planes(const float* vol, const unsigned char* labels, const int* 
   if (h_rot) memcpy(p.rot, h_rot, sizeof(double) * 9);
   for (int c = 0; c < C; ++c) p.bg_value[c] = h_bg_value ? h_bg_value[c] : 0.f;
   p.bg_class = bg_class;
+  // 1/spacing of each voxel axis: only seeds the cell search, the axis tables decide the result
+  for (int k = 0; k < 3; ++k) p.inv_step[k] = h_inv_step[k];
+  return MPU_OK;
+}
+
+int mpu_sample_planes(const float* vol, const unsigned char* labels, const int* h_dims, int C,
+                      const float* gx, const float* gy, const float* gz, const double* h_inv_step,
+                      const double* h_rot,
+                      const double* planes, int n_planes, int dim, double span,
+                      const float* h_bg_value, int bg_class, const double* h_center,
+                      const double* h_scale, float* out_f32, void* out_padded_bf16, int cpad,
+                      unsigned char* out_labels, void* stream) {
+  SamplerParams p;
+  MPU_TRY(fill_sampler_params(p, "mpu_sample_planes", vol, labels, h_dims, C, gx, gy, gz, h_inv_step, h_rot, planes,
+                              n_planes, dim, span, h_bg_value, bg_class));
+  if (out_padded_bf16 && cpad < C) {
+    set_error("mpu_sample_planes: padded channel count %d < C=%d", cpad, C);
+    return MPU_ERR_ARG;
+  }
   p.apply_scaler = (h_center && h_scale) ? 1 : 0;
   for (int c = 0; c < C; ++c) {
     p.center[c] = h_center ? h_center[c] : 0.0;
@@ -647,11 +721,36 @@ int mpu_sample_planes(const float* vol, const unsigned char* labels, const int* 
   p.out_pad = reinterpret_cast<__nv_bfloat16*>(out_padded_bf16);
   p.cpad = cpad;
   p.out_lab = out_labels;
-  // 1/spacing of each voxel axis: only seeds the cell search, the axis tables decide the result
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  for (int k = 0; k < 3; ++k) p.inv_step[k] = h_inv_step[k];
   const long long total = (long long)n_planes * dim * dim;
   sample_planes_kernel<<<grid_for(total, 256), 256, 0, st>>>(p);
+  count_launch();
+  MPU_CUDA(cudaGetLastError());
+  return MPU_OK;
+}
+
+int mpu_probe_planes(const float* vol, const unsigned char* labels, const int* h_dims, int C,
+                     const float* gx, const float* gy, const float* gz, const double* h_inv_step,
+                     const double* h_rot, const double* planes, int n_planes, int dim, double span,
+                     const float* h_bg_value, int bg_class, unsigned int* class_mask, unsigned int* valid,
+                     void* stream) {
+  SamplerParams p;
+  MPU_TRY(fill_sampler_params(p, "mpu_probe_planes", vol, labels, h_dims, C, gx, gy, gz, h_inv_step, h_rot, planes,
+                              n_planes, dim, span, h_bg_value, bg_class));
+  if (!class_mask && !valid) {
+    set_error("mpu_probe_planes: no output requested");
+    return MPU_ERR_ARG;
+  }
+  if (n_planes > 65535) {
+    set_error("mpu_probe_planes: at most 65535 candidate planes per call");
+    return MPU_ERR_ARG;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (class_mask) MPU_CUDA(cudaMemsetAsync(class_mask, 0, sizeof(unsigned int) * n_planes, st));
+  if (valid) MPU_CUDA(cudaMemsetAsync(valid, 0, sizeof(unsigned int) * n_planes, st));
+  int bx = (dim * dim + 255) / 256;
+  if (bx > 16) bx = 16;
+  probe_planes_kernel<<<dim3(bx, n_planes), 256, 0, st>>>(p, class_mask, valid);
   count_launch();
   MPU_CUDA(cudaGetLastError());
   return MPU_OK;

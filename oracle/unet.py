@@ -116,6 +116,41 @@ class _RoundBwd(torch.autograd.Function):
         return _bf16(g)
 
 
+class _ReluMask(torch.autograd.Function):
+    """relu whose BACKWARD mask is given (teacher forcing: the mask of the forced activation, so that an
+    activation that is +tiny on the device and -tiny here - or the reverse - does not switch a gradient path)."""
+
+    @staticmethod
+    def forward(ctx, pre, mask):
+        ctx.save_for_backward(mask)
+        return pre.clamp_min(0)
+
+    @staticmethod
+    def backward(ctx, g):
+        (mask,) = ctx.saved_tensors
+        return g * mask, None
+
+
+class _GradTap(torch.autograd.Function):
+    """Identity in forward.  In backward it records the gradient the oracle computed at this point
+    (`seen[name]`, NHWC) and - teacher forcing of the BACKWARD pass - replaces it by `forced[name]` when
+    given, so that every layer's backward arithmetic is checked locally: oracle(layer backward of the
+    device's own upstream gradient) against the device's downstream gradient."""
+
+    @staticmethod
+    def forward(ctx, x, name, seen, forced):
+        ctx.name, ctx.seen, ctx.forced = name, seen, forced
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        if ctx.seen is not None:
+            ctx.seen[ctx.name] = g.detach().permute(0, 2, 3, 1).numpy().copy()
+        if ctx.forced is not None and ctx.name in ctx.forced:
+            g = torch.as_tensor(ctx.forced[ctx.name], dtype=g.dtype).permute(0, 3, 1, 2).contiguous()
+        return g, None, None, None
+
+
 def collapse_upconv_weights(w):
     """w [2,2,Cin,Cout] -> dict {(a,b): [((di,dj), W[Cin,Cout]) ...]}: the four sub-pixel phases of
     nearest-2x-upsample followed by the 2x2 SAME conv (unet.py:159-163) as 1/2/2/4-tap convs on the
@@ -153,7 +188,7 @@ class UNetOracle:
         return out
 
     # -- layers (NCHW internally) -----------------------------------------------------------------
-    def _conv(self, x, name, emu, relu=True):
+    def _conv(self, x, name, emu, relu=True, mask=None):
         w = self.P[name]["kernel"]  # HWIO
         b = self.P[name]["bias"]
         k = w.shape[0]
@@ -171,10 +206,10 @@ class UNetOracle:
             raise ValueError(k)
         y = y + b.view(1, -1, 1, 1)
         if relu:
-            y = F.relu(y)
+            y = F.relu(y) if mask is None else _ReluMask.apply(y, mask)
         return _RoundFwd.apply(y) if emu else y
 
-    def _upconv(self, x, name, emu):
+    def _upconv(self, x, name, emu, mask=None):
         """UpSampling2D(2) + Conv2D(k=2, SAME, relu) (unet.py:159-163)."""
         w = self.P[name]["kernel"]
         b = self.P[name]["bias"]
@@ -182,7 +217,7 @@ class UNetOracle:
             up = x.repeat_interleave(2, 2).repeat_interleave(2, 3)
             up = F.pad(up, (0, 1, 0, 1))
             y = F.conv2d(up, w.permute(3, 2, 0, 1)) + b.view(1, -1, 1, 1)
-            return F.relu(y)
+            return F.relu(y) if mask is None else _ReluMask.apply(y, mask)
         x = _RoundBwd.apply(x)
         B, C, h, ww = x.shape
         xp = F.pad(x, (0, 1, 0, 1))
@@ -194,7 +229,8 @@ class UNetOracle:
                 wq = _RoundFwd.apply(wc)  # [Cin, Cout]
                 acc = acc + torch.einsum("bchw,co->bohw", xp[:, :, di:di + h, dj:dj + ww], wq)
             y[:, :, a::2, bb::2] = acc
-        y = F.relu(y + b.view(1, -1, 1, 1))
+        y = y + b.view(1, -1, 1, 1)
+        y = F.relu(y) if mask is None else _ReluMask.apply(y, mask)
         return _RoundFwd.apply(y)
 
     def _bn(self, x, name, training, emu, stats_out=None):
@@ -215,50 +251,68 @@ class UNetOracle:
         return _RoundFwd.apply(y) if emu else y
 
     def logits(self, x_nhwc, training=False, emulate_bf16=False, stats_out=None, capture=None,
-               force=None):
+               force=None, computed=None, grad_seen=None, force_grad=None):
         """`force` {name: NHWC array}: teacher forcing - the forward VALUE of the named activation is
         replaced by the given one (gradients still flow through the computed expression), so a backward
-        comparison is not polluted by forward rounding chaos."""
+        comparison is not polluted by forward rounding chaos.
+        `computed` (out): the value the oracle computed for each activation BEFORE forcing, i.e. this
+        layer's output from the forced inputs - the per-layer forward residual is computed[name] vs force[name].
+        `grad_seen` (out) / `force_grad` (in): the same for the backward pass (see _GradTap); extra tap
+        "skip_<l>" sits on the skip branch of the concat."""
         emu = emulate_bf16
+        taps = grad_seen is not None or force_grad is not None
 
         def cap(name, t):
+            if computed is not None:
+                computed[name] = t.detach().permute(0, 2, 3, 1).numpy().copy()
             if force is not None and name in force:
-                f = torch.as_tensor(force[name], dtype=t.dtype).permute(0, 3, 1, 2)
-                t = t + (f - t).detach()
+                f = torch.as_tensor(force[name], dtype=t.dtype).permute(0, 3, 1, 2).contiguous()
+                t = f + (t - t.detach())  # value exactly f, gradient flows to the computed expression
             if capture is not None:
                 capture[name] = t.detach().permute(0, 2, 3, 1).numpy().copy()
+            if taps and t.requires_grad:
+                t = _GradTap.apply(t, name, grad_seen, force_grad)
             return t
+
+        def fm(name):
+            """ReLU backward mask of a forced post-ReLU activation (None when not forced)."""
+            if force is None or name not in force:
+                return None
+            return (torch.as_tensor(force[name]).permute(0, 3, 1, 2) > 0).to(self.dtype).contiguous()
 
         x = torch.as_tensor(x_nhwc, dtype=self.dtype).permute(0, 3, 1, 2)
         if emu:
             x = _bf16(x)
         skips = []
         for i in range(self.depth):
-            x = self._conv(x, "encoder_L%d_conv1" % i, emu)
+            x = self._conv(x, "encoder_L%d_conv1" % i, emu, mask=fm("a1_%d" % i))
             x = cap("a1_%d" % i, x)
-            x = self._conv(x, "encoder_L%d_conv2" % i, emu)
+            x = self._conv(x, "encoder_L%d_conv2" % i, emu, mask=fm("a2_%d" % i))
             x = cap("a2_%d" % i, x)
             x = self._bn(x, "encoder_L%d_BN" % i, training, emu, stats_out)
             x = cap("b_%d" % i, x)
             skips.append(x)
             x = F.max_pool2d(x, 2)
             x = cap("pooled_%d" % i, x)
-        x = self._conv(x, "bottom_conv1", emu)
+        x = self._conv(x, "bottom_conv1", emu, mask=fm("a1_%d" % self.depth))
         x = cap("a1_%d" % self.depth, x)
-        x = self._conv(x, "bottom_conv2", emu)
+        x = self._conv(x, "bottom_conv2", emu, mask=fm("a2_%d" % self.depth))
         x = cap("a2_%d" % self.depth, x)
         x = self._bn(x, "bottom_BN", training, emu, stats_out)
         x = cap("b_%d" % self.depth, x)
         for i in range(self.depth):
             l = self.depth - 1 - i
-            x = self._upconv(x, "upsample_L%d_conv1" % i, emu)
+            x = self._upconv(x, "upsample_L%d_conv1" % i, emu, mask=fm("u_%d" % l))
             x = cap("u_%d" % l, x)
             x = self._bn(x, "upsample_L%d_BN1" % i, training, emu, stats_out)
             x = cap("bn1_%d" % l, x)
-            x = torch.cat([skips[self.depth - 1 - i], x], dim=1)
-            x = self._conv(x, "upsample_L%d_conv2" % i, emu)
+            sk = skips[self.depth - 1 - i]
+            if taps and sk.requires_grad:
+                sk = _GradTap.apply(sk, "skip_%d" % l, grad_seen, force_grad)
+            x = torch.cat([sk, x], dim=1)
+            x = self._conv(x, "upsample_L%d_conv2" % i, emu, mask=fm("c2_%d" % l))
             x = cap("c2_%d" % l, x)
-            x = self._conv(x, "upsample_L%d_conv3" % i, emu)
+            x = self._conv(x, "upsample_L%d_conv3" % i, emu, mask=fm("c3_%d" % l))
             x = cap("c3_%d" % l, x)
             x = self._bn(x, "upsample_L%d_BN2" % i, training, emu, stats_out)
             x = cap("bn2_%d" % l, x)
@@ -273,14 +327,15 @@ class UNetOracle:
             return torch.softmax(self.logits(x_nhwc, training, emulate_bf16, capture=capture), dim=-1).numpy()
 
     def loss_and_grads(self, x_nhwc, y, sample_weight=None, emulate_bf16=False, loss_scale="sum",
-                       force=None):
+                       force=None, computed=None, grad_seen=None, force_grad=None, capture=None):
         """One training forward/backward.  y [B,H,W] (or [B,HW,1]) integer labels.
         Returns (mean loss, {(layer, param): grad ndarray}, batch BN stats {name: (mean, unbiased var)})."""
         for _, _, t in self.trainable():
             t.requires_grad_(True)
             t.grad = None
         stats = {}
-        z = self.logits(x_nhwc, True, emulate_bf16, stats, force=force)
+        z = self.logits(x_nhwc, True, emulate_bf16, stats, capture=capture, force=force, computed=computed,
+                        grad_seen=grad_seen, force_grad=force_grad)
         B, H, W, C = z.shape
         yy = torch.as_tensor(np.asarray(y).reshape(B, H, W).astype(np.int64))
         logp = torch.log_softmax(z, dim=-1)

@@ -330,6 +330,17 @@ CASES = {
     "wgrad_split": (wgrad_case, dict(B=2, H=32, W=32, Cin=128, Cout=128, BN=128, G=3, splits=8)),
     "wgrad_c96": (wgrad_case, dict(B=2, H=32, W=32, Cin=90, Cout=90, BN=96, G=3, splits=4)),
     "wgrad_n256": (wgrad_case, dict(B=2, H=16, W=16, Cin=362, Cout=362, BN=256, G=2, splits=2)),
+    # channel counts of the deep levels at complexity_factor 2 (the benchmark configuration)
+    "fwd_724": (conv_case, dict(B=2, H=32, W=32, Cin=724, Cout=724, BN=0)),
+    "fwd_1448_16x16": (conv_case, dict(B=2, H=16, W=16, Cin=1448, Cout=1448, BN=0)),
+    "fwd_two_src_724": (conv_case, dict(B=2, H=32, W=32, Cin=724, Cout=724, BN=0, two_src=True)),
+    "fwd_1448_to_724_mask": (conv_case, dict(B=2, H=32, W=32, Cin=1448, Cout=724, BN=0, mask=True, relu=False,
+                                             bias=False)),
+    "upconv_1448_to_724": (upconv_case, dict(B=2, h=16, w_=16, Cin=1448, Cout=724, BN=0)),
+    "upconv_181_to_90": (upconv_case, dict(B=1, h=128, w_=128, Cin=181, Cout=90, BN=0)),
+    "wgrad_724": (wgrad_case, dict(B=2, H=32, W=32, Cin=724, Cout=724, BN=0, G=3, splits=0)),
+    "wgrad_1448_16x16": (wgrad_case, dict(B=2, H=16, W=16, Cin=1448, Cout=1448, BN=0, G=3, splits=0)),
+    "wgrad_1448_to_724": (wgrad_case, dict(B=2, H=32, W=32, Cin=1448, Cout=724, BN=0, G=3, splits=0)),
 }
 
 

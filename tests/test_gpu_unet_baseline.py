@@ -1,0 +1,174 @@
+"""Parity of the U-Net engine AT THE BENCHMARK CONFIGURATION (BASELINE.json configs[1]/[2]): complexity_factor 2
+=> 90/181/362/724/1448 filters (mpunet/bin/defaults/MultiPlanar/train_hparams.yaml:82, mpunet/models/unet.py:91,120),
+256x256 slices, 5 classes, 1 channel - the shapes the throughput numbers are quoted on: 2..12 output-channel tiles,
+up to 23 K-chunks, K = 13 032 accumulation depth, 724+724 two-source concat, head_kernel<*,5>.
+
+Checker: oracle/unet.py (torch-CPU restatement of the Keras graph; PARITY UNPINNED against TensorFlow itself - TF 2.3.2
+cannot be installed here - see the oracle's header), rounding to bf16 exactly where the device stores bf16.
+
+Bars (floating point path, written here as the north star asks):
+  * inference (moving-statistics BN): probabilities within 1e-3 max-abs, arg-max label map bit-exact;
+  * train step, LAYER-LOCAL (oracle teacher-forced in both directions with the device's own tensors): every
+    forward activation - including batch-statistics BN-apply and the fused BN+max-pool - and every
+    back-propagated activation gradient within ONE bf16 ulp (+1e-4 x rms floor for values that cancel to ~0);
+    every parameter gradient within 2e-3 of its tensor maximum with cosine > 0.99999;
+  * train step, chained backward (only forward values forced, the oracle back-propagates on its own): the single
+    one-ulp flips of every layer's gradient (each 0.4 % of one element) travel down the whole chain, so the bar is
+    looser the deeper the tensor: within 3 % of the tensor maximum, cosine > 0.9995 (measured on B200: head-side
+    tensors 1e-5, encoder_L0_conv1 - the end of the chain - 1.0 % / 0.99996 at cf=2 and 1.6 % / 0.99987 at the tiny
+    configuration).  That this is flip noise and NOT a mismatched rounding site is what the layer-local test
+    proves: with the upstream gradient forced every layer agrees to <= 1 ulp and every parameter gradient to 2e-6.
+    Loss equal to 1e-5 relative.
+"""
+import numpy as np
+import pytest
+
+import unet_parity_tools as upt
+
+pytestmark = pytest.mark.gpu
+
+CFGS = {"bench_cf2_256": dict(dim=256, batch=2, cf=2.0, classes=5, channels=1),
+        "small_cf0125_64": dict(dim=64, batch=4, cf=0.125, classes=3, channels=1)}
+CFG = {}
+
+
+@pytest.fixture(scope="module", params=list(CFGS))
+def setup(request):
+    CFG.clear()
+    CFG.update(CFGS[request.param])
+    from multiplanarunet_b200.models import UNet
+    from oracle.unet import UNetOracle, filters_for, init_params
+    rng = np.random.RandomState(5)
+    P = init_params(CFG["classes"], CFG["channels"], 4, CFG["cf"], seed=2, randomize_bn=True)
+    for d in P.values():
+        if "bias" in d:
+            d["bias"] = (0.05 * rng.randn(*d["bias"].shape)).astype(np.float32)
+    # a smooth field + noise (random-noise slices make every class equally likely everywhere: all ties)
+    low = rng.randn(CFG["batch"], CFG["dim"] // 16, CFG["dim"] // 16, 1)
+    x = np.kron(low, np.ones((1, 16, 16, 1))) + 0.3 * rng.randn(CFG["batch"], CFG["dim"], CFG["dim"], 1)
+    x = x.astype(np.float32)
+    y = rng.randint(0, CFG["classes"], size=(CFG["batch"], CFG["dim"], CFG["dim"])).astype(np.uint8)
+    sw = rng.uniform(0.5, 1.5, size=CFG["batch"]).astype(np.float32)
+    model = UNet(n_classes=CFG["classes"], dim=CFG["dim"], n_channels=CFG["channels"],
+                 complexity_factor=CFG["cf"], max_batch=CFG["batch"], training=True)
+    model.set_keras_weights(P)
+    enc, bottom, _ = filters_for(4, CFG["cf"])
+    if CFG["cf"] == 2.0:
+        assert enc + [bottom] == [90, 181, 362, 724, 1448]
+    return dict(P=P, x=x, y=y, sw=sw, model=model, chans=enc + [bottom],
+                oracle=UNetOracle(CFG["classes"], CFG["channels"], 4, CFG["cf"], params=P))
+
+
+def test_param_count_is_the_reference_models(setup):
+    """62.05 M parameters at cf=2 (Keras count_params incl. BN moving statistics)."""
+    from oracle.unet import count_params
+    n = setup["model"].count_params()
+    assert n == count_params(setup["P"]) + sum(2 * d["moving_mean"].size for d in setup["P"].values()
+                                               if "moving_mean" in d)
+    if CFG["cf"] == 2.0:
+        assert 62.0e6 < n < 62.2e6
+
+
+def test_inference_at_benchmark_config(setup):
+    got = setup["model"].predict_on_batch(setup["x"])
+    ref = setup["oracle"].predict(setup["x"], emulate_bf16=True)
+    ref32 = setup["oracle"].predict(setup["x"], emulate_bf16=False)
+    err = float(np.abs(got - ref).max())
+    flips = float((got.argmax(-1) != ref.argmax(-1)).mean())
+    err32 = float(np.abs(got - ref32).max())
+    flips32 = float((got.argmax(-1) != ref32.argmax(-1)).mean())
+    print("inference: max|p - oracle_bf16| = %.3g (labels differ at %.3g of pixels); "
+          "vs the fp32 oracle: %.3g (labels differ at %.3g); oracle_bf16 vs oracle_fp32: %.3g"
+          % (err, flips, err32, flips32, float(np.abs(ref - ref32).max())))
+    # north-star bar at the benchmark configuration; the tiny random-weight net is numerically harsher (its
+    # bf16-rounding oracle itself sits 1.3e-3 from the fp32 oracle), bar 2e-3 there as in test_gpu_variants
+    bar = 1e-3 if CFG["cf"] == 2.0 else 2e-3
+    assert err < bar
+    # arg-max: identical wherever the decision is wider than the probability tolerance (a label can only differ
+    # where the two largest probabilities are closer than twice the error bar: a tie broken by one rounding)
+    t2 = np.sort(ref, axis=-1)[..., -2:]
+    clear = (t2[..., 1] - t2[..., 0]) > 2 * bar
+    assert np.array_equal(got.argmax(-1)[clear], ref.argmax(-1)[clear])
+    assert flips < 2e-3, flips
+    assert np.allclose(got.sum(-1), 1.0, atol=1e-5)
+    # pure fp32 restatement: bf16 storage shows, still within 5e-3 and labels equal outside near-ties
+    assert err32 < 5e-3
+    top2 = np.sort(ref32, axis=-1)[..., -2:]
+    decided = (top2[..., 1] - top2[..., 0]) > 1e-2
+    assert np.array_equal(got.argmax(-1)[decided], ref32.argmax(-1)[decided])
+
+
+def test_train_step_layer_local_residuals_and_gradients(setup):
+    m, P, x, y, sw, chans = (setup[k] for k in ("model", "P", "x", "y", "sw", "chans"))
+    from oracle.unet import UNetOracle
+    m.set_keras_weights(P)
+    loss_sum, force, fgrad = upt.run_staged_backward(m, x, y, sw, chans)
+    grads = m.get_flat_grads_as_keras()
+    loss = loss_sum / (CFG["batch"] * CFG["dim"] ** 2)
+
+    # ---- both directions forced: layer-local residuals
+    oracle = UNetOracle(CFG["classes"], CFG["channels"], 4, CFG["cf"], params=P)
+    computed, seen = {}, {}
+    loss_ref, grads_loc, _ = oracle.loss_and_grads(x, y, sw, emulate_bf16=True, force=force, computed=computed,
+                                                   grad_seen=seen, force_grad=fgrad)
+    assert abs(loss - loss_ref) < 1e-5 * max(1.0, abs(loss_ref))
+    worst_f = worst_b = 0.0
+    report = []
+    for name in sorted(force):
+        r, frac = upt.residual(computed[name], force[name])
+        report.append("fwd %-10s %.3f ulp, %.4f differ" % (name, r, frac))
+        worst_f = max(worst_f, r)
+    for name in sorted(fgrad):
+        g = seen[name]
+        if name.split("_")[0] in upt.RELU_POINTS:
+            g = g * (force[name] > 0)
+        r, frac = upt.residual(g, fgrad[name])
+        report.append("bwd %-10s %.3f ulp, %.4f differ" % (name, r, frac))
+        if r > 1.0:
+            report.append(upt.worst_elements(g, fgrad[name]))
+        worst_b = max(worst_b, r)
+    print("\n".join(report))
+    worst_p, bad_p = 0.0, []
+    for key, r in grads_loc.items():
+        g = grads[key]
+        cos = float((g * r).sum() / (np.linalg.norm(g) * np.linalg.norm(r) + 1e-30))
+        rel = float(np.abs(g - r).max() / (np.abs(r).max() + 1e-30))
+        print("param grad (local) %-28s rel %.3g cos %.7f" % ("%s/%s" % key, rel, cos))
+        worst_p = max(worst_p, rel)
+        if not (cos > 0.99999 and rel < 2e-3):
+            bad_p.append((key, cos, rel))
+            o = np.unravel_index(np.argmax(np.abs(g - r)), r.shape)
+            print("   worst at %s: ref %.6g got %.6g; |ref|max %.4g" % (tuple(int(i) for i in o), r[o], g[o], np.abs(r).max()))
+    print("worst forward residual %.3f ulp, worst backward residual %.3f ulp, worst local param-grad error %.3g"
+          % (worst_f, worst_b, worst_p))
+    assert worst_f <= 1.0, worst_f
+    assert worst_b <= 1.0, worst_b
+    assert not bad_p, bad_p
+
+    # ---- chained backward: only forward values forced (the round-1 test, at this configuration, tighter)
+    oracle = UNetOracle(CFG["classes"], CFG["channels"], 4, CFG["cf"], params=P)
+    _, grads_ref, stats = oracle.loss_and_grads(x, y, sw, emulate_bf16=True, force=force)
+    for key, r in grads_ref.items():
+        g = grads[key]
+        cos = float((g * r).sum() / (np.linalg.norm(g) * np.linalg.norm(r) + 1e-30))
+        rel = float(np.abs(g - r).max() / (np.abs(r).max() + 1e-30))
+        print("param grad (chained) %-28s rel %.3g cos %.7f" % ("%s/%s" % key, rel, cos))
+        if not (cos > 0.9995 and rel < 0.03):
+            bad_p.append((key, cos, rel))
+    assert not bad_p, bad_p
+    W2 = m.get_keras_weights()
+    for name, (mean, var) in stats.items():
+        assert np.abs(W2[name]["moving_mean"] - (0.99 * P[name]["moving_mean"] + 0.01 * mean)).max() < 1e-5
+        assert np.abs(W2[name]["moving_variance"] - (0.99 * P[name]["moving_variance"] + 0.01 * var)).max() < 1e-5
+
+
+@pytest.mark.parametrize("case", ["fwd_724", "fwd_1448_16x16", "fwd_two_src_724", "fwd_1448_to_724_mask",
+                                  "upconv_1448_to_724", "upconv_181_to_90", "wgrad_724", "wgrad_1448_16x16",
+                                  "wgrad_1448_to_724"])
+def test_gemm_at_benchmark_channel_counts(case):
+    """Raw multi-tap GEMM kernels through the C ABI at the deep levels' channel counts (6..12 channel tiles,
+    12..46 K-chunks) against torch fp32 conv2d on the same bf16 operands: |err| <= 0.02 + 1 % (bf16 output
+    rounding is 0.4 %; K up to 26 064 products accumulate in fp32)."""
+    import bringup_gemm as bg
+    fn, kw = bg.CASES[case]
+    assert fn(**kw), case
