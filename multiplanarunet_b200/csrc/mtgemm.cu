@@ -61,6 +61,9 @@ static constexpr uint32_t kStageHalfBytes = 128u * 256u;     // epilogue staging
 //              gradients, accumulated in registers across tiles), transpose through shared memory, then
 //              row-wise coalesced 16-byte stores (optional ReLU-backward mask applied there).
 // ------------------------------------------------------------------------------------------------
+// W_MN: weights read MN-major from the forward layout (dgrad).  PROF: CTA 0 accumulates role stall cycles in p.dbg
+// (bring-up only; the production instantiations carry no timing code).
+template <bool W_MN, bool PROF>
 __global__ void __launch_bounds__(kFwdThreads, 1) mtgemm_fwd_kernel(const __grid_constant__ FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -118,123 +121,143 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mtgemm_fwd_kernel(const __grid
 
   const int total_tiles = p.m_tiles * p.n_tiles;
   const int kchunks = p.chunks0 + p.chunks1;
-  const bool prof = p.dbg != nullptr && blockIdx.x == 0;
+  const bool prof = PROF && p.dbg != nullptr && blockIdx.x == 0;
   long long w0 = 0, w1 = 0, w2 = 0;
   const long long t_start = prof ? clock64() : 0;
 
   if (warp == 0) {
-    // ===== TMA producer (warp-uniform loop, one elected lane issues) =====
-    int as = 0, ws = 0;
-    uint32_t aph = 0, wph = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m0 = (tile / p.n_tiles) * kPT;
-      const int n0 = (tile % p.n_tiles) * 128;
-      for (int g = 0; g < p.ngroups; ++g) {
-        const TapGroup& G = p.groups[g];
-        const int arow = m0 + G.a_off;
-        for (int c = 0; c < kchunks; ++c) {
-          timed_wait(a_empty(as), aph ^ 1u, prof ? &w0 : nullptr);
-          const uint32_t a_dst = a_base + (uint32_t)as * kSlabBytes;
-          int kcol, ccol;
-          const CUtensorMap *mhi, *mlo;
-          if (c < p.chunks0) {
-            ccol = c * 64;
-            kcol = ccol;
-            mhi = &p.tmA0_hi;
-            mlo = &p.tmA0_lo;
-          } else {
-            ccol = (c - p.chunks0) * 64;
-            kcol = p.kofs1 + ccol;
-            mhi = &p.tmA1_hi;
-            mlo = &p.tmA1_lo;
-          }
-          if (elect_one()) {
+    // ===== TMA producer 1: activation slabs -> ring A =====
+    // The two operand streams have their own producer threads (warp 0: slabs, warp 3: weight tiles): a single
+    // sequential producer that blocks on a full slab ring cannot refill freed weight slots (and vice versa), which
+    // showed up as the MMA thread waiting on w_full while the producer sat in a_empty.
+    if (elect_one()) {
+      int as = 0;
+      uint32_t aph = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m0 = (tile / p.n_tiles) * kPT;
+        for (int g = 0; g < p.ngroups; ++g) {
+          const int arow = m0 + p.groups[g].a_off;
+          for (int c = 0; c < kchunks; ++c) {
+            timed_wait(a_empty(as), aph ^ 1u, prof ? &w0 : nullptr);
+            const uint32_t a_dst = a_base + (uint32_t)as * kSlabBytes;
+            const bool src0 = c < p.chunks0;
+            const int ccol = (src0 ? c : c - p.chunks0) * 64;
+            const CUtensorMap* mhi = src0 ? &p.tmA0_hi : &p.tmA1_hi;
+            const CUtensorMap* mlo = src0 ? &p.tmA0_lo : &p.tmA1_lo;
             mbar_expect_tx(a_full(as), kSlabBytes);
             tma_load_2d(mhi, a_full(as), a_dst, ccol, arow);
             tma_load_2d(mlo, a_full(as), a_dst + 136u * 128u, ccol, arow + 136);
-          }
-          __syncwarp();
-          if (++as == NA) { as = 0; aph ^= 1u; }
-          for (int t = 0; t < G.ntaps; ++t) {
-            timed_wait(w_empty(ws), wph ^ 1u, prof ? &w1 : nullptr);
-            if (elect_one()) {
-              mbar_expect_tx(w_full(ws), kWTileBytes);
-              const uint32_t w_dst = w_base + (uint32_t)ws * kWTileBytes;
-              if (!p.w_mn) {
-                tma_load_2d(&p.tmW, w_full(ws), w_dst, kcol, G.w_idx[t] * p.w_rows_per_tap + n0);
-              } else {  // two 64-channel atoms of [64 K rows][64 channels]
-                const int wrow = G.w_idx[t] * p.w_rows_per_tap + kcol;
-                tma_load_2d(&p.tmW, w_full(ws), w_dst, n0, wrow);
-                tma_load_2d(&p.tmW, w_full(ws), w_dst + 8192u, n0 + 64, wrow);
-              }
-            }
-            __syncwarp();
-            if (++ws == NW) { ws = 0; wph ^= 1u; }
+            if (++as == NA) { as = 0; aph ^= 1u; }
           }
         }
       }
+      if (prof) p.dbg[0] = w0;
     }
-    if (prof && lane == 0) {
-      p.dbg[0] = w0;
-      p.dbg[1] = w1;
+    __syncwarp();
+  } else if (warp == 3) {
+    // ===== TMA producer 2: weight tiles -> ring W =====
+    if (elect_one()) {
+      int ws = 0;
+      uint32_t wph = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n0 = (tile % p.n_tiles) * 128;
+        for (int g = 0; g < p.ngroups; ++g) {
+          const int ntaps = p.groups[g].ntaps;
+          // row (K-major: output channel row; MN-major: K row) of each tap's block in the weight matrix
+          const int r0 = p.groups[g].w_idx[0] * p.w_rows_per_tap + (W_MN ? 0 : n0);
+          const int r1 = p.groups[g].w_idx[1] * p.w_rows_per_tap + (W_MN ? 0 : n0);
+          const int r2 = p.groups[g].w_idx[2] * p.w_rows_per_tap + (W_MN ? 0 : n0);
+          for (int c = 0; c < kchunks; ++c) {
+            const int kcol = c < p.chunks0 ? c * 64 : p.kofs1 + (c - p.chunks0) * 64;
+            for (int t = 0; t < ntaps; ++t) {
+              timed_wait(w_empty(ws), wph ^ 1u, prof ? &w1 : nullptr);
+              const uint32_t w_dst = w_base + (uint32_t)ws * kWTileBytes;
+              const int wr = t == 0 ? r0 : (t == 1 ? r1 : r2);
+              mbar_expect_tx(w_full(ws), kWTileBytes);
+              if (!W_MN) {
+                tma_load_2d(&p.tmW, w_full(ws), w_dst, kcol, wr);
+              } else {  // two 64-channel atoms of [64 K rows][64 channels]
+                tma_load_2d(&p.tmW, w_full(ws), w_dst, n0, wr + kcol);
+                tma_load_2d(&p.tmW, w_full(ws), w_dst + 8192u, n0 + 64, wr + kcol);
+              }
+              if (++ws == NW) { ws = 0; wph ^= 1u; }
+            }
+          }
+        }
+      }
+      if (prof) p.dbg[1] = w1;
     }
+    __syncwarp();
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    const uint32_t idesc = make_idesc_bf16(128, kPT, p.w_mn, 0);
-    int as = 0, ws = 0;
-    uint32_t aph = 0, wph = 0;
-    int acs = 0;
-    uint32_t acph = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      timed_wait(tempty_bar(acs), acph ^ 1u, prof ? &w2 : nullptr);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(acs * kPT);
-      uint32_t first = 1;
-      for (int g = 0; g < p.ngroups; ++g) {
-        const TapGroup& G = p.groups[g];
-        for (int c = 0; c < kchunks; ++c) {
-          timed_wait(a_full(as), aph, prof ? &w0 : nullptr);
-          const uint32_t a_addr = a_base + (uint32_t)as * kSlabBytes;
-          // K=16 steps that hold real channels in this 64-channel chunk (the rest is TMA zero fill)
-          const int crem = c < p.chunks0 ? p.c0_valid - c * 64 : p.c1_valid - (c - p.chunks0) * 64;
-          const int ksteps = crem >= 64 ? 4 : (crem + 15) >> 4;
-          for (int t = 0; t < G.ntaps; ++t) {
-            timed_wait(w_full(ws), wph, prof ? &w1 : nullptr);
-            tc_fence_after();
-            if (elect_one()) {
-              // K-major weights: K step = +32 B inside the 128 B row.  MN-major weights (w_mn): K step =
-              // 16 rows = +2048 B, channel atoms 8192 B apart.
-              const uint64_t w_desc = p.w_mn
-                                          ? make_desc_sw128(w_base + (uint32_t)ws * kWTileBytes, 8192, 1024)
-                                          : make_desc_sw128(w_base + (uint32_t)ws * kWTileBytes, 16, 1024);
-              const uint64_t w_step = p.w_mn ? 128u : 2u;  // in 16-byte units
-              const uint64_t x_desc = make_desc_sw128(a_addr + (uint32_t)G.shift[t] * 128u, 16, 1024);
-#pragma unroll
-              for (int kk = 0; kk < 4; ++kk) {
-                if (kk < ksteps)
-                  mma_bf16_ss(d_tmem, w_desc + (uint64_t)kk * w_step, x_desc + (uint64_t)(kk * 2), idesc,
-                              (first && kk == 0) ? 0u : 1u);
+    // ONE elected thread runs the whole role (waits, descriptor arithmetic, issue, commits): measured on B200
+    // (tests/mma_issue_bench.cu, profiles/r02_mma_issue_cost.txt) the tensor pipe sustains its floor of N/2 cycles
+    // per M=128 MMA with both operands in shared memory, concurrent TMA refill, tcgen05.ld traffic and row-shifted
+    // descriptors - what held the round-1 loop at ~190 cycles per MMA was the ~100-instruction, latency-chained
+    // issue path per tap (constant-bank lookups with register indices, R2UR chains, per-tap elect/reconverge).
+    // Everything that does not change inside a tile is hoisted; a tap costs one mbarrier wait, two 64-bit adds
+    // per MMA and one commit.
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_bf16(128, kPT, W_MN ? 1 : 0, 0);
+      const uint64_t w_hi = (W_MN ? make_desc_sw128(0, 8192, 1024) : make_desc_sw128(0, 16, 1024));
+      const uint64_t x_hi = make_desc_sw128(0, 16, 1024);
+      constexpr uint64_t w_step = W_MN ? 128u : 2u;  // K = 16 step in 16-byte units (MN-major: 16 rows = 2048 B)
+      const uint32_t a_lo0 = (a_base & 0x3FFFFu) >> 4, w_lo0 = (w_base & 0x3FFFFu) >> 4;
+      // 64-channel chunks whose tail holds fewer than 4 K=16 steps of real channels (the rest is TMA zero fill)
+      const int tail_c0 = (p.c0_valid & 63) ? p.chunks0 - 1 : -1;
+      const int tail_k0 = ((p.c0_valid & 63) + 15) >> 4;
+      const int tail_c1 = (p.chunks1 > 0 && (p.c1_valid & 63)) ? kchunks - 1 : -1;
+      const int tail_k1 = ((p.c1_valid & 63) + 15) >> 4;
+      int as = 0, ws = 0;
+      uint32_t aph = 0, wph = 0;
+      int acs = 0;
+      uint32_t acph = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        timed_wait(tempty_bar(acs), acph ^ 1u, prof ? &w2 : nullptr);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acs * kPT);
+        uint32_t acc = 0;
+        for (int g = 0; g < p.ngroups; ++g) {
+          const int ntaps = p.groups[g].ntaps;
+          const uint32_t sh0 = (uint32_t)p.groups[g].shift[0] * 8u, sh1 = (uint32_t)p.groups[g].shift[1] * 8u,
+                         sh2 = (uint32_t)p.groups[g].shift[2] * 8u;  // row shift in 16-byte units
+          for (int c = 0; c < kchunks; ++c) {
+            timed_wait(a_full(as), aph, prof ? &w0 : nullptr);
+            const uint32_t a_lo = a_lo0 + (uint32_t)as * (kSlabBytes >> 4);
+            const int ks = c == tail_c0 ? tail_k0 : (c == tail_c1 ? tail_k1 : 4);
+            for (int t = 0; t < ntaps; ++t) {
+              timed_wait(w_full(ws), wph, prof ? &w1 : nullptr);
+              tc_fence_after();
+              const uint64_t wd = w_hi | (uint64_t)(w_lo0 + (uint32_t)ws * (kWTileBytes >> 4));
+              const uint64_t xd = x_hi | (uint64_t)(a_lo + (t == 0 ? sh0 : (t == 1 ? sh1 : sh2)));
+              if (ks == 4) {
+                mma_bf16_ss(d_tmem, wd, xd, idesc, acc);
+                mma_bf16_ss(d_tmem, wd + w_step, xd + 2, idesc, 1u);
+                mma_bf16_ss(d_tmem, wd + 2 * w_step, xd + 4, idesc, 1u);
+                mma_bf16_ss(d_tmem, wd + 3 * w_step, xd + 6, idesc, 1u);
+              } else {
+                for (int kk = 0; kk < ks; ++kk)
+                  mma_bf16_ss(d_tmem, wd + (uint64_t)kk * w_step, xd + (uint64_t)(2 * kk), idesc, kk ? 1u : acc);
               }
+              acc = 1u;
               mma_commit(w_empty(ws));
-              if (t == G.ntaps - 1) mma_commit(a_empty(as));
+              if (++ws == NW) { ws = 0; wph ^= 1u; }
             }
-            __syncwarp();
-            first = 0;
-            if (++ws == NW) { ws = 0; wph ^= 1u; }
+            mma_commit(a_empty(as));
+            if (++as == NA) { as = 0; aph ^= 1u; }
           }
-          if (++as == NA) { as = 0; aph ^= 1u; }
         }
+        mma_commit(tfull_bar(acs));
+        if (++acs == 2) { acs = 0; acph ^= 1u; }
       }
-      if (elect_one()) mma_commit(tfull_bar(acs));
-      __syncwarp();
-      if (++acs == 2) { acs = 0; acph ^= 1u; }
+      if (prof) {
+        p.dbg[2] = w0;
+        p.dbg[3] = w1;
+        p.dbg[4] = w2;
+        p.dbg[7] = clock64() - t_start;
+      }
     }
-    if (prof && lane == 0) {
-      p.dbg[2] = w0;
-      p.dbg[3] = w1;
-      p.dbg[4] = w2;
-      p.dbg[7] = clock64() - t_start;
-    }
+    __syncwarp();
   } else if (warp >= 4) {
     // ===== epilogue =====
     const int q = warp & 3;              // TMEM lane quarter: channels q*32 .. q*32+31 of the tile
@@ -282,21 +305,24 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mtgemm_fwd_kernel(const __grid
       const long long te0 = prof_e ? clock64() : 0;
       const float bias = (p.bias && ch < p.n_valid) ? __ldg(p.bias + ch) : 0.f;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acs * kPT + half * 128);
-#pragma unroll 2
-      for (int c0 = 0; c0 < 128; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld16(t_row + (uint32_t)c0, r);
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t r[2][16];
+        tmem_ld16(t_row + (uint32_t)c0, r[0]);  // two loads in flight before the wait
+        tmem_ld16(t_row + (uint32_t)c0 + 16u, r[1]);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float v = __uint_as_float(r[j]) + bias;
-          if (p.relu) v = fmaxf(v, 0.f);
-          const __nv_bfloat16 hb = __float2bfloat16_rn(v);
-          stg[(c0 + j) * 128 + ch_local] = hb;
-          if (p.stats && orow_s[c0 + j] >= 0) {
-            const float vr = __bfloat162float(hb);
-            s_sum += vr;
-            s_sq = fmaf(vr, vr, s_sq);
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float v = __uint_as_float(r[h][j]) + bias;
+            if (p.relu) v = fmaxf(v, 0.f);
+            const __nv_bfloat16 hb = __float2bfloat16_rn(v);
+            stg[(c0 + h * 16 + j) * 128 + ch_local] = hb;
+            if (p.stats && orow_s[c0 + h * 16 + j] >= 0) {
+              const float vr = __bfloat162float(hb);
+              s_sum += vr;
+              s_sq = fmaf(vr, vr, s_sq);
+            }
           }
         }
       }
@@ -384,12 +410,14 @@ __global__ void __launch_bounds__(kThreads, 1)
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  // work decomposition
+  // work decomposition: the CTAs that read the same pixel range (all kernel rows, output-channel tiles and
+  // input-channel tiles of one K split) are neighbours in the grid, so they run in the same wave and share the
+  // X / dY lines through L2 instead of re-streaming them from HBM (round 1: 2.4x the algorithmic DRAM bytes)
   int w = blockIdx.x;
-  const int split = w % p.splits; w /= p.splits;
   const int gi = w % p.ngroups;   w /= p.ngroups;
   const int co_t = w % p.co_tiles; w /= p.co_tiles;
-  const int ci_t = w;
+  const int ci_t = w % p.ci_tiles; w /= p.ci_tiles;
+  const int split = w;
   const WgradGroup& grp = p.groups[gi];
   const int ci0 = ci_t * CA * 64, co0 = co_t * 128;
   const int kb0 = split * p.kblocks_per_split;
@@ -419,51 +447,54 @@ __global__ void __launch_bounds__(kThreads, 1)
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
-    int s = 0;
-    uint32_t ph = 0;
-    for (int kb = kb0; kb < kb1; ++kb) {
-      const int r0 = kb * 64;
-      mbar_wait(empty_bar(s), ph ^ 1u);
-      const uint32_t st = smem_base + (uint32_t)s * stage_bytes;
-      if (elect_one()) {
+    // TMA producer: one elected thread runs the whole role
+    if (elect_one()) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        const int r0 = kb * 64;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        const uint32_t st = smem_base + (uint32_t)s * stage_bytes;
         mbar_expect_tx(full_bar(s), stage_bytes);
         tma_load_2d(&p.tmDY, full_bar(s), st, co0, r0 + grp.dy_off);
         tma_load_2d(&p.tmDY, full_bar(s), st + 8192u, co0 + 64, r0 + grp.dy_off);
         for (int a = 0; a < CA; ++a)
           tma_load_2d(&p.tmX, full_bar(s), st + kWgABytes + (uint32_t)a * kWgAtomBytes, ci0 + a * 64,
                       r0 + grp.x_off);
+        if (++s == S) { s = 0; ph ^= 1u; }
       }
-      __syncwarp();
-      if (++s == S) { s = 0; ph ^= 1u; }
     }
+    __syncwarp();
   } else if (warp == 1) {
-    const uint32_t idesc = make_idesc_bf16(128, ncol, 1, 1);
-    int s = 0;
-    uint32_t ph = 0;
-    for (int kb = 0; kb < nkb; ++kb) {
-      mbar_wait(full_bar(s), ph);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t st = smem_base + (uint32_t)s * stage_bytes;
-        const uint32_t bst = st + kWgABytes;
+    // MMA issuer: one elected thread; descriptor high words hoisted (see mtgemm_fwd_kernel)
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_bf16(128, ncol, 1, 1);
+      // K step = 16 pixel rows = 2048 B.  A: co atoms 8192 B apart.  B: "atom" j = slab shifted by
+      // j rows (LBO = 128 B) -> the taps of this kernel row side by side along N.
+      const uint64_t a_hi = make_desc_sw128(0, 8192, 1024), b_hi = make_desc_sw128(0, 128, 1024);
+      const uint32_t lo0 = (smem_base & 0x3FFFFu) >> 4;
+      int s = 0;
+      uint32_t ph = 0;
+      uint32_t acc = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint32_t st_lo = lo0 + (uint32_t)s * (stage_bytes >> 4);
+        const uint64_t ad = a_hi | (uint64_t)st_lo;
         for (int a = 0; a < CA; ++a) {
           const uint32_t d_tmem = tmem_base + (uint32_t)(a * ncol);
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            // K step = 16 pixel rows = 2048 B.  A: co atoms 8192 B apart.  B: "atom" j = slab shifted by
-            // j rows (LBO = 128 B) -> the taps of this kernel row side by side along N.
-            const uint64_t a_desc = make_desc_sw128(st + (uint32_t)kk * 2048u, 8192, 1024);
-            const uint64_t b_desc =
-                make_desc_sw128(bst + (uint32_t)a * kWgAtomBytes + (uint32_t)kk * 2048u, 128, 1024);
-            mma_bf16_ss(d_tmem, a_desc, b_desc, idesc, (kb | kk) != 0 ? 1u : 0u);
-          }
+          const uint64_t bd = b_hi | (uint64_t)(st_lo + (kWgABytes >> 4) + (uint32_t)a * (kWgAtomBytes >> 4));
+          mma_bf16_ss(d_tmem, ad, bd, idesc, acc);
+          mma_bf16_ss(d_tmem, ad + 128, bd + 128, idesc, 1u);
+          mma_bf16_ss(d_tmem, ad + 256, bd + 256, idesc, 1u);
+          mma_bf16_ss(d_tmem, ad + 384, bd + 384, idesc, 1u);
         }
+        acc = 1u;
         mma_commit(empty_bar(s));
+        if (++s == S) { s = 0; ph ^= 1u; }
       }
-      __syncwarp();
-      if (++s == S) { s = 0; ph ^= 1u; }
+      mma_commit(done_bar);
     }
-    if (elect_one()) mma_commit(done_bar);
     __syncwarp();
   } else if (warp >= 4) {
     const int q = warp & 3;
@@ -559,6 +590,11 @@ int num_sms() {
 }
 
 static int g_fwd_attr_set = 0, g_wgrad_attr_set = 0;
+typedef void (*FwdKernel)(const FwdParams);
+static FwdKernel fwd_kernel_for(bool w_mn, bool prof) {
+  if (prof) return w_mn ? mtgemm_fwd_kernel<true, true> : mtgemm_fwd_kernel<false, true>;
+  return w_mn ? mtgemm_fwd_kernel<true, false> : mtgemm_fwd_kernel<false, false>;
+}
 static constexpr int kDefaultSmemReserveKB = 0;
 static constexpr int kDynSmem = 232448 - 1024;  // leave room for static smem (none) and the driver
 
@@ -676,14 +712,15 @@ int launch_fwd(FwdParams& p, cudaStream_t stream) {
   p.m_tiles = (p.M_rows + kPT - 1) / kPT;
   p.n_tiles = (p.n_valid + 127) / 128;
   if (!g_fwd_attr_set) {
-    MPU_CUDA(cudaFuncSetAttribute(mtgemm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  kDynSmem));
+    for (int i = 0; i < 4; ++i)
+      MPU_CUDA(cudaFuncSetAttribute(fwd_kernel_for(i & 1, i & 2), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    kDynSmem));
     g_fwd_attr_set = 1;
   }
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   gemm_timer_begin(stream);
-  mtgemm_fwd_kernel<<<grid, kFwdThreads, kDynSmem - smem_reserve(), stream>>>(p);
+  fwd_kernel_for(p.w_mn != 0, p.dbg != nullptr)<<<grid, kFwdThreads, kDynSmem - smem_reserve(), stream>>>(p);
   gemm_timer_end(stream);
   count_launch();
   MPU_CUDA(cudaGetLastError());
