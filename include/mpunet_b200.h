@@ -159,6 +159,19 @@ int mpu_map_fuse(const void* const* h_pred_ptrs, int V, int C, int dim, int n_pl
                  const double* h_mean, const float* W, const float* b, int sum_fusion,
                  unsigned char* labels_out, float* probs_out, float* combined_out, void* stream);
 
+/* The same operation when every axis is an np.linspace (what the reference's grids are: in-plane axis
+ * np.linspace(-hd, hd, dim), sample_grid.py:227-233 in test mode; plane offsets np.linspace(-bounds, bounds, n),
+ * sequences/isotrophic_live_view_sequence_2d.py:62): the axis values g[i] = fl(fl(i*step) + start), g[n-1] = stop are
+ * recomputed in registers instead of looked up, and the C probabilities of a pixel are gathered with aligned 16-byte
+ * loads.  The CALLER guarantees the tables equal that formula bit for bit (the Python shim checks and otherwise calls
+ * mpu_map_fuse); results are then identical to mpu_map_fuse.  All h_ arguments are host pointers:
+ * h_inv_basis [V][9], h_ax_lin [3] = start, step, stop, h_off_lin [V][3].  2 <= C <= 8. */
+int mpu_map_fuse_linspace(const void* const* h_pred_ptrs, int V, int C, int dim, int n_planes,
+                          const double* h_inv_basis, const double* h_ax_lin, const double* h_off_lin,
+                          const int* h_dims, const double* h_affine3x3, const double* h_mean, const float* W,
+                          const float* b, int sum_fusion, unsigned char* labels_out, float* probs_out,
+                          float* combined_out, void* stream);
+
 /* ---- fusion-layer training ---------------------------------------------------------------------------
  * Replaces FusionModel.fit's train step (bin/train_fusion.py:196-213; loss evaluate/loss_functions.py:
  * 207-246 with uniform weights; regulariser models/fusion_model.py:9-11).  X [n][V][C] f32, y [n] u8.

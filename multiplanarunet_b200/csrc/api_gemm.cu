@@ -21,6 +21,18 @@ const char* last_error() { return g_err; }
 
 long long g_launch_count = 0;
 
+int sm_count() {
+  static int cache[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (!cache[dev]) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) return 148;
+    cache[dev] = n;
+  }
+  return cache[dev];
+}
+
 // GEMM event timer: when enabled, every tensor-core GEMM launch is bracketed by a CUDA event pair on
 // its own stream; mpu_profile_gemm_read() synchronises and sums the elapsed times.
 static bool g_timer_on = false;

@@ -19,6 +19,8 @@ inline void count_launch(int n = 1) { g_launch_count += n; }
 void gemm_timer_begin(cudaStream_t st);
 void gemm_timer_end(cudaStream_t st);
 bool gemm_timer_on();
+// multiprocessor count of the CURRENT device (cached per device ordinal)
+int sm_count();
 }  // namespace mpu
 
 #define MPU_CUDA(expr)                                                                   \

@@ -579,17 +579,15 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t col
   return MPU_OK;
 }
 
-int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-  }
-  return n;
-}
+int num_sms() { return sm_count(); }
 
-static int g_fwd_attr_set = 0, g_wgrad_attr_set = 0;
+// cudaFuncSetAttribute is per device: one flag per device ordinal
+static bool g_fwd_attr_set[64] = {false}, g_wgrad_attr_set[64] = {false};
+static int cur_dev() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < 64) ? dev : 0;
+}
 typedef void (*FwdKernel)(const FwdParams);
 static FwdKernel fwd_kernel_for(bool w_mn, bool prof) {
   if (prof) return w_mn ? mtgemm_fwd_kernel<true, true> : mtgemm_fwd_kernel<false, true>;
@@ -711,11 +709,11 @@ int launch_fwd(FwdParams& p, cudaStream_t stream) {
   p.w_slots = NW;
   p.m_tiles = (p.M_rows + kPT - 1) / kPT;
   p.n_tiles = (p.n_valid + 127) / 128;
-  if (!g_fwd_attr_set) {
+  if (!g_fwd_attr_set[cur_dev()]) {
     for (int i = 0; i < 4; ++i)
       MPU_CUDA(cudaFuncSetAttribute(fwd_kernel_for(i & 1, i & 2), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     kDynSmem));
-    g_fwd_attr_set = 1;
+    g_fwd_attr_set[cur_dev()] = true;
   }
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
@@ -798,10 +796,10 @@ int launch_wgrad(WgradParams& p, cudaStream_t stream) {
     return MPU_ERR_ARG;
   }
   p.stages = S;
-  if (!g_wgrad_attr_set) {
+  if (!g_wgrad_attr_set[cur_dev()]) {
     MPU_CUDA(cudaFuncSetAttribute(mtgemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   kDynSmem));
-    g_wgrad_attr_set = 1;
+    g_wgrad_attr_set[cur_dev()] = true;
   }
   const int grid = p.ci_tiles * p.co_tiles * p.ngroups * p.splits;
   gemm_timer_begin(stream);

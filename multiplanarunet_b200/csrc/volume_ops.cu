@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include <cuda_bf16.h>
@@ -232,6 +233,13 @@ struct MapFuseParams {
   uint8_t* labels_out;               // [X][Y][Z] or null
   float* probs_out;                  // [X][Y][Z][C] or null
   float* combined_out;               // [V][X][Y][Z][C] or null
+  // Analytic axes (fast path): every axis is an np.linspace, g[i] = fl(fl(i * step) + start) for i < n-1 and
+  // g[n-1] = stop (numpy/_core/function_base.py); the host verifies the tables bit for bit before enabling it.
+  int analytic;
+  double ax_start, ax_step, ax_stop;
+  double off_start[kMaxViews], off_step[kMaxViews], off_stop[kMaxViews];
+  double ib[kMaxViews][9];           // host copy of inv_basis for the fast path
+  long long pred_elems;              // floats per view stack (guards the 16-byte over-read at the very end)
 };
 
 // Persistent blocks walk (i, j) lines of the voxel grid, threads walk k: no per-voxel integer division.  The
@@ -342,20 +350,199 @@ __global__ void __launch_bounds__(256) map_fuse_kernel(const MapFuseParams p) {
   }
 }
 
+// ---- fast path: analytic axes, no table lookups, 16-byte gathers -------------------------------------------
+// The table version above is bound by the L1/TEX pipe (97 % busy, profiles/r02_ncu_full_volume_kernels_summary.txt):
+// per voxel and view it issues ~24 shared-memory table reads for the three index searches and NC scattered 4-byte
+// loads.  Here the axis values are recomputed in registers exactly as numpy's linspace produced them, and the NC
+// probabilities of a pixel (a 4-byte-aligned run of NC floats) are fetched with ceil((NC+3)/4) aligned 16-byte loads.
+struct LinAxis {
+  double start, step, stop, inv;
+  int n;
+  __device__ __forceinline__ double at(int i) const {
+    return i == n - 1 ? stop : __dadd_rn(__dmul_rn((double)i, step), start);
+  }
+};
+
+// searchsorted(g, x, 'left') - 1 clamped to [0, n-2], the nearest-neighbour decision t <= .5 and the OOB test of
+// regular_grid_interpolator.py:219-223,252-270 on an analytic axis.  Returns the selected index; *oob accumulates.
+// Which cell x falls in only matters through the midpoint rule (a point on a node selects that node from either
+// side), so the continuous index r = (x - start) / step decides everything unless its fractional part is within 1e-6
+// of .5 - six orders of magnitude above every rounding difference between r and the reference's t (|r| < 1e3,
+// double precision) - and only that sliver takes the reference's exact sequence of operations.
+__device__ __noinline__ int nearest_on_axis_exact(double start, double step, double stop, double inv, int n, double x) {
+  // scalars by value: a struct passed by reference would force the caller to keep it in local memory
+  const LinAxis a = {start, step, stop, inv, n};
+  int i = (int)floor((x - a.start) * a.inv);
+  i = max(0, min(a.n - 2, i));
+  double g0 = a.at(i), g1 = a.at(i + 1);
+  while (i < a.n - 2 && g1 < x) {
+    ++i;
+    g0 = g1;
+    g1 = a.at(i + 1);
+  }
+  while (i > 0 && !(g0 < x)) {
+    --i;
+    g1 = g0;
+    g0 = a.at(i);
+  }
+  return lower_half(__dsub_rn(x, g0), __dsub_rn(g1, g0)) ? i : i + 1;
+}
+
+__device__ __forceinline__ int nearest_on_axis(const LinAxis& a, double x, bool* oob) {
+  *oob = *oob || x < a.start || x > a.stop;
+  const double r = (x - a.start) * a.inv;
+  const double fl = floor(r);
+  const double f = r - fl;
+  if (fabs(f - 0.5) > 1e-6) {
+    const int s = (int)fl + (f > 0.5 ? 1 : 0);
+    return max(0, min(a.n - 1, s));
+  }
+  return nearest_on_axis_exact(a.start, a.step, a.stop, a.inv, a.n, x);
+}
+
+template <int NC, bool VEC>
+__global__ void __launch_bounds__(256, 4) map_fuse_lin_kernel(const __grid_constant__ MapFuseParams p) {
+  constexpr int NW = (NC + 3 + 3) / 4;  // aligned 16-byte words covering NC floats at any 4-byte phase
+  const long long plane = (long long)p.Y * p.Z;
+  const long long total = (long long)p.X * plane;
+  const int lines = p.X * p.Y;
+  __shared__ float s_w[kMaxViews * NC + NC];  // fusion weights and bias: broadcast reads
+  if (!p.sum_fusion) {
+    for (int t = threadIdx.x; t < p.V * NC; t += blockDim.x) s_w[t] = p.W[t];
+    for (int t = threadIdx.x; t < NC; t += blockDim.x) s_w[kMaxViews * NC + t] = p.b[t];
+  }
+  __syncthreads();
+  // lines are dealt round-robin: all resident blocks then work inside the same ~2-voxel-thick slab of the volume,
+  // whose pixels of every view stay in L2 (measured: giving each block a run of consecutive lines instead spreads
+  // the blocks over the whole volume and multiplies the DRAM traffic by 2.5)
+  for (int line = blockIdx.x; line < lines; line += gridDim.x) {
+    const int i = line / p.Y, j = line - i * p.Y;
+    for (int k = threadIdx.x; k < p.Z; k += blockDim.x) {
+      const long long idx = (long long)line * p.Z + k;
+      double xr[3];
+      xr[0] = __dsub_rn(dot3(p.affine + 0, (double)i, (double)j, (double)k), p.mean[0]);
+      xr[1] = __dsub_rn(dot3(p.affine + 3, (double)i, (double)j, (double)k), p.mean[1]);
+      xr[2] = __dsub_rn(dot3(p.affine + 6, (double)i, (double)j, (double)k), p.mean[2]);
+      float z[NC];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) z[c] = 0.f;
+      for (int v = 0; v < p.V; ++v) {
+        const double* ib = p.ib[v];
+        const double q0 = dot3(ib + 0, xr[0], xr[1], xr[2]);
+        const double q1 = dot3(ib + 3, xr[0], xr[1], xr[2]);
+        const double q2 = dot3(ib + 6, xr[0], xr[1], xr[2]);
+        const LinAxis ax = {p.ax_start, p.ax_step, p.ax_stop, p.inv_step_ax, p.dim};
+        const LinAxis of = {p.off_start[v], p.off_step[v], p.off_stop[v], p.inv_step_off[v], p.n_planes};
+        bool oob = false;
+        const int s0 = nearest_on_axis(ax, q0, &oob);
+        const int s1 = nearest_on_axis(ax, q1, &oob);
+        const int s2 = nearest_on_axis(of, q2, &oob);
+        float x[NC];
+        if (oob) {
+#pragma unroll
+          for (int c = 0; c < NC; ++c) x[c] = c == 0 ? 1.f : 0.f;
+        } else {
+          const long long e = (((long long)s2 * p.dim + s0) * p.dim + s1) * NC;  // first float of the pixel
+          const float* src = p.pred[v] + e;
+          const int ph = (int)((reinterpret_cast<uintptr_t>(src) >> 2) & 3);     // 4-byte phase inside 16 bytes
+          if (VEC && e - ph + 4 * NW <= p.pred_elems) {
+            const uint4* a16 = reinterpret_cast<const uint4*>(src - ph);
+            uint32_t w[4 * NW];
+#pragma unroll
+            for (int t = 0; t < NW; ++t) {
+              const uint4 q = __ldg(a16 + t);
+              w[4 * t] = q.x; w[4 * t + 1] = q.y; w[4 * t + 2] = q.z; w[4 * t + 3] = q.w;
+            }
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+              const uint32_t u = ph == 0 ? w[c] : (ph == 1 ? w[c + 1] : (ph == 2 ? w[c + 2] : w[c + 3]));
+              x[c] = __uint_as_float(u);
+            }
+          } else {  // last pixels of the stack: stay inside the buffer
+#pragma unroll
+            for (int c = 0; c < NC; ++c) x[c] = __ldg(src + c);
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          if (p.combined_out) p.combined_out[((long long)v * total + idx) * NC + c] = x[c];
+          if (p.sum_fusion) z[c] = __fadd_rn(z[c], x[c]);
+          else z[c] = __fadd_rn(z[c], __fmul_rn(s_w[v * NC + c], x[c]));
+        }
+      }
+      float pr[NC];
+      if (p.sum_fusion) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) pr[c] = z[c];
+      } else {
+        float m = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          z[c] = __fadd_rn(z[c], s_w[kMaxViews * NC + c]);
+          m = fmaxf(m, z[c]);
+        }
+        float sum = 0.f;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          pr[c] = expf(__fsub_rn(z[c], m));
+          sum = __fadd_rn(sum, pr[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < NC; ++c) pr[c] = __fdiv_rn(pr[c], sum);
+      }
+      int best = 0;
+      float bv = pr[0];
+#pragma unroll
+      for (int c = 1; c < NC; ++c)
+        if (pr[c] > bv) {
+          bv = pr[c];
+          best = c;
+        }
+      if (p.labels_out) p.labels_out[idx] = (uint8_t)best;
+      if (p.probs_out) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) p.probs_out[idx * NC + c] = pr[c];
+      }
+    }
+  }
+}
+
+template <int NC>
+static int launch_map_fuse_lin(const MapFuseParams& p, cudaStream_t st) {
+  int occ = 1;
+  const int sms = sm_count();
+  static int vec = -1;  // bring-up knob: MPU_MAPFUSE_VEC=0 gathers with 4-byte loads
+  if (vec < 0) {
+    const char* e = getenv("MPU_MAPFUSE_VEC");
+    vec = e ? atoi(e) : 1;
+  }
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, map_fuse_lin_kernel<NC, true>, 256, 0) != cudaSuccess) occ = 1;
+  const int lines = p.X * p.Y;
+  const int grid = std::max(1, std::min(lines, sms * std::max(occ, 1)));
+  if (vec) map_fuse_lin_kernel<NC, true><<<grid, 256, 0, st>>>(p);
+  else map_fuse_lin_kernel<NC, false><<<grid, 256, 0, st>>>(p);
+  count_launch();
+  MPU_CUDA(cudaGetLastError());
+  return MPU_OK;
+}
+
 template <int NC>
 int launch_map_fuse(const MapFuseParams& p, cudaStream_t st) {
+  if constexpr (NC > 0) {
+    if (p.analytic) return launch_map_fuse_lin<NC>(p, st);
+  }
   const size_t smem = sizeof(double) * ((size_t)p.dim + (size_t)p.V * p.n_planes + (size_t)p.V * 9);
   const int lines = p.X * p.Y;
   int occ = 1;
   if (smem <= 40 * 1024) {
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, map_fuse_kernel<NC, true>, 256, smem) != cudaSuccess)
       occ = 1;
-    const int grid = std::max(1, std::min(lines, 148 * std::max(occ, 1)));
+    const int grid = std::max(1, std::min(lines, sm_count() * std::max(occ, 1)));
     map_fuse_kernel<NC, true><<<grid, 256, smem, st>>>(p);
   } else {
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, map_fuse_kernel<NC, false>, 256, 0) != cudaSuccess)
       occ = 1;
-    const int grid = std::max(1, std::min(lines, 148 * std::max(occ, 1)));
+    const int grid = std::max(1, std::min(lines, sm_count() * std::max(occ, 1)));
     map_fuse_kernel<NC, false><<<grid, 256, 0, st>>>(p);
   }
   count_launch();
@@ -425,6 +612,131 @@ __global__ void fusion_grad_kernel(const float* __restrict__ X, const uint8_t* _
   }
 }
 
+// Compile-time (V, C) variant: everything lives in registers (the generic kernel above indexes its accumulators
+// dynamically, which puts them in local memory: 687 MB of DRAM writes per 256^3 pass, profiles/r02_ncu_full_volume_
+// kernels_summary.txt).  One point = V*C consecutive floats, read with 8-byte loads (V*C even) - each thread walks
+// its own row, the warp covers 32 consecutive rows, so every fetched line is fully used out of L1.
+template <int V, int C>
+__global__ void __launch_bounds__(128, 4) fusion_grad_kernel_t(const float* __restrict__ X, const uint8_t* __restrict__ y,
+                                                               long long n, const float* __restrict__ W,
+                                                               const float* __restrict__ b, double* __restrict__ accum) {
+  constexpr int VC = V * C, NACC = VC + C + 1;
+  constexpr int kChunkFloats = 32 * VC;          // one warp iteration = 32 consecutive points
+  constexpr int kVec = kChunkFloats / 4;         // float4 per chunk (32 * VC is a multiple of 4)
+  __shared__ double fsm[4][NACC];
+  // Each warp stages its 32 points (32 * VC contiguous floats) through shared memory with fully coalesced 16-byte
+  // loads: per-thread row walks touch 32 different lines per load instruction and saturate the L1 tag stage
+  // (measured 0.83 ms per 256^3 pass against 0.31 ms of HBM time).
+  __shared__ __align__(16) float stage[4][kChunkFloats];
+  float loc[NACC];
+#pragma unroll
+  for (int k = 0; k < NACC; ++k) loc[k] = 0.f;
+  float w[VC], bb[C];
+#pragma unroll
+  for (int k = 0; k < VC; ++k) w[k] = W[k];
+#pragma unroll
+  for (int c = 0; c < C; ++c) bb[c] = b[c];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long nchunks = (n + 31) / 32;
+  const long long wstride = (long long)gridDim.x * 4;
+  float* st = stage[warp];
+  for (long long ch = (long long)blockIdx.x * 4 + warp; ch < nchunks; ch += wstride) {
+    const long long p0 = ch * 32;
+    const long long f0 = p0 * VC;                 // first float of the chunk: 16-byte aligned (32 * VC * 4 bytes)
+    const long long fend = n * VC;
+    __syncwarp();
+    if (f0 + kChunkFloats <= fend) {
+      const float4* src = reinterpret_cast<const float4*>(X + f0);
+#pragma unroll
+      for (int j = 0; j < (kVec + 31) / 32; ++j) {
+        const int v4 = j * 32 + lane;
+        if (v4 < kVec) reinterpret_cast<float4*>(st)[v4] = __ldg(src + v4);
+      }
+    } else {
+      for (int k = lane; k < kChunkFloats; k += 32) st[k] = f0 + k < fend ? __ldg(X + f0 + k) : 0.f;
+    }
+    __syncwarp();
+    const long long i = p0 + lane;
+    if (i < n) {
+      float x[VC];
+#pragma unroll
+      for (int k = 0; k < VC; ++k) x[k] = st[lane * VC + k];
+      const int lab = y[i];
+      float z[C], pr[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        float s = 0.f;
+#pragma unroll
+        for (int v = 0; v < V; ++v) s += w[v * C + c] * x[v * C + c];
+        z[c] = s + bb[c];
+      }
+      float m = z[0];
+#pragma unroll
+      for (int c = 1; c < C; ++c) m = fmaxf(m, z[c]);
+      float se = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        pr[c] = __expf(z[c] - m);
+        se += pr[c];
+      }
+      const float inv = __fdividef(1.f, se);
+      float pl = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        pr[c] *= inv;
+        pl = c == lab ? pr[c] : pl;
+      }
+      // dice_c = 2 o_c p_c / (p_c + o_c + eps) vanishes (with its derivative) for every class but the label's:
+      // loss = 1 - dice_l / C,  d loss / d p_l = -2 (1 + eps) / (p_l + 1 + eps)^2 / C,
+      // dz_c = p_c (dp_c - sum_k dp_k p_k) = dp_l p_c ([c == l] - p_l)
+      const float den = pl + 1.f + 1e-6f;
+      const float rden = __fdividef(1.f, den);
+      loc[NACC - 1] += 1.f - 2.f * pl * rden * (1.f / (float)C);
+      const float dpl = -2.f * (1.f + 1e-6f) * rden * rden * (1.f / (float)C);
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const float dz = dpl * pr[c] * ((c == lab ? 1.f : 0.f) - pl);
+        loc[VC + c] += dz;
+#pragma unroll
+        for (int v = 0; v < V; ++v) loc[v * C + c] += dz * x[v * C + c];
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NACC; ++k) {
+    double v = (double)loc[k];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) fsm[warp][k] = v;
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < NACC; k += blockDim.x) {
+    double s = 0;
+#pragma unroll
+    for (int ww = 0; ww < 4; ++ww) s += fsm[ww][k];
+    atomicAdd(accum + k, s);
+  }
+}
+
+template <int V, int C>
+static int launch_fusion_grad_t(const float* X, const unsigned char* y, long long n, const float* W, const float* b,
+                                double* accum, cudaStream_t st) {
+  int occ = 2;
+  const int sms = sm_count();
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fusion_grad_kernel_t<V, C>, 128, 0) != cudaSuccess || occ < 1)
+    occ = 1;
+  if ((reinterpret_cast<uintptr_t>(X) & 15) != 0) {
+    set_error("mpu_fusion_grad: X must be 16-byte aligned");
+    return MPU_ERR_ARG;
+  }
+  long long blocks = (n + 127) / 128;
+  if (blocks > (long long)sms * occ) blocks = (long long)sms * occ;
+  if (blocks < 1) blocks = 1;
+  fusion_grad_kernel_t<V, C><<<(int)blocks, 128, 0, st>>>(X, y, n, W, b, accum);
+  count_launch();
+  MPU_CUDA(cudaGetLastError());
+  return MPU_OK;
+}
+
 // Adam on the 35 fusion parameters (+ L2 regulariser gradients); one thread per parameter.
 __global__ void fusion_adam_kernel(float* W, float* b, float* m, float* v, const double* accum,
                                    double n_points, int V, int C, float reg, float lr_t, float b1,
@@ -442,7 +754,8 @@ __global__ void fusion_adam_kernel(float* W, float* b, float* m, float* v, const
   *prm = *prm - lr_t * mi / (sqrtf(vi) + eps);
 }
 
-inline int grid_for(long long work, int threads, int cap = 148 * 16) {
+inline int grid_for(long long work, int threads, int cap = 0) {
+  if (cap <= 0) cap = sm_count() * 16;
   long long g = (work + threads - 1) / threads;
   if (g > cap) g = cap;
   if (g < 1) g = 1;
@@ -756,21 +1069,18 @@ int mpu_probe_planes(const float* vol, const unsigned char* labels, const int* h
   return MPU_OK;
 }
 
-int mpu_map_fuse(const void* const* h_pred_ptrs, int V, int C, int dim, int n_planes,
-                 const double* inv_basis, const double* ax, const double* offsets,
-                 const double* h_inv_step, const int* h_dims, const double* h_affine3x3,
-                 const double* h_mean, const float* W, const float* b, int sum_fusion,
-                 unsigned char* labels_out, float* probs_out, float* combined_out, void* stream) {
-  if (!h_pred_ptrs || V < 1 || V > kMaxViews || C < 1 || C > kMaxClasses || !inv_basis || !ax ||
-      !offsets || !h_inv_step || !h_dims || !h_affine3x3 || !h_mean) {
-    set_error("mpu_map_fuse: bad arguments (V=%d C=%d)", V, C);
+static int map_fuse_common(MapFuseParams& p, const char* who, const void* const* h_pred_ptrs, int V, int C, int dim,
+                           int n_planes, const int* h_dims, const double* h_affine3x3, const double* h_mean,
+                           const float* W, const float* b, int sum_fusion, unsigned char* labels_out,
+                           float* probs_out, float* combined_out) {
+  if (!h_pred_ptrs || V < 1 || V > kMaxViews || C < 1 || C > kMaxClasses || !h_dims || !h_affine3x3 || !h_mean) {
+    set_error("%s: bad arguments (V=%d C=%d)", who, V, C);
     return MPU_ERR_ARG;
   }
   if (!sum_fusion && (!W || !b)) {
-    set_error("mpu_map_fuse: fusion weights missing");
+    set_error("%s: fusion weights missing", who);
     return MPU_ERR_ARG;
   }
-  MapFuseParams p;
   memset(&p, 0, sizeof(p));
   p.X = h_dims[0];
   p.Y = h_dims[1];
@@ -780,15 +1090,8 @@ int mpu_map_fuse(const void* const* h_pred_ptrs, int V, int C, int dim, int n_pl
   memcpy(p.affine, h_affine3x3, sizeof(double) * 9);
   memcpy(p.mean, h_mean, sizeof(double) * 3);
   for (int v = 0; v < V; ++v) p.pred[v] = reinterpret_cast<const float*>(h_pred_ptrs[v]);
-  p.inv_basis = inv_basis;
-  p.ax = ax;
-  p.offsets = offsets;
   p.dim = dim;
   p.n_planes = n_planes;
-  p.inv_step_ax = h_inv_step[0];
-  // h_inv_step = [1/spacing of the in-plane axis, 1/spacing of each view's offset axis]
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  for (int v = 0; v < V; ++v) p.inv_step_off[v] = h_inv_step[1 + v];
   p.W = W;
   p.b = b;
   p.sum_fusion = sum_fusion;
@@ -796,10 +1099,14 @@ int mpu_map_fuse(const void* const* h_pred_ptrs, int V, int C, int dim, int n_pl
   p.probs_out = probs_out;
   p.combined_out = combined_out;
   if ((long long)p.X * p.Y > 0x7fffffffLL) {
-    set_error("mpu_map_fuse: volume too large");
+    set_error("%s: volume too large", who);
     return MPU_ERR_ARG;
   }
-  switch (C) {
+  return MPU_OK;
+}
+
+static int map_fuse_dispatch(const MapFuseParams& p, cudaStream_t st) {
+  switch (p.C) {
     case 2: return launch_map_fuse<2>(p, st);
     case 3: return launch_map_fuse<3>(p, st);
     case 4: return launch_map_fuse<4>(p, st);
@@ -811,6 +1118,63 @@ int mpu_map_fuse(const void* const* h_pred_ptrs, int V, int C, int dim, int n_pl
   }
 }
 
+int mpu_map_fuse(const void* const* h_pred_ptrs, int V, int C, int dim, int n_planes,
+                 const double* inv_basis, const double* ax, const double* offsets,
+                 const double* h_inv_step, const int* h_dims, const double* h_affine3x3,
+                 const double* h_mean, const float* W, const float* b, int sum_fusion,
+                 unsigned char* labels_out, float* probs_out, float* combined_out, void* stream) {
+  if (!inv_basis || !ax || !offsets || !h_inv_step) {
+    set_error("mpu_map_fuse: bad arguments (null axis tables)");
+    return MPU_ERR_ARG;
+  }
+  MapFuseParams p;
+  MPU_TRY(map_fuse_common(p, "mpu_map_fuse", h_pred_ptrs, V, C, dim, n_planes, h_dims, h_affine3x3, h_mean, W, b,
+                          sum_fusion, labels_out, probs_out, combined_out));
+  p.inv_basis = inv_basis;
+  p.ax = ax;
+  p.offsets = offsets;
+  // h_inv_step = [1/spacing of the in-plane axis, 1/spacing of each view's offset axis]
+  p.inv_step_ax = h_inv_step[0];
+  for (int v = 0; v < V; ++v) p.inv_step_off[v] = h_inv_step[1 + v];
+  return map_fuse_dispatch(p, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int mpu_map_fuse_linspace(const void* const* h_pred_ptrs, int V, int C, int dim, int n_planes,
+                          const double* h_inv_basis, const double* h_ax_lin, const double* h_off_lin,
+                          const int* h_dims, const double* h_affine3x3, const double* h_mean, const float* W,
+                          const float* b, int sum_fusion, unsigned char* labels_out, float* probs_out,
+                          float* combined_out, void* stream) {
+  if (!h_inv_basis || !h_ax_lin || !h_off_lin || dim < 2 || n_planes < 2) {
+    set_error("mpu_map_fuse_linspace: bad arguments (null axis descriptions or an axis shorter than 2)");
+    return MPU_ERR_ARG;
+  }
+  if (C > 8) {
+    set_error("mpu_map_fuse_linspace: at most 8 classes on the analytic path (use mpu_map_fuse)");
+    return MPU_ERR_ARG;
+  }
+  MapFuseParams p;
+  MPU_TRY(map_fuse_common(p, "mpu_map_fuse_linspace", h_pred_ptrs, V, C, dim, n_planes, h_dims, h_affine3x3, h_mean,
+                          W, b, sum_fusion, labels_out, probs_out, combined_out));
+  p.analytic = 1;
+  p.ax_start = h_ax_lin[0];
+  p.ax_step = h_ax_lin[1];
+  p.ax_stop = h_ax_lin[2];
+  p.inv_step_ax = (double)(dim - 1) / (p.ax_stop - p.ax_start);
+  for (int v = 0; v < V; ++v) {
+    p.off_start[v] = h_off_lin[3 * v];
+    p.off_step[v] = h_off_lin[3 * v + 1];
+    p.off_stop[v] = h_off_lin[3 * v + 2];
+    p.inv_step_off[v] = (double)(n_planes - 1) / (p.off_stop[v] - p.off_start[v]);
+    memcpy(p.ib[v], h_inv_basis + 9 * v, sizeof(double) * 9);
+  }
+  p.pred_elems = (long long)n_planes * dim * dim * C;
+  if (C == 1) {  // a single class has nothing to gather in vectors; the table kernel's template covers 2..8
+    set_error("mpu_map_fuse_linspace: needs at least 2 classes");
+    return MPU_ERR_ARG;
+  }
+  return map_fuse_dispatch(p, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int mpu_fusion_grad(const float* X, const unsigned char* y, long long n, int V, int C, const float* W,
                     const float* b, double* accum, void* stream) {
   if (!X || !y || !W || !b || !accum || V < 1 || C < 1 || C > kMaxClasses || V * C > 128) {
@@ -818,10 +1182,25 @@ int mpu_fusion_grad(const float* X, const unsigned char* y, long long n, int V, 
     return MPU_ERR_ARG;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (n <= 0) return MPU_OK;
+  // the reference's configurations (6 views; bin/train_fusion.py) with 2..8 classes run fully in registers
+  if (V == 6) {
+    switch (C) {
+      case 2: return launch_fusion_grad_t<6, 2>(X, y, n, W, b, accum, st);
+      case 3: return launch_fusion_grad_t<6, 3>(X, y, n, W, b, accum, st);
+      case 4: return launch_fusion_grad_t<6, 4>(X, y, n, W, b, accum, st);
+      case 5: return launch_fusion_grad_t<6, 5>(X, y, n, W, b, accum, st);
+      case 6: return launch_fusion_grad_t<6, 6>(X, y, n, W, b, accum, st);
+      case 7: return launch_fusion_grad_t<6, 7>(X, y, n, W, b, accum, st);
+      case 8: return launch_fusion_grad_t<6, 8>(X, y, n, W, b, accum, st);
+      default: break;
+    }
+  }
+  if (V == 3 && C == 5) return launch_fusion_grad_t<3, 5>(X, y, n, W, b, accum, st);
   const int threads = 256;
   const int nacc = V * C + C + 1;
   const size_t smem = sizeof(double) * (threads / 32) * nacc;
-  fusion_grad_kernel<<<grid_for(n, threads, 148 * 4), threads, smem, st>>>(X, y, n, V, C, W, b, accum);
+  fusion_grad_kernel<<<grid_for(n, threads, sm_count() * 4), threads, smem, st>>>(X, y, n, V, C, W, b, accum);
   count_launch();
   MPU_CUDA(cudaGetLastError());
   return MPU_OK;
@@ -852,7 +1231,7 @@ int mpu_label_counts(const unsigned char* y_true, const unsigned char* y_pred, c
   if (n == 0) return MPU_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   long long blocks = (n + 256 * 16 - 1) / (256 * 16);
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks > sm_count() * 8) blocks = sm_count() * 8;
   label_counts_kernel<<<(int)blocks, 256, 0, st>>>(y_true, scores ? nullptr : y_pred, scores, n, n_classes,
                                                    reinterpret_cast<unsigned long long*>(counts));
   count_launch();
@@ -876,7 +1255,7 @@ int mpu_elastic_2d(const float* x_in, const unsigned char* y_in, double* fields,
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int bx = (H * W + 255) / 256;
-  if (bx > 148 * 4) bx = 148 * 4;
+  if (bx > sm_count() * 4) bx = sm_count() * 4;
   const dim3 gf(bx, 2 * n), gs(bx, n);
   gauss1d_kernel<<<gf, 256, 0, st>>>(fields, scratch, H, W, 0, d_weights, weight_stride, d_radius);
   gauss1d_kernel<<<gf, 256, 0, st>>>(scratch, fields, H, W, 1, d_weights, weight_stride, d_radius);

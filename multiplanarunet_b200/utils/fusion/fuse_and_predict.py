@@ -26,14 +26,39 @@ def voxel_grid_center(shape3, affine3x3):
     return np.asarray(affine3x3, dtype=np.float64).dot((np.asarray(shape3, dtype=np.float64) - 1) / 2)
 
 
+def linspace_params(axis):
+    """(start, step, stop) if `axis` is bit for bit what np.linspace(start, stop, n) returns - numpy builds it as
+    arange(n) * step + start with step = (stop - start) / (n - 1) and then overwrites the last element with stop
+    (numpy/_core/function_base.py) - else None.  The reference's grids are exactly such arrays (in-plane axis:
+    sample_grid.py:227-233 via np.linspace in test mode; offsets: isotrophic_live_view_sequence_2d.py:62)."""
+    a = np.ascontiguousarray(axis, dtype=np.float64)
+    n = a.shape[0]
+    if a.ndim != 1 or n < 2:
+        return None
+    start, stop = float(a[0]), float(a[-1])
+    step = (stop - start) / (n - 1)
+    if not (step > 0) or not np.isfinite(step):
+        return None
+    ref = np.arange(0, n, dtype=np.float64) * step + start
+    ref[-1] = stop
+    return (start, step, stop) if np.array_equal(ref, a) else None
+
+
 def _map_fuse(pred_tensors, grids, inv_bases, shape3, affine3x3, W=None, b=None, sum_fusion=False,
-              want_labels=True, want_probs=False, want_combined=False):
+              want_labels=True, want_probs=False, want_combined=False, force_tables=False):
     import torch
     V = len(pred_tensors)
     dev = pred_tensors[0].device
     n_planes, dim, _, C = pred_tensors[0].shape
     ax = np.asarray(grids[0][0], dtype=np.float64)
     offsets = np.stack([np.asarray(g[2], dtype=np.float64) for g in grids])
+    lin_ax = linspace_params(ax)
+    lin_off = [linspace_params(o) for o in offsets]
+    same_axes = all(np.array_equal(np.asarray(g[0]), ax) and np.array_equal(np.asarray(g[1]), ax) for g in grids)
+    import os
+    force_tables = force_tables or os.environ.get("MPU_MAPFUSE_TABLES") == "1"  # bring-up knob
+    use_lin = (not force_tables and 2 <= C <= 8 and lin_ax is not None and all(l is not None for l in lin_off)
+               and same_axes and all(t.is_contiguous() for t in pred_tensors))
     inv_step = [(len(ax) - 1) / (ax[-1] - ax[0])] + [(offsets.shape[1] - 1) / (o[-1] - o[0]) for o in offsets]
     ax_d = torch.from_numpy(ax).to(dev)
     off_d = torch.from_numpy(np.ascontiguousarray(offsets)).to(dev)
@@ -48,6 +73,16 @@ def _map_fuse(pred_tensors, grids, inv_bases, shape3, affine3x3, W=None, b=None,
         bd = torch.as_tensor(np.asarray(b, dtype=np.float32).reshape(C)).to(dev).contiguous()
     ptrs = (ctypes.c_void_p * V)(*[t.data_ptr() for t in pred_tensors])
     mean = voxel_grid_center(shape3, affine3x3)
+    if use_lin:
+        check(lib.mpu_map_fuse_linspace(ptrs, V, C, dim, n_planes,
+                                        _C.double_array(np.stack(inv_bases).astype(np.float64).ravel()),
+                                        _C.double_array(lin_ax), _C.double_array(np.asarray(lin_off).ravel()),
+                                        _C.int_array([X, Y, Z]),
+                                        _C.double_array(np.asarray(affine3x3, dtype=np.float64).ravel()),
+                                        _C.double_array(mean), _C.ptr(Wd), _C.ptr(bd), int(bool(sum_fusion)),
+                                        _C.ptr(labels), _C.ptr(probs), _C.ptr(combined), _C.current_stream()),
+              "mpu_map_fuse_linspace")
+        return labels, probs, combined
     check(lib.mpu_map_fuse(ptrs, V, C, dim, n_planes, _C.ptr(ib_d), _C.ptr(ax_d), _C.ptr(off_d),
                            _C.double_array(inv_step), _C.int_array([X, Y, Z]),
                            _C.double_array(np.asarray(affine3x3, dtype=np.float64).ravel()),

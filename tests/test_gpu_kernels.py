@@ -67,6 +67,55 @@ def test_mapping_matches_reference_goldens():
         assert np.array_equal(combined.cpu().numpy(), z["mapped"].astype(np.float32))
 
 
+def test_map_fuse_linspace_path_equals_table_path():
+    """mpu_map_fuse_linspace (axis values recomputed in registers, 16-byte gathers) against mpu_map_fuse (axis
+    tables) on the same inputs: labels, probabilities and the per-view mapped volumes must be IDENTICAL, for every
+    class count the fast path is instantiated for, with a sheared / rotated affine, odd sizes, and views whose
+    stacks leave parts of the volume out of bounds."""
+    import torch
+    from multiplanarunet_b200.interpolation import plane_basis, view_offsets
+    from multiplanarunet_b200.utils.fusion.fuse_and_predict import _map_fuse, linspace_params
+    rng = np.random.RandomState(5)
+    th = 0.4
+    R = np.array([[np.cos(th), -np.sin(th), 0.1], [np.sin(th), np.cos(th), 0], [0, 0.05, 1]])
+    for C in (2, 3, 4, 5, 7, 8):
+        dim, span, n, V = 37, 33.0, 45, 3
+        shape = (29, 31, 23)
+        affine = R.dot(np.diag([1.0, 0.7, 1.3]))
+        g = np.linspace(-(span // 2), span // 2, dim)
+        views = [(0.3, 0.5, 0.8), (0, 0, 1), (-0.7, 0.1, 0.2)]
+        preds = [torch.rand(n, dim, dim, C, device="cuda") for _ in views]
+        grids = [(g, g, view_offsets(dim, span, n))] * V
+        assert linspace_params(g) is not None and linspace_params(grids[0][2]) is not None
+        ibs = [np.linalg.inv(plane_basis(v, 0.)) for v in views]
+        W = rng.uniform(0.5, 1.5, (V, C)).astype(np.float32)
+        b = (0.1 * rng.randn(C)).astype(np.float32)
+        a = _map_fuse(preds, grids, ibs, shape, affine, W, b, want_probs=True, want_combined=True)
+        t = _map_fuse(preds, grids, ibs, shape, affine, W, b, want_probs=True, want_combined=True, force_tables=True)
+        for x, y in zip(a, t):
+            assert torch.equal(x, y), C
+        a = _map_fuse(preds, grids, ibs, shape, affine, sum_fusion=True)
+        t = _map_fuse(preds, grids, ibs, shape, affine, sum_fusion=True, force_tables=True)
+        assert torch.equal(a[0], t[0])
+        assert 0.02 < float((a[0] == 0).float().mean()) < 0.98 or C == 2
+    # systematic exact ties: integer-spaced axes, voxel centres exactly half way between nodes (tie -> lower index)
+    dim, span, n, C = 33, 32.0, 33, 5
+    g = np.linspace(-(span // 2), span // 2, dim)
+    offs = view_offsets(dim, span, n)
+    assert np.array_equal(g, np.arange(-16.0, 17.0)) and np.array_equal(offs, g)
+    preds = [torch.rand(n, dim, dim, C, device="cuda") for _ in range(2)]
+    ibs = [np.linalg.inv(plane_basis(v, 0.)) for v in [(0, 0, 1), (1, 0, 0)]]
+    W = np.ones((2, C), np.float32)
+    a = _map_fuse(preds, [(g, g, offs)] * 2, ibs, (30, 30, 30), np.eye(3), W, np.zeros(C, np.float32),
+                  want_probs=True, want_combined=True)
+    t = _map_fuse(preds, [(g, g, offs)] * 2, ibs, (30, 30, 30), np.eye(3), W, np.zeros(C, np.float32),
+                  want_probs=True, want_combined=True, force_tables=True)
+    for x, y in zip(a, t):
+        assert torch.equal(x, y)
+    # voxel 0 sits at -14.5: the tie goes to node -15 = index 1 on every axis of the axis-aligned view
+    assert torch.equal(a[2][0][0, 0, 0], preds[0][1, 1, 1])
+
+
 def test_map_fuse_full_size_properties():
     """256^3 x 6 views x 5 classes (BASELINE config 3 size): size-independent properties.
     (a) one-hot per-view predictions of a constant class fuse to that class inside the sampled region and
