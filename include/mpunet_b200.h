@@ -193,6 +193,14 @@ int mpu_interp_points(const float* vol, const unsigned char* labels, const int* 
                       const double* coords, long long n, const float* h_bg_value, int bg_class,
                       float* out_f32, unsigned char* out_labels, void* stream);
 
+/* Leaf sums of numpy's pairwise summation of the real-space voxel coordinates A . (i, j, k) (C order over the volume),
+ * for the exact centre that get_voxel_grid_real_space subtracts: np.mean(grid_points_real_space, axis=0),
+ * interpolation/sample_grid.py:117-118.  leaf_start / leaf_len (device, [n_leaves]) are the <= 128-element blocks of
+ * numpy's pairwise_sum recursion; out (device double [3][n_leaves]) receives each block's sum per coordinate, summed
+ * in numpy's 8-accumulator order.  The host combines the binary tree (interpolation/voxel_center.py). */
+int mpu_voxel_leaf_sums(const int* h_dims, const double* h_affine3x3, const long long* leaf_start, const int* leaf_len,
+                        long long n_leaves, double* out, void* stream);
+
 /* Confusion-matrix counts for the validation callback and dice_all: ADDS into counts [3][n_classes] int64
  * (device): [0] true == c & pred == c (TP), [1] true == c (relevant), [2] pred == c (selected).
  * pred is either y_pred (u8 labels) or, when scores != NULL, the first arg-max of scores [n][n_classes] f32.

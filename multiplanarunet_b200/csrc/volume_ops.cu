@@ -834,6 +834,51 @@ __global__ void sample_points_kernel(const PointsParams p) {
   }
 }
 
+// ---- exact centre of the voxel grid ------------------------------------------------------------------------------
+// get_voxel_grid_real_space subtracts np.mean(A . (i, j, k)) over ALL voxels (sample_grid.py:117-118).  numpy sums each
+// coordinate with its pairwise scheme: blocks of <= 128 elements are summed with 8 interleaved accumulators
+// (numpy/_core/src/umath/loops_utils.h.src, pairwise_sum) and the block sums are combined by a binary tree whose
+// split points the host derives from the element count.  This kernel produces the block ("leaf") sums in exactly that
+// operation order, from elements evaluated exactly as the mapping kernel evaluates them (BLAS-style fma chain);
+// the host combines the tree (multiplanarunet_b200/interpolation/voxel_center.py).  One thread per (leaf, coordinate).
+__global__ void voxel_leaf_sums_kernel(int Y, int Z, double a0, double a1, double a2, double b0, double b1, double b2,
+                                       double c0, double c1, double c2, const long long* __restrict__ leaf_start,
+                                       const int* __restrict__ leaf_len, long long n_leaves, double* __restrict__ out) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 3 * n_leaves) return;
+  const int r = (int)(t / n_leaves);
+  const long long leaf = t - (long long)r * n_leaves;
+  const double m[3] = {r == 0 ? a0 : (r == 1 ? b0 : c0), r == 0 ? a1 : (r == 1 ? b1 : c1),
+                       r == 0 ? a2 : (r == 1 ? b2 : c2)};
+  const long long s = leaf_start[leaf];
+  const int n = leaf_len[leaf];
+  const long long yz = (long long)Y * Z;
+  auto elem = [&](long long idx) {
+    const long long i = idx / yz;
+    const long long rem = idx - i * yz;
+    const long long j = rem / Z, k = rem - j * Z;
+    return dot3(m, (double)i, (double)j, (double)k);
+  };
+  double res;
+  if (n < 8) {
+    res = 0.0;
+    for (int q = 0; q < n; ++q) res = __dadd_rn(res, elem(s + q));
+  } else {
+    double acc[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] = elem(s + q);
+    int q = 8;
+    for (; q < n - (n % 8); q += 8) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc[u] = __dadd_rn(acc[u], elem(s + q + u));
+    }
+    res = __dadd_rn(__dadd_rn(__dadd_rn(acc[0], acc[1]), __dadd_rn(acc[2], acc[3])),
+                    __dadd_rn(__dadd_rn(acc[4], acc[5]), __dadd_rn(acc[6], acc[7])));
+    for (; q < n; ++q) res = __dadd_rn(res, elem(s + q));
+  }
+  out[t] = res;
+}
+
 // ---- confusion-matrix counts ---------------------------------------------------------------------------
 // counts[0][c] = #(true == c & pred == c), counts[1][c] = #(true == c), counts[2][c] = #(pred == c)
 // (TP / relevant / selected of callbacks/validation.py:117-131; the three sums of evaluate/metrics.py:12-23).
@@ -1217,6 +1262,21 @@ int mpu_fusion_adam(float* W, float* b, float* m, float* v, const double* accum,
   const int n = V * C + C;
   fusion_adam_kernel<<<(n + 63) / 64, 64, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       W, b, m, v, accum, n_points, V, C, reg, (float)lr_t, beta1, beta2, eps);
+  count_launch();
+  MPU_CUDA(cudaGetLastError());
+  return MPU_OK;
+}
+
+int mpu_voxel_leaf_sums(const int* h_dims, const double* h_affine3x3, const long long* leaf_start, const int* leaf_len,
+                        long long n_leaves, double* out, void* stream) {
+  if (!h_dims || !h_affine3x3 || !leaf_start || !leaf_len || !out || n_leaves < 1) {
+    set_error("mpu_voxel_leaf_sums: bad arguments");
+    return MPU_ERR_ARG;
+  }
+  const double* A = h_affine3x3;
+  const long long work = 3 * n_leaves;
+  voxel_leaf_sums_kernel<<<(unsigned)((work + 127) / 128), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      h_dims[1], h_dims[2], A[0], A[1], A[2], A[3], A[4], A[5], A[6], A[7], A[8], leaf_start, leaf_len, n_leaves, out);
   count_launch();
   MPU_CUDA(cudaGetLastError());
   return MPU_OK;

@@ -45,6 +45,56 @@ def plane_basis(norm_vector, noise_sd=0.):
     return np.column_stack((u, v, n_hat))
 
 
+def _row_norms(x):
+    """np.linalg.norm of every row, bit-identical to the per-vector call (both go through the BLAS dot of the numpy
+    build: a batched matmul reproduces it, an elementwise sum of squares does not in ~10 % of the rows)."""
+    return np.sqrt(np.matmul(x[:, None, :], x[:, :, None]).reshape(-1))
+
+
+def plane_basis_batch(norm_vectors, noise):
+    """plane_basis for n planes at once: norm_vectors [n, 3], noise [n, 3] float64 (the vector added to n_hat) ->
+    bases [n, 3, 3] float64, bit-identical to n calls of plane_basis (tests/test_host_surface.py).  320 candidate
+    planes of a training batch take ~0.3 ms instead of ~55 ms."""
+    nv = np.asarray(norm_vectors)
+    n = nv.shape[0]
+    n_hat = np.array(nv, np.float32)
+    n_hat /= _row_norms(n_hat)[:, None]
+    n_hat += np.asarray(noise, dtype=np.float64)
+    n_hat /= _row_norms(n_hat)[:, None]
+    flip = np.all(n_hat[:, :-1] < 0.2, axis=1)
+    n_hat[flip, :-1] = np.abs(n_hat[flip, :-1])
+    flat = np.all(np.isclose(n_hat[:, :-1], 0), axis=1)
+    tilted = n_hat.copy()
+    tilted[:, -1] = tilted[:, -1] + 1
+    tilted /= _row_norms(tilted)[:, None]
+    axis = np.cross(n_hat, tilted)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        axis = axis / _row_norms(axis)[:, None]
+    theta = np.deg2rad(-90)
+    qa = np.cos(theta / 2.0)
+    q = -axis * np.sin(theta / 2.0)
+    qb, qc, qd = q[:, 0], q[:, 1], q[:, 2]
+    R = np.empty((n, 3, 3), dtype=np.float64)
+    R[:, 0, 0] = qa * qa + qb * qb - qc * qc - qd * qd
+    R[:, 0, 1] = 2 * (qb * qc + qa * qd)
+    R[:, 0, 2] = 2 * (qb * qd - qa * qc)
+    R[:, 1, 0] = 2 * (qb * qc - qa * qd)
+    R[:, 1, 1] = qa * qa + qc * qc - qb * qb - qd * qd
+    R[:, 1, 2] = 2 * (qc * qd + qa * qb)
+    R[:, 2, 0] = 2 * (qb * qd + qa * qc)
+    R[:, 2, 1] = 2 * (qc * qd - qa * qb)
+    R[:, 2, 2] = qa * qa + qd * qd - qb * qb - qc * qc
+    u = np.matmul(R, n_hat.astype(np.float64)[:, :, None]).reshape(n, 3)
+    v = np.cross(n_hat, u)
+    u[flat] = (1, 0, 0)
+    v[flat] = (0, 1, 0)
+    out = np.empty((n, 3, 3), dtype=np.float64)
+    out[:, :, 0] = u
+    out[:, :, 1] = v
+    out[:, :, 2] = n_hat
+    return out
+
+
 def sample_plane_at(norm_vector, sample_dim, real_space_span, offset_from_center, noise_sd,
                     test_mode=False):
     """Mirror of sample_grid.py:192-244 that returns the plane PARAMETERS instead of the dense grid:

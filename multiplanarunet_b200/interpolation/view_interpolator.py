@@ -79,6 +79,25 @@ class ViewInterpolator(object):
                                     _C.current_stream()), "mpu_sample_planes")
         return out_f32, out_labels
 
+    def probe_planes(self, bases, offsets, dim, span):
+        """Class-presence bit masks and `is_valid_im` flags of n candidate planes without materialising them
+        (mpu_probe_planes).  Returns (class_mask uint32 [n], valid uint32 [n]) device tensors."""
+        import torch
+        offsets = np.atleast_1d(np.asarray(offsets, dtype=np.float64))
+        n = offsets.shape[0]
+        planes = np.empty((n, 10), dtype=np.float64)
+        planes[:, :9] = np.asarray(bases, dtype=np.float64).reshape(n, 9)
+        planes[:, 9] = offsets
+        planes_d = torch.from_numpy(planes).to(self.device, non_blocking=True)
+        masks = torch.empty(2, n, dtype=torch.int32, device=self.device)
+        rot = _C.double_array(np.asarray(self.rot_mat, dtype=np.float64).ravel()) if self.rot_mat is not None else None
+        check(lib.mpu_probe_planes(_C.ptr(self.vol), _C.ptr(self.labels), _C.int_array(self.im_shape[:3]),
+                                   self.n_channels, _C.ptr(self._g[0]), _C.ptr(self._g[1]), _C.ptr(self._g[2]),
+                                   self._inv_step, rot, _C.ptr(planes_d), n, int(dim), ctypes.c_double(float(span)),
+                                   _C.float_array(self.bg_value), self.bg_class, _C.ptr(masks[0]), _C.ptr(masks[1]),
+                                   _C.current_stream()), "mpu_probe_planes")
+        return masks[0], masks[1]
+
     # -- reference call surface on explicit grids (view_interpolator.py:54-101) --------------------------
     def apply_rotation(self, mgrid):
         """Grid [3, ...] float64 -> grid aligned with the voxel axes (`rot_mat . points`), host numpy like the

@@ -10,7 +10,22 @@ statistics, preprocessing/scaling.py:47-88), `.sample_weight`, `.predict_mode`.
 """
 import numpy as np
 
-from ..interpolation import ViewInterpolator, plane_basis, view_offsets
+from ..interpolation import ViewInterpolator, plane_basis, plane_basis_batch, view_offsets
+
+
+def robust_scaler_stats(image):
+    """Per-channel (center_, scale_) of sklearn's RobustScaler fitted on ALL voxels of a [X,Y,Z,C] float32 volume, as
+    MultiChannelScaler.fit does (preprocessing/scaling.py:47-73; sklearn.preprocessing.RobustScaler.fit: nanmedian,
+    nanpercentile(25, 75), zero ranges -> 1).  float64 [C] each; pinned against the reference's fitted scaler in
+    tests/golden/view_stack_*.npz."""
+    center, scale = [], []
+    for c in range(image.shape[-1]):
+        col = np.ascontiguousarray(image[..., c], dtype=np.float32).reshape(-1, 1)
+        center.append(float(np.nanmedian(col, axis=0)[0]))
+        q = np.nanpercentile(col, (25.0, 75.0), axis=0)
+        sc = float(q[1][0] - q[0][0])
+        scale.append(sc if sc != 0.0 and abs(sc) >= 10 * np.finfo(np.float64).eps else 1.0)
+    return np.asarray(center, dtype=np.float64), np.asarray(scale, dtype=np.float64)
 
 
 class SyntheticImage(object):
@@ -35,12 +50,7 @@ class SyntheticImage(object):
             pct = float(bg_value[:-3])
             bg_value = [float(np.percentile(image[..., c], pct)) for c in range(self.n_channels)]
         self.bg_value = bg_value
-        flat = image.reshape(-1, self.n_channels)
-        q = np.percentile(flat, [25.0, 50.0, 75.0], axis=0)
-        self.scaler_center = q[1].astype(np.float64)
-        iqr = (q[2] - q[0]).astype(np.float64)
-        iqr[iqr == 0] = 1.0
-        self.scaler_scale = iqr
+        self.scaler_center, self.scaler_scale = robust_scaler_stats(image)
         self.interpolator = ViewInterpolator(image, self.labels, self.affine, bg_value=bg_value,
                                              bg_class=bg_class, device=device)
 
@@ -117,6 +127,7 @@ class IsotrophicLiveViewSequence2D(object):
         return Xn, yn, grid, inv_basis
 
     # -- training batches --------------------------------------------------------------------------
+    # -- the reference's acceptance rules on class-presence vectors (isotrophic_live_view_sequence.py:98-128) -------
     def _validate_lab_vec(self, present, has_fg, cur_bs):
         new_mask = has_fg + present
         if np.all(new_mask):
@@ -132,58 +143,84 @@ class IsotrophicLiveViewSequence2D(object):
             return True, 0
         return False, 0
 
-    def sample_batch_device(self, out_padded=None, cpad=0, max_tries=10, rng=np.random):
-        """One training batch of random oblique planes.  Candidate planes for every slot are drawn up
-        front (view, offset ~ U(-span//2, span//2), normal noise) and their LABELS sampled in one
-        launch; the sequential accept/reject rules of …_2d.py:119-161 then run on tiny per-plane
-        class-presence masks on the host, and only the accepted planes get the trilinear image pass.
-        Returns (x [B,dim,dim,C] f32 tensor | None if out_padded, y [B,dim,dim] uint8 tensor, w [B])."""
-        import torch
-        B, dim, span = self.batch_size, self.sample_dim, self.real_space_span
+    def draw_candidates(self, max_tries=10, rng=np.random):
+        """Candidate planes of one batch, drawn like `_get_valid_slice_from` draws them (…_2d.py:128-144: view index,
+        offset ~ U(-span//2, span//2), normal noise sd `noise_sd`) but for all B x max_tries tries up front.
+        Returns (image index [B], view index [B,T], offsets [B,T], noise [B,T,3])."""
+        B, T = self.batch_size, max_tries
+        sphere_r = self.real_space_span // 2
         im_idx = rng.randint(0, len(self.images), B)
-        sphere_r = span // 2
-        chosen_bases = np.empty((B, 3, 3))
-        chosen_offs = np.empty(B)
-        has_fg_count, has_fg_vec = 0, np.zeros_like(self.fg_classes)
-        # candidates: B x max_tries planes, labels only
-        cand_bases = np.empty((B, max_tries, 3, 3))
-        cand_offs = np.empty((B, max_tries))
+        view_idx = rng.randint(0, len(self.views), size=(B, T))
+        offs = rng.uniform(-sphere_r, sphere_r, size=(B, T))
+        noise = rng.normal(scale=self.noise_sd, size=(B, T, 3)) if self.noise_sd else np.zeros((B, T, 3))
+        return im_idx, view_idx, offs, noise
+
+    def select_slices(self, present, valid_im):
+        """The sequential accept / reject loop of `_get_valid_slice_from` (…_2d.py:119-161) for every slot of a batch,
+        on per-candidate facts: present [B,T,n_fg] bool = np.isin(fg_classes, lab), valid_im [B,T] bool = is_valid_im.
+        As in the reference, the class-coverage vector `has_fg_vec` starts from zeros for EVERY slot (the caller's
+        vector is never updated: `_get_valid_slice_from` rebinds a local) and accumulates over the tries of one slot;
+        a candidate rejected by is_valid_im does not count its foreground.  Returns (picks [B], has_fg_count)."""
+        B, T = present.shape[:2]
+        picks = np.empty(B, dtype=np.int64)
+        has_fg_count = 0
         for s in range(B):
-            for t in range(max_tries):
-                view = self.views[rng.randint(0, len(self.views), 1)[0]]
-                cand_offs[s, t] = rng.uniform(-sphere_r, sphere_r, 1)[0]
-                cand_bases[s, t] = plane_basis(view, rng.normal(scale=self.noise_sd, size=3))
-        present = np.zeros((B, max_tries, len(self.fg_classes)), dtype=bool)
-        for i, image in enumerate(self.images):
-            slots = np.where(im_idx == i)[0]
-            if len(slots) == 0:
-                continue
-            _, lab = image.interpolator.sample_planes(cand_bases[slots].reshape(-1, 3, 3),
-                                                      cand_offs[slots].ravel(), dim, span,
-                                                      want_f32=False, want_labels=True)
-            onehot = torch.zeros(lab.shape[0], self.n_classes, dtype=torch.bool, device=lab.device)
-            onehot.scatter_(1, lab.view(lab.shape[0], -1).long(), True)
-            present[slots] = onehot[:, 1:].cpu().numpy().reshape(len(slots), max_tries, -1)
-        for s in range(B):
-            pick = max_tries - 1
-            for t in range(max_tries):
-                last = t == max_tries - 1
+            has_fg_vec = np.zeros_like(self.fg_classes)
+            picks[s] = T - 1
+            for t in range(T):
+                last = t == T - 1
                 if self.force_all_fg and not last:
                     ok, has_fg_vec = self._validate_lab_vec(present[s, t], has_fg_vec, s)
                     if not ok:
                         continue
                 ok, change = self._validate_lab(present[s, t], has_fg_count, s)
                 if ok or last:
-                    has_fg_count += change
-                    pick = t
-                    break
-            chosen_bases[s], chosen_offs[s] = cand_bases[s, pick], cand_offs[s, pick]
+                    if last or valid_im[s, t]:
+                        has_fg_count += change
+                        picks[s] = t
+                        break
+        return picks, has_fg_count
+
+    def sample_batch_device(self, out_padded=None, cpad=0, max_tries=10, rng=np.random, candidates=None,
+                            return_picks=False):
+        """One training batch of random oblique planes (the reference's __getitem__, …_2d.py:163-216).  All
+        B x max_tries candidate planes are probed in ONE launch per image (mpu_probe_planes: class-presence bits from
+        the nearest-label gather, `is_valid_im` from the trilinear image) and the two small flag arrays come back in a
+        single copy; the reference's sequential accept / reject rules run on them on the host, and only the accepted
+        planes are materialised (trilinear image + labels + RobustScaler), optionally straight into the U-Net's bf16
+        input tensor.  `candidates` = (image index, view index, offsets, noise) replaces the random draws (tests).
+        Returns (x [B,dim,dim,C] f32 tensor | None if out_padded, y [B,dim,dim] uint8 tensor, w [B])."""
+        import torch
+        B, dim, span = self.batch_size, self.sample_dim, self.real_space_span
+        im_idx, view_idx, cand_offs, noise = candidates if candidates is not None else self.draw_candidates(max_tries, rng)
+        T = view_idx.shape[1]
+        cand_bases = plane_basis_batch(self.views[view_idx.ravel()], noise.reshape(-1, 3)).reshape(B, T, 3, 3)
+        nfg = len(self.fg_classes)
+        present = np.zeros((B, T, nfg), dtype=bool)
+        valid_im = np.zeros((B, T), dtype=bool)
+        pending = []
+        for i, image in enumerate(self.images):
+            slots = np.where(im_idx == i)[0]
+            if len(slots) == 0:
+                continue
+            cm, vd = image.interpolator.probe_planes(cand_bases[slots].reshape(-1, 3, 3), cand_offs[slots].ravel(),
+                                                     dim, span)
+            pending.append((slots, torch.stack([cm, vd]).to("cpu", non_blocking=False)))
+        for slots, flags in pending:
+            flags = flags.numpy().astype(np.int64) & 0xFFFFFFFF
+            cm = flags[0].reshape(len(slots), T)
+            present[slots] = ((cm[..., None] >> np.asarray(self.fg_classes)[None, None, :]) & 1).astype(bool)
+            valid_im[slots] = flags[1].reshape(len(slots), T) != 0
+        picks, _ = self.select_slices(present, valid_im)
+        ar = np.arange(B)
+        chosen_bases, chosen_offs = cand_bases[ar, picks], cand_offs[ar, picks]
         if self.list_of_augmenters and out_padded is not None:
             raise NotImplementedError("augmenters need the float32 batch: call sample_batch_device() without "
                                       "out_padded and pack the augmented batch")
+        dev = self.images[0].interpolator.device
         x = torch.empty(B, dim, dim, self.images[0].n_channels, dtype=torch.float32,
-                        device=self.images[0].interpolator.device) if out_padded is None else None
-        y = torch.empty(B, dim, dim, dtype=torch.uint8, device=self.images[0].interpolator.device)
+                        device=dev) if out_padded is None else None
+        y = torch.empty(B, dim, dim, dtype=torch.uint8, device=dev)
         w = np.empty(B, dtype=np.float32)
         for i, image in enumerate(self.images):
             slots = np.where(im_idx == i)[0]
@@ -193,18 +230,21 @@ class IsotrophicLiveViewSequence2D(object):
             xi, yi = image.interpolator.sample_planes(
                 chosen_bases[slots], chosen_offs[slots], dim, span, center=image.scaler_center,
                 scale=image.scaler_scale, out_padded=out_padded if contiguous else None, cpad=cpad,
-                want_f32=(out_padded is None) or not contiguous, want_labels=True)
-            if x is not None:
-                x[torch.as_tensor(slots, device=x.device)] = xi
-            elif not contiguous:
-                raise NotImplementedError("direct U-Net input writes need a single resident image per rank")
-            y[torch.as_tensor(slots, device=y.device)] = yi
+                want_f32=(out_padded is None) or not contiguous, want_labels=True,
+                out_f32=x if (contiguous and x is not None) else None, out_labels=y if contiguous else None)
+            if not contiguous:
+                if x is None:
+                    raise NotImplementedError("direct U-Net input writes need a single resident image per rank")
+                x[torch.as_tensor(slots, device=dev)] = xi
+                y[torch.as_tensor(slots, device=dev)] = yi
             w[slots] = image.sample_weight
         if self.list_of_augmenters:
             bg_values = [self.images[i].interpolator.bg_value for i in im_idx]
             wl = list(w)
             x, y, wl = self.augment(x, y, wl, bg_values)
             w = np.asarray(wl, dtype=np.float32)
+        if return_picks:
+            return x, y, w, picks
         return x, y, w
 
     def __getitem__(self, idx):

@@ -20,10 +20,22 @@ def predict_volume(model, X, batch_size=8, axis=0):
     return np.moveaxis(pred, source=0, destination=axis)
 
 
+_CENTER_CACHE = {}
+
+
 def voxel_grid_center(shape3, affine3x3):
-    """The centre get_voxel_grid_real_space subtracts (sample_grid.py:117-118) = mean over all voxels
-    of A.(i,j,k); evaluated in closed form A.((n-1)/2) instead of averaging 3 x prod(shape) doubles."""
-    return np.asarray(affine3x3, dtype=np.float64).dot((np.asarray(shape3, dtype=np.float64) - 1) / 2)
+    """The centre get_voxel_grid_real_space subtracts (sample_grid.py:117-118): np.mean over all voxels of
+    A.(i,j,k), reproduced bit for bit (numpy's pairwise summation, interpolation/voxel_center.py - leaf sums on the
+    device, tree on the host; ~1 ms for 256^3).  The closed form A.((n-1)/2) differs in the last bits for affines
+    that are not exact in binary, which can flip a nearest-neighbour tie.  Cached per (shape, affine)."""
+    from ...interpolation.voxel_center import voxel_grid_center_exact
+    A = np.ascontiguousarray(np.asarray(affine3x3, dtype=np.float64)[:3, :3])
+    key = (tuple(int(v) for v in shape3), A.tobytes())
+    if key not in _CENTER_CACHE:
+        if len(_CENTER_CACHE) > 64:
+            _CENTER_CACHE.clear()
+        _CENTER_CACHE[key] = voxel_grid_center_exact(shape3, A)
+    return _CENTER_CACHE[key]
 
 
 def linspace_params(axis):

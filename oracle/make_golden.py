@@ -46,11 +46,11 @@ def main():
         print("sampler_%s: %d planes" % (case["name"], len(ims)))
 
     # ---- mapping: nearest gather of per-view prediction stacks onto the voxel grid
+    class Img:
+        pass
+
     for case in gi.MAPPING_CASES:
         preds, grids, inv_bases, shape, affine = gi.mapping_inputs(case)
-
-        class Img:
-            pass
         img = Img()
         img.shape = tuple(shape) + (1,)
         img.affine = affine
@@ -62,8 +62,89 @@ def main():
                             vgrid_corner=vgrid[:, :2, :2, :2])
         print("mapping_%s: %s" % (case["name"], np.stack(mapped).shape))
 
-    # ---- Elastic2D: the reference function with numpy's global RNG seeded per case
+    # ---- exact grid centre: what get_voxel_grid_real_space subtracts (voxel 0 sits at A.0 = 0, so centred[0] = -mean)
+    centers = {}
+    for k, (shape, kind) in enumerate(gi.VOXEL_CENTER_CASES):
+        img = Img()
+        img.shape = tuple(shape) + (1,)
+        img.affine = gi.voxel_center_affine(kind)
+        vg = sg.get_voxel_grid_real_space(img)
+        centers["mean_%d" % k] = -vg[:, 0, 0, 0]
+        centers["corner_%d" % k] = vg[:, -1, -1, -1]
+    np.savez_compressed(os.path.join(out_dir, "voxel_center.npz"), **centers)
+    print("voxel_center: %d cases" % len(gi.VOXEL_CENTER_CASES))
+
+    # ---- inference view stacks: the reference's IsotrophicLiveViewSequence2D.get_view_from (7 worker threads) on a
+    #      duck-typed image with the reference's ViewInterpolator and MultiChannelScaler(RobustScaler)
     import importlib
+    seq2d = importlib.import_module("mpunet.sequences.isotrophic_live_view_sequence_2d")
+    scaling = importlib.import_module("mpunet.preprocessing.scaling")
+    for case in gi.VIEW_STACK_CASES:
+        vol, lab, affine, bg = gi.view_stack_inputs(case)
+        image = Img()
+        image.image, image.labels, image.affine, image.shape = vol, lab, affine, vol.shape
+        image.n_channels, image.predict_mode = vol.shape[-1], False
+        image.interpolator = vi.ViewInterpolator(vol, lab, affine, bg_value=bg, bg_class=0)
+        image.scaler = scaling.get_scaler("RobustScaler").fit(vol)
+        seq = object.__new__(seq2d.IsotrophicLiveViewSequence2D)
+        seq.sample_dim, seq.real_space_span, seq.logger = case["dim"], case["span"], (lambda *a, **k: None)
+        X, y, grid, inv_basis = seq.get_view_from(image, case["view"], case["n_planes"])
+        np.savez_compressed(os.path.join(out_dir, "view_stack_%s.npz" % case["name"]), X=X, y=y, axis=grid[0],
+                            offsets=grid[2], inv_basis=inv_basis,
+                            center=np.array([float(s_.center_[0]) for s_ in image.scaler.scalers]),
+                            scale=np.array([float(s_.scale_[0]) for s_ in image.scaler.scalers]))
+        print("view_stack_%s: X %s %s, scaler centre %s" % (case["name"], X.shape, X.dtype,
+                                                            [float(s_.center_[0]) for s_ in image.scaler.scalers]))
+
+    # ---- training-batch rejection rules: the reference's _get_valid_slice_from / validate_lab(_vec) / is_valid_im
+    #      with np.random replaced by a replay of the candidate list
+    for case in gi.BATCH_RULE_CASES:
+        vol, lab, views, cand_view, cand_off, cand_noise, bg = gi.batch_rule_inputs(case)
+        image = Img()
+        image.interpolator = vi.ViewInterpolator(vol, lab, np.eye(4), bg_value=bg, bg_class=0)
+        image.scaler = scaling.get_scaler("RobustScaler").fit(vol)
+        seq = object.__new__(seq2d.IsotrophicLiveViewSequence2D)
+        seq.sample_dim, seq.real_space_span, seq.noise_sd, seq.views = case["dim"], case["span"], 0.1, views
+        seq._batch_size, seq.n_classes, seq.fg_batch_fraction = case["B"], case["n_classes"], case["fg_frac"]
+        seq.force_all_fg_switch, seq.fg_classes, seq.is_validation = "auto", np.arange(1, case["n_classes"]), False
+        state = {"slot": 0, "try": -1}
+
+        class Replay(object):
+            @staticmethod
+            def randint(lo, hi, size=None):
+                state["try"] += 1
+                return np.array([cand_view[state["slot"], state["try"]]])
+
+            @staticmethod
+            def uniform(lo, hi, size=None):
+                return np.array([cand_off[state["slot"], state["try"]]])
+
+            @staticmethod
+            def normal(scale=1.0, size=None):
+                return cand_noise[state["slot"], state["try"]].copy()
+
+        saved = (np.random.randint, np.random.uniform, np.random.normal)
+        np.random.randint, np.random.uniform, np.random.normal = Replay.randint, Replay.uniform, Replay.normal
+        try:
+            picks, fg_counts, ims, labs = [], [], [], []
+            has_fg_count, has_fg_vec = 0, np.zeros_like(seq.fg_classes)
+            for slot in range(case["B"]):
+                state["slot"], state["try"] = slot, -1
+                im, lb, has_fg_count = seq._get_valid_slice_from(image=image, max_tries=case["tries"],
+                                                                 has_fg_vec=has_fg_vec, has_fg_count=has_fg_count,
+                                                                 cur_bs=slot)
+                picks.append(state["try"])
+                fg_counts.append(has_fg_count)
+                ims.append(im)
+                labs.append(lb)
+        finally:
+            np.random.randint, np.random.uniform, np.random.normal = saved
+        x = np.asarray(seq.scale(ims, [image.scaler] * len(ims)))
+        np.savez_compressed(os.path.join(out_dir, "batch_rules_%s.npz" % case["name"]), picks=np.array(picks),
+                            fg_counts=np.array(fg_counts), x=x, y=np.asarray(labs))
+        print("batch_rules_%s: picks %s fg counts %s" % (case["name"], picks, fg_counts))
+
+    # ---- Elastic2D: the reference function with numpy's global RNG seeded per case
     ed = importlib.import_module("mpunet.augmentation.elastic_deformation")
     outs = {}
     for case in gi.ELASTIC_CASES:

@@ -160,6 +160,46 @@ def sample_plane(image, labels, pixdims, basis, dim, span, offset, bg_value, bg_
     return im, lab
 
 
+def is_valid_im(im, bg_value):
+    """isotrophic_live_view_sequence.py:91-96: a slice is rejected when every channel is (np.isclose) background."""
+    return any(bool(np.any(~np.isclose(im[..., i], bg))) for i, bg in enumerate(bg_value))
+
+
+def select_slices(present, valid_im, batch_size, n_fg_slices, force_all_fg, n_fg_classes):
+    """The reference's batch loop (isotrophic_live_view_sequence_2d.py:119-161,163-190 with the rules of
+    isotrophic_live_view_sequence.py:98-128) on per-candidate facts.  present [B,T,n_fg] bool, valid_im [B,T] bool.
+    Note `has_fg_vec`: __getitem__ passes its own zeros vector to every slot and _get_valid_slice_from only rebinds
+    a local name, so class coverage is tracked within the tries of one slot only.  Returns (picks, fg counts)."""
+    B, T = present.shape[:2]
+    picks, counts = [], []
+    has_fg_count = 0
+    for cur_bs in range(B):
+        has_fg_vec = np.zeros(n_fg_classes, dtype=np.int64)
+        tries = 0
+        while tries < T:
+            tries += 1
+            lab_present = present[cur_bs, tries - 1]
+            if force_all_fg and tries < T:
+                new_mask = has_fg_vec + lab_present
+                if np.all(new_mask) or np.sum(new_mask == 0) < (batch_size - cur_bs):
+                    has_fg_vec = new_mask
+                else:
+                    continue
+            if np.any(lab_present):
+                valid_lab, fg_change = True, 1
+            elif (n_fg_slices - has_fg_count) < (batch_size - cur_bs):
+                valid_lab, fg_change = True, 0
+            else:
+                valid_lab, fg_change = False, 0
+            if valid_lab or tries == T:
+                if tries == T or valid_im[cur_bs, tries - 1]:
+                    has_fg_count += fg_change
+                    break
+        picks.append(tries - 1)
+        counts.append(has_fg_count)
+    return np.asarray(picks), np.asarray(counts)
+
+
 def view_offsets(dim, span, n_planes="same+20"):
     """isotrophic_live_view_sequence_2d.py:47-62."""
     sample_res = span / (dim - 1)

@@ -11,7 +11,39 @@ SAMPLER_CASES = [
 MAPPING_CASES = [
     dict(name="iso", shape=(18, 14, 22), pix=(1.0, 1.0, 1.0), dim=24, span=22, n_planes=30, C=4,
          views=[(0.3, 0.5, 0.8), (0, 0, 1), (-0.7, 0.1, 0.2)], seed=21),
+    # rotated + sheared + anisotropic affine: real-space coordinates and the grid centre are no longer exact in binary
+    dict(name="rot", shape=(17, 15, 21), pix=None, dim=26, span=28, n_planes=33, C=5,
+         views=[(0.3, 0.5, 0.8), (0, 0, 1), (0.6, -0.2, 0.4)], seed=22),
 ]
+
+
+def rotated_affine():
+    th = 0.3
+    R = np.array([[np.cos(th), -np.sin(th), 0.1], [np.sin(th), np.cos(th), 0], [0.02, 0.05, 1]])
+    A = np.eye(4)
+    A[:3, :3] = R.dot(np.diag([1.0, 0.7, 1.3]))
+    return A
+
+
+def rotated_affine_dyadic():
+    """A genuinely rotated affine (3-4-5 rotations about z and x) whose column norms come out EXACTLY (1, 0.5, 2):
+    the reference multiplies its float32 voxel axes by these float64 pixdims (sample_grid.py:83-85), which stays
+    float32 under the numpy 1.x it pins and becomes float64 under numpy >= 2 (NEP 50) - identical values only when
+    the products are exact.  The view-stack golden uses this affine so that it pins the reference's behaviour in
+    both numpy generations (the product follows the pinned 1.x semantics: float32 axes)."""
+    Rz = np.array([[0.6, -0.8, 0], [0.8, 0.6, 0], [0, 0, 1.0]])
+    Rx = np.array([[1.0, 0, 0], [0, 0.8, -0.6], [0, 0.6, 0.8]])
+    A = np.eye(4)
+    A[:3, :3] = Rz.dot(Rx).dot(np.diag([1.0, 0.5, 2.0]))
+    return A
+
+
+VOXEL_CENTER_CASES = [((18, 14, 22), "diag"), ((17, 15, 21), "rot"), ((64, 64, 64), "rot"), ((37, 129, 5), "rot"),
+                      ((100, 90, 80), "rot"), ((7, 3, 2), "rot")]
+
+
+def voxel_center_affine(kind):
+    return rotated_affine() if kind == "rot" else np.diag([1.0, 0.7, 2.0, 1.0])
 
 
 def sampler_volume(case):
@@ -37,7 +69,7 @@ def mapping_inputs(case):
         preds.append(p)
         grids.append((g, g, sampler.view_offsets(case["dim"], case["span"], case["n_planes"])))
         inv_bases.append(np.linalg.inv(sampler.plane_basis(v)))
-    affine = np.diag(list(case["pix"]) + [1.0])
+    affine = rotated_affine() if case["pix"] is None else np.diag(list(case["pix"]) + [1.0])
     return preds, grids, inv_bases, case["shape"], affine
 
 
@@ -53,3 +85,49 @@ def elastic_inputs(case):
     im = rng.randn(case["H"], case["W"], case["C"]).astype(np.float32)
     lab = rng.randint(0, 5, size=(case["H"], case["W"])).astype(np.uint8)
     return im, lab
+
+
+# ---- inference view stacks (sequences/isotrophic_live_view_sequence_2d.py:29-117 + preprocessing/scaling.py) ----------
+VIEW_STACK_CASES = [
+    dict(name="iso", shape=(18, 14, 22), affine="diag", dim=24, span=22, n_planes="same+20", view=(0.3, 0.5, 0.8), seed=31),
+    dict(name="rot", shape=(16, 20, 12), affine="rot", dim=20, span=24, n_planes=9, view=(0.05, 0.1, 0.99), seed=32),
+]
+
+
+def view_stack_inputs(case):
+    rng = np.random.RandomState(case["seed"])
+    vol = (rng.randn(*case["shape"], 2) * [3.0, 0.5] + [10.0, -1.0]).astype(np.float32)
+    lab = rng.randint(0, 4, size=case["shape"]).astype(np.uint8)
+    affine = rotated_affine_dyadic() if case["affine"] == "rot" else np.diag([1.0, 1.0, 1.0, 1.0])
+    bg = [float(np.float32(np.percentile(vol[..., c], 1))) for c in range(2)]
+    return vol, lab, affine, bg
+
+
+# ---- training-batch rejection rules (sequences/isotrophic_live_view_sequence_2d.py:119-161 and
+#      isotrophic_live_view_sequence.py:91-128) driven from a fixed candidate list --------------------------------------
+BATCH_RULE_CASES = [
+    dict(name="sparse_fg", shape=(24, 24, 24), dim=24, span=40, B=12, n_classes=5, tries=10, fg_frac=0.5, seed=41),
+    dict(name="dense_small_batch", shape=(20, 20, 20), dim=16, span=20, B=3, n_classes=5, tries=10, fg_frac=0.7, seed=42),
+]
+
+
+def batch_rule_inputs(case):
+    """Volume whose foreground classes are small blobs (so that many candidate planes miss them), a span larger
+    than the volume (so that some planes are entirely out of bounds: is_valid_im), and the candidate list
+    [B][tries] = (view index, offset, normal noise[3]) every implementation is driven from."""
+    rng = np.random.RandomState(case["seed"])
+    X, Y, Z = case["shape"]
+    vol = rng.randn(X, Y, Z, 1).astype(np.float32)
+    lab = np.zeros(case["shape"], np.uint8)
+    for c in range(1, case["n_classes"]):
+        ctr = rng.randint(4, X - 4, 3)
+        r = 2 + (c % 2)
+        lab[ctr[0] - r:ctr[0] + r, ctr[1] - r:ctr[1] + r, ctr[2] - r:ctr[2] + r] = c
+    views = np.array([[0.3, 0.5, 0.8], [0, 0, 1.0], [1.0, 0, 0], [-0.7, 0.1, 0.2]])
+    views = views / np.linalg.norm(views, axis=1, keepdims=True)
+    sphere_r = case["span"] // 2
+    cand_view = rng.randint(0, len(views), size=(case["B"], case["tries"]))
+    cand_off = rng.uniform(-sphere_r, sphere_r, size=(case["B"], case["tries"]))
+    cand_noise = rng.normal(scale=0.1, size=(case["B"], case["tries"], 3))
+    bg = [float(np.float32(np.percentile(vol[..., 0], 1)))]
+    return vol, lab, views, cand_view, cand_off, cand_noise, bg

@@ -1,0 +1,89 @@
+"""GPU paths pinned to outputs of the UNMODIFIED reference (tests/golden/, made by oracle/make_golden.py under
+oracle/ref_shim.py) for the pieces round 1 had only compared oracle <-> repo:
+
+  * IsotrophicLiveViewSequence2D.get_view_from + RobustScaler (sequences/isotrophic_live_view_sequence_2d.py:29-117,
+    preprocessing/scaling.py:75-88): X, y, grid and inv_basis bit-exact, incl. a rotated affine (apply_rotation);
+  * the training-batch rejection sampler (…_2d.py:119-161, isotrophic_live_view_sequence.py:91-128) driven from the
+    same candidate list as the reference: identical accept decisions (class-presence rules AND is_valid_im), and the
+    accepted, scaled batch bit-exact;
+  * the exact grid centre of get_voxel_grid_real_space (sample_grid.py:117-118) for rotated / sheared affines.
+Integer / index work: bit-exact.  Float32 images: bit-exact (float64 arithmetic in the reference's order)."""
+import os
+
+import numpy as np
+import pytest
+
+import golden_inputs as gi
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_get_view_from_matches_reference():
+    from multiplanarunet_b200.sequences import IsotrophicLiveViewSequence2D, SyntheticImage
+    for case in gi.VIEW_STACK_CASES:
+        z = np.load(os.path.join(GOLD, "view_stack_%s.npz" % case["name"]))
+        vol, lab, affine, bg = gi.view_stack_inputs(case)
+        image = SyntheticImage(vol, lab, affine, bg_value=bg)
+        assert np.array_equal(image.scaler_center, z["center"]) and np.array_equal(image.scaler_scale, z["scale"])
+        assert (image.interpolator.rot_mat is not None) == (case["affine"] == "rot")
+        seq = IsotrophicLiveViewSequence2D([image], views=[case["view"]], sample_dim=case["dim"],
+                                           real_space_span=case["span"], n_classes=4, is_validation=True)
+        X, y, grid, inv_basis = seq.get_view_from(image, case["view"], case["n_planes"])
+        assert X.dtype == np.float32 and X.shape == z["X"].shape
+        assert np.array_equal(X, z["X"]), (case["name"], float(np.abs(X - z["X"]).max()))
+        assert np.array_equal(y, z["y"])
+        assert np.array_equal(grid[0], z["axis"]) and np.array_equal(grid[1], z["axis"])
+        assert np.array_equal(grid[2], z["offsets"]) and np.array_equal(inv_basis, z["inv_basis"])
+        # the same planes written straight into the U-Net's bf16 input layout
+        import torch
+        n, dim, cpad = X.shape[2], case["dim"], 8
+        pad = torch.zeros(n * (dim + 2) * (dim + 2), cpad, dtype=torch.bfloat16, device="cuda")
+        seq.get_view_stack_device(image, case["view"], case["n_planes"], out_padded=pad, cpad=cpad, want_f32=False,
+                                  want_labels=False)
+        got = pad.view(n, dim + 2, dim + 2, cpad)[:, 1:-1, 1:-1, :2].float().cpu().numpy()
+        exp = torch.as_tensor(np.moveaxis(z["X"], 2, 0)).to(torch.bfloat16).float().numpy()
+        assert np.array_equal(got, exp)
+
+
+def test_batch_sampler_accept_decisions_match_reference():
+    from multiplanarunet_b200.sequences import IsotrophicLiveViewSequence2D, SyntheticImage
+    for case in gi.BATCH_RULE_CASES:
+        z = np.load(os.path.join(GOLD, "batch_rules_%s.npz" % case["name"]))
+        vol, lab, views, cand_view, cand_off, cand_noise, bg = gi.batch_rule_inputs(case)
+        image = SyntheticImage(vol, lab, np.eye(4), bg_value=bg)
+        seq = IsotrophicLiveViewSequence2D([image], views=views, sample_dim=case["dim"], real_space_span=case["span"],
+                                           n_classes=case["n_classes"], batch_size=case["B"],
+                                           fg_batch_fraction=case["fg_frac"])
+        cands = (np.zeros(case["B"], dtype=np.int64), cand_view, cand_off, cand_noise)
+        x, y, w, picks = seq.sample_batch_device(max_tries=case["tries"], candidates=cands, return_picks=True)
+        assert np.array_equal(picks, z["picks"]), (case["name"], picks, z["picks"])
+        assert np.array_equal(x.cpu().numpy(), z["x"]) and np.array_equal(y.cpu().numpy(), z["y"])
+        # probe flags against per-plane facts of the materialised candidates
+        from multiplanarunet_b200.interpolation import plane_basis_batch
+        B, T = cand_view.shape
+        bases = plane_basis_batch(views[cand_view.ravel()], cand_noise.reshape(-1, 3))
+        cm, vd = image.interpolator.probe_planes(bases, cand_off.ravel(), case["dim"], case["span"])
+        im, lb = image.interpolator.sample_planes(bases, cand_off.ravel(), case["dim"], case["span"])
+        lbn, imn = lb.cpu().numpy(), im.cpu().numpy()
+        for k in range(B * T):
+            mask = 0
+            for c in np.unique(lbn[k]):
+                mask |= 1 << int(c)
+            assert int(cm[k].item()) & 0xFFFFFFFF == mask
+            assert bool(vd[k].item()) == bool(np.any(~np.isclose(imn[k][..., 0], bg[0])))
+
+
+def test_exact_voxel_grid_centre_matches_reference():
+    from multiplanarunet_b200.interpolation.voxel_center import voxel_grid_center_exact
+    z = np.load(os.path.join(GOLD, "voxel_center.npz"))
+    for k, (shape, kind) in enumerate(gi.VOXEL_CENTER_CASES):
+        A = gi.voxel_center_affine(kind)[:3, :3]
+        mean = voxel_grid_center_exact(shape, A)
+        assert np.array_equal(mean, z["mean_%d" % k]), (shape, kind, mean - z["mean_%d" % k])
+        closed = A.dot((np.asarray(shape, float) - 1) / 2)
+        if kind == "rot" and np.prod(shape) > 1000:
+            assert not np.array_equal(closed, mean)  # the closed form is NOT what the reference subtracts
+    # full-size volume: finite, close to the closed form
+    m = voxel_grid_center_exact((256, 256, 256), gi.rotated_affine()[:3, :3])
+    assert np.allclose(m, gi.rotated_affine()[:3, :3].dot(np.full(3, 127.5)), rtol=1e-13)

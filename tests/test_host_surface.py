@@ -139,3 +139,21 @@ def test_get_sequence_registry():
         get_sequence([object()], False, **dict(kw, intrp_style="bogus"))
     with pytest.raises(NotImplementedError):
         get_sequence([object()], False, augmenters=[dict(cls_name="Elastic3D", kwargs={})], **kw)
+
+
+def test_plane_basis_batch_is_bit_identical_to_plane_basis():
+    """The vectorised basis construction used for the 320 candidate planes of a training batch equals the scalar
+    mirror of sample_grid.py:192-224 bit for bit, including the |n| < 0.2 flip and the flat-normal special case."""
+    import numpy as np
+    from multiplanarunet_b200.interpolation import plane_basis, plane_basis_batch
+    rng = np.random.RandomState(3)
+    n = 3000
+    views = rng.randn(n, 3)
+    views[:40] = [0, 0, 1]
+    views[40:80] = [0.1, 0.15, 0.9]
+    views[80:120] = [-0.3, -0.1, 0.9]
+    noise = rng.normal(scale=0.1, size=(n, 3))
+    noise[:20] = 0
+    B = plane_basis_batch(views, noise)
+    for i in range(n):
+        assert np.array_equal(B[i], plane_basis(views[i], noise[i].copy())), i

@@ -123,3 +123,101 @@ def test_elastic_matches_reference_goldens():
         assert np.array_equal(l, z["lab_" + case["name"]]), case["name"]
     # the strong case must exercise the out-of-bounds fill
     assert np.any(z["im_strong"] == np.float32(0.5))
+
+
+def test_view_stack_matches_reference_goldens():
+    """oracle.sampler.get_view_from + robust_scale against the reference's IsotrophicLiveViewSequence2D.get_view_from
+    (7 threads, reference ViewInterpolator, MultiChannelScaler(RobustScaler)) - tests/golden/view_stack_*.npz."""
+    for case in gi.VIEW_STACK_CASES:
+        z = np.load(os.path.join(GOLD, "view_stack_%s.npz" % case["name"]))
+        vol, lab, affine, bg = gi.view_stack_inputs(case)
+        pix = np.linalg.norm(affine[:3, :3], axis=0)
+        rot = None
+        if case["affine"] == "rot":
+            rot = np.diag(pix).dot(np.linalg.inv(affine[:3, :3]))
+        X, y, grid, inv_basis = sampler.get_view_from(vol, lab, pix, case["view"], case["dim"], case["span"], bg, 0,
+                                                      z["center"], z["scale"], case["n_planes"], rot_mat=rot)
+        assert X.dtype == np.float32 and np.array_equal(X, z["X"]), case["name"]
+        assert np.array_equal(y, z["y"])
+        assert np.array_equal(grid[0], z["axis"]) and np.array_equal(grid[2], z["offsets"])
+        assert np.array_equal(inv_basis, z["inv_basis"])
+
+
+def test_batch_rules_match_reference_goldens():
+    """The acceptance decisions of the reference's _get_valid_slice_from over a fixed candidate list
+    (tests/golden/batch_rules_*.npz) against (a) the oracle restatement and (b) the PRODUCT's host-side rule loop
+    (IsotrophicLiveViewSequence2D.select_slices), both fed per-candidate facts computed by the numpy oracle."""
+    from multiplanarunet_b200.sequences.isotrophic_live_view_sequence_2d import IsotrophicLiveViewSequence2D
+    saw_invalid_im = saw_no_fg = saw_retry = False
+    for case in gi.BATCH_RULE_CASES:
+        z = np.load(os.path.join(GOLD, "batch_rules_%s.npz" % case["name"]))
+        vol, lab, views, cand_view, cand_off, cand_noise, bg = gi.batch_rule_inputs(case)
+        B, T = cand_view.shape
+        nfg = case["n_classes"] - 1
+        present = np.zeros((B, T, nfg), bool)
+        valid = np.zeros((B, T), bool)
+        for s in range(B):
+            for t in range(T):
+                basis = sampler.plane_basis(views[cand_view[s, t]], cand_noise[s, t])
+                im, lb = sampler.sample_plane(vol, lab, (1, 1, 1), basis, case["dim"], case["span"], cand_off[s, t], bg, 0)
+                present[s, t] = np.isin(np.arange(1, case["n_classes"]), lb)
+                valid[s, t] = sampler.is_valid_im(im, bg)
+        saw_invalid_im |= not valid.all()
+        saw_no_fg |= not present.any(-1).all()
+        saw_retry |= bool((z["picks"] > 0).any())
+        n_fg_slices = int(np.ceil(B * case["fg_frac"]))
+        picks, counts = sampler.select_slices(present, valid, B, n_fg_slices, B > nfg, nfg)
+        assert np.array_equal(picks, z["picks"]) and np.array_equal(counts, z["fg_counts"]), case["name"]
+        seq = IsotrophicLiveViewSequence2D([], views=views, sample_dim=case["dim"], real_space_span=case["span"],
+                                           n_classes=case["n_classes"], batch_size=B, fg_batch_fraction=case["fg_frac"])
+        picks2, count2 = seq.select_slices(present, valid)
+        assert np.array_equal(picks2, z["picks"]) and count2 == z["fg_counts"][-1], case["name"]
+        # accepted planes: scaled image and labels equal the reference's batch
+        from multiplanarunet_b200.sequences.isotrophic_live_view_sequence_2d import robust_scaler_stats
+        cen, scl = robust_scaler_stats(vol)
+        for s in range(B):
+            t = picks[s]
+            basis = sampler.plane_basis(views[cand_view[s, t]], cand_noise[s, t])
+            im, lb = sampler.sample_plane(vol, lab, (1, 1, 1), basis, case["dim"], case["span"], cand_off[s, t], bg, 0,
+                                          cen, scl)
+            assert np.array_equal(im, z["x"][s]) and np.array_equal(lb, z["y"][s])
+    assert saw_invalid_im and saw_no_fg and saw_retry  # the cases exercise both rejection reasons
+
+
+def test_pairwise_tree_reproduces_numpy_sum_and_reference_centre():
+    """interpolation/voxel_center.py: the recursion tree of numpy's pairwise_sum, and (with leaf sums taken on the
+    host here) the exact grid centre the reference subtracts (tests/golden/voxel_center.npz)."""
+    from multiplanarunet_b200.interpolation.voxel_center import combine, pairwise_tree
+    z = np.load(os.path.join(GOLD, "voxel_center.npz"))
+
+    def leaf_sum(a):
+        n = len(a)
+        if n < 8:
+            res = 0.0
+            for v in a:
+                res += v
+            return res
+        r = list(a[:8])
+        i = 8
+        while i < n - (n % 8):
+            for j in range(8):
+                r[j] += a[i + j]
+            i += 8
+        res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]))
+        while i < n:
+            res += a[i]
+            i += 1
+        return res
+
+    for k, (shape, kind) in enumerate(gi.VOXEL_CENTER_CASES):
+        if np.prod(shape) > 300000:
+            continue  # pure-Python leaves: keep the CPU suite fast (the GPU test covers every case)
+        A = gi.voxel_center_affine(kind)[:3, :3]
+        grid = np.mgrid[0:shape[0]:1, 0:shape[1]:1, 0:shape[2]:1]
+        pts = np.stack([g.ravel() for g in grid], 1)
+        real = A.dot(pts.T).T
+        n = len(pts)
+        ls, ll, _, _, _ = pairwise_tree(n)
+        mean = np.array([combine(n, np.array([leaf_sum(real[s:s + l, r].tolist()) for s, l in zip(ls, ll)])) / n
+                         for r in range(3)])
+        assert np.array_equal(mean, z["mean_%d" % k]), (shape, kind)
