@@ -176,9 +176,23 @@ int mpu_map_fuse_linspace(const void* const* h_pred_ptrs, int V, int C, int dim,
  * Replaces FusionModel.fit's train step (bin/train_fusion.py:196-213; loss evaluate/loss_functions.py:
  * 207-246 with uniform weights; regulariser models/fusion_model.py:9-11).  X [n][V][C] f32, y [n] u8.
  * mpu_fusion_grad ADDS into accum (double [V*C + C + 1] = dW | db | sum of per-point losses); all-reduce
- * accum across ranks, then mpu_fusion_adam applies mean gradient + regulariser with Keras Adam. */
+ * accum across ranks, then mpu_fusion_adam applies mean gradient + regulariser with Keras Adam.
+ * mpu_fusion_adam with n_points <= 0 takes the point count from accum[V*C + C + 1] (device): the count is all-reduced in
+ * the same message as the sums, so a multi-rank step needs no host synchronisation. */
 int mpu_fusion_grad(const float* X, const unsigned char* y, long long n, int V, int C, const float* W,
                     const float* b, double* accum, void* stream);
+/* The same with a shuffled epoch: point i of the batch is row index[i] of X / y (device int64 [n]) - Keras'
+ * fit(shuffle=True) without materialising X[perm].  index == NULL: rows 0..n-1. */
+int mpu_fusion_grad_indexed(const float* X, const unsigned char* y, const long long* index, long long n, int V, int C,
+                            const float* W, const float* b, double* accum, void* stream);
+/* Single-process train step in ONE launch: gradient sums, then the last block to finish applies the Adam update
+ * (+ regulariser), writes the batch's mean dice loss to loss_out (device double, optional), and zeroes accum and
+ * counter for the next batch.  accum (double [V*C + C + 1]) and counter (uint32) must be zero before the first call.
+ * With several ranks use mpu_fusion_grad_indexed + all-reduce + mpu_fusion_adam instead. */
+int mpu_fusion_train_step(const float* X, const unsigned char* y, const long long* index, long long n, int V, int C,
+                          float* W, float* b, float* m, float* v, double* accum, unsigned int* counter,
+                          double* loss_out, float reg, float lr, float beta1, float beta2, float eps, int step,
+                          void* stream);
 int mpu_fusion_adam(float* W, float* b, float* m, float* v, const double* accum, double n_points,
                     int V, int C, float reg, float lr, float beta1, float beta2, float eps, int step,
                     void* stream);

@@ -80,13 +80,23 @@ def entry_func(args=None):
             Xs.append(X)
             ys.append(torch.as_tensor(image.labels.reshape(-1)).to(model.device))
             ld.unload(i)
-        X, y = torch.cat(Xs), torch.cat(ys)
+        if Xs:
+            X, y = torch.cat(Xs), torch.cat(ys)
+        else:  # a rank without images in this round still takes part in every collective
+            X = torch.zeros(0, len(views), build["n_classes"], dtype=torch.float32, device=model.device)
+            y = torch.zeros(0, dtype=torch.uint8, device=model.device)
         perm = torch.randperm(X.shape[0], device=X.device)
-        n_val = int(0.2 * X.shape[0])
+        n_val = int(0.2 * X.shape[0])            # validation_split=0.2 of the reference's fit (train_fusion.py:205)
         tr, va = perm[n_val:], perm[:n_val]
+        # every rank must run the same number of batches per epoch and of epochs: agree on the maximum
+        steps = torch.tensor([(int(tr.numel()) + a.batch_size - 1) // a.batch_size], device=model.device)
+        if D.world_size() > 1:
+            torch.distributed.all_reduce(steps, op=torch.distributed.ReduceOp.MAX)
+        steps = max(int(steps.item()), 1)
         best, wait = np.inf, 0
         for ep in range(a.epochs):
-            loss = fm.fit(X[tr], y[tr], batch_size=a.batch_size, epochs=1, verbose=0)[-1]
+            fm.fit(X, y, batch_size=a.batch_size, epochs=1, verbose=0, index=tr, steps_per_epoch=steps)
+            loss = fm.evaluate(X[va], y[va]) if n_val else float("nan")   # val_loss drives early stopping (:199-203)
             if loss < best - 1e-6:
                 best, wait = loss, 0
             else:

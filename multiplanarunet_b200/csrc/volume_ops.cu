@@ -616,18 +616,44 @@ __global__ void fusion_grad_kernel(const float* __restrict__ X, const uint8_t* _
 // dynamically, which puts them in local memory: 687 MB of DRAM writes per 256^3 pass, profiles/r02_ncu_full_volume_
 // kernels_summary.txt).  One point = V*C consecutive floats, read with 8-byte loads (V*C even) - each thread walks
 // its own row, the warp covers 32 consecutive rows, so every fetched line is fully used out of L1.
+// One Adam step on the fusion parameters from the accumulated gradient sums (shared by the stand-alone Adam kernel
+// and the fused single-process train step).  k indexes [W (V*C) | b (C)].
+__device__ __forceinline__ void fusion_adam_update(int k, float* W, float* b, float* m, float* v, double grad_sum,
+                                                   double n_points, int nW, int C, float reg, float lr_t, float b1,
+                                                   float b2, float eps) {
+  float* prm = k < nW ? W + k : b + (k - nW);
+  const float cnt = k < nW ? (float)nW : (float)C;
+  const float g = (float)(grad_sum / n_points) + reg * 2.f * (*prm) / cnt;
+  const float mi = b1 * m[k] + (1.f - b1) * g;
+  const float vi = b2 * v[k] + (1.f - b2) * g * g;
+  m[k] = mi;
+  v[k] = vi;
+  *prm = *prm - lr_t * mi / (sqrtf(vi) + eps);
+}
+
+struct FusionStepArgs {  // optional fused Adam (single process): the last block to finish applies the update
+  float *Wp, *bp, *m, *v;
+  unsigned int* counter;   // zero before the launch; reset by the kernel
+  double* loss_out;        // receives the batch's mean loss (without regulariser), or null
+  float reg, lr_t, b1, b2, eps;
+  int fused;
+};
+
 template <int V, int C>
 __global__ void __launch_bounds__(128, 4) fusion_grad_kernel_t(const float* __restrict__ X, const uint8_t* __restrict__ y,
-                                                               long long n, const float* __restrict__ W,
-                                                               const float* __restrict__ b, double* __restrict__ accum) {
+                                                               const long long* __restrict__ index, long long n,
+                                                               const float* __restrict__ W, const float* __restrict__ b,
+                                                               double* __restrict__ accum, const FusionStepArgs fs) {
   constexpr int VC = V * C, NACC = VC + C + 1;
-  constexpr int kChunkFloats = 32 * VC;          // one warp iteration = 32 consecutive points
+  constexpr int kChunkFloats = 32 * VC;          // one warp iteration = 32 points
   constexpr int kVec = kChunkFloats / 4;         // float4 per chunk (32 * VC is a multiple of 4)
   __shared__ double fsm[4][NACC];
-  // Each warp stages its 32 points (32 * VC contiguous floats) through shared memory with fully coalesced 16-byte
-  // loads: per-thread row walks touch 32 different lines per load instruction and saturate the L1 tag stage
-  // (measured 0.83 ms per 256^3 pass against 0.31 ms of HBM time).
+  // Each warp stages its 32 points (32 * VC floats) through shared memory with coalesced loads: per-thread row walks
+  // touch 32 different lines per load instruction and saturate the L1 tag stage (measured 0.83 ms per 256^3 pass
+  // against 0.31 ms of HBM time).  With `index` (a shuffled epoch: point i is row index[i], the reference's
+  // fit(shuffle=True)) the rows are gathered 8 bytes per lane, 15 lanes per row for V*C = 30.
   __shared__ __align__(16) float stage[4][kChunkFloats];
+  __shared__ int s_last;
   float loc[NACC];
 #pragma unroll
   for (int k = 0; k < NACC; ++k) loc[k] = 0.f;
@@ -642,18 +668,39 @@ __global__ void __launch_bounds__(128, 4) fusion_grad_kernel_t(const float* __re
   float* st = stage[warp];
   for (long long ch = (long long)blockIdx.x * 4 + warp; ch < nchunks; ch += wstride) {
     const long long p0 = ch * 32;
-    const long long f0 = p0 * VC;                 // first float of the chunk: 16-byte aligned (32 * VC * 4 bytes)
-    const long long fend = n * VC;
     __syncwarp();
-    if (f0 + kChunkFloats <= fend) {
-      const float4* src = reinterpret_cast<const float4*>(X + f0);
-#pragma unroll
-      for (int j = 0; j < (kVec + 31) / 32; ++j) {
-        const int v4 = j * 32 + lane;
-        if (v4 < kVec) reinterpret_cast<float4*>(st)[v4] = __ldg(src + v4);
+    if (index) {
+      // rows are 8-byte aligned when V*C is even: gather float2 pieces, consecutive lanes inside one row
+      const long long mine = p0 + lane < n ? index[p0 + lane] : 0;
+      if (VC % 2 == 0) {
+        constexpr int kPieces = VC / 2;
+        for (int e = lane; e < 32 * kPieces; e += 32) {
+          const int row = e / kPieces, col = e - row * kPieces;
+          const long long src_row = __shfl_sync(0xffffffffu, mine, row);
+          const float2 t = p0 + row < n ? __ldg(reinterpret_cast<const float2*>(X + src_row * VC) + col)
+                                        : make_float2(0.f, 0.f);
+          reinterpret_cast<float2*>(st)[e] = t;
+        }
+      } else {
+        for (int e = lane; e < kChunkFloats; e += 32) {
+          const int row = e / VC, col = e - row * VC;
+          const long long src_row = __shfl_sync(0xffffffffu, mine, row);
+          st[e] = p0 + row < n ? __ldg(X + src_row * VC + col) : 0.f;
+        }
       }
     } else {
-      for (int k = lane; k < kChunkFloats; k += 32) st[k] = f0 + k < fend ? __ldg(X + f0 + k) : 0.f;
+      const long long f0 = p0 * VC;               // first float of the chunk: 16-byte aligned (32 * VC * 4 bytes)
+      const long long fend = n * VC;
+      if (f0 + kChunkFloats <= fend) {
+        const float4* src = reinterpret_cast<const float4*>(X + f0);
+#pragma unroll
+        for (int j = 0; j < (kVec + 31) / 32; ++j) {
+          const int v4 = j * 32 + lane;
+          if (v4 < kVec) reinterpret_cast<float4*>(st)[v4] = __ldg(src + v4);
+        }
+      } else {
+        for (int k = lane; k < kChunkFloats; k += 32) st[k] = f0 + k < fend ? __ldg(X + f0 + k) : 0.f;
+      }
     }
     __syncwarp();
     const long long i = p0 + lane;
@@ -661,7 +708,7 @@ __global__ void __launch_bounds__(128, 4) fusion_grad_kernel_t(const float* __re
       float x[VC];
 #pragma unroll
       for (int k = 0; k < VC; ++k) x[k] = st[lane * VC + k];
-      const int lab = y[i];
+      const int lab = y[index ? index[i] : i];
       float z[C], pr[C];
 #pragma unroll
       for (int c = 0; c < C; ++c) {
@@ -715,11 +762,31 @@ __global__ void __launch_bounds__(128, 4) fusion_grad_kernel_t(const float* __re
     for (int ww = 0; ww < 4; ++ww) s += fsm[ww][k];
     atomicAdd(accum + k, s);
   }
+  if (!fs.fused) return;
+  // fused Adam: the block that arrives last sees every block's contribution
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(fs.counter, 1u) == gridDim.x - 1 ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  volatile double* acc_v = accum;
+  if (threadIdx.x < VC + C)
+    fusion_adam_update(threadIdx.x, fs.Wp, fs.bp, fs.m, fs.v, acc_v[threadIdx.x], (double)n, VC, C, fs.reg, fs.lr_t,
+                       fs.b1, fs.b2, fs.eps);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (fs.loss_out) *fs.loss_out = acc_v[NACC - 1] / (double)n;
+    *fs.counter = 0u;
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < NACC; k += blockDim.x) accum[k] = 0.0;  // ready for the next batch
 }
 
 template <int V, int C>
-static int launch_fusion_grad_t(const float* X, const unsigned char* y, long long n, const float* W, const float* b,
-                                double* accum, cudaStream_t st) {
+static int launch_fusion_grad_t(const float* X, const unsigned char* y, const long long* index, long long n,
+                                const float* W, const float* b, double* accum, const FusionStepArgs& fs,
+                                cudaStream_t st) {
   int occ = 2;
   const int sms = sm_count();
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fusion_grad_kernel_t<V, C>, 128, 0) != cudaSuccess || occ < 1)
@@ -731,7 +798,7 @@ static int launch_fusion_grad_t(const float* X, const unsigned char* y, long lon
   long long blocks = (n + 127) / 128;
   if (blocks > (long long)sms * occ) blocks = (long long)sms * occ;
   if (blocks < 1) blocks = 1;
-  fusion_grad_kernel_t<V, C><<<(int)blocks, 128, 0, st>>>(X, y, n, W, b, accum);
+  fusion_grad_kernel_t<V, C><<<(int)blocks, 128, 0, st>>>(X, y, index, n, W, b, accum, fs);
   count_launch();
   MPU_CUDA(cudaGetLastError());
   return MPU_OK;
@@ -744,14 +811,9 @@ __global__ void fusion_adam_kernel(float* W, float* b, float* m, float* v, const
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   const int nW = V * C;
   if (k >= nW + C) return;
-  float* prm = k < nW ? W + k : b + (k - nW);
-  const float cnt = k < nW ? (float)nW : (float)C;
-  const float g = (float)(accum[k] / n_points) + reg * 2.f * (*prm) / cnt;
-  const float mi = b1 * m[k] + (1.f - b1) * g;
-  const float vi = b2 * v[k] + (1.f - b2) * g * g;
-  m[k] = mi;
-  v[k] = vi;
-  *prm = *prm - lr_t * mi / (sqrtf(vi) + eps);
+  // n_points <= 0: the (all-reduced) point count travels with the sums, in accum[V*C + C + 1]
+  const double np_ = n_points > 0 ? n_points : accum[nW + C + 1];
+  fusion_adam_update(k, W, b, m, v, accum[k], np_, nW, C, reg, lr_t, b1, b2, eps);
 }
 
 inline int grid_for(long long work, int threads, int cap = 0) {
@@ -1220,28 +1282,50 @@ int mpu_map_fuse_linspace(const void* const* h_pred_ptrs, int V, int C, int dim,
   return map_fuse_dispatch(p, reinterpret_cast<cudaStream_t>(stream));
 }
 
+static int fusion_grad_dispatch(const float* X, const unsigned char* y, const long long* index, long long n, int V, int C,
+                                const float* W, const float* b, double* accum, const FusionStepArgs& fs,
+                                cudaStream_t st, bool* handled) {
+  *handled = true;
+  // the reference's configurations (6 views; bin/train_fusion.py) with 2..8 classes run fully in registers
+  if (V == 6) {
+    switch (C) {
+      case 2: return launch_fusion_grad_t<6, 2>(X, y, index, n, W, b, accum, fs, st);
+      case 3: return launch_fusion_grad_t<6, 3>(X, y, index, n, W, b, accum, fs, st);
+      case 4: return launch_fusion_grad_t<6, 4>(X, y, index, n, W, b, accum, fs, st);
+      case 5: return launch_fusion_grad_t<6, 5>(X, y, index, n, W, b, accum, fs, st);
+      case 6: return launch_fusion_grad_t<6, 6>(X, y, index, n, W, b, accum, fs, st);
+      case 7: return launch_fusion_grad_t<6, 7>(X, y, index, n, W, b, accum, fs, st);
+      case 8: return launch_fusion_grad_t<6, 8>(X, y, index, n, W, b, accum, fs, st);
+      default: break;
+    }
+  }
+  if (V == 3 && C == 5) return launch_fusion_grad_t<3, 5>(X, y, index, n, W, b, accum, fs, st);
+  *handled = false;
+  return MPU_OK;
+}
+
 int mpu_fusion_grad(const float* X, const unsigned char* y, long long n, int V, int C, const float* W,
                     const float* b, double* accum, void* stream) {
+  return mpu_fusion_grad_indexed(X, y, nullptr, n, V, C, W, b, accum, stream);
+}
+
+int mpu_fusion_grad_indexed(const float* X, const unsigned char* y, const long long* index, long long n, int V, int C,
+                            const float* W, const float* b, double* accum, void* stream) {
+  if (n <= 0) return MPU_OK;  // an empty shard contributes nothing (its rank still joins the all-reduce)
   if (!X || !y || !W || !b || !accum || V < 1 || C < 1 || C > kMaxClasses || V * C > 128) {
     set_error("mpu_fusion_grad: bad arguments (V=%d C=%d)", V, C);
     return MPU_ERR_ARG;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (n <= 0) return MPU_OK;
-  // the reference's configurations (6 views; bin/train_fusion.py) with 2..8 classes run fully in registers
-  if (V == 6) {
-    switch (C) {
-      case 2: return launch_fusion_grad_t<6, 2>(X, y, n, W, b, accum, st);
-      case 3: return launch_fusion_grad_t<6, 3>(X, y, n, W, b, accum, st);
-      case 4: return launch_fusion_grad_t<6, 4>(X, y, n, W, b, accum, st);
-      case 5: return launch_fusion_grad_t<6, 5>(X, y, n, W, b, accum, st);
-      case 6: return launch_fusion_grad_t<6, 6>(X, y, n, W, b, accum, st);
-      case 7: return launch_fusion_grad_t<6, 7>(X, y, n, W, b, accum, st);
-      case 8: return launch_fusion_grad_t<6, 8>(X, y, n, W, b, accum, st);
-      default: break;
-    }
+  FusionStepArgs fs;
+  memset(&fs, 0, sizeof(fs));
+  bool handled = false;
+  MPU_TRY(fusion_grad_dispatch(X, y, index, n, V, C, W, b, accum, fs, st, &handled));
+  if (handled) return MPU_OK;
+  if (index) {
+    set_error("mpu_fusion_grad_indexed: (V=%d, C=%d) has no gather variant (supported: V=6 with 2..8 classes)", V, C);
+    return MPU_ERR_ARG;
   }
-  if (V == 3 && C == 5) return launch_fusion_grad_t<3, 5>(X, y, n, W, b, accum, st);
   const int threads = 256;
   const int nacc = V * C + C + 1;
   const size_t smem = sizeof(double) * (threads / 32) * nacc;
@@ -1251,10 +1335,35 @@ int mpu_fusion_grad(const float* X, const unsigned char* y, long long n, int V, 
   return MPU_OK;
 }
 
+int mpu_fusion_train_step(const float* X, const unsigned char* y, const long long* index, long long n, int V, int C,
+                          float* W, float* b, float* m, float* v, double* accum, unsigned int* counter,
+                          double* loss_out, float reg, float lr, float beta1, float beta2, float eps, int step,
+                          void* stream) {
+  if (!X || !y || !W || !b || !m || !v || !accum || !counter || n <= 0 || step < 1) {
+    set_error("mpu_fusion_train_step: bad arguments");
+    return MPU_ERR_ARG;
+  }
+  FusionStepArgs fs;
+  fs.Wp = W; fs.bp = b; fs.m = m; fs.v = v;
+  fs.counter = counter;
+  fs.loss_out = loss_out;
+  fs.reg = reg;
+  fs.lr_t = (float)((double)lr * sqrt(1.0 - pow((double)beta2, step)) / (1.0 - pow((double)beta1, step)));
+  fs.b1 = beta1; fs.b2 = beta2; fs.eps = eps;
+  fs.fused = 1;
+  bool handled = false;
+  MPU_TRY(fusion_grad_dispatch(X, y, index, n, V, C, W, b, accum, fs, reinterpret_cast<cudaStream_t>(stream), &handled));
+  if (!handled) {
+    set_error("mpu_fusion_train_step: (V=%d, C=%d) not instantiated (supported: V=6 with 2..8 classes, V=3 C=5)", V, C);
+    return MPU_ERR_ARG;
+  }
+  return MPU_OK;
+}
+
 int mpu_fusion_adam(float* W, float* b, float* m, float* v, const double* accum, double n_points,
                     int V, int C, float reg, float lr, float beta1, float beta2, float eps, int step,
                     void* stream) {
-  if (!W || !b || !m || !v || !accum || n_points <= 0) {
+  if (!W || !b || !m || !v || !accum) {
     set_error("mpu_fusion_adam: bad arguments");
     return MPU_ERR_ARG;
   }

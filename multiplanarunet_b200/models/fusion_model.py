@@ -69,42 +69,89 @@ class FusionModel(object):
         raise NotImplementedError("fusion inference is fused with the mapping gather: use "
                                   "multiplanarunet_b200.utils.fusion.predict_multi_view")
 
-    def train_on_batch(self, X, y, all_reduce=True):
-        """One Adam step on a batch of points; X [n,V,C] f32 tensor (device), y [n] uint8 tensor.
-        Returns the mean loss (incl. regulariser) over the GLOBAL batch."""
+    def _distributed(self):
         import torch
-        n = X.shape[0]
-        self._accum.zero_()
-        check(lib.mpu_fusion_grad(_C.ptr(X), _C.ptr(y), ctypes.c_longlong(n), self.n_inputs, self.n_classes,
-                                  _C.ptr(self.W), _C.ptr(self.b), _C.ptr(self._accum), _C.current_stream()),
-              "mpu_fusion_grad")
-        n_total = float(n)
-        if all_reduce and torch.distributed.is_available() and torch.distributed.is_initialized():
-            cnt = torch.tensor([float(n)], dtype=torch.float64, device=self.device)
-            torch.distributed.all_reduce(self._accum)
-            torch.distributed.all_reduce(cnt)
-            n_total = float(cnt.item())
+        return torch.distributed.is_available() and torch.distributed.is_initialized() and \
+            torch.distributed.get_world_size() > 1
+
+    def train_on_batch(self, X, y, all_reduce=True, index=None, loss_out=None):
+        """One Adam step on a batch of points; X [N,V,C] f32 tensor (device), y [N] uint8 tensor.  With `index`
+        (device int64 [n]) the batch is rows index[i] of X / y - a slice of a shuffled epoch, gathered inside the
+        kernel.  Single process: ONE launch (mpu_fusion_train_step: gradient sums, the last block applies Adam).
+        Several ranks: local sums, SUM all-reduce of the 36 doubles and the point count, identical Adam on every rank.
+        Returns the mean dice loss of the GLOBAL batch as a 0-d device tensor (float64)."""
+        import torch
+        n = int(index.shape[0]) if index is not None else int(X.shape[0])
         self.iterations += 1
+        if not (all_reduce and self._distributed()):
+            if not hasattr(self, "_counter"):
+                self._counter = torch.zeros(1, dtype=torch.int32, device=self.device)
+                self._loss1 = torch.zeros(1, dtype=torch.float64, device=self.device)
+                self._accum.zero_()
+            out = loss_out if loss_out is not None else self._loss1
+            check(lib.mpu_fusion_train_step(_C.ptr(X), _C.ptr(y), _C.ptr(index), ctypes.c_longlong(n), self.n_inputs,
+                                            self.n_classes, _C.ptr(self.W), _C.ptr(self.b), _C.ptr(self._m),
+                                            _C.ptr(self._v), _C.ptr(self._accum), _C.ptr(self._counter), _C.ptr(out),
+                                            ctypes.c_float(self.reg), ctypes.c_float(self.lr),
+                                            ctypes.c_float(self.beta_1), ctypes.c_float(self.beta_2),
+                                            ctypes.c_float(self.epsilon), int(self.iterations), _C.current_stream()),
+                  "mpu_fusion_train_step")
+            return out[0]
+        self._accum.zero_()
+        check(lib.mpu_fusion_grad_indexed(_C.ptr(X), _C.ptr(y), _C.ptr(index), ctypes.c_longlong(n), self.n_inputs,
+                                          self.n_classes, _C.ptr(self.W), _C.ptr(self.b), _C.ptr(self._accum),
+                                          _C.current_stream()), "mpu_fusion_grad_indexed")
+        if not hasattr(self, "_red"):
+            self._red = torch.zeros(self._accum.numel() + 1, dtype=torch.float64, device=self.device)
+        self._red[:-1].copy_(self._accum)
+        self._red[-1] = float(n)
+        torch.distributed.all_reduce(self._red)          # gradient sums, loss sum and point count in one message
         check(lib.mpu_fusion_adam(_C.ptr(self.W), _C.ptr(self.b), _C.ptr(self._m), _C.ptr(self._v),
-                                  _C.ptr(self._accum), ctypes.c_double(n_total), self.n_inputs,
+                                  _C.ptr(self._red), ctypes.c_double(0.0), self.n_inputs,
                                   self.n_classes, ctypes.c_float(self.reg), ctypes.c_float(self.lr),
                                   ctypes.c_float(self.beta_1), ctypes.c_float(self.beta_2),
                                   ctypes.c_float(self.epsilon), int(self.iterations), _C.current_stream()),
               "mpu_fusion_adam")
-        return self._accum[-1] / n_total
+        loss = self._red[-2] / self._red[-1]
+        if loss_out is not None:
+            loss_out.copy_(loss.reshape(1))
+        return loss
 
-    def fit(self, X, y, batch_size=2 ** 17, epochs=30, verbose=1, shuffle=True, **kw):
-        """Epoch loop over device-resident points (bin/train_fusion.py:196-213)."""
+    def evaluate(self, X, y, batch_size=2 ** 20):
+        """Mean dice loss (without regulariser) over a point set, no update (validation_split of the reference's fit)."""
         import torch
-        n = X.shape[0]
+        acc = torch.zeros_like(self._accum)
+        check(lib.mpu_fusion_grad_indexed(_C.ptr(X), _C.ptr(y), _C.ptr(None), ctypes.c_longlong(int(X.shape[0])),
+                                          self.n_inputs, self.n_classes, _C.ptr(self.W), _C.ptr(self.b), _C.ptr(acc),
+                                          _C.current_stream()), "mpu_fusion_grad_indexed")
+        tot = torch.stack([acc[-1], torch.tensor(float(X.shape[0]), dtype=torch.float64, device=self.device)])
+        if self._distributed():
+            torch.distributed.all_reduce(tot)
+        return float((tot[0] / tot[1]).item())
+
+    def fit(self, X, y, batch_size=2 ** 17, epochs=30, verbose=1, shuffle=True, index=None, steps_per_epoch=None, **kw):
+        """Epoch loop over device-resident points (bin/train_fusion.py:196-213).  Every epoch draws a permutation and
+        walks it in slices: the kernel gathers the rows, X is never copied.  `index` restricts the epoch to a subset of
+        the rows (the training part of a validation split); `steps_per_epoch` fixes the number of batches (ranks with
+        different point counts must run the same number of collectives: short ranks wrap around)."""
+        import torch
+        rows = index if index is not None else None
+        n = int(rows.shape[0]) if rows is not None else int(X.shape[0])
+        nb = steps_per_epoch or (n + batch_size - 1) // batch_size
         hist = []
         for ep in range(epochs):
             perm = torch.randperm(n, device=X.device) if shuffle else torch.arange(n, device=X.device)
-            losses = []
-            for s in range(0, n, batch_size):
-                idx = perm[s:s + batch_size]
-                losses.append(self.train_on_batch(X[idx].contiguous(), y[idx].contiguous()))
-            hist.append(float(torch.stack(losses).mean().item()))
+            if rows is not None:
+                perm = rows[perm]
+            if steps_per_epoch and n > 0 and nb * batch_size > n:  # short rank: wrap around to `nb` full batches
+                perm = perm.repeat((nb * batch_size + n - 1) // n)[:nb * batch_size]
+            losses = torch.zeros(nb, dtype=torch.float64, device=X.device)
+            for k in range(nb):
+                idx = perm[k * batch_size:(k + 1) * batch_size]
+                if idx.numel() == 0 and not self._distributed():
+                    break  # (a rank with no points still joins every all-reduce)
+                self.train_on_batch(X, y, index=idx, loss_out=losses[k:k + 1])
+            hist.append(float(losses.mean().item()))
             if self.stop_training:
                 break
         return hist

@@ -399,11 +399,19 @@ class UNet(object):
                                 ctypes.c_float(o.beta_2), ctypes.c_float(o.epsilon), int(o.iterations),
                                 ctypes.c_float(grad_scale), _C.current_stream()), "mpu_unet_adam")
 
-    def train_on_batch(self, x, y, sample_weight=None):
-        loss = self.forward_backward(x, y, sample_weight)
+    def train_on_batch_async(self, x, y, sample_weight=None):
+        """One train step (forward + loss + backward, gradient all-reduce overlapped with backward when a process
+        group is up, Adam) without a host synchronisation.  x / y / sample_weight may be numpy arrays, pinned host
+        tensors or device tensors.  Returns the mean loss as a 0-d device tensor (float64)."""
+        loss = self.forward_backward_overlapped(x, y, sample_weight)
         self.apply_gradients()
         H, W, _ = self.img_shape
-        return float(loss.item()) / (self._last_B * H * W)
+        return loss[0] / float(self._last_B * H * W)
+
+    def train_on_batch(self, x, y, sample_weight=None):
+        """Keras' model.train_on_batch: the step above, returning the mean loss as a Python float (one 8-byte
+        device->host read)."""
+        return float(self.train_on_batch_async(x, y, sample_weight).item())
 
     def fit(self, x, steps_per_epoch=None, epochs=1, callbacks=None, initial_epoch=0, verbose=1,
             train_on_batch=None, sync_stop=None, **kw):

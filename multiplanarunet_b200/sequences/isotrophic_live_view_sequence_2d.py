@@ -247,6 +247,13 @@ class IsotrophicLiveViewSequence2D(object):
             return x, y, w, picks
         return x, y, w
 
+    def prefetched(self, depth=2, max_tries=10, rng=None):
+        """Endless iterator of training batches (x, y, w) sampled AHEAD of the consumer: a worker thread runs
+        sample_batch_device on its own CUDA stream (candidate probe, flag read-back, accepted planes, augmenters), so
+        the rejection sampler's host round trip overlaps the previous train step instead of serialising with it
+        (the reference hides its CPU sampler behind 5 Keras generator workers, train/trainer.py:246-257)."""
+        return BatchPrefetcher(self, depth, max_tries, rng)
+
     def __getitem__(self, idx):
         """Reference batch layout (…_2d.py:163-216 + prepare_batches): x [B,dim,dim,C] f32,
         y [B,dim*dim,1] uint8, w [B]."""
@@ -256,3 +263,64 @@ class IsotrophicLiveViewSequence2D(object):
 
     def __len__(self):
         return 10 ** 6
+
+
+class BatchPrefetcher(object):
+    """Background producer of training batches; see IsotrophicLiveViewSequence2D.prefetched."""
+
+    def __init__(self, seq, depth=2, max_tries=10, rng=None):
+        import queue
+        import threading
+        import torch
+        self.seq, self.max_tries = seq, max_tries
+        self.rng = rng if rng is not None else np.random.RandomState(np.random.randint(0, 2 ** 31 - 1))
+        self.device = seq.images[0].interpolator.device
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.q = queue.Queue(maxsize=depth)
+        self._stop = False
+        self._err = None
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def _run(self):
+        import torch
+        try:
+            torch.cuda.set_device(self.device)
+            while not self._stop:
+                with torch.cuda.stream(self.stream):
+                    x, y, w = self.seq.sample_batch_device(max_tries=self.max_tries, rng=self.rng)
+                    wt = torch.as_tensor(np.asarray(w, dtype=np.float32)).to(self.device, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(self.stream)
+                while not self._stop:
+                    try:
+                        self.q.put((x, y, wt, ev), timeout=0.2)
+                        break
+                    except Exception:
+                        continue
+        except Exception as e:  # surfaced to the consumer
+            self._err = e
+            self.q.put(None)
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        import torch
+        item = self.q.get()
+        if item is None:
+            raise self._err
+        x, y, w, ev = item
+        torch.cuda.current_stream(self.device).wait_event(ev)
+        for t in (x, y, w):  # the tensors were allocated on the worker's stream
+            t.record_stream(torch.cuda.current_stream(self.device))
+        return x, y, w
+
+    def close(self):
+        self._stop = True
+        try:
+            while True:
+                self.q.get_nowait()
+        except Exception:
+            pass
+        self.thread.join(timeout=2)

@@ -10,7 +10,9 @@ def fit_loop(model, batches, steps_per_epoch, epochs, callbacks=None, initial_ep
     sync_stop: optional callable(bool) -> bool agreeing on the stop flag across ranks.
     Returns {"loss": [...], <every scalar a callback logged>: [...]} like Keras' History.history."""
     callbacks = list(callbacks or [])
-    step = train_on_batch or model.train_on_batch
+    # the model's asynchronous step (loss stays on the device) lets the host queue the next step while this one
+    # runs; the losses of an epoch are read back once, at its end
+    step = train_on_batch or getattr(model, "train_on_batch_async", None) or model.train_on_batch
     log = logger or getattr(model, "logger", print)
     history = {}
     for cb in callbacks:
@@ -27,8 +29,8 @@ def fit_loop(model, batches, steps_per_epoch, epochs, callbacks=None, initial_ep
             losses = []
             for _ in range(steps_per_epoch or 1):
                 bx, by, bw = next(it)
-                losses.append(float(step(bx, by, bw)))
-            logs = {"loss": float(np.mean(losses))}
+                losses.append(step(bx, by, bw))
+            logs = {"loss": float(np.mean([float(v.item()) if hasattr(v, "item") else float(v) for v in losses]))}
             for cb in callbacks:
                 cb.on_epoch_end(epoch, logs)
             for k, v in logs.items():

@@ -108,7 +108,9 @@ def mapfuse_case():
 
 
 def fusion_train_case():
+    import ctypes
     import torch
+    from multiplanarunet_b200 import _C
     from multiplanarunet_b200.models import FusionModel
     from oracle import fusion
     rng = np.random.RandomState(2)
@@ -121,25 +123,38 @@ def fusion_train_case():
     b0 = (0.1 * rng.randn(C)).astype(np.float32)
     fm.set_weights([W0, b0])
     Xd, yd = torch.as_tensor(X).cuda(), torch.as_tensor(y).cuda()
+    ok = True
+    lref, dW, db = fusion.gdl_loss_and_grads(X, y, W0, b0)
+    # gradient sums of the kernel (contiguous rows and through a permutation index) against the float64 oracle
+    perm = torch.randperm(N, device="cuda")
+    inv = torch.empty_like(perm)
+    inv[perm] = torch.arange(N, device="cuda")
+    for tag, Xk, yk, idx in (("rows", Xd, yd, None), ("indexed", Xd[perm].contiguous(), yd[perm].contiguous(), inv)):
+        acc = torch.zeros(V * C + C + 1, dtype=torch.float64, device="cuda")
+        _C.check(_C.lib.mpu_fusion_grad_indexed(_C.ptr(Xk), _C.ptr(yk), _C.ptr(idx), ctypes.c_longlong(N), V, C,
+                                                _C.ptr(fm.W), _C.ptr(fm.b), _C.ptr(acc), _C.current_stream()))
+        a = acc.cpu().numpy()
+        gW = a[:V * C].reshape(V, C) / N + 1e-6 * 2 * W0 / W0.size
+        gb = a[V * C:V * C + C] / N + 1e-6 * 2 * b0 / b0.size
+        eW, eb = np.abs(gW - dW).max() / np.abs(dW).max(), np.abs(gb - db).max() / np.abs(db).max()
+        el = abs(a[-1] / N + 1e-6 * (W0 ** 2).mean() + 1e-6 * (b0 ** 2).mean() - lref)
+        print("fusion grads[%s]: dW rel err %.3g  db rel err %.3g  loss err %.3g" % (tag, eW, eb, el))
+        ok = ok and eW < 1e-3 and eb < 1e-3 and el < 1e-5
+    # one fused train step (gradient + Adam in one launch) against the oracle's Adam
     loss = fm.train_on_batch(Xd, yd)
     torch.cuda.synchronize()
-    acc = fm._accum.cpu().numpy()
-    lref, dW, db = fusion.gdl_loss_and_grads(X, y, W0, b0)
-    gW = acc[:V * C].reshape(V, C) / N + 1e-6 * 2 * W0 / W0.size
-    gb = acc[V * C:V * C + C] / N + 1e-6 * 2 * b0 / b0.size
-    print("fusion grads: dW rel err %.3g  db rel err %.3g  loss gpu(no reg) %.6f ref %.6f" %
-          (np.abs(gW - dW).max() / np.abs(dW).max(), np.abs(gb - db).max() / np.abs(db).max(),
-           float(loss), lref))
     th, m, v = np.concatenate([W0.ravel(), b0]).astype(np.float64), np.zeros(V * C + C), np.zeros(V * C + C)
     th, m, v = fusion.adam_step(th, np.concatenate([dW.ravel(), db]), m, v, 1, 1e-3)
     W1, b1 = fm.get_weights()
     err = max(np.abs(W1.ravel() - th[:V * C]).max(), np.abs(b1.ravel() - th[V * C:]).max())
-    print("fusion adam: max |param - oracle| = %.3g (step size 1e-3)" % err)
-    ok = np.abs(gW - dW).max() / np.abs(dW).max() < 1e-3 and err < 2e-5
-    # a few epochs reduce the loss
+    print("fusion fused step: max |param - oracle| = %.3g (step size 1e-3), loss %.6f (oracle, no reg, %.6f)" % (
+        err, float(loss), lref - 1e-6 * (W0 ** 2).mean() - 1e-6 * (b0 ** 2).mean()))
+    ok = ok and err < 2e-5 and float(fm._accum.abs().max()) == 0.0 and int(fm._counter.item()) == 0
+    # a few shuffled epochs reduce the loss; evaluate() agrees with the last epoch's scale
     hist = fm.fit(Xd, yd, batch_size=4096, epochs=3)
-    print("fusion fit losses:", ["%.5f" % h for h in hist])
-    return ok and hist[-1] <= hist[0]
+    ev = fm.evaluate(Xd, yd)
+    print("fusion fit losses:", ["%.5f" % h for h in hist], "evaluate %.5f" % ev)
+    return ok and hist[-1] <= hist[0] and abs(ev - hist[-1]) < 0.05
 
 
 if __name__ == "__main__":
