@@ -193,6 +193,14 @@ int mpu_fusion_train_step(const float* X, const unsigned char* y, const long lon
                           float* W, float* b, float* m, float* v, double* accum, unsigned int* counter,
                           double* loss_out, float reg, float lr, float beta1, float beta2, float eps, int step,
                           void* stream);
+/* One single-process EPOCH: ceil(n / batch) fused train steps over the rows perm[0..n) (device int64; NULL = rows in
+ * order), Adam step numbers first_step, first_step + 1, ...; losses_out (device double [ceil(n / batch)], optional)
+ * receives every batch's mean dice loss.  The host loop of FusionModel.fit (bin/train_fusion.py:196-213) in C: one
+ * launch per batch, nothing else between them. */
+int mpu_fusion_train_epoch(const float* X, const unsigned char* y, const long long* perm, long long n,
+                           long long batch, int V, int C, float* W, float* b, float* m, float* v, double* accum,
+                           unsigned int* counter, double* losses_out, float reg, float lr, float beta1, float beta2,
+                           float eps, int first_step, void* stream);
 int mpu_fusion_adam(float* W, float* b, float* m, float* v, const double* accum, double n_points,
                     int V, int C, float reg, float lr, float beta1, float beta2, float eps, int step,
                     void* stream);

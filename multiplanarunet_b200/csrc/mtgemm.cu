@@ -48,7 +48,9 @@ static constexpr int kPT = 256;                              // pixels per CTA t
 static constexpr uint32_t kSlabRows = kPT + 8;               // 264: room for tap shifts of up to 7 rows
 static constexpr uint32_t kSlabBytes = kSlabRows * 128u;     // 33792 (multiple of 1024)
 static constexpr uint32_t kWTileBytes = 128u * 128u;         // 128 output channels x 64 K
-static constexpr uint32_t kStageHalfBytes = 128u * 256u;     // epilogue staging: 128 pixels x 128 ch bf16
+static constexpr uint32_t kWStageBytes = 2u * kWTileBytes;    // one weight-ring stage = the tiles of TWO consecutive
+                                                             // (chunk, tap) items behind one mbarrier: 8 MMAs per wait
+static constexpr uint32_t kStageHalfBytes = 64u * 256u;      // epilogue staging per pixel half: up to 64 pixels x 128 ch bf16
 
 // ------------------------------------------------------------------------------------------------
 // Forward-type kernel (forward conv, dgrad, upsample-conv phases).  Persistent over CTA tiles of
@@ -71,8 +73,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mtgemm_fwd_kernel(const __grid
   const int NA = p.a_slots, NW = p.w_slots;
   const uint32_t a_base = smem_base;
   const uint32_t w_base = a_base + (uint32_t)NA * kSlabBytes;
-  const uint32_t stg_off = (uint32_t)NA * kSlabBytes + (uint32_t)NW * kWTileBytes;  // 2 x 32 KB staging
-  const uint32_t orow_off = stg_off + 2u * kStageHalfBytes;                          // int[256]
+  const uint32_t stg_off = (uint32_t)NA * kSlabBytes + (uint32_t)NW * kWStageBytes;  // 2 x 16 KB staging
+  const uint32_t stg_half = (uint32_t)p.stg_px * 256u;                               // bytes of one half's staging
+  const uint32_t orow_off = stg_off + 2u * stg_half;                                 // int[256]
   const uint32_t bar_base = smem_base + orow_off + 1024u;
   auto a_full = [&](int s) { return bar_base + 8u * s; };
   auto a_empty = [&](int s) { return bar_base + 8u * (NA + s); };
@@ -144,9 +147,13 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mtgemm_fwd_kernel(const __grid
             const int ccol = (src0 ? c : c - p.chunks0) * 64;
             const CUtensorMap* mhi = src0 ? &p.tmA0_hi : &p.tmA1_hi;
             const CUtensorMap* mlo = src0 ? &p.tmA0_lo : &p.tmA1_lo;
-            mbar_expect_tx(a_full(as), kSlabBytes);
-            tma_load_2d(mhi, a_full(as), a_dst, ccol, arow);
-            tma_load_2d(mlo, a_full(as), a_dst + 136u * 128u, ccol, arow + 136);
+            if (PROF && (p.dbg_flags & 2)) {
+              mbar_arrive(a_full(as));
+            } else {
+              mbar_expect_tx(a_full(as), kSlabBytes);
+              tma_load_2d(mhi, a_full(as), a_dst, ccol, arow);
+              tma_load_2d(mlo, a_full(as), a_dst + 136u * 128u, ccol, arow + 136);
+            }
             if (++as == NA) { as = 0; aph ^= 1u; }
           }
         }
@@ -155,34 +162,55 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mtgemm_fwd_kernel(const __grid
     }
     __syncwarp();
   } else if (warp == 3) {
-    // ===== TMA producer 2: weight tiles -> ring W =====
+    // ===== TMA producer 2: weight tiles -> ring W (two consecutive (chunk, tap) items per stage) =====
     if (elect_one()) {
       int ws = 0;
       uint32_t wph = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int n0 = (tile % p.n_tiles) * 128;
-        for (int g = 0; g < p.ngroups; ++g) {
-          const int ntaps = p.groups[g].ntaps;
-          // row (K-major: output channel row; MN-major: K row) of each tap's block in the weight matrix
-          const int r0 = p.groups[g].w_idx[0] * p.w_rows_per_tap + (W_MN ? 0 : n0);
-          const int r1 = p.groups[g].w_idx[1] * p.w_rows_per_tap + (W_MN ? 0 : n0);
-          const int r2 = p.groups[g].w_idx[2] * p.w_rows_per_tap + (W_MN ? 0 : n0);
-          for (int c = 0; c < kchunks; ++c) {
-            const int kcol = c < p.chunks0 ? c * 64 : p.kofs1 + (c - p.chunks0) * 64;
-            for (int t = 0; t < ntaps; ++t) {
-              timed_wait(w_empty(ws), wph ^ 1u, prof ? &w1 : nullptr);
-              const uint32_t w_dst = w_base + (uint32_t)ws * kWTileBytes;
+        int g = 0, c = 0, t = 0;
+        int ntaps = p.groups[0].ntaps;
+        // row (K-major: output channel row; MN-major: K row) of each tap's block in the weight matrix
+        int r0 = p.groups[0].w_idx[0] * p.w_rows_per_tap + (W_MN ? 0 : n0);
+        int r1 = p.groups[0].w_idx[1] * p.w_rows_per_tap + (W_MN ? 0 : n0);
+        int r2 = p.groups[0].w_idx[2] * p.w_rows_per_tap + (W_MN ? 0 : n0);
+        int left = p.items_per_tile;
+        while (left > 0) {
+          const int nit = left >= 2 ? 2 : 1;
+          timed_wait(w_empty(ws), wph ^ 1u, prof ? &w1 : nullptr);
+          const uint32_t w_dst = w_base + (uint32_t)ws * kWStageBytes;
+          if (!(PROF && (p.dbg_flags & 4))) mbar_expect_tx(w_full(ws), (uint32_t)nit * kWTileBytes);
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            if (i < nit) {
+              const int kcol = c < p.chunks0 ? c * 64 : p.kofs1 + (c - p.chunks0) * 64;
               const int wr = t == 0 ? r0 : (t == 1 ? r1 : r2);
-              mbar_expect_tx(w_full(ws), kWTileBytes);
-              if (!W_MN) {
-                tma_load_2d(&p.tmW, w_full(ws), w_dst, kcol, wr);
+              const uint32_t dst = w_dst + (uint32_t)i * kWTileBytes;
+              if (PROF && (p.dbg_flags & 4)) {
+                // bring-up: no weight traffic
+              } else if (!W_MN) {
+                tma_load_2d(&p.tmW, w_full(ws), dst, kcol, wr);
               } else {  // two 64-channel atoms of [64 K rows][64 channels]
-                tma_load_2d(&p.tmW, w_full(ws), w_dst, n0, wr + kcol);
-                tma_load_2d(&p.tmW, w_full(ws), w_dst + 8192u, n0 + 64, wr + kcol);
+                tma_load_2d(&p.tmW, w_full(ws), dst, n0, wr + kcol);
+                tma_load_2d(&p.tmW, w_full(ws), dst + 8192u, n0 + 64, wr + kcol);
               }
-              if (++ws == NW) { ws = 0; wph ^= 1u; }
+              if (++t == ntaps) {
+                t = 0;
+                if (++c == kchunks) {
+                  c = 0;
+                  if (++g < p.ngroups) {
+                    ntaps = p.groups[g].ntaps;
+                    r0 = p.groups[g].w_idx[0] * p.w_rows_per_tap + (W_MN ? 0 : n0);
+                    r1 = p.groups[g].w_idx[1] * p.w_rows_per_tap + (W_MN ? 0 : n0);
+                    r2 = p.groups[g].w_idx[2] * p.w_rows_per_tap + (W_MN ? 0 : n0);
+                  }
+                }
+              }
             }
           }
+          if (PROF && (p.dbg_flags & 4)) mbar_arrive(w_full(ws));
+          left -= nit;
+          if (++ws == NW) { ws = 0; wph ^= 1u; }
         }
       }
       if (prof) p.dbg[1] = w1;
@@ -217,18 +245,28 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mtgemm_fwd_kernel(const __grid
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acs * kPT);
         uint32_t acc = 0;
-        for (int g = 0; g < p.ngroups; ++g) {
-          const int ntaps = p.groups[g].ntaps;
-          const uint32_t sh0 = (uint32_t)p.groups[g].shift[0] * 8u, sh1 = (uint32_t)p.groups[g].shift[1] * 8u,
-                         sh2 = (uint32_t)p.groups[g].shift[2] * 8u;  // row shift in 16-byte units
-          for (int c = 0; c < kchunks; ++c) {
-            timed_wait(a_full(as), aph, prof ? &w0 : nullptr);
-            const uint32_t a_lo = a_lo0 + (uint32_t)as * (kSlabBytes >> 4);
-            const int ks = c == tail_c0 ? tail_k0 : (c == tail_c1 ? tail_k1 : 4);
-            for (int t = 0; t < ntaps; ++t) {
-              timed_wait(w_full(ws), wph, prof ? &w1 : nullptr);
-              tc_fence_after();
-              const uint64_t wd = w_hi | (uint64_t)(w_lo0 + (uint32_t)ws * (kWTileBytes >> 4));
+        int g = 0, c = 0, t = 0;
+        int ntaps = p.groups[0].ntaps;
+        uint32_t sh0 = (uint32_t)p.groups[0].shift[0] * 8u, sh1 = (uint32_t)p.groups[0].shift[1] * 8u,
+                 sh2 = (uint32_t)p.groups[0].shift[2] * 8u;  // row shifts in 16-byte units
+        uint32_t a_lo = 0;
+        int ks = 4;
+        int left = p.items_per_tile;
+        while (left > 0) {
+          const int nit = left >= 2 ? 2 : 1;
+          timed_wait(w_full(ws), wph, prof ? &w1 : nullptr);
+          tc_fence_after();
+          const uint32_t w_lo = w_lo0 + (uint32_t)ws * (kWStageBytes >> 4);
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            if (i < nit) {
+              if (t == 0) {  // first tap of a (group, chunk): its slab must have landed
+                timed_wait(a_full(as), aph, prof ? &w0 : nullptr);
+                tc_fence_after();
+                a_lo = a_lo0 + (uint32_t)as * (kSlabBytes >> 4);
+                ks = c == tail_c0 ? tail_k0 : (c == tail_c1 ? tail_k1 : 4);
+              }
+              const uint64_t wd = w_hi | (uint64_t)(w_lo + (uint32_t)i * (kWTileBytes >> 4));
               const uint64_t xd = x_hi | (uint64_t)(a_lo + (t == 0 ? sh0 : (t == 1 ? sh1 : sh2)));
               if (ks == 4) {
                 mma_bf16_ss(d_tmem, wd, xd, idesc, acc);
@@ -236,16 +274,30 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mtgemm_fwd_kernel(const __grid
                 mma_bf16_ss(d_tmem, wd + 2 * w_step, xd + 4, idesc, 1u);
                 mma_bf16_ss(d_tmem, wd + 3 * w_step, xd + 6, idesc, 1u);
               } else {
+#pragma unroll 1
                 for (int kk = 0; kk < ks; ++kk)
                   mma_bf16_ss(d_tmem, wd + (uint64_t)kk * w_step, xd + (uint64_t)(2 * kk), idesc, kk ? 1u : acc);
               }
               acc = 1u;
-              mma_commit(w_empty(ws));
-              if (++ws == NW) { ws = 0; wph ^= 1u; }
+              if (++t == ntaps) {  // last tap of the chunk: the slab is free once these MMAs retire
+                mma_commit(a_empty(as));
+                if (++as == NA) { as = 0; aph ^= 1u; }
+                t = 0;
+                if (++c == kchunks) {
+                  c = 0;
+                  if (++g < p.ngroups) {
+                    ntaps = p.groups[g].ntaps;
+                    sh0 = (uint32_t)p.groups[g].shift[0] * 8u;
+                    sh1 = (uint32_t)p.groups[g].shift[1] * 8u;
+                    sh2 = (uint32_t)p.groups[g].shift[2] * 8u;
+                  }
+                }
+              }
             }
-            mma_commit(a_empty(as));
-            if (++as == NA) { as = 0; aph ^= 1u; }
           }
+          mma_commit(w_empty(ws));
+          left -= nit;
+          if (++ws == NW) { ws = 0; wph ^= 1u; }
         }
         mma_commit(tfull_bar(acs));
         if (++acs == 2) { acs = 0; acph ^= 1u; }
@@ -264,7 +316,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mtgemm_fwd_kernel(const __grid
     const int half = (warp - 4) >> 2;    // pixel half: columns half*128 .. +127
     const int et = threadIdx.x - 128 - half * 128;  // 0..127 inside the half
     const int ch_local = q * 32 + lane;
-    __nv_bfloat16* stg = reinterpret_cast<__nv_bfloat16*>(smem_al + stg_off + (uint32_t)half * kStageHalfBytes);
+    __nv_bfloat16* stg = reinterpret_cast<__nv_bfloat16*>(smem_al + stg_off + (uint32_t)half * stg_half);
     int* orow_s = reinterpret_cast<int*>(smem_al + orow_off) + half * 128;
     const int plane = p.map.Hp * p.map.Wp;
     const bool prof_e = prof && warp == 4 && lane == 0;
@@ -305,49 +357,65 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mtgemm_fwd_kernel(const __grid
       const long long te0 = prof_e ? clock64() : 0;
       const float bias = (p.bias && ch < p.n_valid) ? __ldg(p.bias + ch) : 0.f;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acs * kPT + half * 128);
-      for (int c0 = 0; c0 < 128; c0 += 32) {
-        uint32_t r[2][16];
-        tmem_ld16(t_row + (uint32_t)c0, r[0]);  // two loads in flight before the wait
-        tmem_ld16(t_row + (uint32_t)c0 + 16u, r[1]);
-        tmem_ld_wait();
+      if (PROF && (p.dbg_flags & 1)) {  // bring-up: release the accumulator untouched
+        tc_fence_before();
+        mbar_arrive(tempty_bar(acs));
+        named_bar_sync(1 + half, 128);
+        if (++acs == 2) { acs = 0; acph ^= 1u; }
+        continue;
+      }
+      // the 128 pixels of this half go through a small staging buffer in passes of SP = 64 or 32 pixels (16 / 8 KB
+      // per half): a 32 KB buffer per half would cost the weight ring its third stage, and for deep-K layers the
+      // 8 KB variant pays for a third activation slab
+      const int SP = p.stg_px, rows_w = SP >> 2;
+      for (int px0 = 0; px0 < 128; px0 += SP) {
+        if (px0) named_bar_sync(1 + half, 128);  // copy-out of the previous pass is done with the staging buffer
+        for (int c0 = 0; c0 < SP; c0 += 32) {
+          uint32_t r[2][16];
+          tmem_ld16(t_row + (uint32_t)(px0 + c0), r[0]);  // two loads in flight before the wait
+          tmem_ld16(t_row + (uint32_t)(px0 + c0) + 16u, r[1]);
+          tmem_ld_wait();
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+          for (int h = 0; h < 2; ++h) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float v = __uint_as_float(r[h][j]) + bias;
-            if (p.relu) v = fmaxf(v, 0.f);
-            const __nv_bfloat16 hb = __float2bfloat16_rn(v);
-            stg[(c0 + h * 16 + j) * 128 + ch_local] = hb;
-            if (p.stats && orow_s[c0 + h * 16 + j] >= 0) {
-              const float vr = __bfloat162float(hb);
-              s_sum += vr;
-              s_sq = fmaf(vr, vr, s_sq);
+            for (int j = 0; j < 16; ++j) {
+              float v = __uint_as_float(r[h][j]) + bias;
+              if (p.relu) v = fmaxf(v, 0.f);
+              const __nv_bfloat16 hb = __float2bfloat16_rn(v);
+              stg[(c0 + h * 16 + j) * 128 + ch_local] = hb;
+              if (p.stats && orow_s[px0 + c0 + h * 16 + j] >= 0) {
+                const float vr = __bfloat162float(hb);
+                s_sum += vr;
+                s_sq = fmaf(vr, vr, s_sq);
+              }
             }
           }
         }
-      }
-      tc_fence_before();
-      mbar_arrive(tempty_bar(acs));  // accumulator drained: the MMA warp may start the next tile
-      named_bar_sync(1 + half, 128);
-      // row-wise copy-out: 16 chunks of 16 B per pixel row (128 channels), 2 rows per warp instruction
-      {
-        const int nchunk = min(16, (p.n_valid - n0 + 7) >> 3);
-        const int sub = lane >> 4, chunk = lane & 15;
-        for (int r0 = q * 32; r0 < q * 32 + 32; r0 += 2) {
-          const int rr = r0 + sub;
-          const int orow = orow_s[rr];
-          if (orow >= 0 && chunk < nchunk) {
-            uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 128 + chunk * 8);
-            const long long o = (long long)orow;
-            if (p.mask) {
-              const uint4 mk = *reinterpret_cast<const uint4*>(p.mask + o * p.ldm + n0 + chunk * 8);
-              const __nv_bfloat16* mb = reinterpret_cast<const __nv_bfloat16*>(&mk);
-              __nv_bfloat16* vb = reinterpret_cast<__nv_bfloat16*>(&val);
+        if (px0 + SP == 128) {
+          tc_fence_before();
+          mbar_arrive(tempty_bar(acs));  // accumulator drained: the MMA warp may start the next tile
+        }
+        named_bar_sync(1 + half, 128);
+        // row-wise copy-out: 16 chunks of 16 B per pixel row (128 channels), 2 rows per warp instruction
+        {
+          const int nchunk = min(16, (p.n_valid - n0 + 7) >> 3);
+          const int sub = lane >> 4, chunk = lane & 15;
+          for (int r0 = q * rows_w; r0 < q * rows_w + rows_w; r0 += 2) {
+            const int rr = r0 + sub;
+            const int orow = orow_s[px0 + rr];
+            if (orow >= 0 && chunk < nchunk) {
+              uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 128 + chunk * 8);
+              const long long o = (long long)orow;
+              if (p.mask) {
+                const uint4 mk = *reinterpret_cast<const uint4*>(p.mask + o * p.ldm + n0 + chunk * 8);
+                const __nv_bfloat16* mb = reinterpret_cast<const __nv_bfloat16*>(&mk);
+                __nv_bfloat16* vb = reinterpret_cast<__nv_bfloat16*>(&val);
 #pragma unroll
-              for (int j = 0; j < 8; ++j)
-                if (!(__bfloat162float(mb[j]) > 0.f)) vb[j] = __float2bfloat16_rn(0.f);
+                for (int j = 0; j < 8; ++j)
+                  if (!(__bfloat162float(mb[j]) > 0.f)) vb[j] = __float2bfloat16_rn(0.f);
+              }
+              *reinterpret_cast<uint4*>(p.out + o * p.ldo + n0 + chunk * 8) = val;
             }
-            *reinterpret_cast<uint4*>(p.out + o * p.ldo + n0 + chunk * 8) = val;
           }
         }
       }
@@ -670,6 +738,7 @@ int fwd_setup(FwdParams& p, const FwdDesc& d) {
   p.relu = d.relu;
   p.stats = d.stats;
   p.dbg = g_fwd_dbg;
+  if (const char* e = getenv("MPU_FWD_DEBUG")) p.dbg_flags = atoi(e);
   const long long imgs = (d.M_rows + (long long)d.map.Hp * d.map.Wp - 1) / ((long long)d.map.Hp * d.map.Wp);
   if ((long long)d.map.oHp * d.map.oWp * imgs > 2147483647LL) {
     set_error("fwd_setup: output row index exceeds 32 bits");
@@ -692,15 +761,20 @@ static int smem_reserve() {
 }
 
 int launch_fwd(FwdParams& p, cudaStream_t stream) {
-  const int fixed = 2 * (int)kStageHalfBytes + 1024;  // epilogue staging + row table
-  const int budget = kSmemBudget - smem_reserve();
+  // Two slabs + three weight stages + 64-pixel epilogue passes.  Measured alternative (MPU_FWD_NA=3 MPU_FWD_SP=32: a
+  // third slab paid for by 32-pixel passes): the MMA thread's a_full waits drop from 12-20 % to 4 %, but its w_full
+  // waits rise by as much (the three-slab burst at every tile start queues ahead of the weight tiles) - no net gain
+  // on levels 2-3, 5 % slower at 16x16 (profiles/r02_perf_gemm_pairs.txt).
   int NA = 2;
-  int NW = (budget - fixed - NA * (int)kSlabBytes) / (int)kWTileBytes;
-  if (const char* e = getenv("MPU_FWD_NA")) {  // bring-up overrides
-    NA = atoi(e);
-    NW = (budget - fixed - NA * (int)kSlabBytes) / (int)kWTileBytes;
-  }
+  if (const char* e = getenv("MPU_FWD_NA")) NA = atoi(e);  // bring-up override
+  p.stg_px = NA >= 3 ? 32 : 64;
+  if (const char* e = getenv("MPU_FWD_SP")) p.stg_px = atoi(e) == 32 ? 32 : 64;
+  const int fixed = 2 * p.stg_px * 256 + 1024;  // epilogue staging + row table
+  const int budget = kSmemBudget - smem_reserve();
+  int NW = (budget - fixed - NA * (int)kSlabBytes) / (int)kWStageBytes;   // stages of two weight tiles
   if (NW > 8) NW = 8;
+  p.items_per_tile = 0;
+  for (int g = 0; g < p.ngroups; ++g) p.items_per_tile += p.groups[g].ntaps * (p.chunks0 + p.chunks1);
   if (NA < 1 || NW < 2) {
     set_error("launch_fwd: not enough shared memory (NA=%d NW=%d)", NA, NW);
     return MPU_ERR_ARG;

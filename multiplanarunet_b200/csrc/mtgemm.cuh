@@ -58,8 +58,12 @@ struct FwdParams {
   int relu;
   double* stats;                 // optional [2][n_valid]: per-channel sum / sum of squares of the stored
                                  // (bf16-rounded) outputs over valid pixels (BatchNorm statistics, bias grads)
-  int a_slots, w_slots;
+  int a_slots, w_slots;          // slab ring slots; weight ring stages (two tiles each)
+  int stg_px;                    // pixels per epilogue staging pass (64 or 32)
+  int items_per_tile;            // (group, chunk, tap) items of one output tile = weight tiles streamed per tile
   long long* dbg;                // optional [8] cycle counters written by CTA 0 (bring-up profiling)
+  int dbg_flags;                 // bring-up only (env MPU_FWD_DEBUG): 1 = epilogue drains nothing, 2 = no slab loads,
+                                 // 4 = no weight loads (results are garbage; isolates the pipeline stages' cost)
 };
 
 // Host-side description of one forward-type GEMM; fwd_setup builds tensor maps + tap groups from it.

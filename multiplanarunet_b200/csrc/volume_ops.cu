@@ -1360,6 +1360,28 @@ int mpu_fusion_train_step(const float* X, const unsigned char* y, const long lon
   return MPU_OK;
 }
 
+int mpu_fusion_train_epoch(const float* X, const unsigned char* y, const long long* perm, long long n,
+                           long long batch, int V, int C, float* W, float* b, float* m, float* v, double* accum,
+                           unsigned int* counter, double* losses_out, float reg, float lr, float beta1, float beta2,
+                           float eps, int first_step, void* stream) {
+  if (batch < 1 || n < 1) {
+    set_error("mpu_fusion_train_epoch: bad batch / point count");
+    return MPU_ERR_ARG;
+  }
+  int step = first_step;
+  long long k = 0;
+  for (long long s = 0; s < n; s += batch, ++k, ++step) {
+    const long long nb = n - s < batch ? n - s : batch;
+    MPU_TRY(mpu_fusion_train_step(X, y, perm ? perm + s : nullptr, nb, V, C, W, b, m, v, accum, counter,
+                                  losses_out ? losses_out + k : nullptr, reg, lr, beta1, beta2, eps, step, stream));
+    if (!perm) {  // contiguous rows: advance the base pointers instead
+      X += nb * (long long)V * C;
+      y += nb;
+    }
+  }
+  return MPU_OK;
+}
+
 int mpu_fusion_adam(float* W, float* b, float* m, float* v, const double* accum, double n_points,
                     int V, int C, float reg, float lr, float beta1, float beta2, float eps, int step,
                     void* stream) {

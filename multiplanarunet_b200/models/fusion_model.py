@@ -146,6 +146,26 @@ class FusionModel(object):
             if steps_per_epoch and n > 0 and nb * batch_size > n:  # short rank: wrap around to `nb` full batches
                 perm = perm.repeat((nb * batch_size + n - 1) // n)[:nb * batch_size]
             losses = torch.zeros(nb, dtype=torch.float64, device=X.device)
+            if not self._distributed() and n > 0:
+                # the whole epoch in one C call: one fused launch per batch, no host work between them
+                if not hasattr(self, "_counter"):
+                    self._counter = torch.zeros(1, dtype=torch.int32, device=self.device)
+                    self._loss1 = torch.zeros(1, dtype=torch.float64, device=self.device)
+                    self._accum.zero_()
+                perm = perm[:nb * batch_size].contiguous()
+                check(lib.mpu_fusion_train_epoch(_C.ptr(X), _C.ptr(y), _C.ptr(perm), ctypes.c_longlong(int(perm.shape[0])),
+                                                 ctypes.c_longlong(int(batch_size)), self.n_inputs, self.n_classes,
+                                                 _C.ptr(self.W), _C.ptr(self.b), _C.ptr(self._m), _C.ptr(self._v),
+                                                 _C.ptr(self._accum), _C.ptr(self._counter), _C.ptr(losses),
+                                                 ctypes.c_float(self.reg), ctypes.c_float(self.lr),
+                                                 ctypes.c_float(self.beta_1), ctypes.c_float(self.beta_2),
+                                                 ctypes.c_float(self.epsilon), int(self.iterations + 1),
+                                                 _C.current_stream()), "mpu_fusion_train_epoch")
+                self.iterations += (int(perm.shape[0]) + batch_size - 1) // batch_size
+                hist.append(float(losses.mean().item()))
+                if self.stop_training:
+                    break
+                continue
             for k in range(nb):
                 idx = perm[k * batch_size:(k + 1) * batch_size]
                 if idx.numel() == 0 and not self._distributed():
