@@ -269,7 +269,8 @@ def fusion_config(args, where, world):
     return {"workload": "train_fusion epochs over %d^3 x 6 views x %d classes mapped softmax points per GPU, batch 2^17 "
                         "per rank, shuffled every epoch" % (args.dim, args.classes), "where": where,
             "points_per_gpu": args.dim ** 3, "bytes_per_point": FUSION_BYTES_PER_POINT(6, args.classes),
-            "all_reduce": "36 doubles + point count per batch (NCCL)" if world > 1 else "none (single process)",
+            "all_reduce": ("36 doubles + point count per batch, exchanged inside the train-step kernel over NVLink "
+                           "peer memory (NCCL only for the rendezvous)") if world > 1 else "none (single process)",
             "l2_policy": "2 GB of points per epoch >> 126 MB L2; no explicit flush"}
 
 
@@ -376,9 +377,11 @@ def bench_train_fusion(args, world, rank, dev, epochs, warm_epochs=1):
     y = torch.randint(0, C, (N,), device=dev, dtype=torch.uint8, generator=g)
     fm = FusionModel(V, C, device=dev)
     bs = 2 ** 17
+    peer = fm.enable_peer_exchange() if world > 1 else False   # fused compute + NVLink peer-memory exchange kernel
+    nb_all = (N + bs - 1) // bs
 
     def epoch(_):
-        fm.fit(X, y, batch_size=bs, epochs=1, verbose=0)
+        fm.fit(X, y, batch_size=bs, epochs=1, verbose=0, steps_per_epoch=nb_all if world > 1 else None)
     ms, launches = timed(epoch, warm_epochs, epochs, 0, world, dev)
     bytes_epoch = N * FUSION_BYTES_PER_POINT(V, C)
     gbs = world * bytes_epoch * epochs / (ms * 1e-3) / 1e9
@@ -404,7 +407,9 @@ def bench_train_fusion(args, world, rank, dev, epochs, warm_epochs=1):
             "epochs": epochs, "batches_per_epoch": (N + bs - 1) // bs, "launches": int(launches),
             "kernel_ms_per_pass": k_ms, "kernel_gbytes_per_sec": bytes_epoch / k_ms / 1e6,
             "kernel_frac_of_measured_hbm": bytes_epoch / k_ms / 1e6 / hbm, "hbm_peak_gbs": hbm,
-            "last_W_mean": float(fm.W.mean().item())}
+            "last_W_mean": float(fm.W.mean().item()),
+            "exchange": ("fused into the train-step kernel over NVLink peer memory (no NCCL per batch)" if peer
+                         else ("NCCL all-reduce per batch" if world > 1 else "none"))}
 
 
 def main():
@@ -535,8 +540,8 @@ def main():
     def step_value(s):
         sample_into_unet(s)
         # SUM all-reduce of the gradients (MirroredStrategy's aggregation) overlapped with backward
-        model.forward_backward_overlapped(None, y_dev, None, input_packed=True, batch=B)
-        model.apply_gradients()
+        # and Adam applied range by range as each reduction completes
+        model.forward_backward_overlapped(None, y_dev, None, input_packed=True, batch=B, fuse_adam=True)
 
     clocks = ClockSampler(local) if rank == 0 else None
     if clocks:

@@ -111,6 +111,12 @@ int mpu_unet_grad_ranges(void* handle, long long* h_out8);
 /* Keras Adam step t (1-based) over the whole parameter buffer; refreshes the bf16 GEMM operand copies */
 int mpu_unet_adam(void* handle, float lr, float beta1, float beta2, float eps, int step,
                   float grad_scale, void* stream);
+/* The same update on one [begin, end) float range of the parameter buffer (the ranges of mpu_unet_grad_ranges): a
+ * data-parallel step applies it to each range as soon as that range's all-reduce has completed, so the update of
+ * the early ranges overlaps the reduction of the last one.  finish != 0 (on the last range of a step) refreshes the
+ * derived bf16 operand copies.  The bf16 shadow of the range is written by the same kernel. */
+int mpu_unet_adam_range(void* handle, long long begin, long long end, float lr, float beta1, float beta2, float eps,
+                        int step, float grad_scale, int finish, void* stream);
 int mpu_unet_debug_buffer(void* handle, int level, int which, void** ptr, long long* rows, int* C);
 
 /* ---- oblique-plane sampler -------------------------------------------------------------------------
@@ -187,7 +193,8 @@ int mpu_fusion_grad_indexed(const float* X, const unsigned char* y, const long l
                             const float* W, const float* b, double* accum, void* stream);
 /* Single-process train step in ONE launch: gradient sums, then the last block to finish applies the Adam update
  * (+ regulariser), writes the batch's mean dice loss to loss_out (device double, optional), and zeroes accum and
- * counter for the next batch.  accum (double [V*C + C + 1]) and counter (uint32) must be zero before the first call.
+ * counter for the next batch.  accum (double [V*C + C + 1]) and counter (see mpu_fusion_train_epoch) must be zero
+ * before the first call.
  * With several ranks use mpu_fusion_grad_indexed + all-reduce + mpu_fusion_adam instead. */
 int mpu_fusion_train_step(const float* X, const unsigned char* y, const long long* index, long long n, int V, int C,
                           float* W, float* b, float* m, float* v, double* accum, unsigned int* counter,
@@ -196,11 +203,30 @@ int mpu_fusion_train_step(const float* X, const unsigned char* y, const long lon
 /* One single-process EPOCH: ceil(n / batch) fused train steps over the rows perm[0..n) (device int64; NULL = rows in
  * order), Adam step numbers first_step, first_step + 1, ...; losses_out (device double [ceil(n / batch)], optional)
  * receives every batch's mean dice loss.  The host loop of FusionModel.fit (bin/train_fusion.py:196-213) in C: one
- * launch per batch, nothing else between them. */
+ * launch per batch, nothing else between them.
+ * `counter` (here and in mpu_fusion_train_step / _epoch_peer) is a device buffer of mpu_fusion_scratch_bytes() bytes,
+ * zeroed once: the arrival counter followed by per-block partial sums (the blocks' contributions are combined by the
+ * last block in a fixed order: no atomics, bit-reproducible). */
+int mpu_fusion_scratch_bytes(void);
 int mpu_fusion_train_epoch(const float* X, const unsigned char* y, const long long* perm, long long n,
                            long long batch, int V, int C, float* W, float* b, float* m, float* v, double* accum,
                            unsigned int* counter, double* losses_out, float reg, float lr, float beta1, float beta2,
                            float eps, int first_step, void* stream);
+/* One MULTI-RANK epoch with the gradient exchange fused into the train-step kernel (the compute step followed by a
+ * collective of bin/train_fusion.py's data-parallel fit): after its local sums, every rank's last block stores them
+ * into every peer's mailbox over NVLink peer memory, raises the peer's flag to the step's sequence number, waits for
+ * all flags of its own mailbox, adds the contributions in rank order and applies Adam - one launch per batch, no
+ * NCCL call and no host round trip; parameters stay bit-identical on all ranks.
+ *   h_peer_mail[world]: device pointers to every rank's mailbox (mpu_fusion_mailbox_bytes() bytes each, zeroed once,
+ *   allocated in peer-mapped memory, e.g. torch.distributed._symmetric_memory); every rank calls this with the same
+ *   n_batches / first_step / first_seq (sequence numbers must be >= 1 and never reused); a rank whose points run out
+ *   before n_batches contributes empty batches.  world <= 8. */
+int mpu_fusion_mailbox_bytes(void);
+int mpu_fusion_train_epoch_peer(const float* X, const unsigned char* y, const long long* perm, long long n,
+                                long long batch, long long n_batches, int V, int C, float* W, float* b, float* m,
+                                float* v, double* accum, unsigned int* counter, double* losses_out, float reg, float lr,
+                                float beta1, float beta2, float eps, int first_step, const void* const* h_peer_mail,
+                                int world, int rank, unsigned long long first_seq, void* stream);
 int mpu_fusion_adam(float* W, float* b, float* m, float* v, const double* accum, double n_points,
                     int V, int C, float reg, float lr, float beta1, float beta2, float eps, int step,
                     void* stream);

@@ -771,17 +771,49 @@ __global__ void __launch_bounds__(kHeadTile)
 }
 
 // ---- optimizer / weight layout ---------------------------------------------------------------------
+__device__ __forceinline__ float adam_one(float p, float g, float& m, float& v, float lr_t, float b1, float b2,
+                                          float eps, float gscale) {
+  const float gi = g * gscale;
+  m = b1 * m + (1.f - b1) * gi;
+  v = b2 * v + (1.f - b2) * gi * gi;
+  return p - lr_t * m / (sqrtf(v) + eps);
+}
+
+// 16-byte accesses on the aligned body ([head, head + 4 * nvec)), scalar on the at most 3 + 3 edge elements
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, long long n, float lr_t, float b1, float b2, float eps,
                             float gscale, __nv_bfloat16* __restrict__ shadow) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-       i += (long long)gridDim.x * blockDim.x) {
-    const float gi = g[i] * gscale;
-    const float mi = b1 * m[i] + (1.f - b1) * gi;
-    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+  const long long head = min(n, (long long)((4 - ((reinterpret_cast<uintptr_t>(p) >> 2) & 3)) & 3));
+  const long long nvec = (n - head) >> 2;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  for (long long i = tid; i < nvec; i += nth) {
+    const long long e = head + 4 * i;
+    float4 pv = *reinterpret_cast<const float4*>(p + e);
+    const float4 gv = *reinterpret_cast<const float4*>(g + e);
+    float4 mv = *reinterpret_cast<const float4*>(m + e);
+    float4 vv = *reinterpret_cast<const float4*>(v + e);
+    pv.x = adam_one(pv.x, gv.x, mv.x, vv.x, lr_t, b1, b2, eps, gscale);
+    pv.y = adam_one(pv.y, gv.y, mv.y, vv.y, lr_t, b1, b2, eps, gscale);
+    pv.z = adam_one(pv.z, gv.z, mv.z, vv.z, lr_t, b1, b2, eps, gscale);
+    pv.w = adam_one(pv.w, gv.w, mv.w, vv.w, lr_t, b1, b2, eps, gscale);
+    *reinterpret_cast<float4*>(p + e) = pv;
+    *reinterpret_cast<float4*>(m + e) = mv;
+    *reinterpret_cast<float4*>(v + e) = vv;
+    if (shadow) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(pv.x, pv.y), hi = __floats2bfloat162_rn(pv.z, pv.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&lo);
+      pk.y = *reinterpret_cast<uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(shadow + e) = pk;
+    }
+  }
+  const long long edge = head + (n - head - 4 * nvec);  // scalar elements: [0, head) and [head + 4 nvec, n)
+  for (long long k = tid; k < edge; k += nth) {
+    const long long i = k < head ? k : head + 4 * nvec + (k - head);
+    float mi = m[i], vi = v[i];
+    const float pn = adam_one(p[i], g[i], mi, vi, lr_t, b1, b2, eps, gscale);
     m[i] = mi;
     v[i] = vi;
-    const float pn = p[i] - lr_t * mi / (sqrtf(vi) + eps);
     p[i] = pn;
     if (shadow) shadow[i] = __float2bfloat16_rn(pn);
   }
@@ -1125,7 +1157,8 @@ int launch_head_train(const __nv_bfloat16* x, Geo g, int C, const float* Wh, con
 
 int launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr_t, float b1,
                 float b2, float eps, float gscale, __nv_bfloat16* shadow, cudaStream_t st) {
-  adam_kernel<<<grid_for(n, 256), 256, 0, st>>>(p, g, m, v, n, lr_t, b1, b2, eps, gscale, shadow);
+  if (n <= 0) return MPU_OK;
+  adam_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, st>>>(p, g, m, v, n, lr_t, b1, b2, eps, gscale, shadow);
   count_launch();
   MPU_CUDA(cudaGetLastError());
   return MPU_OK;

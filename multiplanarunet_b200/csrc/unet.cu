@@ -893,6 +893,20 @@ int mpu_unet_adam(void* handle, float lr, float beta1, float beta2, float eps, i
   return derive_weights(*u, st);
 }
 
+int mpu_unet_adam_range(void* handle, long long begin, long long end, float lr, float beta1, float beta2, float eps,
+                        int step, float grad_scale, int finish, void* stream) {
+  UNet* u = reinterpret_cast<UNet*>(handle);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (!u->cfg.training || begin < 0 || end > u->n_params || begin > end) {
+    set_error("adam_range: bad handle state or range [%lld, %lld)", begin, end);
+    return MPU_ERR_ARG;
+  }
+  const double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, step)) / (1.0 - pow((double)beta1, step));
+  MPU_TRY(launch_adam(u->params + begin, u->grads + begin, u->adam_m + begin, u->adam_v + begin, end - begin,
+                      (float)lr_t, beta1, beta2, eps, grad_scale, u->shadow + begin, st));
+  return finish ? derive_weights(*u, st) : MPU_OK;
+}
+
 // debug / test access to internal activations: which = 0:a1 1:a2 2:b 3:pooled 4:u 5:bn1 6:c2 7:c3 8:bn2
 // 9:gout 10:s1 11:s2 12:dcat 13:dzu 14:dpool
 int mpu_unet_debug_buffer(void* handle, int level, int which, void** ptr, long long* rows, int* C) {

@@ -74,6 +74,31 @@ class FusionModel(object):
         return torch.distributed.is_available() and torch.distributed.is_initialized() and \
             torch.distributed.get_world_size() > 1
 
+    def enable_peer_exchange(self, group=None):
+        """Multi-rank training with the gradient exchange fused into the train-step kernel: allocates this rank's
+        mailbox in peer-mapped memory (torch.distributed._symmetric_memory: CUDA IPC / fabric handles over NVLink) and
+        exchanges the pointers.  Afterwards fit() runs mpu_fusion_train_epoch_peer - one launch per batch, no NCCL
+        call per step.  Returns False (and keeps the NCCL path) when symmetric memory is unavailable."""
+        import torch
+        import torch.distributed as dist
+        if not self._distributed() or dist.get_world_size() > 8:
+            return False
+        try:
+            import torch.distributed._symmetric_memory as symm
+            nbytes = int(lib.mpu_fusion_mailbox_bytes())
+            box = symm.empty(nbytes, dtype=torch.uint8, device=self.device)
+            box.zero_()
+            hdl = symm.rendezvous(box, group if group is not None else dist.group.WORLD)
+            ptrs = [int(p_) for p_ in hdl.buffer_ptrs]
+            torch.cuda.synchronize()
+            dist.barrier()
+        except Exception as e:  # noqa: BLE001 - fall back to NCCL, say why
+            print("FusionModel: peer exchange unavailable (%s); using NCCL all-reduce per batch" % (e,))
+            return False
+        self._peer = dict(box=box, hdl=hdl, ptrs=(ctypes.c_void_p * len(ptrs))(*ptrs), world=dist.get_world_size(),
+                          rank=dist.get_rank(), seq=1)
+        return True
+
     def train_on_batch(self, X, y, all_reduce=True, index=None, loss_out=None):
         """One Adam step on a batch of points; X [N,V,C] f32 tensor (device), y [N] uint8 tensor.  With `index`
         (device int64 [n]) the batch is rows index[i] of X / y - a slice of a shuffled epoch, gathered inside the
@@ -85,7 +110,7 @@ class FusionModel(object):
         self.iterations += 1
         if not (all_reduce and self._distributed()):
             if not hasattr(self, "_counter"):
-                self._counter = torch.zeros(1, dtype=torch.int32, device=self.device)
+                self._counter = torch.zeros(int(lib.mpu_fusion_scratch_bytes()), dtype=torch.uint8, device=self.device)
                 self._loss1 = torch.zeros(1, dtype=torch.float64, device=self.device)
                 self._accum.zero_()
             out = loss_out if loss_out is not None else self._loss1
@@ -146,10 +171,32 @@ class FusionModel(object):
             if steps_per_epoch and n > 0 and nb * batch_size > n:  # short rank: wrap around to `nb` full batches
                 perm = perm.repeat((nb * batch_size + n - 1) // n)[:nb * batch_size]
             losses = torch.zeros(nb, dtype=torch.float64, device=X.device)
+            if self._distributed() and getattr(self, "_peer", None) is not None and steps_per_epoch:
+                # fused compute + peer-memory exchange: the whole epoch in one C call, one launch per batch
+                if not hasattr(self, "_counter"):
+                    self._counter = torch.zeros(int(lib.mpu_fusion_scratch_bytes()), dtype=torch.uint8, device=self.device)
+                    self._loss1 = torch.zeros(1, dtype=torch.float64, device=self.device)
+                    self._accum.zero_()
+                pr = self._peer
+                perm = perm.contiguous() if n > 0 else torch.zeros(1, dtype=torch.int64, device=X.device)
+                check(lib.mpu_fusion_train_epoch_peer(
+                    _C.ptr(X), _C.ptr(y), _C.ptr(perm), ctypes.c_longlong(n), ctypes.c_longlong(int(batch_size)),
+                    ctypes.c_longlong(int(nb)), self.n_inputs, self.n_classes, _C.ptr(self.W), _C.ptr(self.b),
+                    _C.ptr(self._m), _C.ptr(self._v), _C.ptr(self._accum), _C.ptr(self._counter), _C.ptr(losses),
+                    ctypes.c_float(self.reg), ctypes.c_float(self.lr), ctypes.c_float(self.beta_1),
+                    ctypes.c_float(self.beta_2), ctypes.c_float(self.epsilon), int(self.iterations + 1), pr["ptrs"],
+                    pr["world"], pr["rank"], ctypes.c_ulonglong(pr["seq"]), _C.current_stream()),
+                    "mpu_fusion_train_epoch_peer")
+                pr["seq"] += nb
+                self.iterations += nb
+                hist.append(float(losses.mean().item()))
+                if self.stop_training:
+                    break
+                continue
             if not self._distributed() and n > 0:
                 # the whole epoch in one C call: one fused launch per batch, no host work between them
                 if not hasattr(self, "_counter"):
-                    self._counter = torch.zeros(1, dtype=torch.int32, device=self.device)
+                    self._counter = torch.zeros(int(lib.mpu_fusion_scratch_bytes()), dtype=torch.uint8, device=self.device)
                     self._loss1 = torch.zeros(1, dtype=torch.float64, device=self.device)
                     self._accum.zero_()
                 perm = perm[:nb * batch_size].contiguous()

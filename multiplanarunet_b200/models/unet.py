@@ -356,14 +356,17 @@ class UNet(object):
         self._last_B = B
         return self._loss_dev
 
-    def forward_backward_overlapped(self, x, y, sample_weight=None, input_packed=False, batch=None):
+    def forward_backward_overlapped(self, x, y, sample_weight=None, input_packed=False, batch=None, fuse_adam=False):
         """forward_backward with the gradient all-reduce overlapped with backward: parameter ranges whose
         gradients are final after each backward stage are all-reduced asynchronously (NCCL stream) while
         the next stage computes.  Falls back to forward_backward when no process group is initialised."""
         import torch
         import torch.distributed as dist
         if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
-            return self.forward_backward(x, y, sample_weight, input_packed, batch)
+            loss = self.forward_backward(x, y, sample_weight, input_packed, batch)
+            if fuse_adam:
+                self.apply_gradients()
+            return loss
         B = batch if input_packed else self._pack(x)
         H, W, _ = self.img_shape
         yy = y if torch.is_tensor(y) else torch.as_tensor(np.ascontiguousarray(y).reshape(B, H, W).astype(np.uint8))
@@ -386,10 +389,22 @@ class UNet(object):
             check(lib.mpu_unet_backward_stage(self._h, B, stage, st), "mpu_unet_backward_stage")
             for (a, b) in ([self._ranges[stage]] if stage < 2 else self._ranges[2:]):
                 if b > a:
-                    works.append(dist.all_reduce(self.grads[a:b], async_op=True))
-        for w in works:
-            w.wait()
+                    works.append(((a, b), dist.all_reduce(self.grads[a:b], async_op=True)))
         self._last_B = B
+        if fuse_adam:
+            # Adam range by range, each as soon as ITS all-reduce is done: the update of the early (large) ranges
+            # overlaps the reduction of the last one
+            o = self.optimizer
+            o.iterations += 1
+            for k, ((a, b), w) in enumerate(works):
+                w.wait()
+                check(lib.mpu_unet_adam_range(self._h, ctypes.c_longlong(a), ctypes.c_longlong(b), ctypes.c_float(o.lr),
+                                              ctypes.c_float(o.beta_1), ctypes.c_float(o.beta_2),
+                                              ctypes.c_float(o.epsilon), int(o.iterations), ctypes.c_float(1.0),
+                                              int(k == len(works) - 1), st), "mpu_unet_adam_range")
+            return self._loss_dev
+        for _, w in works:
+            w.wait()
         return self._loss_dev
 
     def apply_gradients(self, grad_scale=1.0):
@@ -403,8 +418,7 @@ class UNet(object):
         """One train step (forward + loss + backward, gradient all-reduce overlapped with backward when a process
         group is up, Adam) without a host synchronisation.  x / y / sample_weight may be numpy arrays, pinned host
         tensors or device tensors.  Returns the mean loss as a 0-d device tensor (float64)."""
-        loss = self.forward_backward_overlapped(x, y, sample_weight)
-        self.apply_gradients()
+        loss = self.forward_backward_overlapped(x, y, sample_weight, fuse_adam=True)
         H, W, _ = self.img_shape
         return loss[0] / float(self._last_B * H * W)
 
