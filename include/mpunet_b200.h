@@ -41,16 +41,17 @@ int mpu_profile_gemm_read(double* total_ms, int* launches);
 int mpu_mtgemm_fwd(const void* A0, long long rowsA0, int C0, int ldA0, const void* A1,
                    long long rowsA1, int C1, int ldA1, const void* W, int w_taps, int n_phys,
                    int k_total, int ntaps, const int* h_tap_a_off, const int* h_tap_w, int M_rows,
-                   int BN, int Hp, int Wp, int oHp, int oWp, int s, int py, int px, void* out, int ldo,
+                   int Hp, int Wp, int oHp, int oWp, int s, int py, int px, void* out, int ldo,
                    const float* bias, const void* mask, int ldm, int relu, void* stream);
 
+/* dW[tap][co][dw_col0 + ci] += sum_m X[m + h_tap_x_off[tap]][ci] * dY[m + h_tap_dy_off[tap]][co] over rows_total
+ * anchor rows m (h_tap_dy_off may be NULL = 0; taps at consecutive X rows of one dY offset share one MMA).
+ * dW is fp32 [taps][w_rows_per_tap][ldw], accumulated with vector reductions (zero it first); splits = 0 chooses
+ * the K split. */
 int mpu_mtgemm_wgrad(const void* X, long long rowsX, int Cx, int ldX, const void* dY,
                      long long rowsDY, int Cy, int ldDY, int ntaps, const int* h_tap_x_off,
-                     const int* h_tap_w, int ngroups, const int* h_group_first,
-                     const int* h_group_count, const int* h_group_dy_off, int rows_total, int BN,
-                     int splits, float* dW, int ldw, int w_rows_per_tap, int dw_col0, int ci_valid,
-                     int co_valid, int a_lbo, int a_sbo, int b_lbo, int b_sbo, int kstep_bytes,
-                     void* stream);
+                     const int* h_tap_dy_off, const int* h_tap_w, long long rows_total, int splits, float* dW,
+                     int ldw, int w_rows_per_tap, int dw_col0, void* stream);
 
 /* ---- 2D U-Net engine ------------------------------------------------------------------------------
  * Replaces the Keras model built by mpunet/models/unet.py:26-216 (`UNet`, selected by name through

@@ -13,44 +13,50 @@ class Augmenter(object):
         raise NotImplementedError
 
 
+def _checked_range(value, what):
+    """A scalar stays a scalar; a pair must be (low, high) with low < high (the YAML's `[0, 450]` style)."""
+    if not isinstance(value, (list, tuple)):
+        return value
+    if len(value) != 2:
+        raise ValueError("%s must be a number or a [low, high] pair, got %r" % (what, value))
+    low, high = value
+    if not low < high:
+        raise ValueError("%s range %r is empty (low must be below high)" % (what, value))
+    return (low, high)
+
+
+def _draw(value):
+    """Scalar: itself; (low, high): one uniform draw from numpy's global generator (same call as the reference, so a
+    seeded run consumes the stream identically: np.random.uniform(low, high, 1)[0])."""
+    if isinstance(value, tuple):
+        return np.random.uniform(value[0], value[1], 1)[0]
+    return value
+
+
 class Elastic(Augmenter):
+    """Parameters of the elastic deformation augmenters (mpunet/augmentation/augmenters.py:41-84): displacement
+    strength `alpha` and smoothness `sigma`, each fixed or drawn per slice from a range, the probability of
+    deforming a slice, and the sample weight given to deformed slices."""
+
     def __init__(self, alpha, sigma, apply_prob, aug_weight=0.33):
         super().__init__()
-        if isinstance(alpha, (list, tuple)):
-            if len(alpha) != 2:
-                raise ValueError("Invalid list of alphas specified '%s'. Should be 2 numbers." % (alpha,))
-            if alpha[1] <= alpha[0]:
-                raise ValueError("alpha upper is smaller than sigma lower (%s)" % (alpha,))
-        if isinstance(sigma, (list, tuple)):
-            if len(sigma) != 2:
-                raise ValueError("Invalid list of sigmas specified '%s'. Should be 2 numbers." % (sigma,))
-            if sigma[1] <= sigma[0]:
-                raise ValueError("Sigma upper is smaller than sigma lower (%s)" % (sigma,))
-        if apply_prob > 1 or apply_prob < 0:
-            raise ValueError("Apply probability is invalid with value %3.f" % apply_prob)
-        self._alpha = alpha
-        self._sigma = sigma
+        self._alpha = _checked_range(alpha, "alpha")
+        self._sigma = _checked_range(sigma, "sigma")
+        if not 0 <= apply_prob <= 1:
+            raise ValueError("apply_prob must lie in [0, 1], got %r" % (apply_prob,))
         self.apply_prob = apply_prob
         self.weight = aug_weight
         self.__name__ = "Elastic"
 
-    @property
-    def alpha(self):
-        if isinstance(self._alpha, (list, tuple)):
-            return np.random.uniform(self._alpha[0], self._alpha[1], 1)[0]
-        return self._alpha
+    alpha = property(lambda self: _draw(self._alpha))
+    sigma = property(lambda self: _draw(self._sigma))
 
-    @property
-    def sigma(self):
-        if isinstance(self._sigma, (list, tuple)):
-            return np.random.uniform(self._sigma[0], self._sigma[1], 1)[0]
-        return self._sigma
+    def __repr__(self):
+        return "%s(alpha=%s, sigma=%s, apply_prob=%.3f)" % (self.__name__, list(self._alpha) if isinstance(
+            self._alpha, tuple) else self._alpha, list(self._sigma) if isinstance(self._sigma, tuple) else self._sigma,
+            self.apply_prob)
 
-    def __str__(self):
-        return "%s(alpha=%s, sigma=%s, apply_prob=%.3f)" % (self.__name__, self._alpha, self._sigma,
-                                                            self.apply_prob)
-
-    __repr__ = __str__
+    __str__ = __repr__
 
 
 class Elastic2D(Elastic):

@@ -222,12 +222,29 @@ def entry_func(args=None):
     validate_project_dir(project_dir)
     if a.overwrite and a.continue_training:
         raise ValueError("Cannot both continue training and overwrite the previous training session.")
-    if a.overwrite and int(os.environ.get("RANK", "0")) == 0:
-        remove_previous_session(project_dir)
-    elif not a.continue_training and os.path.exists(os.path.join(project_dir, "model")) and \
+    if not a.overwrite and not a.continue_training and os.path.exists(os.path.join(project_dir, "model")) and \
             os.listdir(os.path.join(project_dir, "model")):
         raise OSError("There seems to be a previous training session at '%s'. Use --overwrite or "
                       "--continue_training." % project_dir)
     if a.force_GPU:
         os.environ["CUDA_VISIBLE_DEVICES"] = a.force_GPU
+    if a.overwrite:
+        # under torchrun only rank 0 deletes, and nobody touches the project dir before it is done
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        marker = os.path.join(project_dir, ".overwrite_done_%s" % os.environ.get("TORCHELASTIC_RUN_ID", "single"))
+        if int(os.environ.get("RANK", "0")) == 0:
+            remove_previous_session(project_dir)
+            if world > 1:
+                open(marker, "w").close()
+        elif world > 1:
+            import time
+            for _ in range(600):
+                if os.path.exists(marker):
+                    break
+                time.sleep(0.1)
     run(project_dir, a)
+    if a.overwrite and int(os.environ.get("RANK", "0")) == 0:
+        try:
+            os.remove(os.path.join(project_dir, ".overwrite_done_%s" % os.environ.get("TORCHELASTIC_RUN_ID", "single")))
+        except OSError:
+            pass

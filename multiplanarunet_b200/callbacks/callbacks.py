@@ -10,7 +10,6 @@ bin/train.py through on_train_begin / on_epoch_begin / on_epoch_end, with `model
 import csv
 import os
 import warnings
-from datetime import datetime
 
 import numpy as np
 
@@ -261,83 +260,96 @@ class DividerLine(Callback):
 
 
 class DelayedCallback(object):
-    """mpunet/callbacks/callbacks.py:88-115: activates the wrapped callback's on_epoch_end from epoch
-    `start_from` (1-based) on."""
+    """Holds another callback back until epoch `start_from` (counted from 1, like the YAML's `start_from`): its
+    on_epoch_end is forwarded only from then on; every other attribute resolves to the wrapped object.
+    Behaviour of the reference's wrapper of the same name (mpunet/callbacks/callbacks.py:88-115)."""
 
     def __init__(self, callback, start_from=0, logger=None):
-        self.logger = logger or print
         self.callback = callback
-        self.start_from = start_from
+        self.start_from = int(start_from)
+        self.logger = logger or print
 
-    def __getattr__(self, item):
-        return getattr(self.callback, item)
+    def __getattr__(self, name):
+        # only called for attributes this wrapper does not define itself
+        return getattr(self.callback, name)
+
+    def is_active(self, epoch):
+        return epoch + 1 >= self.start_from
 
     def on_epoch_end(self, epoch, logs=None):
-        if epoch >= self.start_from - 1:
-            self.callback.on_epoch_end(epoch, logs=logs)
-        else:
-            self.logger("[%s] Not active at epoch %i - will be at %i" % (self.callback.__class__.__name__,
-                                                                         epoch + 1, self.start_from))
+        if self.is_active(epoch):
+            return self.callback.on_epoch_end(epoch, logs=logs)
+        self.logger("[%s] waiting: epoch %d < start_from %d" % (type(self.callback).__name__, epoch + 1,
+                                                                self.start_from))
 
 
 class TrainTimer(Callback):
-    """mpunet/callbacks/callbacks.py:118-163: adds epoch_minutes / train_hours to the logs; optional wall-clock
-    limit."""
+    """Wall-clock bookkeeping per epoch: writes `epoch_minutes` and `train_hours` into the epoch logs (so CSVLogger
+    records them) and stops training once `max_minutes` of total time are used up.  Log keys and the stop rule follow
+    the reference's TrainTimer (mpunet/callbacks/callbacks.py:118-163)."""
 
     def __init__(self, logger=None, max_minutes=None, verbose=1):
         super().__init__()
         self.logger = logger or print
         self.max_minutes = int(max_minutes) if max_minutes else None
         self.verbose = bool(verbose)
-        self.train_begin_time = None
-        self.prev_epoch_time = None
+        self._t_train = None
+        self._t_epoch = None
+
+    @staticmethod
+    def _now():
+        import time
+        return time.monotonic()
 
     def on_train_begin(self, logs=None):
-        self.train_begin_time = datetime.now()
+        self._t_train = self._now()
 
     def on_epoch_begin(self, epoch, logs=None):
-        self.prev_epoch_time = datetime.now()
+        self._t_epoch = self._now()
 
     def on_epoch_end(self, epoch, logs=None):
-        end_time = datetime.now()
-        epoch_time = end_time - self.prev_epoch_time
-        train_time = end_time - self.train_begin_time
-        self.prev_epoch_time = end_time
-        train_hours = round(train_time.total_seconds() / 3600, 4)
-        epoch_minutes = round(epoch_time.total_seconds() / 60, 4)
-        logs["epoch_minutes"] = epoch_minutes
-        logs["train_hours"] = train_hours
+        now = self._now()
+        minutes = (now - (self._t_epoch if self._t_epoch is not None else now)) / 60.0
+        hours = (now - (self._t_train if self._t_train is not None else now)) / 3600.0
+        self._t_epoch = now
+        if logs is not None:
+            logs["epoch_minutes"] = round(minutes, 4)
+            logs["train_hours"] = round(hours, 4)
         if self.verbose:
-            self.logger("[TrainTimer] Epoch time: %.2f minutes - Total train time: %.2f hours"
-                        % (epoch_minutes, train_hours))
-        if self.max_minutes and train_hours * 60 > self.max_minutes:
-            self.logger("Stopping training. Training ran for {} minutes, max_minutes of {} was specified on the "
-                        "TrainTimer callback.".format(train_hours * 60, self.max_minutes))
+            self.logger("[TrainTimer] epoch took %.2f min, training so far %.2f h" % (minutes, hours))
+        if self.max_minutes and hours * 60.0 > self.max_minutes:
+            self.logger("[TrainTimer] time budget of %d min exhausted after %.1f min: stopping" % (self.max_minutes,
+                                                                                                   hours * 60.0))
             self.model.stop_training = True
 
 
 class FGBatchBalancer(Callback):
-    """mpunet/callbacks/callbacks.py:166-209: forced foreground fraction of a batch = 1 - validation recall of
-    the previous epoch (at least 0.01)."""
+    """Adapts the fraction of slices per batch that must contain foreground to how much foreground the model still
+    misses: fg_batch_fraction := max(0.01, 1 - val_recall) on the training (and optionally validation) sequence after
+    every epoch.  Needs the Validation callback to have run first in the same epoch; switches itself off when the
+    logs carry no `val_recall`.  Rule of the reference's FGBatchBalancer (mpunet/callbacks/callbacks.py:166-209)."""
+
+    MIN_FRACTION = 0.01
 
     def __init__(self, train_data, val_data=None, logger=None):
         super().__init__()
-        self.data = (("train", train_data), ("val", val_data))
+        self.sequences = {"train": train_data, "val": val_data}
         self.logger = logger or print
         self.active = True
 
     def on_epoch_end(self, epoch, logs=None):
         if not self.active:
-            return None
-        recall = (logs or {}).get("val_recall")
+            return
+        recall = None if logs is None else logs.get("val_recall")
         if recall is None:
-            self.logger("[FGBatchBalancer] No val_recall in logs. Disabling callback. Did you put this callback "
-                        "before the validation callback?")
             self.active = False
-        else:
-            fraction = max(0.01, 1 - recall)
-            for name, data in self.data:
-                if data is not None:
-                    data.fg_batch_fraction = fraction
-                    self.logger("[FGBatchBalancer] Setting FG fraction for %s to: %.4f - Now %s/%s"
-                                % (name, fraction, data.n_fg_slices, data.batch_size))
+            self.logger("[FGBatchBalancer] the epoch logs hold no val_recall (is this callback listed after "
+                        "Validation?) - switching off")
+            return
+        fraction = max(self.MIN_FRACTION, 1.0 - float(recall))
+        for name, seq in self.sequences.items():
+            if seq is None:
+                continue
+            seq.fg_batch_fraction = fraction
+            self.logger("[FGBatchBalancer] %s: fg_batch_fraction = %.4f (%d of %d slices per batch)"
+                        % (name, fraction, seq.n_fg_slices, seq.batch_size))

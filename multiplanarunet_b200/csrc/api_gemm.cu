@@ -92,7 +92,7 @@ int mpu_profile_gemm_read(double* total_ms, int* launches) {
 
 int mpu_mtgemm_fwd(const void* A0, long long rowsA0, int C0, int ldA0, const void* A1,
                    long long rowsA1, int C1, int ldA1, const void* W, int w_taps, int n_phys,
-                   int k_total, int ntaps, const int* tap_a_off, const int* tap_w, int M_rows, int BN,
+                   int k_total, int ntaps, const int* tap_a_off, const int* tap_w, int M_rows,
                    int Hp, int Wp, int oHp, int oWp, int s, int py, int px, void* out, int ldo,
                    const float* bias, const void* mask, int ldm, int relu, void* stream) {
   if (!A0 || !W || !out || ntaps < 1 || ntaps > kMaxTaps) {
@@ -106,7 +106,6 @@ int mpu_mtgemm_fwd(const void* A0, long long rowsA0, int C0, int ldA0, const voi
   d.W = W; d.w_taps = w_taps; d.n_phys = n_phys; d.k_total = k_total;
   d.ntaps = ntaps; d.tap_a_off = tap_a_off; d.tap_w = tap_w;
   d.M_rows = M_rows;
-  d.BN = BN;
   d.map = RowMap{Hp, Wp, oHp, oWp, s, py, px};
   d.out = out; d.ldo = ldo; d.bias = bias; d.mask = mask; d.ldm = ldm; d.relu = relu;
   d.stats = nullptr;
@@ -117,27 +116,18 @@ int mpu_mtgemm_fwd(const void* A0, long long rowsA0, int C0, int ldA0, const voi
 
 int mpu_mtgemm_wgrad(const void* X, long long rowsX, int Cx, int ldX, const void* dY,
                      long long rowsDY, int Cy, int ldDY, int ntaps, const int* tap_x_off,
-                     const int* tap_w, int ngroups, const int* group_first, const int* group_count,
-                     const int* group_dy_off, int rows_total, int BN, int splits, float* dW, int ldw,
-                     int w_rows_per_tap, int dw_col0, int ci_valid, int co_valid, int a_lbo, int a_sbo,
-                     int b_lbo, int b_sbo, int kstep_bytes, void* stream) {
-  if (!X || !dY || !dW || ntaps < 1 || ntaps > kMaxTaps || ngroups < 1 || ngroups > kMaxTaps) {
+                     const int* tap_dy_off, const int* tap_w, long long rows_total, int splits, float* dW,
+                     int ldw, int w_rows_per_tap, int dw_col0, void* stream) {
+  if (!X || !dY || !dW || !tap_x_off || !tap_w || ntaps < 1 || ntaps > kMaxTaps) {
     set_error("mpu_mtgemm_wgrad: bad arguments");
     return MPU_ERR_ARG;
   }
-  (void)ngroups; (void)group_first; (void)group_count; (void)a_lbo; (void)a_sbo; (void)b_lbo; (void)b_sbo;
-  (void)kstep_bytes; (void)ci_valid; (void)co_valid;
-  // per-tap dY offsets from the legacy group description
-  int dy_off[kMaxTaps] = {0};
-  for (int g = 0; g < ngroups; ++g)
-    for (int t = group_first[g]; t < group_first[g] + group_count[g] && t < ntaps; ++t) dy_off[t] = group_dy_off[g];
   WgradDesc d;
   memset(&d, 0, sizeof(d));
   d.X = X; d.rowsX = rowsX; d.Cx = Cx; d.ldX = ldX;
   d.dY = dY; d.rowsDY = rowsDY; d.Cy = Cy; d.ldDY = ldDY;
-  d.ntaps = ntaps; d.tap_x_off = tap_x_off; d.tap_dy_off = dy_off; d.tap_w = tap_w;
+  d.ntaps = ntaps; d.tap_x_off = tap_x_off; d.tap_dy_off = tap_dy_off; d.tap_w = tap_w;
   d.rows_total = rows_total;
-  d.BN = BN > 160 ? 0 : BN;
   d.splits = splits;
   d.dW = dW; d.ldw = ldw; d.w_rows_per_tap = w_rows_per_tap; d.dw_col0 = dw_col0;
   WgradParams p;

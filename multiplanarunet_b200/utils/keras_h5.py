@@ -33,9 +33,35 @@ def _pad8(n):
 # =====================================================================================================
 # reader
 # =====================================================================================================
+class VLenStr(object):
+    """Marks an attribute value the writer should store as a variable-length string (h5py's encoding of str/bytes)."""
+
+    def __init__(self, value):
+        self.value = value
+
+
 class _Datatype(object):
     def __init__(self, cls, size, np_dtype=None, strpad=None):
         self.cls, self.size, self.np_dtype, self.strpad = cls, size, np_dtype, strpad
+
+
+class _UnsupportedAttr(object):
+    """Placeholder for an attribute whose datatype this subset reader cannot decode: opening the file must not
+    fail because of it (Keras writes `backend` / `keras_version` next to the weights), only READING it does."""
+
+    def __init__(self, name, why):
+        self.name, self.why = name, why
+
+
+class _Attrs(dict):
+    def __getitem__(self, key):
+        v = dict.__getitem__(self, key)
+        if isinstance(v, _UnsupportedAttr):
+            raise NotImplementedError("attribute %r: %s" % (v.name, v.why))
+        return v
+
+    def get(self, key, default=None):
+        return self[key] if key in self else default
 
 
 class H5Node(object):
@@ -43,10 +69,14 @@ class H5Node(object):
         self._f = f
         self._addr = addr
         self._msgs = f._read_object_header(addr)
-        self.attrs = {}
+        self.attrs = _Attrs()
         for mtype, data in self._msgs:
             if mtype == 0x000C:
-                name, value = f._parse_attribute(data)
+                try:
+                    name, value = f._parse_attribute(data)
+                except NotImplementedError as e:
+                    name = f._attribute_name(data)
+                    value = _UnsupportedAttr(name, str(e))
                 self.attrs[name] = value
 
 
@@ -255,8 +285,35 @@ class H5File(H5Group):
         if cls == 3:    # fixed-length string
             return _Datatype(cls, size, np.dtype("S%d" % size), strpad=bits0 & 0x0F)
         if cls == 9:
-            raise NotImplementedError("HDF5 feature not supported: variable-length datatypes")
+            # variable length: bits 0-3 of the class bit field = 1 for strings (what h5py writes for Python str / bytes
+            # attributes such as Keras' `backend` and `keras_version`); sequences of other types are not needed
+            if (bits0 & 0x0F) != 1:
+                raise NotImplementedError("HDF5 feature not supported: variable-length sequences")
+            return _Datatype(cls, size, None, strpad=(bits0 >> 4) & 0x0F)
         raise NotImplementedError("HDF5 feature not supported: datatype class %d" % cls)
+
+    def _attribute_name(self, d):
+        version = d[0]
+        name_size = struct.unpack_from("<H", d, 2)[0]
+        pos = 8 + (1 if version == 3 else 0)
+        return bytes(d[pos:pos + name_size]).split(b"\0")[0].decode("utf8", "replace")
+
+    def _global_heap_object(self, addr, index):
+        """Object `index` of the global heap collection at `addr` (HDF5 spec III.E: "GCOL", version, 3 reserved
+        bytes, collection size; then objects {u16 index, u16 refcount, u32 reserved, length size, data padded to 8})."""
+        b = self.buf
+        if b[addr:addr + 4] != b"GCOL":
+            raise ValueError("bad global heap collection at %d" % addr)
+        total = struct.unpack_from("<Q", b, addr + 8)[0]
+        pos, end = addr + 16, addr + total
+        while pos + 16 <= end:
+            idx, _, _, size = struct.unpack_from("<HHIQ", b, pos)
+            if idx == 0:
+                break  # free space marker
+            if idx == index:
+                return bytes(b[pos + 16:pos + 16 + size])
+            pos += 16 + _pad8(size)
+        raise ValueError("global heap object %d not found in the collection at %d" % (index, addr))
 
     def _parse_attribute(self, d):
         version = d[0]
@@ -285,6 +342,13 @@ class H5File(H5Group):
         dtype = self._parse_datatype(dt)
         shape = self._parse_dataspace(ds)
         n = int(np.prod(shape)) if len(shape) else 1
+        if dtype.cls == 9:  # variable-length strings: {u32 length, heap collection address, u32 object index} each
+            vals = []
+            for k in range(n):
+                length, gaddr, gidx = struct.unpack_from("<IQI", d, pos + 16 * k)
+                vals.append(self._global_heap_object(gaddr, gidx)[:length] if length else b"")
+            arr = np.asarray(vals, dtype=object).reshape(shape) if len(shape) else np.asarray(vals[0], dtype=object)
+            return name, (arr if arr.shape else vals[0])
         arr = np.frombuffer(d, dtype=dtype.np_dtype, count=n, offset=pos).reshape(shape).copy()
         if dtype.cls == 3:
             arr = np.char.rstrip(arr, b"\0") if arr.shape else np.asarray(bytes(arr).rstrip(b"\0"))
@@ -331,7 +395,28 @@ class _Writer(object):
             return struct.pack("<BBBBI", 0x13, 0x01, 0, 0, dt.itemsize)  # null-padded ASCII
         raise TypeError("unsupported dtype %s" % dt)
 
+    def vlen_string_attribute(self, name, value):
+        """Scalar variable-length string attribute as h5py writes a Python str / bytes: the characters live in a global
+        heap collection, the attribute holds {length, collection address, object index}."""
+        raw = value if isinstance(value, bytes) else str(value).encode("utf8")
+        obj = struct.pack("<HHIQ", 1, 1, 0, len(raw)) + raw + b"\0" * (_pad8(len(raw)) - len(raw))
+        free = struct.pack("<HHIQ", 0, 0, 0, 0)
+        total = 16 + len(obj) + len(free)
+        gaddr = self.alloc(b"GCOL" + struct.pack("<B3xQ", 1, total) + obj + free)
+        nm = name.encode("utf8") + b"\0"
+        # datatype class 9 (variable length), version 1, type = string (1), padding null-terminated, charset 0;
+        # size 16 (u32 + 8-byte address + u32); base type: 1-byte fixed string
+        base = struct.pack("<BBBBI", 0x13, 0, 0, 0, 1)
+        dt = struct.pack("<BBBBI", 0x19, 0x01, 0, 0, 16) + base
+        ds = self.dataspace(())
+        body = struct.pack("<BBHHH", 1, 0, len(nm), len(dt), len(ds))
+        for part in (nm, dt, ds):
+            body += part + b"\0" * (_pad8(len(part)) - len(part))
+        return body + struct.pack("<IQI", len(raw), gaddr, 1)
+
     def attribute(self, name, value):
+        if isinstance(value, VLenStr):
+            return self.vlen_string_attribute(name, value.value)
         arr = np.asarray(value)
         if arr.dtype.kind == "U":
             arr = np.char.encode(arr, "utf8")

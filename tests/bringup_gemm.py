@@ -63,7 +63,7 @@ def conv_case(B, H, W, Cin, Cout, BN, cin_phys=None, cout_phys=None, relu=True, 
         ptr(xp), ctypes.c_longlong(B * Hp * Wp), cin_phys, cin_phys,
         ptr(A1), ctypes.c_longlong(B * Hp * Wp if two_src else 0), cin_phys if two_src else 0,
         cin_phys if two_src else 0,
-        ptr(wk), 9, cout_phys, ktot, 9, int_array(taps_off), int_array(taps_w), B * Hp * Wp, BN,
+        ptr(wk), 9, cout_phys, ktot, 9, int_array(taps_off), int_array(taps_w), B * Hp * Wp,
         Hp, Wp, Hp, Wp, 1, 0, 0, ptr(out), cout_phys, ptr(b if bias else None), ptr(mk), cout_phys,
         1 if relu else 0, ctypes.c_void_p(0))
     check(rc, "mpu_mtgemm_fwd")
@@ -118,7 +118,7 @@ def perf_case(B, H, W, Cin, Cout, iters=10, two_src=False):
             ptr(xs[1] if two_src else None), ctypes.c_longlong(B * Hp * Wp if two_src else 0),
             cin_phys if two_src else 0, cin_phys if two_src else 0,
             ptr(wk), 9, cout_phys, nsrc * cin_phys, 9, int_array(taps_off), int_array(list(range(9))),
-            B * Hp * Wp, 0, Hp, Wp, Hp, Wp, 1, 0, 0, ptr(out), cout_phys, ptr(None), ptr(None), 0, 1,
+            B * Hp * Wp, Hp, Wp, Hp, Wp, 1, 0, 0, ptr(out), cout_phys, ptr(None), ptr(None), 0, 1,
             ctypes.c_void_p(0))
         check(rc, "mpu_mtgemm_fwd")
     for _ in range(3):
@@ -164,9 +164,8 @@ def perf_wgrad_case(B, H, W, Cin, Cout, iters=10):
     def run():
         rc = lib.mpu_mtgemm_wgrad(
             ptr(xp), ctypes.c_longlong(rows), cin_phys, cin_phys, ptr(dyp), ctypes.c_longlong(rows),
-            cout_phys, cout_phys, 9, int_array(taps_off), int_array(list(range(9))), 1, int_array([0]),
-            int_array([9]), int_array([0]), rows, 0, 0, ptr(dW), cin_phys, cout_phys, 0, cin_phys,
-            cout_phys, 0, 0, 0, 0, 0, ctypes.c_void_p(0))
+            cout_phys, cout_phys, 9, int_array(taps_off), None, int_array(list(range(9))),
+            ctypes.c_longlong(rows), 0, ptr(dW), cin_phys, cout_phys, 0, ctypes.c_void_p(0))
         check(rc, "mpu_mtgemm_wgrad")
     for _ in range(3):
         run()
@@ -222,7 +221,7 @@ def upconv_case(B, h, w_, Cin, Cout, BN, seed=0):
             rc = lib.mpu_mtgemm_fwd(
                 ptr(xp), ctypes.c_longlong(B * hp * wp), cin_phys, cin_phys, ptr(None),
                 ctypes.c_longlong(0), 0, 0, ptr(wk), len(pairs), cout_phys, cin_phys, len(idx),
-                int_array(offs), int_array(idx), B * hp * wp, BN, hp, wp, Hp, Wp, 2, a, b_, ptr(out),
+                int_array(offs), int_array(idx), B * hp * wp, hp, wp, Hp, Wp, 2, a, b_, ptr(out),
                 cout_phys, ptr(bias), ptr(None), 0, 1, ctypes.c_void_p(0))
             check(rc, "mpu_mtgemm_fwd(upconv)")
     torch.cuda.synchronize()
@@ -263,20 +262,12 @@ def wgrad_case(B, H, W, Cin, Cout, BN, G=3, splits=4, variant=None, seed=0):
     dyp = pad_nhwc(dy, cout_phys)
     dW = torch.zeros(9, cout_phys, cin_phys, dtype=torch.float32, device=dev)
     taps_off = [(ky - 1) * Wp + (kx - 1) for ky in range(3) for kx in range(3)]
-    groups = []
-    t = 0
-    while t < 9:
-        n = min(G, 9 - t)
-        groups.append((t, n, 0))
-        t += n
     v = variant or (0, 0, 0, 0, 0)
     rows = B * Hp * Wp
     rc = lib.mpu_mtgemm_wgrad(
         ptr(xp), ctypes.c_longlong(rows), cin_phys, cin_phys, ptr(dyp), ctypes.c_longlong(rows),
-        cout_phys, cout_phys, 9, int_array(taps_off), int_array(list(range(9))), len(groups),
-        int_array([g[0] for g in groups]), int_array([g[1] for g in groups]),
-        int_array([g[2] for g in groups]), rows, BN, splits, ptr(dW), cin_phys, cout_phys, 0, cin_phys,
-        cout_phys, v[0], v[1], v[2], v[3], v[4], ctypes.c_void_p(0))
+        cout_phys, cout_phys, 9, int_array(taps_off), int_array([0] * 9), int_array(list(range(9))),
+        ctypes.c_longlong(rows), splits, ptr(dW), cin_phys, cout_phys, 0, ctypes.c_void_p(0))
     check(rc, "mpu_mtgemm_wgrad")
     torch.cuda.synchronize()
     xin = x.float().permute(0, 3, 1, 2).requires_grad_(False)

@@ -3,9 +3,7 @@ outputs of the unmodified reference interpolator (tests/golden/sampler_*.npz hol
 from sample_plane_at) - bit-exact image and labels, including the non-axis-aligned affine case (host-side
 apply_rotation) - and against the plane sampler kernel on the same planes.
 
-This entry point was written after the round's GPU budget was used up: it has compiled for sm_100a but had not
-run on hardware when committed.  A failure is therefore reported as xfail ("not yet validated"), not as a red
-suite; the file runs last so that nothing else shares its CUDA context afterwards."""
+Validated on hardware in round 1 (GPUTEST_r01: passed); any failure is a hard failure."""
 import os
 
 import numpy as np
@@ -47,7 +45,4 @@ def _check():
 
 
 def test_interp_points_matches_reference_goldens():
-    try:
-        _check()
-    except (AssertionError, RuntimeError) as e:
-        pytest.xfail("mpu_interp_points is not yet validated on hardware: %s" % (e,))
+    _check()

@@ -144,3 +144,33 @@ def test_unsupported_features_fail_loudly(tmp_path):
         K.H5File(p)["z"]
     with pytest.raises(NotImplementedError):
         K.H5File._parse_datatype(struct.pack("<BBBBI", 0x19, 0, 0, 0, 16))      # variable-length string
+
+
+def test_variable_length_string_attributes_and_unsupported_attributes_do_not_block_loading(tmp_path):
+    """Keras / h5py store `backend` and `keras_version` on the root group as VARIABLE-LENGTH strings (global heap
+    objects).  The reader decodes them, and an attribute of a type it cannot decode only fails when that attribute is
+    read - never when the file is opened or the weights are loaded.  (Still self-validation: no h5py here.)"""
+    import struct
+    from multiplanarunet_b200.utils import keras_h5 as K
+    tree = {"layer_a": {"__attrs__": {"weight_names": np.array([b"layer_a/kernel:0"])},
+                        "layer_a": {"kernel:0": np.arange(6, dtype=np.float32).reshape(2, 3)}}}
+    attrs = {"layer_names": np.array([b"layer_a"]), "backend": K.VLenStr("tensorflow"),
+             "keras_version": K.VLenStr(b"2.4.0")}
+    path = str(tmp_path / "vlen.h5")
+    K.write_h5(path, tree, attrs)
+    f = K.H5File(path)
+    assert f.attrs["backend"] == b"tensorflow" and f.attrs["keras_version"] == b"2.4.0"
+    w = K.load_keras_weights(path)
+    assert np.array_equal(w["layer_a"]["kernel"], np.arange(6, dtype=np.float32).reshape(2, 3))
+    # corrupt the vlen datatype into a variable-length SEQUENCE (class 9, type 0): unsupported -> lazy error
+    raw = bytearray(open(path, "rb").read())
+    pat = struct.pack("<BBBBI", 0x19, 0x01, 0, 0, 16)
+    at = raw.find(pat)
+    assert at > 0
+    raw[at + 1] = 0x00
+    bad = str(tmp_path / "seq.h5")
+    open(bad, "wb").write(bytes(raw))
+    g = K.H5File(bad)                               # opens
+    assert "layer_a" in K.load_keras_weights(bad)   # loads
+    with pytest.raises(NotImplementedError):
+        g.attrs["backend"]
