@@ -118,6 +118,13 @@ int mpu_unet_adam(void* handle, float lr, float beta1, float beta2, float eps, i
  * derived bf16 operand copies.  The bf16 shadow of the range is written by the same kernel. */
 int mpu_unet_adam_range(void* handle, long long begin, long long end, float lr, float beta1, float beta2, float eps,
                         int step, float grad_scale, int finish, void* stream);
+/* kernel_regularizer = l2(l2_reg) of every encoder / bottom / up-path conv (mpunet/models/unet.py:39,95,122-189; the
+ * 1x1 head carries none): for the conv kernels inside the float range [begin, end) of the parameter buffer, adds
+ * grad_coef * w to the gradient buffer and accumulates sum(w^2) into *sumsq_out (device double, caller-zeroed).
+ * Call between the gradient all-reduce and Adam.  Keras adds the scalar penalty to every element of the unreduced
+ * loss tensor, so grad_coef = 2 * l2_reg * grad_scale * (B*H*W) and the reported loss gains l2_reg * sumsq. */
+int mpu_unet_l2_penalty(void* handle, long long begin, long long end, float grad_coef, double* sumsq_out,
+                        void* stream);
 int mpu_unet_debug_buffer(void* handle, int level, int which, void** ptr, long long* rows, int* C);
 
 /* ---- oblique-plane sampler -------------------------------------------------------------------------

@@ -819,6 +819,27 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+// Keras kernel_regularizer=l2(lambda): g += coef * w on one conv kernel, and sum w^2 (warp -> block -> one double atomic)
+__global__ void l2_penalty_kernel(const float* __restrict__ w, float* __restrict__ g, long long n, float coef,
+                                  double* __restrict__ sumsq) {
+  float s = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float wi = w[i];
+    g[i] += coef * wi;
+    s += wi * wi;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  __shared__ float ws[8];
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += (double)ws[k];
+    atomicAdd(sumsq, t);
+  }
+}
+
 __global__ void cast_bf16_kernel(const float* __restrict__ p, __nv_bfloat16* __restrict__ shadow, long long n) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x)
@@ -1159,6 +1180,14 @@ int launch_adam(float* p, const float* g, float* m, float* v, long long n, float
                 float b2, float eps, float gscale, __nv_bfloat16* shadow, cudaStream_t st) {
   if (n <= 0) return MPU_OK;
   adam_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, st>>>(p, g, m, v, n, lr_t, b1, b2, eps, gscale, shadow);
+  count_launch();
+  MPU_CUDA(cudaGetLastError());
+  return MPU_OK;
+}
+
+int launch_l2_penalty(const float* w, float* g, long long n, float coef, double* sumsq, cudaStream_t st) {
+  if (n <= 0) return MPU_OK;
+  l2_penalty_kernel<<<grid_for(n, 256), 256, 0, st>>>(w, g, n, coef, sumsq);
   count_launch();
   MPU_CUDA(cudaGetLastError());
   return MPU_OK;

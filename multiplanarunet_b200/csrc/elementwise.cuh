@@ -72,6 +72,7 @@ int launch_head_train(const __nv_bfloat16* x, Geo g, int C, const float* Wh, con
                       double* loss_sum, float* probs_opt, cudaStream_t st);
 
 // Adam on the flat parameter buffer; also writes the bf16 shadow copy (same indexing) the GEMMs read.
+int launch_l2_penalty(const float* w, float* g, long long n, float coef, double* sumsq, cudaStream_t st);
 int launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr_t, float b1,
                 float b2, float eps, float gscale, __nv_bfloat16* shadow, cudaStream_t st);
 int launch_cast_bf16(const float* p, __nv_bfloat16* shadow, long long n, cudaStream_t st);

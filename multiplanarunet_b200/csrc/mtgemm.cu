@@ -324,10 +324,42 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mtgemm_fwd_kernel(const __grid
     uint32_t acph = 0;
     float s_sum = 0.f, s_sq = 0.f;
     int s_ch = -1;
+    // column reductions of the copy-out phase: this thread always handles the 8 channels n0 + (lane & 15) * 8 ..
+    const bool do_red = p.csum_f != nullptr || p.red_d != nullptr;
+    float cs[8], cy[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) cs[j] = cy[j] = 0.f;
+    int cs_ch = -1;
+    auto flush_red = [&]() {
+      if (cs_ch < 0) return;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {  // the two row slots of a warp (lanes l, l + 16) hold the same channels
+        cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], 16);
+        cy[j] += __shfl_xor_sync(0xffffffffu, cy[j], 16);
+      }
+      if (lane < 16 && cs_ch < p.n_valid) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int c = cs_ch + j;
+          if (p.csum_f) atomicAdd(p.csum_f + c, cs[j]);
+          const int rc = c - p.red_col0;
+          if (p.red_d && rc >= 0 && rc < p.red_C) {
+            atomicAdd(p.red_d + rc, (double)cs[j]);
+            atomicAdd(p.red_d + p.red_C + rc, (double)cy[j]);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) cs[j] = cy[j] = 0.f;
+    };
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m0 = (tile / p.n_tiles) * kPT;
       const int n0 = (tile % p.n_tiles) * 128;
       const int ch = n0 + ch_local;
+      if (do_red && n0 + (lane & 15) * 8 != cs_ch) {  // (warp-uniform: n0 changes for the whole warp at once)
+        flush_red();
+        cs_ch = n0 + (lane & 15) * 8;
+      }
       if (p.stats && ch != s_ch) {  // channel tile changed: flush the register accumulators
         if (s_ch >= 0 && s_ch < p.n_valid) {
           atomicAdd(p.stats + s_ch, (double)s_sum);
@@ -415,6 +447,22 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mtgemm_fwd_kernel(const __grid
                   if (!(__bfloat162float(mb[j]) > 0.f)) vb[j] = __float2bfloat16_rn(0.f);
               }
               *reinterpret_cast<uint4*>(p.out + o * p.ldo + n0 + chunk * 8) = val;
+              if (do_red) {
+                const __nv_bfloat16* vb = reinterpret_cast<const __nv_bfloat16*>(&val);
+                float vf[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  vf[j] = __bfloat162float(vb[j]);
+                  cs[j] += vf[j];
+                }
+                const int rc = n0 + chunk * 8 - p.red_col0;
+                if (p.red_y && rc >= 0 && rc < p.red_C) {
+                  const uint4 yk = *reinterpret_cast<const uint4*>(p.red_y + o * p.red_ldy + rc);
+                  const __nv_bfloat16* yb = reinterpret_cast<const __nv_bfloat16*>(&yk);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) cy[j] = fmaf(vf[j], __bfloat162float(yb[j]), cy[j]);
+                }
+              }
             }
           }
         }
@@ -427,6 +475,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mtgemm_fwd_kernel(const __grid
       atomicAdd(p.stats + s_ch, (double)s_sum);
       atomicAdd(p.stats + p.n_valid + s_ch, (double)s_sq);
     }
+    if (do_red) flush_red();
     if (prof_e) {
       p.dbg[5] = w0;
       p.dbg[6] = w1;
@@ -737,6 +786,16 @@ int fwd_setup(FwdParams& p, const FwdDesc& d) {
   p.ldm = d.ldm;
   p.relu = d.relu;
   p.stats = d.stats;
+  p.csum_f = d.csum_f;
+  p.red_d = d.red_d;
+  p.red_y = reinterpret_cast<const __nv_bfloat16*>(d.red_y);
+  p.red_ldy = d.red_ldy;
+  p.red_col0 = d.red_col0;
+  p.red_C = d.red_C;
+  if (d.red_d && (d.red_col0 % 8 || d.red_C % 8 || (d.red_y && d.red_ldy % 8))) {
+    set_error("fwd_setup: epilogue reduction columns must be multiples of 8");
+    return MPU_ERR_ARG;
+  }
   p.dbg = g_fwd_dbg;
   if (const char* e = getenv("MPU_FWD_DEBUG")) p.dbg_flags = atoi(e);
   const long long imgs = (d.M_rows + (long long)d.map.Hp * d.map.Wp - 1) / ((long long)d.map.Hp * d.map.Wp);

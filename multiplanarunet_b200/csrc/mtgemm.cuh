@@ -58,6 +58,12 @@ struct FwdParams {
   int relu;
   double* stats;                 // optional [2][n_valid]: per-channel sum / sum of squares of the stored
                                  // (bf16-rounded) outputs over valid pixels (BatchNorm statistics, bias grads)
+  // Column reductions of the STORED (rounded, masked) outputs, taken in the row-wise copy-out phase - what the
+  // backward pass otherwise computes with separate passes over the tensor just written:
+  float* csum_f;                 // optional [n_valid] fp32 += sum over pixels (a conv's bias gradient = column sum of dz)
+  double* red_d;                 // optional [2][red_C] += [sum out | sum out * y] for output channels red_col0 ..
+  const __nv_bfloat16* red_y;    //   red_col0 + red_C - 1, y = red_y[out row][ch - red_col0] (BatchNorm backward's
+  int red_ldy, red_col0, red_C;  //   sum g and sum g*y when this GEMM produces the gradient g at a BN output)
   int a_slots, w_slots;          // slab ring slots; weight ring stages (two tiles each)
   int stg_px;                    // pixels per epilogue staging pass (64 or 32)
   int items_per_tile;            // (group, chunk, tap) items of one output tile = weight tiles streamed per tile
@@ -79,6 +85,8 @@ struct FwdDesc {
   void* out; int ldo;
   const float* bias; const void* mask; int ldm; int relu;
   double* stats;                                     // optional [2][n_phys]
+  float* csum_f;                                     // optional column sums (see FwdParams)
+  double* red_d; const void* red_y; int red_ldy, red_col0, red_C;
 };
 
 // wgrad tap group: taps of one kernel row share one X slab (64+8 pixel rows) and one dY tile

@@ -6,6 +6,7 @@
 // (C_phys = channels rounded up to 8; padded channels stay exactly zero in forward and backward).
 // All convolutions run as multi-tap GEMMs on tcgen05 (mtgemm.cu); BN / pool / head / Adam are the
 // HBM-bound kernels of elementwise.cu.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -257,6 +258,24 @@ static void layout_workspace(UNet& u, bool dry) {
   }
 }
 
+// Column reductions a forward-type GEMM takes over its stored outputs in the epilogue (mtgemm.cuh FwdParams):
+// the bias gradient of the conv whose dz this GEMM writes, and / or BatchNorm backward's [sum g | sum g*y].
+struct EpiRed {
+  float* csum_f = nullptr;
+  double* red_d = nullptr;
+  const bf16* red_y = nullptr;
+  int red_ldy = 0, red_col0 = 0, red_C = 0;
+};
+static void apply_red(FwdDesc& d, const EpiRed* r) {
+  if (!r) return;
+  d.csum_f = r->csum_f;
+  d.red_d = r->red_d;
+  d.red_y = r->red_y;
+  d.red_ldy = r->red_ldy;
+  d.red_col0 = r->red_col0;
+  d.red_C = r->red_C;
+}
+
 // ---- GEMM wrappers ----------------------------------------------------------------------------------
 static void taps3x3(int Wp, int* off) {
   for (int ky = 0; ky < 3; ++ky)
@@ -267,7 +286,7 @@ static void taps3x3(int Wp, int* off) {
 static int gemm_same(const bf16* A0, int C0, int ldA0, const bf16* A1, int C1, int ldA1, const bf16* W,
                      int ntap, int n_phys, int k_total, Geo g, bf16* out, int ldo, const float* bias,
                      const bf16* mask, int ldm, int relu, cudaStream_t st, double* stats = nullptr,
-                     int w_mn = 0, int w_rows = 0, bool flip = false) {
+                     int w_mn = 0, int w_rows = 0, bool flip = false, const EpiRed* red = nullptr) {
   int off[kMaxTaps] = {0}, widx[kMaxTaps];
   if (ntap == 9) taps3x3(g.Wp(), off);
   for (int t = 0; t < ntap; ++t) widx[t] = flip ? ntap - 1 - t : t;
@@ -282,6 +301,7 @@ static int gemm_same(const bf16* A0, int C0, int ldA0, const bf16* A1, int C1, i
   d.out = out; d.ldo = ldo; d.bias = bias; d.mask = mask; d.ldm = ldm; d.relu = relu;
   d.stats = stats;
   d.w_mn = w_mn; d.w_rows = w_rows;
+  apply_red(d, red);
   FwdParams p;
   MPU_TRY(fwd_setup(p, d));
   return launch_fwd(p, st);
@@ -290,7 +310,7 @@ static int gemm_same(const bf16* A0, int C0, int ldA0, const bf16* A1, int C1, i
 // dX = sum_taps dZ[m - off] . W[tap]  for a 3x3 conv layer L (K = L.co_phys, outputs = L.k_phys channels):
 // either from the forward weights read MN-major with flipped tap index, or from the transposed copy
 static int gemm_dgrad3x3(UNet& u, const bf16* dz, const ConvL& L, Geo g, bf16* out, const bf16* mask, int ldm,
-                         cudaStream_t st);
+                         cudaStream_t st, const EpiRed* red = nullptr);
 
 // nearest-2x upsample + 2x2 SAME conv + bias + ReLU as four phase GEMMs on the low-res grid.
 // side stream starts after everything enqueued on st so far
@@ -347,7 +367,8 @@ static int gemm_upconv(UNet& u, const bf16* X, int Cx, Geo glo, const ConvL& L, 
 }
 
 // dIn[m_lo] = sum over the 9 (phase, tap) pairs of dZ[phase][m_lo - off] . Wc[pair]  (dZ phase-major)
-static int gemm_upconv_dgrad(UNet& u, const bf16* dzu, const ConvL& L, Geo glo, bf16* out, cudaStream_t st) {
+static int gemm_upconv_dgrad(UNet& u, const bf16* dzu, const ConvL& L, Geo glo, bf16* out, cudaStream_t st,
+                             const EpiRed* red = nullptr) {
   const long long rows_lo = glo.rows();
   int off[kMaxTaps], widx[kMaxTaps];
   for (int i = 0; i < 9; ++i) {
@@ -368,18 +389,19 @@ static int gemm_upconv_dgrad(UNet& u, const bf16* dzu, const ConvL& L, Geo glo, 
   d.M_rows = (int)rows_lo;
   d.map = RowMap{glo.Hp(), glo.Wp(), glo.Hp(), glo.Wp(), 1, 0, 0};
   d.out = out; d.ldo = L.k_phys;
+  apply_red(d, red);
   FwdParams p;
   MPU_TRY(fwd_setup(p, d));
   return launch_fwd(p, st);
 }
 
 static int gemm_dgrad3x3(UNet& u, const bf16* dz, const ConvL& L, Geo g, bf16* out, const bf16* mask, int ldm,
-                         cudaStream_t st) {
+                         cudaStream_t st, const EpiRed* red) {
   if (u.dgrad_mn)
     return gemm_same(dz, L.co_phys, L.co_phys, nullptr, 0, 0, L.wf, 9, L.k_phys, L.co_phys, g, out, L.k_phys,
-                     nullptr, mask, ldm, 0, st, nullptr, 1, L.co_phys, true);
+                     nullptr, mask, ldm, 0, st, nullptr, 1, L.co_phys, true, red);
   return gemm_same(dz, L.co_phys, L.co_phys, nullptr, 0, 0, L.wd, 9, L.k_phys, L.co_phys, g, out, L.k_phys,
-                   nullptr, mask, ldm, 0, st);
+                   nullptr, mask, ldm, 0, st, nullptr, 0, 0, false, red);
 }
 
 // dW[tap][co][col0 + ci] += sum_m X[m+off_tap][ci] * dZ[m][co]   (3x3 / 1-tap, same resolution)
@@ -512,8 +534,9 @@ static int forward(UNet& u, int B, int training, cudaStream_t st) {
   return MPU_OK;
 }
 
+// sums_ready: [sum g | sum g*y] were already accumulated into bn.sums by the epilogue of the GEMM that produced gA
 static int bn_backward(UNet& u, BnL& bn, const bf16* y, const bf16* gA, int ldA, const bf16* gP, Geo g,
-                       bf16* dz, int phase_major, float* dbias, cudaStream_t st) {
+                       bf16* dz, int phase_major, float* dbias, cudaStream_t st, bool sums_ready = false) {
   BnBwdArgs a;
   a.y = y;
   a.gA = gA;
@@ -526,7 +549,7 @@ static int bn_backward(UNet& u, BnL& bn, const bf16* y, const bf16* gA, int ldA,
   a.gamma = u.params + bn.g_off;
   a.g = g;
   a.C = bn.c_phys;
-  MPU_TRY(launch_bn_bwd_reduce(a, bn.sums, st));
+  if (!sums_ready) MPU_TRY(launch_bn_bwd_reduce(a, bn.sums, st));
   return launch_bn_bwd_apply(a, bn.sums, dz, phase_major, u.grads + bn.g_off, u.grads + bn.b_off, dbias,
                              st);
 }
@@ -535,14 +558,16 @@ static int bn_backward(UNet& u, BnL& bn, const bf16* y, const bf16* gA, int ldA,
 // wgrad conv2, dgrad conv2 (masked by a1 -> dz1), bias1, wgrad conv1, optional dgrad conv1.
 static int block_tail_backward(UNet& u, ConvL& c1, ConvL& c2, const bf16* xin0, int cx0, const bf16* xin1,
                                int cx1, const bf16* a1, const bf16* dz2, bf16* dz1, bf16* dxin, int C,
-                               Geo g, cudaStream_t st, cudaStream_t sb) {
+                               Geo g, cudaStream_t st, cudaStream_t sb, const EpiRed* dxin_red = nullptr) {
   float* G = u.grads;
   // weight / bias gradients run on the side stream sb; the dgrad chain (critical path) stays on st
   MPU_TRY(fork_side(u, st, sb));  // dz2 is ready
   MPU_TRY(wgrad_same(a1, C, C, dz2, C, 9, g, G + c2.w_off, c2.k_phys, c2.co_phys, 0, sb));
-  MPU_TRY(gemm_dgrad3x3(u, dz2, c2, g, dz1, a1, C, st));
+  // the dgrad that writes dz1 also sums its columns: conv1's bias gradient (was a separate colsum pass)
+  EpiRed bias_red;
+  bias_red.csum_f = G + c1.b_off;
+  MPU_TRY(gemm_dgrad3x3(u, dz2, c2, g, dz1, a1, C, st, &bias_red));
   MPU_TRY(fork_side(u, st, sb));  // dz1 is ready
-  MPU_TRY(launch_colsum(dz1, g.rows(), C, C, G + c1.b_off, sb));
   if (!xin1 && cx0 == 8 && c1.k_phys == 8 && u.cfg.n_channels <= 4 && xin0 == u.x_in)
     // first conv of the network: K = 9 * n_channels is too thin for the tensor cores
     MPU_TRY(launch_conv_first_wgrad(xin0, dz1, g, u.cfg.n_channels, c1.co_phys, G + c1.w_off, c1.k_phys, sb));
@@ -550,7 +575,7 @@ static int block_tail_backward(UNet& u, ConvL& c1, ConvL& c2, const bf16* xin0, 
     MPU_TRY(wgrad_same(xin0, cx0, cx0, dz1, C, 9, g, G + c1.w_off, c1.k_phys, c1.co_phys, 0, sb));
   if (xin1)
     MPU_TRY(wgrad_same(xin1, cx1, cx1, dz1, C, 9, g, G + c1.w_off, c1.k_phys, c1.co_phys, cx0, sb));
-  if (dxin) MPU_TRY(gemm_dgrad3x3(u, dz1, c1, g, dxin, nullptr, 0, st));
+  if (dxin) MPU_TRY(gemm_dgrad3x3(u, dz1, c1, g, dxin, nullptr, 0, st, dxin_red));
   return MPU_OK;
 }
 
@@ -587,20 +612,31 @@ static int backward_up(UNet& u, int B, cudaStream_t st, cudaStream_t sb) {
     ConvL& c1 = u.up_conv(i, 0);
     ConvL& c2 = u.up_conv(i, 1);
     ConvL& c3 = u.up_conv(i, 2);
-    // BN2 backward: gradient wrt bn2_l is in L.gout
-    MPU_TRY(bn_backward(u, u.up_bn(i, 1), L.c3, L.gout, L.C, nullptr, g, L.s1, 0, G + c3.b_off, st));
-    // conv3 / conv2 ([skip | bn1] concat input) backward; dgrad of conv2 -> dcat [rows][2C]
-    MPU_TRY(block_tail_backward(u, c2, c3, L.b, L.C, L.bn1, L.C, L.c2, L.s1, L.s2, L.dcat, L.C, g, st, sb));
+    // BN2 backward: gradient wrt bn2_l is in L.gout; for l > 0 the upsample-conv dgrad of the previous block
+    // already left [sum g | sum g*y] in the BN's sums (level 0's gradient comes from the head kernel)
+    MPU_TRY(bn_backward(u, u.up_bn(i, 1), L.c3, L.gout, L.C, nullptr, g, L.s1, 0, G + c3.b_off, st, l > 0));
+    // conv3 / conv2 ([skip | bn1] concat input) backward; dgrad of conv2 -> dcat [rows][2C]; its second half is the
+    // gradient at BN1's output: the dgrad epilogue accumulates BN1's reduction sums against y = u
+    BnL& bn1 = u.up_bn(i, 0);
+    MPU_CUDA(cudaMemsetAsync(bn1.sums, 0, sizeof(double) * 2 * L.C, st));
+    EpiRed r1;
+    r1.red_d = bn1.sums; r1.red_y = L.u; r1.red_ldy = L.C; r1.red_col0 = L.C; r1.red_C = L.C;
+    MPU_TRY(block_tail_backward(u, c2, c3, L.b, L.C, L.bn1, L.C, L.c2, L.s1, L.s2, L.dcat, L.C, g, st, sb, &r1));
     // BN1 backward on the second half of dcat -> dz of the upsample-conv, phase-major
-    MPU_TRY(bn_backward(u, u.up_bn(i, 0), L.u, L.dcat + L.C, 2 * L.C, nullptr, g, L.dzu, 1,
-                        G + c1.b_off, st));
+    MPU_TRY(bn_backward(u, bn1, L.u, L.dcat + L.C, 2 * L.C, nullptr, g, L.dzu, 1, G + c1.b_off, st, true));
     // upsample-conv backward
     const bf16* xin = (l + 1 == d) ? Lo.b : Lo.bn2;
     MPU_TRY(fork_side(u, st, sb));  // dzu is ready
     MPU_CUDA(cudaMemsetAsync(u.dwc, 0, sizeof(float) * 9 * c1.co_phys * c1.k_phys, sb));
     MPU_TRY(wgrad_upconv(xin, Lo.C, L.dzu, c1, glo, u.dwc, sb));
     MPU_TRY(launch_fold_upconv_grad(u.dwc, G + c1.w_off, c1.co_phys, c1.k_phys, sb));
-    MPU_TRY(gemm_upconv_dgrad(u, L.dzu, c1, glo, Lo.gout, st));
+    // the gradient it writes sits at a BN output (BN2 of the next coarser up block, or the bottom BN): take that
+    // BN's reduction sums in the epilogue
+    BnL& bnn = (l + 1 == d) ? u.enc_bn(d) : u.up_bn(i - 1, 1);
+    MPU_CUDA(cudaMemsetAsync(bnn.sums, 0, sizeof(double) * 2 * Lo.C, st));
+    EpiRed r2;
+    r2.red_d = bnn.sums; r2.red_y = (l + 1 == d) ? Lo.a2 : Lo.c3; r2.red_ldy = Lo.C; r2.red_col0 = 0; r2.red_C = Lo.C;
+    MPU_TRY(gemm_upconv_dgrad(u, L.dzu, c1, glo, Lo.gout, st, &r2));
     MPU_TRY(block_end(u, st, sb));
   }
   return MPU_OK;
@@ -614,8 +650,8 @@ static int backward_enc_level(UNet& u, int B, int l, cudaStream_t st, cudaStream
   const Geo g = geo_b(u, l, B);
   ConvL& c1 = u.enc_conv(l, 0);
   ConvL& c2 = u.enc_conv(l, 1);
-  if (l == d) {
-    MPU_TRY(bn_backward(u, u.enc_bn(l), L.a2, L.gout, L.C, nullptr, g, L.s1, 0, G + c2.b_off, st));
+  if (l == d) {  // (sums left by the upsample-conv dgrad of the last up block, backward stage 0)
+    MPU_TRY(bn_backward(u, u.enc_bn(l), L.a2, L.gout, L.C, nullptr, g, L.s1, 0, G + c2.b_off, st, true));
   } else {
     // skip gradient = first half of dcat_l; pooled gradient = dpool_l (from level l+1's conv1 dgrad)
     MPU_TRY(bn_backward(u, u.enc_bn(l), L.a2, L.dcat, 2 * L.C, L.dpool, g, L.s1, 0, G + c2.b_off, st));
@@ -905,6 +941,26 @@ int mpu_unet_adam_range(void* handle, long long begin, long long end, float lr, 
   MPU_TRY(launch_adam(u->params + begin, u->grads + begin, u->adam_m + begin, u->adam_v + begin, end - begin,
                       (float)lr_t, beta1, beta2, eps, grad_scale, u->shadow + begin, st));
   return finish ? derive_weights(*u, st) : MPU_OK;
+}
+
+// Keras kernel_regularizer=l2(l2) on every conv of the encoder / bottom / up path (not the 1x1 head:
+// mpunet/models/unet.py:114-196): for the conv kernels inside the parameter range [begin, end) adds
+// grad_coef * w to the gradient and accumulates sum w^2 into *sumsq_out (device double, NOT zeroed here).
+int mpu_unet_l2_penalty(void* handle, long long begin, long long end, float grad_coef, double* sumsq_out,
+                        void* stream) {
+  UNet* u = reinterpret_cast<UNet*>(handle);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (!u->cfg.training || begin < 0 || end > u->n_params || begin > end || !sumsq_out) {
+    set_error("l2_penalty: bad handle state, range [%lld, %lld) or null output", begin, end);
+    return MPU_ERR_ARG;
+  }
+  for (size_t i = 0; i + 1 < u->convs.size(); ++i) {  // the head is last and carries no regulariser
+    const ConvL& L = u->convs[i];
+    const long long n = (long long)L.ntap_master * L.co_phys * L.k_phys;
+    const long long a = std::max(begin, L.w_off), b = std::min(end, L.w_off + n);
+    if (b > a) MPU_TRY(launch_l2_penalty(u->params + a, u->grads + a, b - a, grad_coef, sumsq_out, st));
+  }
+  return MPU_OK;
 }
 
 // debug / test access to internal activations: which = 0:a1 1:a2 2:b 3:pooled 4:u 5:bn1 6:c2 7:c3 8:bn2

@@ -75,8 +75,8 @@ class UNet(object):
         if out_activation != "softmax" or activation != "relu" or kernel_size != 3 or padding != "same":
             raise NotImplementedError("B200 UNet implements the reference defaults only: relu convs, "
                                       "3x3 kernels, 'same' padding, softmax output")
-        if l2_reg:
-            raise NotImplementedError("l2_reg is not implemented on the B200 path")
+        if l2_reg is not None and not (0.0 <= float(l2_reg) <= 1.0):
+            raise ValueError("l2_reg must be a float in [0, 1], got %r" % (l2_reg,))
         if not torch.cuda.is_available():
             raise RuntimeError("multiplanarunet_b200.UNet needs a CUDA device (no CPU fallback)")
         self.logger = logger or print
@@ -117,6 +117,7 @@ class UNet(object):
                 self.grads = self.adam_m = self.adam_v = None
             self.workspace = torch.empty(ws.value, dtype=torch.uint8, device=self.device)
             self._loss_dev = torch.zeros(1, dtype=torch.float64, device=self.device)
+            self._l2_sumsq = torch.zeros(1, dtype=torch.float64, device=self.device)
             h = ctypes.c_void_p()
             check(lib.mpu_unet_create(ctypes.byref(cfg), _C.ptr(self.params), _C.ptr(self.grads),
                                       _C.ptr(self.adam_m), _C.ptr(self.adam_v), _C.ptr(self.bn_state),
@@ -396,8 +397,10 @@ class UNet(object):
             # overlaps the reduction of the last one
             o = self.optimizer
             o.iterations += 1
+            self._l2_begin()
             for k, ((a, b), w) in enumerate(works):
                 w.wait()
+                self._l2_penalty(a, b)
                 check(lib.mpu_unet_adam_range(self._h, ctypes.c_longlong(a), ctypes.c_longlong(b), ctypes.c_float(o.lr),
                                               ctypes.c_float(o.beta_1), ctypes.c_float(o.beta_2),
                                               ctypes.c_float(o.epsilon), int(o.iterations), ctypes.c_float(1.0),
@@ -407,9 +410,27 @@ class UNet(object):
             w.wait()
         return self._loss_dev
 
+    # kernel_regularizer=l2(l2_reg) (mpunet/models/unet.py:122-189).  Keras adds the scalar penalty to every element
+    # of the unreduced [B, H*W] loss tensor it differentiates (Reduction.NONE), so next to a data gradient
+    # scaled by g the penalty's gradient is g * (B*H*W) * 2 * l2_reg * w; the reported (mean) loss gains l2_reg * sum(w^2).
+    def _l2_begin(self):
+        if self.l2_reg:
+            self._l2_sumsq.zero_()
+
+    def _l2_penalty(self, begin, end):
+        if not self.l2_reg:
+            return
+        H, W, _ = self.img_shape
+        g = (1.0 if self.loss_scale_mode == "sum" else 1.0 / (self._last_B * H * W)) * self._last_B * H * W
+        check(lib.mpu_unet_l2_penalty(self._h, ctypes.c_longlong(begin), ctypes.c_longlong(end),
+                                      ctypes.c_float(2.0 * float(self.l2_reg) * g),
+                                      _C.ptr(self._l2_sumsq), _C.current_stream()), "mpu_unet_l2_penalty")
+
     def apply_gradients(self, grad_scale=1.0):
         o = self.optimizer
         o.iterations += 1
+        self._l2_begin()
+        self._l2_penalty(0, self.grads.numel())  # Adam's grad_scale then applies to data and penalty alike
         check(lib.mpu_unet_adam(self._h, ctypes.c_float(o.lr), ctypes.c_float(o.beta_1),
                                 ctypes.c_float(o.beta_2), ctypes.c_float(o.epsilon), int(o.iterations),
                                 ctypes.c_float(grad_scale), _C.current_stream()), "mpu_unet_adam")
@@ -420,7 +441,8 @@ class UNet(object):
         tensors or device tensors.  Returns the mean loss as a 0-d device tensor (float64)."""
         loss = self.forward_backward_overlapped(x, y, sample_weight, fuse_adam=True)
         H, W, _ = self.img_shape
-        return loss[0] / float(self._last_B * H * W)
+        mean = loss[0] / float(self._last_B * H * W)
+        return mean + float(self.l2_reg) * self._l2_sumsq[0] if self.l2_reg else mean
 
     def train_on_batch(self, x, y, sample_weight=None):
         """Keras' model.train_on_batch: the step above, returning the mean loss as a Python float (one 8-byte

@@ -156,3 +156,38 @@ def test_staged_backward_equals_single_call(setup):
     assert spans[0][0] == 0 and spans[-1][1] == m.grads.numel()
     assert all(spans[i][1] == spans[i + 1][0] for i in range(3))
     assert _C.lib.mpu_unet_backward_stage(m._h, B, 3, st) != 0
+
+
+def test_l2_reg_matches_keras_kernel_regularizer():
+    """kernel_regularizer=l2(l2_reg) on every encoder / bottom / up conv kernel, none on the 1x1 head, biases or BN
+    (mpunet/models/unet.py:122-189): penalty gradient next to the sum-of-pixels data gradient is (B*H*W) * 2*l2*w,
+    and the reported mean loss gains l2 * sum(w^2)."""
+    import torch
+    from multiplanarunet_b200.models import UNet
+    rng = np.random.RandomState(5)
+    l2 = 1e-3
+    m = UNet(n_classes=3, dim=32, n_channels=1, complexity_factor=0.125, max_batch=2, training=True, seed=2, l2_reg=l2)
+    x = rng.randn(2, 32, 32, 1).astype(np.float32)
+    y = rng.randint(0, 3, size=(2, 32, 32)).astype(np.uint8)
+    m.forward_backward(x, y)
+    g0 = m.grads.clone()
+    m._l2_begin()
+    m._l2_penalty(0, m.grads.numel())
+    torch.cuda.synchronize()
+    diff = (m.grads - g0)
+    expect = torch.zeros_like(diff)
+    sumsq = 0.0
+    for info in m._infos:
+        if info["kind"] != 0 or info["name"] == "conv2d":
+            continue
+        n = info["ksize"] ** 2 * info["co_phys"] * info["k_phys"]
+        w = m.params[info["off0"]:info["off0"] + n]
+        expect[info["off0"]:info["off0"] + n] = 2 * l2 * (2 * 32 * 32) * w
+        sumsq += float((w.double() ** 2).sum())
+    assert sumsq > 0
+    assert float((diff - expect).abs().max()) <= 1e-6 * float(expect.abs().max())
+    assert abs(float(m._l2_sumsq[0]) - sumsq) <= 1e-6 * sumsq
+    # the public step reports data loss + penalty and still trains
+    m2 = UNet(n_classes=3, dim=32, n_channels=1, complexity_factor=0.125, max_batch=2, training=True, seed=2)
+    la, lb = m.train_on_batch(x, y), m2.train_on_batch(x, y)
+    assert abs((la - lb) - l2 * sumsq) <= 1e-5 * max(1.0, abs(la))
