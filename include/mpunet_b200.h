@@ -101,6 +101,13 @@ int mpu_unet_forward(void* handle, int B, int bn_training, float* probs_out, voi
  * grad_scale multiplies dlogits (1 = Keras' sum-of-unreduced-losses semantics). */
 int mpu_unet_train_step(void* handle, int B, const unsigned char* labels, const float* sample_w,
                         float grad_scale, double* loss_sum, float* probs_opt, void* stream);
+/* Single-process train step with the optimizer inside: mpu_unet_train_step, then per parameter range the l2 penalty
+ * (l2_grad_coef != 0: see mpu_unet_l2_penalty; l2_sumsq is zeroed here) and Keras Adam step `step`, each range as soon
+ * as its gradients are final - on an internal stream, overlapped with the remaining backward stages.  Identical
+ * results to the three separate calls (trainer.py:246-257's model.fit step). */
+int mpu_unet_train_step_adam(void* handle, int B, const unsigned char* labels, const float* sample_w,
+                             float grad_scale, double* loss_sum, float* probs_opt, float lr, float beta1, float beta2,
+                             float eps, int step, float l2_grad_coef, double* l2_sumsq, void* stream);
 /* The same step split for data-parallel overlap: forward + loss, then backward stage 0 (up path),
  * 1 (bottom block), 2 (encoder).  mpu_unet_grad_ranges fills 4 [begin,end) float ranges of `grads`:
  * [0] complete after stage 0, [1] after stage 1, [2] and [3] after stage 2 - each can be all-reduced
@@ -213,8 +220,9 @@ int mpu_fusion_train_step(const float* X, const unsigned char* y, const long lon
  * receives every batch's mean dice loss.  The host loop of FusionModel.fit (bin/train_fusion.py:196-213) in C: one
  * launch per batch, nothing else between them.
  * `counter` (here and in mpu_fusion_train_step / _epoch_peer) is a device buffer of mpu_fusion_scratch_bytes() bytes,
- * zeroed once: the arrival counter followed by per-block partial sums (the blocks' contributions are combined by the
- * last block in a fixed order: no atomics, bit-reproducible). */
+ * zeroed once: the 16-byte arrival counter followed by space reserved for per-block partial sums.  (Combining the
+ * blocks' partials in a fixed order by the last block was measured slower than the 36 double atomics per block -
+ * 7.7 vs 4.7 ms per epoch - and is switched off; sums are accumulated with fp64 atomics, whose order varies.) */
 int mpu_fusion_scratch_bytes(void);
 int mpu_fusion_train_epoch(const float* X, const unsigned char* y, const long long* perm, long long n,
                            long long batch, int V, int C, float* W, float* b, float* m, float* v, double* accum,

@@ -20,6 +20,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <unordered_map>
 
 namespace mpu {
 
@@ -65,15 +67,23 @@ static constexpr uint32_t kStageHalfBytes = 64u * 256u;      // epilogue staging
 // ------------------------------------------------------------------------------------------------
 // W_MN: weights read MN-major from the forward layout (dgrad).  PROF: CTA 0 accumulates role stall cycles in p.dbg
 // (bring-up only; the production instantiations carry no timing code).
-template <bool W_MN, bool PROF>
+// CL2: launched as clusters of two CTAs that work on the two 128-channel tiles of the SAME 256-pixel tile in lockstep:
+// every activation slab is fetched from L2 once per cluster - each CTA issues half of the slab's TMA boxes with
+// .multicast::cluster to both CTAs - which halves the slab traffic that starves level 1 (its 130-pixel padded rows are
+// too long for the 9-tap slab; profiles/r02_fwd_ablation.txt).  A slab slot is released by the tcgen05.commit of BOTH
+// CTAs' MMA threads (multicast arrive), so each producer knows both copies are free before it overwrites them.
+// RED: the epilogue additionally takes column reductions of the stored tile (FwdParams::csum_f / red_d); a separate
+// instantiation so that the plain kernels carry neither its registers nor its branches.
+template <bool W_MN, bool PROF, bool CL2, bool RED>
 __global__ void __launch_bounds__(kFwdThreads, 1) mtgemm_fwd_kernel(const __grid_constant__ FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
   const int NA = p.a_slots, NW = p.w_slots;
+  const uint32_t slab_bytes = (uint32_t)p.slab_rows * 128u;  // multiple of 1024
   const uint32_t a_base = smem_base;
-  const uint32_t w_base = a_base + (uint32_t)NA * kSlabBytes;
-  const uint32_t stg_off = (uint32_t)NA * kSlabBytes + (uint32_t)NW * kWStageBytes;  // 2 x 16 KB staging
+  const uint32_t w_base = a_base + (uint32_t)NA * slab_bytes;
+  const uint32_t stg_off = (uint32_t)NA * slab_bytes + (uint32_t)NW * kWStageBytes;  // 2 x 16 KB staging
   const uint32_t stg_half = (uint32_t)p.stg_px * 256u;                               // bytes of one half's staging
   const uint32_t orow_off = stg_off + 2u * stg_half;                                 // int[256]
   const uint32_t bar_base = smem_base + orow_off + 1024u;
@@ -101,7 +111,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mtgemm_fwd_kernel(const __grid
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < NA; ++s) {
       mbar_init(a_full(s), 1);
-      mbar_init(a_empty(s), 1);
+      mbar_init(a_empty(s), CL2 ? 2 : 1);
     }
     for (int s = 0; s < NW; ++s) {
       mbar_init(w_full(s), 1);
@@ -119,10 +129,19 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mtgemm_fwd_kernel(const __grid
   }
   tc_fence_before();
   __syncthreads();
+  if (CL2) cluster_sync_all();  // the partner's barriers are initialised before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  // Work units: plain mode - one (pixel tile, channel tile) per CTA and step, channel tile fastest; cluster mode - one
+  // (pixel tile, channel-tile PAIR) per cluster and step, CTA rank r takes channel tile 2 * pair + r.
+  const int crank = CL2 ? (int)cluster_ctarank() : 0;
+  const int n_div = CL2 ? (p.n_tiles >> 1) : p.n_tiles;
+  const int total_tiles = p.m_tiles * n_div;
+  const int unit0 = CL2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int unit_step = CL2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  auto pix_tile = [&](int unit) { return unit / n_div; };
+  auto ch_tile = [&](int unit) { return CL2 ? (unit % n_div) * 2 + crank : unit % n_div; };
   const int kchunks = p.chunks0 + p.chunks1;
   const bool prof = PROF && p.dbg != nullptr && blockIdx.x == 0;
   long long w0 = 0, w1 = 0, w2 = 0;
@@ -136,23 +155,34 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mtgemm_fwd_kernel(const __grid
     if (elect_one()) {
       int as = 0;
       uint32_t aph = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m0 = (tile / p.n_tiles) * kPT;
+      for (int tile = unit0; tile < total_tiles; tile += unit_step) {
+        const int m0 = pix_tile(tile) * kPT;
         for (int g = 0; g < p.ngroups; ++g) {
           const int arow = m0 + p.groups[g].a_off;
           for (int c = 0; c < kchunks; ++c) {
             timed_wait(a_empty(as), aph ^ 1u, prof ? &w0 : nullptr);
-            const uint32_t a_dst = a_base + (uint32_t)as * kSlabBytes;
+            const uint32_t a_dst = a_base + (uint32_t)as * slab_bytes;
             const bool src0 = c < p.chunks0;
             const int ccol = (src0 ? c : c - p.chunks0) * 64;
             const CUtensorMap* mhi = src0 ? &p.tmA0_hi : &p.tmA1_hi;
             const CUtensorMap* mlo = src0 ? &p.tmA0_lo : &p.tmA1_lo;
-            if (PROF && (p.dbg_flags & 2)) {
+            if (PROF && !CL2 && (p.dbg_flags & 2)) {
               mbar_arrive(a_full(as));
             } else {
-              mbar_expect_tx(a_full(as), kSlabBytes);
-              tma_load_2d(mhi, a_full(as), a_dst, ccol, arow);
-              tma_load_2d(mlo, a_full(as), a_dst + 136u * 128u, ccol, arow + 136);
+              mbar_expect_tx(a_full(as), slab_bytes);  // all boxes land in this CTA, whoever issues them
+              if (!CL2) {
+                tma_load_2d(mhi, a_full(as), a_dst, ccol, arow);
+                tma_load_2d(mlo, a_full(as), a_dst + 136u * 128u, ccol, arow + 136);
+                if (p.ext_rows > 0)
+                  tma_load_2d(src0 ? &p.tmA0_ext : &p.tmA1_ext, a_full(as), a_dst + 264u * 128u, ccol, arow + 264);
+              } else if (crank == 0) {
+                tma_load_2d_multicast(mhi, a_full(as), a_dst, ccol, arow, (uint16_t)3);
+              } else {
+                tma_load_2d_multicast(mlo, a_full(as), a_dst + 136u * 128u, ccol, arow + 136, (uint16_t)3);
+                if (p.ext_rows > 0)
+                  tma_load_2d_multicast(src0 ? &p.tmA0_ext : &p.tmA1_ext, a_full(as), a_dst + 264u * 128u, ccol,
+                                        arow + 264, (uint16_t)3);
+              }
             }
             if (++as == NA) { as = 0; aph ^= 1u; }
           }
@@ -166,14 +196,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mtgemm_fwd_kernel(const __grid
     if (elect_one()) {
       int ws = 0;
       uint32_t wph = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n0 = (tile % p.n_tiles) * 128;
+      for (int tile = unit0; tile < total_tiles; tile += unit_step) {
+        const int n0 = ch_tile(tile) * 128;
         int g = 0, c = 0, t = 0;
         int ntaps = p.groups[0].ntaps;
-        // row (K-major: output channel row; MN-major: K row) of each tap's block in the weight matrix
-        int r0 = p.groups[0].w_idx[0] * p.w_rows_per_tap + (W_MN ? 0 : n0);
-        int r1 = p.groups[0].w_idx[1] * p.w_rows_per_tap + (W_MN ? 0 : n0);
-        int r2 = p.groups[0].w_idx[2] * p.w_rows_per_tap + (W_MN ? 0 : n0);
+        const int rbase = W_MN ? 0 : n0;
         int left = p.items_per_tile;
         while (left > 0) {
           const int nit = left >= 2 ? 2 : 1;
@@ -184,7 +211,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mtgemm_fwd_kernel(const __grid
           for (int i = 0; i < 2; ++i) {
             if (i < nit) {
               const int kcol = c < p.chunks0 ? c * 64 : p.kofs1 + (c - p.chunks0) * 64;
-              const int wr = t == 0 ? r0 : (t == 1 ? r1 : r2);
+              // row (K-major: output channel row; MN-major: K row) of the tap's block in the weight matrix
+              const int wr = p.groups[g].w_idx[t] * p.w_rows_per_tap + rbase;
               const uint32_t dst = w_dst + (uint32_t)i * kWTileBytes;
               if (PROF && (p.dbg_flags & 4)) {
                 // bring-up: no weight traffic
@@ -198,12 +226,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mtgemm_fwd_kernel(const __grid
                 t = 0;
                 if (++c == kchunks) {
                   c = 0;
-                  if (++g < p.ngroups) {
-                    ntaps = p.groups[g].ntaps;
-                    r0 = p.groups[g].w_idx[0] * p.w_rows_per_tap + (W_MN ? 0 : n0);
-                    r1 = p.groups[g].w_idx[1] * p.w_rows_per_tap + (W_MN ? 0 : n0);
-                    r2 = p.groups[g].w_idx[2] * p.w_rows_per_tap + (W_MN ? 0 : n0);
-                  }
+                  if (++g < p.ngroups) ntaps = p.groups[g].ntaps;
+                  else g = 0;  // (tile finished; keeps the index of the look-ups above in range)
                 }
               }
             }
@@ -240,15 +264,15 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mtgemm_fwd_kernel(const __grid
       uint32_t aph = 0, wph = 0;
       int acs = 0;
       uint32_t acph = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = unit0; tile < total_tiles; tile += unit_step) {
         timed_wait(tempty_bar(acs), acph ^ 1u, prof ? &w2 : nullptr);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acs * kPT);
         uint32_t acc = 0;
         int g = 0, c = 0, t = 0;
         int ntaps = p.groups[0].ntaps;
-        uint32_t sh0 = (uint32_t)p.groups[0].shift[0] * 8u, sh1 = (uint32_t)p.groups[0].shift[1] * 8u,
-                 sh2 = (uint32_t)p.groups[0].shift[2] * 8u;  // row shifts in 16-byte units
+        uint32_t sh = (uint32_t)p.groups[0].shift[0] * 8u;  // row shift of the CURRENT tap in 16-byte units, looked up
+                                                            // one tap ahead (the constant-bank load is off the issue path)
         uint32_t a_lo = 0;
         int ks = 4;
         int left = p.items_per_tile;
@@ -263,11 +287,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mtgemm_fwd_kernel(const __grid
               if (t == 0) {  // first tap of a (group, chunk): its slab must have landed
                 timed_wait(a_full(as), aph, prof ? &w0 : nullptr);
                 tc_fence_after();
-                a_lo = a_lo0 + (uint32_t)as * (kSlabBytes >> 4);
+                a_lo = a_lo0 + (uint32_t)as * (slab_bytes >> 4);
                 ks = c == tail_c0 ? tail_k0 : (c == tail_c1 ? tail_k1 : 4);
               }
               const uint64_t wd = w_hi | (uint64_t)(w_lo + (uint32_t)i * (kWTileBytes >> 4));
-              const uint64_t xd = x_hi | (uint64_t)(a_lo + (t == 0 ? sh0 : (t == 1 ? sh1 : sh2)));
+              const uint64_t xd = x_hi | (uint64_t)(a_lo + sh);
               if (ks == 4) {
                 mma_bf16_ss(d_tmem, wd, xd, idesc, acc);
                 mma_bf16_ss(d_tmem, wd + w_step, xd + 2, idesc, 1u);
@@ -280,19 +304,17 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mtgemm_fwd_kernel(const __grid
               }
               acc = 1u;
               if (++t == ntaps) {  // last tap of the chunk: the slab is free once these MMAs retire
-                mma_commit(a_empty(as));
+                if (CL2) mma_commit_multicast(a_empty(as), (uint16_t)3);
+                else mma_commit(a_empty(as));
                 if (++as == NA) { as = 0; aph ^= 1u; }
                 t = 0;
                 if (++c == kchunks) {
                   c = 0;
-                  if (++g < p.ngroups) {
-                    ntaps = p.groups[g].ntaps;
-                    sh0 = (uint32_t)p.groups[g].shift[0] * 8u;
-                    sh1 = (uint32_t)p.groups[g].shift[1] * 8u;
-                    sh2 = (uint32_t)p.groups[g].shift[2] * 8u;
-                  }
+                  if (++g < p.ngroups) ntaps = p.groups[g].ntaps;
+                  else g = 0;
                 }
               }
+              sh = (uint32_t)p.groups[g].shift[t] * 8u;
             }
           }
           mma_commit(w_empty(ws));
@@ -325,7 +347,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mtgemm_fwd_kernel(const __grid
     float s_sum = 0.f, s_sq = 0.f;
     int s_ch = -1;
     // column reductions of the copy-out phase: this thread always handles the 8 channels n0 + (lane & 15) * 8 ..
-    const bool do_red = p.csum_f != nullptr || p.red_d != nullptr;
+    const bool do_red = RED && (p.csum_f != nullptr || p.red_d != nullptr);
     float cs[8], cy[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) cs[j] = cy[j] = 0.f;
@@ -352,9 +374,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mtgemm_fwd_kernel(const __grid
 #pragma unroll
       for (int j = 0; j < 8; ++j) cs[j] = cy[j] = 0.f;
     };
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m0 = (tile / p.n_tiles) * kPT;
-      const int n0 = (tile % p.n_tiles) * 128;
+    for (int tile = unit0; tile < total_tiles; tile += unit_step) {
+      const int m0 = pix_tile(tile) * kPT;
+      const int n0 = ch_tile(tile) * 128;
       const int ch = n0 + ch_local;
       if (do_red && n0 + (lane & 15) * 8 != cs_ch) {  // (warp-uniform: n0 changes for the whole warp at once)
         flush_red();
@@ -388,6 +410,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mtgemm_fwd_kernel(const __grid
       tc_fence_after();
       const long long te0 = prof_e ? clock64() : 0;
       const float bias = (p.bias && ch < p.n_valid) ? __ldg(p.bias + ch) : 0.f;
+      const bool warp_live = n0 + q * 32 < p.n_valid;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acs * kPT + half * 128);
       if (PROF && (p.dbg_flags & 1)) {  // bring-up: release the accumulator untouched
         tc_fence_before();
@@ -402,7 +425,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mtgemm_fwd_kernel(const __grid
       const int SP = p.stg_px, rows_w = SP >> 2;
       for (int px0 = 0; px0 < 128; px0 += SP) {
         if (px0) named_bar_sync(1 + half, 128);  // copy-out of the previous pass is done with the staging buffer
-        for (int c0 = 0; c0 < SP; c0 += 32) {
+        // a warp whose 32 channels all lie beyond the tensor (90 channels in a 128-row tile: warp q = 3) has nothing
+        // to convert or stage; it still takes part in the barriers and in the row-wise copy-out below
+        for (int c0 = 0; c0 < SP && warp_live; c0 += 32) {
           uint32_t r[2][16];
           tmem_ld16(t_row + (uint32_t)(px0 + c0), r[0]);  // two loads in flight before the wait
           tmem_ld16(t_row + (uint32_t)(px0 + c0) + 16u, r[1]);
@@ -484,6 +509,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mtgemm_fwd_kernel(const __grid
 
   tc_fence_before();
   __syncthreads();
+  if (CL2) cluster_sync_all();  // no CTA leaves while its partner may still multicast data or arrivals into it
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -541,6 +567,10 @@ __global__ void __launch_bounds__(kThreads, 1)
   const int kb1 = min(p.kblocks, kb0 + p.kblocks_per_split);
   const int nkb = max(0, kb1 - kb0);
   const int ncol = 64 * grp.ntaps;  // accumulator columns per ci atom (MMA N)
+  // the last ci tile may hold fewer than CA atoms (181 channels = 3 atoms = tiles of 2 + 1): no loads, MMAs or
+  // reductions for atoms that do not exist
+  const int CAh = min(CA, p.ci_atoms - ci_t * CA);
+  const bool co_hi = co0 + 64 < p.co_valid;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.tmX);
@@ -572,10 +602,12 @@ __global__ void __launch_bounds__(kThreads, 1)
         const int r0 = kb * 64;
         mbar_wait(empty_bar(s), ph ^ 1u);
         const uint32_t st = smem_base + (uint32_t)s * stage_bytes;
-        mbar_expect_tx(full_bar(s), stage_bytes);
+        // the second 64-channel half of the dY tile is not fetched when it lies beyond the tensor (its accumulator
+        // rows are never stored; rows of an MMA are independent)
+        mbar_expect_tx(full_bar(s), (co_hi ? kWgABytes : 8192u) + (uint32_t)CAh * kWgAtomBytes);
         tma_load_2d(&p.tmDY, full_bar(s), st, co0, r0 + grp.dy_off);
-        tma_load_2d(&p.tmDY, full_bar(s), st + 8192u, co0 + 64, r0 + grp.dy_off);
-        for (int a = 0; a < CA; ++a)
+        if (co_hi) tma_load_2d(&p.tmDY, full_bar(s), st + 8192u, co0 + 64, r0 + grp.dy_off);
+        for (int a = 0; a < CAh; ++a)
           tma_load_2d(&p.tmX, full_bar(s), st + kWgABytes + (uint32_t)a * kWgAtomBytes, ci0 + a * 64,
                       r0 + grp.x_off);
         if (++s == S) { s = 0; ph ^= 1u; }
@@ -598,7 +630,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         tc_fence_after();
         const uint32_t st_lo = lo0 + (uint32_t)s * (stage_bytes >> 4);
         const uint64_t ad = a_hi | (uint64_t)st_lo;
-        for (int a = 0; a < CA; ++a) {
+        for (int a = 0; a < CAh; ++a) {
           const uint32_t d_tmem = tmem_base + (uint32_t)(a * ncol);
           const uint64_t bd = b_hi | (uint64_t)(st_lo + (kWgABytes >> 4) + (uint32_t)a * (kWgAtomBytes >> 4));
           mma_bf16_ss(d_tmem, ad, bd, idesc, acc);
@@ -619,7 +651,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     tc_fence_after();
     if (nkb > 0) {
       const int co = co0 + q * 32 + lane;
-      for (int a = 0; a < CA; ++a) {
+      for (int a = 0; a < CAh; ++a) {
         for (int j = 0; j < grp.ntaps; ++j) {
           // tap j sits at slab shift grp.shift[j] (shifts are consecutive 0..ntaps-1 by construction)
           const int tw = grp.w_idx[j];
@@ -676,8 +708,41 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
+// The encoded descriptor is a pure function of its arguments, and a U-Net schedule asks for the same ~250 descriptors
+// every step: they are memoised (per process, mutex-protected) so a GEMM launch costs no driver call after the first step.
+struct TmapKey {
+  const void* base;
+  uint64_t rows, cols, ld;
+  uint32_t box_cols, box_rows;
+  bool operator==(const TmapKey& o) const {
+    return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && box_cols == o.box_cols &&
+           box_rows == o.box_rows;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = reinterpret_cast<uint64_t>(k.base) * 0x9E3779B97F4A7C15ull;
+    h ^= (k.rows + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2));
+    h ^= (k.cols * 0xC2B2AE3D27D4EB4Full + (h << 6) + (h >> 2));
+    h ^= (k.ld * 0x165667B19E3779F9ull + (h << 6) + (h >> 2));
+    h ^= (((uint64_t)k.box_cols << 32 | k.box_rows) + (h << 6) + (h >> 2));
+    return (size_t)h;
+  }
+};
+static std::mutex g_tmap_mu;
+static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
+
 int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
                  uint32_t box_cols, uint32_t box_rows) {
+  const TmapKey key{base, rows, cols, ld_elems, box_cols, box_rows};
+  {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    auto it = g_tmap_cache.find(key);
+    if (it != g_tmap_cache.end()) {
+      *out = it->second;
+      return MPU_OK;
+    }
+  }
   PFN_encodeTiled enc = get_encode();
   if (!enc) return MPU_ERR_CUDA;
   cuuint64_t gdim[2] = {cols, rows};
@@ -693,6 +758,9 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t col
               (unsigned long long)ld_elems, box_cols, box_rows);
     return MPU_ERR_CUDA;
   }
+  std::lock_guard<std::mutex> lk(g_tmap_mu);
+  if (g_tmap_cache.size() > 8192) g_tmap_cache.clear();  // long-lived processes that keep reallocating tensors
+  g_tmap_cache.emplace(key, *out);
   return MPU_OK;
 }
 
@@ -706,17 +774,29 @@ static int cur_dev() {
   return (dev >= 0 && dev < 64) ? dev : 0;
 }
 typedef void (*FwdKernel)(const FwdParams);
-static FwdKernel fwd_kernel_for(bool w_mn, bool prof) {
-  if (prof) return w_mn ? mtgemm_fwd_kernel<true, true> : mtgemm_fwd_kernel<false, true>;
-  return w_mn ? mtgemm_fwd_kernel<true, false> : mtgemm_fwd_kernel<false, false>;
+static FwdKernel fwd_kernel_for(bool w_mn, bool prof, bool cl2, bool red) {
+  if (red) return w_mn ? mtgemm_fwd_kernel<true, false, false, true> : mtgemm_fwd_kernel<false, false, false, true>;
+  if (cl2) {
+    if (prof) return w_mn ? mtgemm_fwd_kernel<true, true, true, false> : mtgemm_fwd_kernel<false, true, true, false>;
+    return w_mn ? mtgemm_fwd_kernel<true, false, true, false> : mtgemm_fwd_kernel<false, false, true, false>;
+  }
+  if (prof) return w_mn ? mtgemm_fwd_kernel<true, true, false, false> : mtgemm_fwd_kernel<false, true, false, false>;
+  return w_mn ? mtgemm_fwd_kernel<true, false, false, false> : mtgemm_fwd_kernel<false, false, false, false>;
 }
+// clusters of 2 that can be co-resident with this kernel's shared-memory footprint (per device; 0 = cluster launch
+// not possible, fall back to independent CTAs)
+static int g_max_clusters[64] = {0};
+static bool g_max_clusters_set[64] = {false};
 static constexpr int kDefaultSmemReserveKB = 0;
 static constexpr int kDynSmem = 232448 - 1024;  // leave room for static smem (none) and the driver
 
 int pick_bn(int n_valid) { return (n_valid + 15) / 16 * 16 > 256 ? 256 : (n_valid + 15) / 16 * 16; }
 
 // bring-up knobs
+static int smem_reserve();
 static int g_fwd_no_slab = 0;
+static int g_fwd_cl2 = 2;   // MPU_FWD_CL2: 0 = never launch slab-sharing clusters, 1 = whenever possible, 2 = policy
+static int g_fwd_wide = 1;  // MPU_FWD_WIDE=0: never build slabs taller than 264 rows (bring-up comparison)
 static long long* g_fwd_dbg = nullptr;
 extern "C" void mpu_debug_set_fwd_mode(int no_slab) { g_fwd_no_slab = no_slab; }
 // device pointer to 8 long longs: role stall cycles of CTA 0 for the next forward-type launches
@@ -726,6 +806,8 @@ int fwd_setup(FwdParams& p, const FwdDesc& d) {
   static bool env_read = false;
   if (!env_read) {  // bring-up override without a rebuild
     if (const char* e = getenv("MPU_FWD_NO_SLAB")) g_fwd_no_slab = atoi(e);
+    if (const char* e = getenv("MPU_FWD_WIDE")) g_fwd_wide = atoi(e);
+    if (const char* e = getenv("MPU_FWD_CL2")) g_fwd_cl2 = atoi(e);
     env_read = true;
   }
   memset(&p, 0, sizeof(p));
@@ -752,7 +834,11 @@ int fwd_setup(FwdParams& p, const FwdDesc& d) {
     MPU_TRY(make_tmap_2d(&p.tmW, d.W, (uint64_t)d.w_taps * d.w_rows, (uint64_t)d.n_phys,
                          (uint64_t)d.n_phys, 64, 64));
   }
-  // group taps that are < 8 rows apart (sorted by offset) into slabs of up to 3 taps
+  // Tap grouping.  Taps sorted by row offset; a group = consecutive taps whose offsets span at most S rows: they share
+  // one slab of 256 + roundup8(S + 1) rows and differ only in the descriptor's row shift.  S = 7 puts the 3 kx taps of
+  // a kernel row into one 264-row slab (3 slabs per K chunk of a 3x3 conv).  Where the padded image rows are short a
+  // larger S covers SEVERAL kernel rows: the candidate spans are the pairwise offset differences; the one with the
+  // fewest slab rows per K chunk that still leaves room for two slabs and three weight stages wins (ties: smaller S).
   int order[kMaxTaps];
   for (int i = 0; i < d.ntaps; ++i) order[i] = i;
   for (int i = 1; i < d.ntaps; ++i)
@@ -761,13 +847,53 @@ int fwd_setup(FwdParams& p, const FwdDesc& d) {
       order[j] = order[j - 1];
       order[j - 1] = t;
     }
+  auto slab_rows_for = [](int S) { return 256 + ((S + 1 + 7) / 8) * 8; };
+  auto count_groups = [&](int S, int max_taps) {
+    int n = 0, i = 0;
+    while (i < d.ntaps) {
+      const int o = d.tap_a_off[order[i]];
+      int k = 0;
+      while (i < d.ntaps && k < max_taps && d.tap_a_off[order[i]] - o <= S) { ++i; ++k; }
+      ++n;
+    }
+    return n;
+  };
+  // shared memory left for slabs with 3 weight stages: staging of 64-pixel passes, or 32-pixel passes if that is
+  // what makes the tall slab fit
+  const int budget = kSmemBudget - smem_reserve();
+  auto fits = [&](int S, int stg_px) {
+    return 2 * slab_rows_for(S) * 128 + 3 * (int)kWStageBytes + 2 * stg_px * 256 + 1024 <= budget;
+  };
+  int bestS = 7;
+  long long best_cost = (long long)count_groups(7, 3) * slab_rows_for(7);
+  if (!g_fwd_no_slab && g_fwd_wide) {
+    for (int i = 0; i < d.ntaps; ++i)
+      for (int j = i + 1; j < d.ntaps; ++j) {
+        const int S = d.tap_a_off[order[j]] - d.tap_a_off[order[i]];
+        if (S <= 7 || !fits(S, 32)) continue;
+        const long long cost = (long long)count_groups(S, kMaxGroupTaps) * slab_rows_for(S);
+        if (cost * 10 < best_cost * 9 || (bestS > 7 && (cost < best_cost || (cost == best_cost && S < bestS)))) {
+          best_cost = cost;
+          bestS = S;
+        }
+      }
+  }
+  const int max_taps = bestS > 7 ? kMaxGroupTaps : 3;
+  p.slab_rows = slab_rows_for(bestS);
+  p.ext_rows = p.slab_rows - (int)kSlabRows;
+  p.stg_px = fits(bestS, 64) ? 64 : 32;
+  if (p.ext_rows > 0) {
+    MPU_TRY(make_tmap_2d(&p.tmA0_ext, d.A0, (uint64_t)d.rowsA0, (uint64_t)d.C0, (uint64_t)d.ldA0, 64, p.ext_rows));
+    if (d.A1)
+      MPU_TRY(make_tmap_2d(&p.tmA1_ext, d.A1, (uint64_t)d.rowsA1, (uint64_t)d.C1, (uint64_t)d.ldA1, 64, p.ext_rows));
+  }
   p.ngroups = 0;
   int i = 0;
   while (i < d.ntaps) {
     TapGroup& G = p.groups[p.ngroups++];
     G.a_off = d.tap_a_off[order[i]];
     G.ntaps = 0;
-    while (i < d.ntaps && G.ntaps < 3 && d.tap_a_off[order[i]] - G.a_off < 8 &&
+    while (i < d.ntaps && G.ntaps < max_taps && d.tap_a_off[order[i]] - G.a_off <= bestS &&
            (!g_fwd_no_slab || G.ntaps < 1)) {
       G.shift[G.ntaps] = d.tap_a_off[order[i]] - G.a_off;
       G.w_idx[G.ntaps] = d.tap_w[order[i]];
@@ -820,17 +946,17 @@ static int smem_reserve() {
 }
 
 int launch_fwd(FwdParams& p, cudaStream_t stream) {
-  // Two slabs + three weight stages + 64-pixel epilogue passes.  Measured alternative (MPU_FWD_NA=3 MPU_FWD_SP=32: a
-  // third slab paid for by 32-pixel passes): the MMA thread's a_full waits drop from 12-20 % to 4 %, but its w_full
-  // waits rise by as much (the three-slab burst at every tile start queues ahead of the weight tiles) - no net gain
-  // on levels 2-3, 5 % slower at 16x16 (profiles/r02_perf_gemm_pairs.txt).
+  // Two slabs + three weight stages + 64-pixel epilogue passes (fwd_setup picked slab height and pass size).
+  // Measured alternative (MPU_FWD_NA=3 MPU_FWD_SP=32: a third slab paid for by 32-pixel passes): the MMA thread's
+  // a_full waits drop from 12-20 % to 4 %, but its w_full waits rise by as much - no net gain on levels 2-3, 5 %
+  // slower at 16x16 (profiles/r02_perf_gemm_pairs.txt).
   int NA = 2;
   if (const char* e = getenv("MPU_FWD_NA")) NA = atoi(e);  // bring-up override
-  p.stg_px = NA >= 3 ? 32 : 64;
+  if (NA >= 3 && p.ext_rows == 0) p.stg_px = 32;
   if (const char* e = getenv("MPU_FWD_SP")) p.stg_px = atoi(e) == 32 ? 32 : 64;
   const int fixed = 2 * p.stg_px * 256 + 1024;  // epilogue staging + row table
   const int budget = kSmemBudget - smem_reserve();
-  int NW = (budget - fixed - NA * (int)kSlabBytes) / (int)kWStageBytes;   // stages of two weight tiles
+  int NW = (budget - fixed - NA * p.slab_rows * 128) / (int)kWStageBytes;   // stages of two weight tiles
   if (NW > 8) NW = 8;
   p.items_per_tile = 0;
   for (int g = 0; g < p.ngroups; ++g) p.items_per_tile += p.groups[g].ntaps * (p.chunks0 + p.chunks1);
@@ -843,15 +969,57 @@ int launch_fwd(FwdParams& p, cudaStream_t stream) {
   p.m_tiles = (p.M_rows + kPT - 1) / kPT;
   p.n_tiles = (p.n_valid + 127) / 128;
   if (!g_fwd_attr_set[cur_dev()]) {
-    for (int i = 0; i < 4; ++i)
-      MPU_CUDA(cudaFuncSetAttribute(fwd_kernel_for(i & 1, i & 2), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    kDynSmem));
+    for (int i = 0; i < 16; ++i)
+      MPU_CUDA(cudaFuncSetAttribute(fwd_kernel_for(i & 1, i & 2, i & 4, i & 8),
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmem));
     g_fwd_attr_set[cur_dev()] = true;
   }
-  const int tiles = p.m_tiles * p.n_tiles;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
+  const int smem = kDynSmem - smem_reserve();
+  // Cluster mode (two CTAs share every activation slab through TMA multicast): needs an even number of channel
+  // tiles.  Default: where the 9-tap slab does not fit (ext_rows == 0) and the conv has >= 2 channel tiles - i.e.
+  // level 1; MPU_FWD_CL2 = 0 never, 1 whenever possible.
+  const bool red = p.csum_f != nullptr || p.red_d != nullptr;  // (own instantiation: neither profiled nor clustered)
+  bool cl2 = !red && p.n_tiles >= 2 && (p.n_tiles & 1) == 0 &&
+             (g_fwd_cl2 == 1 || (g_fwd_cl2 == 2 && p.ext_rows == 0));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchAttribute attr[1];
+  cfg.blockDim = dim3(kFwdThreads, 1, 1);
+  cfg.dynamicSmemBytes = (size_t)smem;
+  cfg.stream = stream;
+  if (cl2) {
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const int dev = cur_dev();
+    if (!g_max_clusters_set[dev]) {
+      cfg.gridDim = dim3(2 * (num_sms() / 2), 1, 1);
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, fwd_kernel_for(p.w_mn != 0, false, true, false), &cfg) != cudaSuccess) {
+        cudaGetLastError();
+        n = 0;
+      }
+      g_max_clusters[dev] = n;
+      g_max_clusters_set[dev] = true;
+    }
+    if (g_max_clusters[dev] < 1) cl2 = false;
+  }
+  const int units = cl2 ? p.m_tiles * (p.n_tiles / 2) : p.m_tiles * p.n_tiles;
+  int grid;
+  if (cl2) {
+    const int nc = units < g_max_clusters[cur_dev()] ? units : g_max_clusters[cur_dev()];
+    grid = 2 * nc;
+  } else {
+    grid = units < num_sms() ? units : num_sms();
+    cfg.attrs = nullptr;
+    cfg.numAttrs = 0;
+  }
+  cfg.gridDim = dim3(grid, 1, 1);
   gemm_timer_begin(stream);
-  fwd_kernel_for(p.w_mn != 0, p.dbg != nullptr)<<<grid, kFwdThreads, kDynSmem - smem_reserve(), stream>>>(p);
+  MPU_CUDA(cudaLaunchKernelEx(&cfg, fwd_kernel_for(p.w_mn != 0, p.dbg != nullptr && !red, cl2, red), p));
   gemm_timer_end(stream);
   count_launch();
   MPU_CUDA(cudaGetLastError());
@@ -903,6 +1071,7 @@ int wgrad_setup(WgradParams& p, const WgradDesc& d) {
   p.ci_valid = d.Cx;
   p.co_valid = d.Cy;
   const int atoms = (d.Cx + 63) / 64;
+  p.ci_atoms = atoms;
   p.CA = atoms >= 2 ? 2 : 1;
   p.ci_tiles = (atoms + p.CA - 1) / p.CA;
   p.co_tiles = (d.Cy + 127) / 128;

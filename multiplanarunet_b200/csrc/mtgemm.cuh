@@ -28,15 +28,20 @@ struct RowMap {
 
 // Taps whose row offsets differ by < 8 share one shared-memory "slab" of A rows: the slab is loaded once
 // and each tap's MMA reads it through a descriptor whose start address is shifted by whole 128 B rows.
+constexpr int kMaxGroupTaps = 9;
 struct TapGroup {
   int a_off;                     // row offset of the slab relative to the anchor row
-  int ntaps;                     // 1..3
-  int shift[3];                  // extra row shift of each tap inside the slab (0..7)
-  int w_idx[3];                  // tap index inside the weight matrix
+  int ntaps;                     // 1..9
+  int shift[kMaxGroupTaps];      // extra row shift of each tap inside the slab (0 .. slab_rows - 257)
+  int w_idx[kMaxGroupTaps];      // tap index inside the weight matrix
 };
 
 struct FwdParams {
   CUtensorMap tmA0_hi, tmA0_lo, tmA1_hi, tmA1_lo;  // activation slabs: boxes of 136 + 128 rows x 64 ch
+  CUtensorMap tmA0_ext, tmA1_ext;                  // + ext_rows more rows when the slab is taller than 264 rows
+  int slab_rows, ext_rows;       // slab = 256 pixels + the largest tap shift of a group, rounded up to 8 rows:
+                                 // 264 rows serve the 3 kx taps of one kernel row; where the padded image rows are
+                                 // short (levels >= 2) ONE slab of 264 + 2*(W+2) rows serves all 9 taps of a 3x3 conv
   CUtensorMap tmW;               // weights: box 128 rows (output channels) x 64 K; or, w_mn, 64 K rows x 64 channels
   int w_mn;                      // 1: weights read MN-major from the FORWARD layout [tap][K rows][channels]
                                  //    (dgrad reuses the forward weights: no transposed copy)
@@ -103,6 +108,7 @@ struct WgradParams {
   int ngroups;
   WgradGroup groups[kMaxTaps];
   int CA;                        // 64-channel ci atoms per CTA (1 or 2)
+  int ci_atoms;                  // 64-channel atoms of X in total (the last ci tile may hold fewer than CA)
   int ci_tiles, co_tiles, splits;  // ci tiles of CA*64 channels, co tiles of 128 channels
   int kblocks;                   // total 64-row K blocks
   int kblocks_per_split;

@@ -172,5 +172,32 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_bf16(int M, int N, int a
   return d;
 }
 
+
+// ---- thread-block cluster helpers (slab multicast between the two CTAs of a cluster) ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA tile load delivered to the same shared-memory offset of every CTA in cta_mask; each destination CTA's mbarrier
+// (same offset) receives the complete_tx of the bytes written into ITS shared memory
+__device__ __forceinline__ void tma_load_2d_multicast(const void* tmap, uint32_t bar, uint32_t dst, int c0, int c1,
+                                                      uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
+// tcgen05.commit whose arrival is delivered to the mbarrier at this offset in every CTA of cta_mask
+__device__ __forceinline__ void mma_commit_multicast(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(cta_mask)
+               : "memory");
+}
+
 }  // namespace ptx
 }  // namespace mpu

@@ -74,6 +74,10 @@ struct UNet {
   bf16* shadow = nullptr;    // bf16 copy of the whole flat parameter buffer (written by Adam); the forward
                              // GEMM operand of every 3x3 conv is a view into it
   bool dgrad_mn = true;      // dgrad reads the forward weights MN-major (no transposed copies)
+  int red_min_level = 99;    // levels >= this take BatchNorm-backward sums / bias column sums in the GEMM epilogue.
+                             // OFF by default: measured slower at every level than the separate HBM passes, which
+                             // overlap with the next GEMM, while the epilogue is on these GEMMs' critical path
+                             // (MPU_EPI_RED_LEVEL, measured in profiles/r02_epilogue_reductions.txt)
   float* dwc = nullptr;      // scratch for collapsed upsample-conv weight gradients
   long long dwc_floats = 0;
   bool training_buffers = false;
@@ -82,11 +86,18 @@ struct UNet {
   // phases): its CTAs fill the SMs that the tail of the kernel on the main stream leaves idle.
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+  // Third stream: the optimizer update of a parameter range whose gradients are final runs while the next backward
+  // stage computes (mpu_unet_train_step_adam); HBM-bound Adam under tensor-bound GEMMs.
+  cudaStream_t opt = nullptr;
+  cudaEvent_t ev_stage = nullptr, ev_opt = nullptr;
   bool overlap = true;
   int blk = 0;  // backward block counter within a stage (ring index of ev_join)
 
   ~UNet() {
     if (side) cudaStreamDestroy(side);
+    if (opt) cudaStreamDestroy(opt);
+    if (ev_stage) cudaEventDestroy(ev_stage);
+    if (ev_opt) cudaEventDestroy(ev_opt);
     if (ev_fork) cudaEventDestroy(ev_fork);
     for (cudaEvent_t e : ev_join)
       if (e) cudaEventDestroy(e);
@@ -558,16 +569,19 @@ static int bn_backward(UNet& u, BnL& bn, const bf16* y, const bf16* gA, int ldA,
 // wgrad conv2, dgrad conv2 (masked by a1 -> dz1), bias1, wgrad conv1, optional dgrad conv1.
 static int block_tail_backward(UNet& u, ConvL& c1, ConvL& c2, const bf16* xin0, int cx0, const bf16* xin1,
                                int cx1, const bf16* a1, const bf16* dz2, bf16* dz1, bf16* dxin, int C,
-                               Geo g, cudaStream_t st, cudaStream_t sb, const EpiRed* dxin_red = nullptr) {
+                               Geo g, cudaStream_t st, cudaStream_t sb, bool fuse_red = false,
+                               const EpiRed* dxin_red = nullptr) {
   float* G = u.grads;
   // weight / bias gradients run on the side stream sb; the dgrad chain (critical path) stays on st
   MPU_TRY(fork_side(u, st, sb));  // dz2 is ready
   MPU_TRY(wgrad_same(a1, C, C, dz2, C, 9, g, G + c2.w_off, c2.k_phys, c2.co_phys, 0, sb));
-  // the dgrad that writes dz1 also sums its columns: conv1's bias gradient (was a separate colsum pass)
+  // conv1's bias gradient = column sums of dz1: taken by the epilogue of the dgrad that writes dz1, or by a
+  // separate pass on the side stream
   EpiRed bias_red;
   bias_red.csum_f = G + c1.b_off;
-  MPU_TRY(gemm_dgrad3x3(u, dz2, c2, g, dz1, a1, C, st, &bias_red));
+  MPU_TRY(gemm_dgrad3x3(u, dz2, c2, g, dz1, a1, C, st, fuse_red ? &bias_red : nullptr));
   MPU_TRY(fork_side(u, st, sb));  // dz1 is ready
+  if (!fuse_red) MPU_TRY(launch_colsum(dz1, g.rows(), C, C, G + c1.b_off, sb));
   if (!xin1 && cx0 == 8 && c1.k_phys == 8 && u.cfg.n_channels <= 4 && xin0 == u.x_in)
     // first conv of the network: K = 9 * n_channels is too thin for the tensor cores
     MPU_TRY(launch_conv_first_wgrad(xin0, dz1, g, u.cfg.n_channels, c1.co_phys, G + c1.w_off, c1.k_phys, sb));
@@ -614,16 +628,19 @@ static int backward_up(UNet& u, int B, cudaStream_t st, cudaStream_t sb) {
     ConvL& c3 = u.up_conv(i, 2);
     // BN2 backward: gradient wrt bn2_l is in L.gout; for l > 0 the upsample-conv dgrad of the previous block
     // already left [sum g | sum g*y] in the BN's sums (level 0's gradient comes from the head kernel)
-    MPU_TRY(bn_backward(u, u.up_bn(i, 1), L.c3, L.gout, L.C, nullptr, g, L.s1, 0, G + c3.b_off, st, l > 0));
+    const bool fuse_here = l >= u.red_min_level, fuse_lo = l + 1 >= u.red_min_level;
+    MPU_TRY(bn_backward(u, u.up_bn(i, 1), L.c3, L.gout, L.C, nullptr, g, L.s1, 0, G + c3.b_off, st,
+                        l > 0 && fuse_here));
     // conv3 / conv2 ([skip | bn1] concat input) backward; dgrad of conv2 -> dcat [rows][2C]; its second half is the
     // gradient at BN1's output: the dgrad epilogue accumulates BN1's reduction sums against y = u
     BnL& bn1 = u.up_bn(i, 0);
-    MPU_CUDA(cudaMemsetAsync(bn1.sums, 0, sizeof(double) * 2 * L.C, st));
+    if (fuse_here) MPU_CUDA(cudaMemsetAsync(bn1.sums, 0, sizeof(double) * 2 * L.C, st));
     EpiRed r1;
     r1.red_d = bn1.sums; r1.red_y = L.u; r1.red_ldy = L.C; r1.red_col0 = L.C; r1.red_C = L.C;
-    MPU_TRY(block_tail_backward(u, c2, c3, L.b, L.C, L.bn1, L.C, L.c2, L.s1, L.s2, L.dcat, L.C, g, st, sb, &r1));
+    MPU_TRY(block_tail_backward(u, c2, c3, L.b, L.C, L.bn1, L.C, L.c2, L.s1, L.s2, L.dcat, L.C, g, st, sb, fuse_here,
+                                fuse_here ? &r1 : nullptr));
     // BN1 backward on the second half of dcat -> dz of the upsample-conv, phase-major
-    MPU_TRY(bn_backward(u, bn1, L.u, L.dcat + L.C, 2 * L.C, nullptr, g, L.dzu, 1, G + c1.b_off, st, true));
+    MPU_TRY(bn_backward(u, bn1, L.u, L.dcat + L.C, 2 * L.C, nullptr, g, L.dzu, 1, G + c1.b_off, st, fuse_here));
     // upsample-conv backward
     const bf16* xin = (l + 1 == d) ? Lo.b : Lo.bn2;
     MPU_TRY(fork_side(u, st, sb));  // dzu is ready
@@ -633,10 +650,10 @@ static int backward_up(UNet& u, int B, cudaStream_t st, cudaStream_t sb) {
     // the gradient it writes sits at a BN output (BN2 of the next coarser up block, or the bottom BN): take that
     // BN's reduction sums in the epilogue
     BnL& bnn = (l + 1 == d) ? u.enc_bn(d) : u.up_bn(i - 1, 1);
-    MPU_CUDA(cudaMemsetAsync(bnn.sums, 0, sizeof(double) * 2 * Lo.C, st));
+    if (fuse_lo) MPU_CUDA(cudaMemsetAsync(bnn.sums, 0, sizeof(double) * 2 * Lo.C, st));
     EpiRed r2;
     r2.red_d = bnn.sums; r2.red_y = (l + 1 == d) ? Lo.a2 : Lo.c3; r2.red_ldy = Lo.C; r2.red_col0 = 0; r2.red_C = Lo.C;
-    MPU_TRY(gemm_upconv_dgrad(u, L.dzu, c1, glo, Lo.gout, st, &r2));
+    MPU_TRY(gemm_upconv_dgrad(u, L.dzu, c1, glo, Lo.gout, st, fuse_lo ? &r2 : nullptr));
     MPU_TRY(block_end(u, st, sb));
   }
   return MPU_OK;
@@ -651,7 +668,8 @@ static int backward_enc_level(UNet& u, int B, int l, cudaStream_t st, cudaStream
   ConvL& c1 = u.enc_conv(l, 0);
   ConvL& c2 = u.enc_conv(l, 1);
   if (l == d) {  // (sums left by the upsample-conv dgrad of the last up block, backward stage 0)
-    MPU_TRY(bn_backward(u, u.enc_bn(l), L.a2, L.gout, L.C, nullptr, g, L.s1, 0, G + c2.b_off, st, true));
+    MPU_TRY(bn_backward(u, u.enc_bn(l), L.a2, L.gout, L.C, nullptr, g, L.s1, 0, G + c2.b_off, st,
+                        l >= u.red_min_level));
   } else {
     // skip gradient = first half of dcat_l; pooled gradient = dpool_l (from level l+1's conv1 dgrad)
     MPU_TRY(bn_backward(u, u.enc_bn(l), L.a2, L.dcat, 2 * L.C, L.dpool, g, L.s1, 0, G + c2.b_off, st));
@@ -659,7 +677,8 @@ static int backward_enc_level(UNet& u, int B, int l, cudaStream_t st, cudaStream
   const bf16* xin = l == 0 ? u.x_in : u.lv[l - 1].pooled;
   const int cx = l == 0 ? u.cin_phys : u.lv[l - 1].C;
   bf16* dxin = l == 0 ? nullptr : u.lv[l - 1].dpool;
-  MPU_TRY(block_tail_backward(u, c1, c2, xin, cx, nullptr, 0, L.a1, L.s1, L.s2, dxin, L.C, g, st, sb));
+  MPU_TRY(block_tail_backward(u, c1, c2, xin, cx, nullptr, 0, L.a1, L.s1, L.s2, dxin, L.C, g, st, sb,
+                              l >= u.red_min_level));
   return block_end(u, st, sb);
 }
 
@@ -738,11 +757,15 @@ int mpu_unet_create(const MpuUNetConfig* cfg, float* params, float* grads, float
   UNet* u = new UNet();
   u->cfg = *cfg;
   if (const char* e = getenv("MPU_DGRAD_MN")) u->dgrad_mn = atoi(e) != 0;
+  if (const char* e = getenv("MPU_EPI_RED_LEVEL")) u->red_min_level = atoi(e);
   if (const char* e = getenv("MPU_OVERLAP")) u->overlap = atoi(e) != 0;
   if (u->overlap) {
     bool ok = cudaStreamCreateWithFlags(&u->side, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&u->ev_fork, cudaEventDisableTiming) == cudaSuccess;
     for (cudaEvent_t& ev : u->ev_join) ok = ok && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&u->opt, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&u->ev_stage, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&u->ev_opt, cudaEventDisableTiming) == cudaSuccess;
     if (!ok) {
       set_error("unet_create: could not create the side stream / events: %s", cudaGetErrorString(cudaGetLastError()));
       delete u;
@@ -884,6 +907,47 @@ int mpu_unet_train_step(void* handle, int B, const unsigned char* labels, const 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   MPU_TRY(train_forward(u, B, labels, sample_w, grad_scale, loss_sum, probs_opt, st));
   return backward(*u, B, st);
+}
+
+// Whole single-process train step with the optimizer overlapped: after each backward stage the parameter ranges whose
+// gradients are final (mpu_unet_grad_ranges) get their l2 penalty + Adam update on a third stream while the next stage
+// computes on the main one (a later stage reads neither the weights nor the gradients of an earlier range).  Results
+// are identical to mpu_unet_train_step + mpu_unet_l2_penalty + mpu_unet_adam.
+int mpu_unet_train_step_adam(void* handle, int B, const unsigned char* labels, const float* sample_w,
+                             float grad_scale, double* loss_sum, float* probs_opt, float lr, float beta1, float beta2,
+                             float eps, int step, float l2_grad_coef, double* l2_sumsq, void* stream) {
+  UNet* u = reinterpret_cast<UNet*>(handle);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  MPU_TRY(train_forward(u, B, labels, sample_w, grad_scale, loss_sum, probs_opt, st));
+  if (l2_grad_coef != 0.f && !l2_sumsq) {
+    set_error("train_step_adam: l2 penalty requested without an output for sum(w^2)");
+    return MPU_ERR_ARG;
+  }
+  long long r[8];
+  MPU_TRY(mpu_unet_grad_ranges(handle, r));
+  const double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, step)) / (1.0 - pow((double)beta1, step));
+  const bool ov = u->overlap && u->opt && !gemm_timer_on();
+  cudaStream_t so = ov ? u->opt : st;
+  if (l2_grad_coef != 0.f) MPU_CUDA(cudaMemsetAsync(l2_sumsq, 0, sizeof(double), st));
+  for (int stage = 0; stage < 3; ++stage) {
+    MPU_TRY(backward_stage(*u, B, stage, st));
+    if (ov) {
+      MPU_CUDA(cudaEventRecord(u->ev_stage, st));
+      MPU_CUDA(cudaStreamWaitEvent(so, u->ev_stage, 0));
+    }
+    for (int k = (stage < 2 ? stage : 2); k <= (stage < 2 ? stage : 3); ++k) {
+      const long long a = r[2 * k], b = r[2 * k + 1];
+      if (b <= a) continue;
+      if (l2_grad_coef != 0.f) MPU_TRY(mpu_unet_l2_penalty(handle, a, b, l2_grad_coef, l2_sumsq, so));
+      MPU_TRY(launch_adam(u->params + a, u->grads + a, u->adam_m + a, u->adam_v + a, b - a, (float)lr_t, beta1,
+                          beta2, eps, 1.0f, u->shadow + a, so));
+    }
+  }
+  if (ov) {
+    MPU_CUDA(cudaEventRecord(u->ev_opt, so));
+    MPU_CUDA(cudaStreamWaitEvent(st, u->ev_opt, 0));
+  }
+  return derive_weights(*u, st);
 }
 
 int mpu_unet_train_forward(void* handle, int B, const unsigned char* labels, const float* sample_w,

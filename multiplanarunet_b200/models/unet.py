@@ -357,6 +357,32 @@ class UNet(object):
         self._last_B = B
         return self._loss_dev
 
+    def _train_step_adam(self, x, y, sample_weight=None, input_packed=False, batch=None):
+        """Single-process step in one C call (mpu_unet_train_step_adam): forward + loss + backward, with the l2 penalty
+        and Adam update of every parameter range issued as soon as its gradients are final, overlapped with the rest
+        of backward.  Same results as forward_backward() + apply_gradients()."""
+        import torch
+        B = batch if input_packed else self._pack(x)
+        H, W, _ = self.img_shape
+        yy = y if torch.is_tensor(y) else torch.as_tensor(np.ascontiguousarray(y).reshape(B, H, W).astype(np.uint8))
+        yy = yy.to(self.device, dtype=torch.uint8, non_blocking=True).contiguous()
+        sw = None
+        if sample_weight is not None:
+            sw = sample_weight if torch.is_tensor(sample_weight) else torch.as_tensor(
+                np.asarray(sample_weight, dtype=np.float32))
+            sw = sw.to(self.device, dtype=torch.float32).contiguous()
+        gscale = 1.0 if self.loss_scale_mode == "sum" else 1.0 / (B * H * W)
+        o = self.optimizer
+        o.iterations += 1
+        l2c = 2.0 * float(self.l2_reg) * gscale * B * H * W if self.l2_reg else 0.0
+        check(lib.mpu_unet_train_step_adam(self._h, B, _C.ptr(yy), _C.ptr(sw), ctypes.c_float(gscale),
+                                           _C.ptr(self._loss_dev), _C.ptr(None), ctypes.c_float(o.lr),
+                                           ctypes.c_float(o.beta_1), ctypes.c_float(o.beta_2),
+                                           ctypes.c_float(o.epsilon), int(o.iterations), ctypes.c_float(l2c),
+                                           _C.ptr(self._l2_sumsq), _C.current_stream()), "mpu_unet_train_step_adam")
+        self._last_B = B
+        return self._loss_dev
+
     def forward_backward_overlapped(self, x, y, sample_weight=None, input_packed=False, batch=None, fuse_adam=False):
         """forward_backward with the gradient all-reduce overlapped with backward: parameter ranges whose
         gradients are final after each backward stage are all-reduced asynchronously (NCCL stream) while
@@ -364,10 +390,9 @@ class UNet(object):
         import torch
         import torch.distributed as dist
         if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
-            loss = self.forward_backward(x, y, sample_weight, input_packed, batch)
             if fuse_adam:
-                self.apply_gradients()
-            return loss
+                return self._train_step_adam(x, y, sample_weight, input_packed, batch)
+            return self.forward_backward(x, y, sample_weight, input_packed, batch)
         B = batch if input_packed else self._pack(x)
         H, W, _ = self.img_shape
         yy = y if torch.is_tensor(y) else torch.as_tensor(np.ascontiguousarray(y).reshape(B, H, W).astype(np.uint8))

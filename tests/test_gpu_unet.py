@@ -158,6 +158,66 @@ def test_staged_backward_equals_single_call(setup):
     assert _C.lib.mpu_unet_backward_stage(m._h, B, 3, st) != 0
 
 
+def test_fused_step_with_overlapped_adam_equals_separate_calls():
+    """mpu_unet_train_step_adam (Adam of each parameter range on a third stream while the next backward stage runs)
+    == forward_backward() + apply_gradients(): same weights, Adam moments and bf16 operand copies after 3 steps, up to
+    the run-to-run reordering of the fp32 / fp64 atomics in the gradient kernels."""
+    import torch
+    from multiplanarunet_b200.models import UNet
+    rng = np.random.RandomState(11)
+    x = rng.randn(4, 32, 32, 2).astype(np.float32)
+    y = (x[..., 0] > 0).astype(np.uint8) + (x[..., 1] > 1).astype(np.uint8)
+    kw = dict(n_classes=3, dim=32, n_channels=2, complexity_factor=0.125, max_batch=4, training=True, seed=4)
+    for l2 in (None, 1e-4):
+        a, b = UNet(l2_reg=l2, **kw), UNet(l2_reg=l2, **kw)
+        assert torch.equal(a.params, b.params)
+        la = lb = None
+        for _ in range(3):
+            la = a.train_on_batch(x, y)                 # fused entry
+            b.forward_backward(x, y)
+            b.apply_gradients()
+            H, W, _ = b.img_shape
+            lb = float(b._loss_dev.item()) / (4 * H * W) + (l2 * float(b._l2_sumsq[0]) if l2 else 0.0)
+        torch.cuda.synchronize()
+        assert abs(la - lb) <= 1e-5 * abs(lb), (la, lb)
+        # Adam normalises the update, so a parameter whose gradient is pure summation noise may move by up to lr per
+        # step in either run; everything else must agree closely
+        d = (a.params - b.params).abs()
+        assert float(d.max()) <= 3 * 1.01 * a.optimizer.lr, float(d.max())
+        assert float((d > 1e-5).float().mean()) < 1e-3
+        assert float((a.adam_m - b.adam_m).abs().max()) <= 1e-3 * float(b.adam_m.abs().max())
+        # the forward pass of both models agrees (bf16 operand copies and derived up-conv weights were refreshed)
+        pa, pb = a.predict_on_batch(x, as_numpy=False), b.predict_on_batch(x, as_numpy=False)
+        assert float((pa - pb).abs().max()) < 5e-3
+
+
+def test_epilogue_reductions_match_separate_passes(monkeypatch):
+    """MPU_EPI_RED_LEVEL=0 moves BatchNorm backward's sum g / sum g*y and the conv bias gradients into the epilogue of
+    the GEMM that writes the gradient tensor (mtgemm_fwd_kernel<.., RED>); off by default because it measured slower
+    (profiles/r02_epilogue_reductions.txt).  Both routes must give the same gradients."""
+    import torch
+    from multiplanarunet_b200.models import UNet
+    rng = np.random.RandomState(21)
+    x = rng.randn(4, 64, 64, 1).astype(np.float32)
+    y = rng.randint(0, 4, size=(4, 64, 64)).astype(np.uint8)
+    kw = dict(n_classes=4, dim=64, n_channels=1, complexity_factor=0.25, max_batch=4, training=True, seed=6)
+    a = UNet(**kw)
+    monkeypatch.setenv("MPU_EPI_RED_LEVEL", "0")
+    b = UNet(**kw)
+    monkeypatch.delenv("MPU_EPI_RED_LEVEL")
+    la = float(a.forward_backward(x, y).item())
+    lb = float(b.forward_backward(x, y).item())
+    torch.cuda.synchronize()
+    assert abs(la - lb) <= 1e-6 * abs(la)
+    ga, gb = a.grads, b.grads
+    for info in a._infos:  # per tensor: kernels / gamma at off0, biases / beta at off1
+        n0 = info["ksize"] ** 2 * info["co_phys"] * info["k_phys"] if info["kind"] == 0 else info["co_phys"]
+        for off, n in ((info["off0"], n0), (info["off1"], info["co_phys"])):
+            ra, rb = ga[off:off + n], gb[off:off + n]
+            scale = float(ra.abs().max())
+            assert float((ra - rb).abs().max()) <= 2e-3 * scale + 1e-6, (info["name"], off)
+
+
 def test_l2_reg_matches_keras_kernel_regularizer():
     """kernel_regularizer=l2(l2_reg) on every encoder / bottom / up conv kernel, none on the 1x1 head, biases or BN
     (mpunet/models/unet.py:122-189): penalty gradient next to the sum-of-pixels data gradient is (B*H*W) * 2*l2*w,
@@ -170,11 +230,12 @@ def test_l2_reg_matches_keras_kernel_regularizer():
     x = rng.randn(2, 32, 32, 1).astype(np.float32)
     y = rng.randint(0, 3, size=(2, 32, 32)).astype(np.uint8)
     m.forward_backward(x, y)
-    g0 = m.grads.clone()
+    torch.cuda.synchronize()
+    m.grads.zero_()  # (adding onto the data gradient would only test fp32 rounding of g + penalty)
     m._l2_begin()
     m._l2_penalty(0, m.grads.numel())
     torch.cuda.synchronize()
-    diff = (m.grads - g0)
+    diff = m.grads.clone()
     expect = torch.zeros_like(diff)
     sumsq = 0.0
     for info in m._infos:
