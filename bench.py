@@ -571,11 +571,15 @@ def main():
     # ---- roofline of the dominant kernels (tensor-core GEMMs), timed live with CUDA events
     # (every rank runs the extra step - it contains the gradient all-reduce - only rank 0 reads the timer)
     roofline = None
+    R_PROF = 3  # serial steps averaged (a single step's sum moved by +-5 % between runs with the power-capped clock)
     check(lib.mpu_profile_gemm(1))
-    step_value(W + K + 1)
+    for r_ in range(R_PROF):
+        step_value(W + K + 1)
     gemm_ms, n_l = ctypes.c_double(), ctypes.c_int()
     check(lib.mpu_profile_gemm_read(ctypes.byref(gemm_ms), ctypes.byref(n_l)))
     check(lib.mpu_profile_gemm(0))
+    gemm_ms.value /= R_PROF
+    n_l.value //= R_PROF
     if rank == 0:
         # algorithmic FLOPs executed by the tensor-core GEMM kernels: 3x forward minus the first conv
         # (CUDA-core kernels, no input gradient) and the 1x1 head (fused softmax/CE kernel)

@@ -795,7 +795,9 @@ int pick_bn(int n_valid) { return (n_valid + 15) / 16 * 16 > 256 ? 256 : (n_vali
 // bring-up knobs
 static int smem_reserve();
 static int g_fwd_no_slab = 0;
-static int g_fwd_cl2 = 2;   // MPU_FWD_CL2: 0 = never launch slab-sharing clusters, 1 = whenever possible, 2 = policy
+static int g_fwd_cl2 = 1;   // MPU_FWD_CL2: 0 = never launch slab-sharing clusters, 1 = whenever the conv has an even
+                            // number of channel tiles (default: +5 % at level 1, +2 % at level 3, neutral at 16x16;
+                            // profiles/r02_perf_gemm_cluster.txt), 2 = only where the 9-tap slab does not fit
 static int g_fwd_wide = 1;  // MPU_FWD_WIDE=0: never build slabs taller than 264 rows (bring-up comparison)
 static long long* g_fwd_dbg = nullptr;
 extern "C" void mpu_debug_set_fwd_mode(int no_slab) { g_fwd_no_slab = no_slab; }
@@ -976,8 +978,7 @@ int launch_fwd(FwdParams& p, cudaStream_t stream) {
   }
   const int smem = kDynSmem - smem_reserve();
   // Cluster mode (two CTAs share every activation slab through TMA multicast): needs an even number of channel
-  // tiles.  Default: where the 9-tap slab does not fit (ext_rows == 0) and the conv has >= 2 channel tiles - i.e.
-  // level 1; MPU_FWD_CL2 = 0 never, 1 whenever possible.
+  // tiles (levels 1, 3, 4 at complexity_factor 2).
   const bool red = p.csum_f != nullptr || p.red_d != nullptr;  // (own instantiation: neither profiled nor clustered)
   bool cl2 = !red && p.n_tiles >= 2 && (p.n_tiles & 1) == 0 &&
              (g_fwd_cl2 == 1 || (g_fwd_cl2 == 2 && p.ext_rows == 0));

@@ -654,35 +654,16 @@ struct FusionStepArgs {  // optional fused Adam: the last block to finish applie
   unsigned char* mail[kMaxPeers];
 };
 
+// One warp-chunk of 32 points of a fusion-training batch: gather / stream the rows into the warp's staging buffer,
+// then one point per lane: softmax(sum_v W.x + b), generalised-dice loss and its gradient sums into loc[].
 template <int V, int C, bool IDX>
-__global__ void __launch_bounds__(128, 4) fusion_grad_kernel_t(const float* __restrict__ X, const uint8_t* __restrict__ y,
-                                                               const long long* __restrict__ index, long long n,
-                                                               const float* __restrict__ W, const float* __restrict__ b,
-                                                               double* __restrict__ accum, const FusionStepArgs fs) {
+__device__ __forceinline__ void fusion_chunk(const float* __restrict__ X, const uint8_t* __restrict__ y,
+                                             const long long* __restrict__ index, long long p0, long long n,
+                                             float* __restrict__ st, int lane, const float (&w)[V * C],
+                                             const float (&bb)[C], float (&loc)[V * C + C + 1]) {
   constexpr int VC = V * C, NACC = VC + C + 1;
-  constexpr int kChunkFloats = 32 * VC;          // one warp iteration = 32 points
-  constexpr int kVec = kChunkFloats / 4;         // float4 per chunk (32 * VC is a multiple of 4)
-  __shared__ double fsm[4][NACC];
-  // Each warp stages its 32 points (32 * VC floats) through shared memory with coalesced loads: per-thread row walks
-  // touch 32 different lines per load instruction and saturate the L1 tag stage (measured 0.83 ms per 256^3 pass
-  // against 0.31 ms of HBM time).  With `index` (a shuffled epoch: point i is row index[i], the reference's
-  // fit(shuffle=True)) the rows are gathered 8 bytes per lane, 15 lanes per row for V*C = 30.
-  __shared__ __align__(16) float stage[4][kChunkFloats];
-  __shared__ int s_last;
-  float loc[NACC];
-#pragma unroll
-  for (int k = 0; k < NACC; ++k) loc[k] = 0.f;
-  float w[VC], bb[C];
-#pragma unroll
-  for (int k = 0; k < VC; ++k) w[k] = W[k];
-#pragma unroll
-  for (int c = 0; c < C; ++c) bb[c] = b[c];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long nchunks = (n + 31) / 32;
-  const long long wstride = (long long)gridDim.x * 4;
-  float* st = stage[warp];
-  for (long long ch = (long long)blockIdx.x * 4 + warp; ch < nchunks; ch += wstride) {
-    const long long p0 = ch * 32;
+  constexpr int kChunkFloats = 32 * VC;
+  constexpr int kVec = kChunkFloats / 4;
     __syncwarp();
     if (IDX) {
       // rows are 8-byte aligned when V*C is even: gather float2 pieces, consecutive lanes inside one row
@@ -774,6 +755,38 @@ __global__ void __launch_bounds__(128, 4) fusion_grad_kernel_t(const float* __re
         for (int v = 0; v < V; ++v) loc[v * C + c] += dz * x[v * C + c];
       }
     }
+  }
+
+template <int V, int C, bool IDX>
+__global__ void __launch_bounds__(128, 4) fusion_grad_kernel_t(const float* __restrict__ X, const uint8_t* __restrict__ y,
+                                                               const long long* __restrict__ index, long long n,
+                                                               const float* __restrict__ W, const float* __restrict__ b,
+                                                               double* __restrict__ accum, const FusionStepArgs fs) {
+  constexpr int VC = V * C, NACC = VC + C + 1;
+  constexpr int kChunkFloats = 32 * VC;          // one warp iteration = 32 points
+  constexpr int kVec = kChunkFloats / 4;         // float4 per chunk (32 * VC is a multiple of 4)
+  __shared__ double fsm[4][NACC];
+  // Each warp stages its 32 points (32 * VC floats) through shared memory with coalesced loads: per-thread row walks
+  // touch 32 different lines per load instruction and saturate the L1 tag stage (measured 0.83 ms per 256^3 pass
+  // against 0.31 ms of HBM time).  With `index` (a shuffled epoch: point i is row index[i], the reference's
+  // fit(shuffle=True)) the rows are gathered 8 bytes per lane, 15 lanes per row for V*C = 30.
+  __shared__ __align__(16) float stage[4][kChunkFloats];
+  __shared__ int s_last;
+  float loc[NACC];
+#pragma unroll
+  for (int k = 0; k < NACC; ++k) loc[k] = 0.f;
+  float w[VC], bb[C];
+#pragma unroll
+  for (int k = 0; k < VC; ++k) w[k] = W[k];
+#pragma unroll
+  for (int c = 0; c < C; ++c) bb[c] = b[c];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long nchunks = (n + 31) / 32;
+  const long long wstride = (long long)gridDim.x * 4;
+  float* st = stage[warp];
+  for (long long ch = (long long)blockIdx.x * 4 + warp; ch < nchunks; ch += wstride) {
+    const long long p0 = ch * 32;
+    fusion_chunk<V, C, IDX>(X, y, index, p0, n, st, lane, w, bb, loc);
   }
 #pragma unroll
   for (int k = 0; k < NACC; ++k) {
@@ -870,6 +883,257 @@ __global__ void __launch_bounds__(128, 4) fusion_grad_kernel_t(const float* __re
   }
   __syncthreads();
   for (int k = threadIdx.x; k < NACC; k += blockDim.x) accum[k] = 0.0;  // ready for the next batch
+}
+
+// ---- persistent epoch kernel -----------------------------------------------------------------------------------
+// FusionModel.fit's epoch (bin/train_fusion.py:196-213) is a chain of dependent Adam steps over 2^17-point batches
+// (128 per 256^3 volume): one launch per batch costs ~35 us of launch + tail + last-block latency for ~3 us of HBM
+// time.  This kernel is launched ONCE per epoch (cooperatively: every block resident) and walks all batches:
+//   per batch: every block adds its gradient sums into accum[k % 3] (fp64 atomics) -> grid barrier (one arrival per
+//   block on a monotonic counter) -> every block reads the 36 totals and applies the SAME Adam update to its own copy
+//   of (W, b, m, v) in shared memory - no broadcast of the new weights, no second barrier.  Block 0 writes the batch
+//   loss, clears the accumulator two batches ahead and stores the parameters at the end.
+// Multi-rank (world > 1): after the grid barrier block 0 exchanges the totals with every peer's mailbox over NVLink
+// (same protocol as the per-batch kernel), adds them in rank order and publishes them in tot[k % 3] behind a flag
+// the other blocks wait on.
+struct FusionEpochArgs {
+  const float* X;
+  const uint8_t* y;
+  const long long* perm;      // null: rows in order
+  long long n, batch, n_batches;
+  float *W, *b, *m, *v;       // parameters and Adam moments (read at start, written by block 0 at the end)
+  double* acc3;               // [3][kMailDoubles], zero at launch
+  double* tot3;               // [3][kMailDoubles] (multi-rank totals)
+  unsigned long long* bar;    // [0] arrivals (monotonic), [1] blocks past the last barrier, [2] published-totals flag
+  double* losses_out;         // [n_batches] or null
+  float reg, lr, b1, b2, eps;
+  int first_step;
+  int world, rank;
+  unsigned long long first_seq;
+  unsigned char* mail[kMaxPeers];
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+template <int V, int C, bool IDX>
+__global__ void __launch_bounds__(128, 3) fusion_epoch_kernel_t(const FusionEpochArgs a) {
+  constexpr int VC = V * C, NP = VC + C, NACC = VC + C + 1;
+  constexpr int kChunkFloats = 32 * VC;
+  __shared__ double fsm[4][NACC];
+  __shared__ __align__(16) float stage[4][kChunkFloats];
+  __shared__ float sP[NP], sM[NP], sV[NP];   // this block's copy of the parameters and Adam moments
+  __shared__ double sTot[NACC + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x < NP) {
+    sP[threadIdx.x] = threadIdx.x < VC ? a.W[threadIdx.x] : a.b[threadIdx.x - VC];
+    sM[threadIdx.x] = a.m[threadIdx.x];
+    sV[threadIdx.x] = a.v[threadIdx.x];
+  }
+  __syncthreads();
+  float* st = stage[warp];
+  const long long wstride = (long long)gridDim.x * 4;
+  // beta^step of Keras' bias correction, carried from step to step (pow() per batch would sit on the critical path)
+  double p1 = pow((double)a.b1, (double)(a.first_step - 1)), p2 = pow((double)a.b2, (double)(a.first_step - 1));
+  for (long long k = 0; k < a.n_batches; ++k) {
+    p1 *= (double)a.b1;
+    p2 *= (double)a.b2;
+    const long long s0 = k * a.batch;
+    const long long nb = s0 < a.n ? (a.n - s0 < a.batch ? a.n - s0 : a.batch) : 0;  // (a rank may run out of points)
+    double* acc = a.acc3 + (k % 3) * kMailDoubles;
+    float w[VC], bb[C], loc[NACC];
+#pragma unroll
+    for (int j = 0; j < VC; ++j) w[j] = sP[j];
+#pragma unroll
+    for (int c = 0; c < C; ++c) bb[c] = sP[VC + c];
+#pragma unroll
+    for (int j = 0; j < NACC; ++j) loc[j] = 0.f;
+    const long long nchunks = (nb + 31) / 32;
+    const float* Xb = IDX ? a.X : a.X + s0 * VC;
+    const uint8_t* yb = IDX ? a.y : a.y + s0;
+    const long long* ib = IDX ? a.perm + s0 : nullptr;
+    for (long long ch = (long long)blockIdx.x * 4 + warp; ch < nchunks; ch += wstride)
+      fusion_chunk<V, C, IDX>(Xb, yb, ib, ch * 32, nb, st, lane, w, bb, loc);
+#pragma unroll
+    for (int j = 0; j < NACC; ++j) {
+      double v = (double)loc[j];
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) fsm[warp][j] = v;
+    }
+    __syncthreads();
+    if (nchunks > (long long)blockIdx.x * 4)  // blocks without a chunk of this batch add nothing
+      for (int j = threadIdx.x; j < NACC; j += blockDim.x)
+        atomicAdd(acc + j, (fsm[0][j] + fsm[1][j]) + (fsm[2][j] + fsm[3][j]));
+    // ---- grid barrier k ----
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      atomicAdd(a.bar, 1ull);
+      const unsigned long long target = (unsigned long long)(k + 1) * gridDim.x;
+      const long long t0 = clock64();
+      while (ld_acquire_u64(a.bar) < target) {
+        if (clock64() - t0 > 4000000000ll) {  // ~2 s: never hang the GPU
+          printf("mpu: fusion epoch barrier timeout (block %d, batch %lld)\n", (int)blockIdx.x, k);
+          __trap();
+        }
+      }
+    }
+    __syncthreads();
+    const double* src = acc;
+    double ntot = (double)nb;
+    if (a.world > 1) {
+      // block 0: exchange with the peers, publish the rank-ordered totals; everybody else waits for the flag
+      double* tot = a.tot3 + (k % 3) * kMailDoubles;
+      const unsigned long long seq = a.first_seq + (unsigned long long)k;
+      if (blockIdx.x == 0) {
+        const int par = (int)(seq & 1ull);
+        const int slot = (par * kMaxPeers + a.rank) * kMailDoubles;
+        for (int t = threadIdx.x; t < a.world * (NACC + 1); t += blockDim.x) {
+          const int peer = t / (NACC + 1), j = t - peer * (NACC + 1);
+          volatile double* dst = reinterpret_cast<volatile double*>(a.mail[peer]) + slot;
+          dst[j] = j < NACC ? __ldcg(acc + j) : (double)nb;
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x < a.world) {
+          volatile unsigned long long* flag =
+              reinterpret_cast<volatile unsigned long long*>(a.mail[threadIdx.x] + kMailFlagOffset) + par * kMaxPeers + a.rank;
+          *flag = seq;
+          __threadfence_system();
+          volatile unsigned long long* mine =
+              reinterpret_cast<volatile unsigned long long*>(a.mail[a.rank] + kMailFlagOffset) + par * kMaxPeers + threadIdx.x;
+          const long long t0 = clock64();
+          while (*mine != seq) {
+            if (clock64() - t0 > 4000000000ll) {
+              printf("mpu: fusion peer exchange timeout (rank %d waiting for rank %d, seq %llu)\n", a.rank,
+                     (int)threadIdx.x, seq);
+              __trap();
+            }
+          }
+          __threadfence_system();
+        }
+        __syncthreads();
+        volatile double* box = reinterpret_cast<volatile double*>(a.mail[a.rank]) + par * kMaxPeers * kMailDoubles;
+        for (int j = threadIdx.x; j <= NACC; j += blockDim.x) {
+          double sum = 0.0;
+          for (int q = 0; q < a.world; ++q) sum += box[q * kMailDoubles + j];  // rank order: same bits on every rank
+          tot[j] = sum;
+        }
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) atomicExch(a.bar + 2, (unsigned long long)(k + 1));
+      }
+      if (threadIdx.x == 0) {
+        const long long t0 = clock64();
+        while (ld_acquire_u64(a.bar + 2) < (unsigned long long)(k + 1)) {
+          if (clock64() - t0 > 4000000000ll) {
+            printf("mpu: fusion epoch totals timeout (block %d, batch %lld)\n", (int)blockIdx.x, k);
+            __trap();
+          }
+        }
+      }
+      __syncthreads();
+      src = tot;
+    }
+    for (int j = threadIdx.x; j <= NACC; j += blockDim.x)
+      sTot[j] = (j < NACC || a.world > 1) ? __ldcg(src + j) : 0.0;
+    __syncthreads();
+    if (a.world > 1) ntot = sTot[NACC];
+    if (threadIdx.x < NP && ntot > 0.0) {  // a step in which no rank had points left changes nothing
+      const float lr_t = (float)((double)a.lr * sqrt(1.0 - p2) / (1.0 - p1));
+      const int j = threadIdx.x;
+      const float cnt = j < VC ? (float)VC : (float)C;
+      const float g = (float)(sTot[j] / ntot) + a.reg * 2.f * sP[j] / cnt;
+      const float mi = a.b1 * sM[j] + (1.f - a.b1) * g;
+      const float vi = a.b2 * sV[j] + (1.f - a.b2) * g * g;
+      sM[j] = mi;
+      sV[j] = vi;
+      sP[j] = sP[j] - lr_t * mi / (sqrtf(vi) + a.eps);
+    }
+    if (blockIdx.x == 0) {
+      if (threadIdx.x == 0 && a.losses_out) a.losses_out[k] = ntot > 0.0 ? sTot[NACC - 1] / ntot : 0.0;
+      // accumulator of batch k + 2 (== the one of batch k - 1, which every block has read before arriving at
+      // barrier k) is cleared now; its next atomics come after barrier k + 1, which needs this block's arrival
+      double* nxt = a.acc3 + ((k + 2) % 3) * kMailDoubles;
+      for (int j = threadIdx.x; j < kMailDoubles; j += blockDim.x) nxt[j] = 0.0;
+    }
+    __syncthreads();
+  }
+  // ---- epilogue: parameters out, barrier state back to zero for the next launch ----
+  if (threadIdx.x == 0) atomicAdd(a.bar + 1, 1ull);
+  if (blockIdx.x == 0) {
+    if (threadIdx.x < NP) {
+      if (threadIdx.x < VC) a.W[threadIdx.x] = sP[threadIdx.x];
+      else a.b[threadIdx.x - VC] = sP[threadIdx.x];
+      a.m[threadIdx.x] = sM[threadIdx.x];
+      a.v[threadIdx.x] = sV[threadIdx.x];
+    }
+    if (threadIdx.x == 0) {  // every block has left the loop: nobody reads the barrier words or accumulators any more
+      const long long t0 = clock64();
+      while (ld_acquire_u64(a.bar + 1) < gridDim.x)
+        if (clock64() - t0 > 4000000000ll) break;
+      a.bar[0] = 0ull;
+      a.bar[1] = 0ull;
+      a.bar[2] = 0ull;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < 3 * kMailDoubles; j += blockDim.x) a.acc3[j] = 0.0;
+  }
+}
+
+template <int V, int C>
+static int launch_fusion_epoch_t(const FusionEpochArgs& a, cudaStream_t st) {
+  int occ = 0;
+  const bool idx = a.perm != nullptr;
+  const void* fn = idx ? (const void*)fusion_epoch_kernel_t<V, C, true> : (const void*)fusion_epoch_kernel_t<V, C, false>;
+  cudaError_t e = idx ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fusion_epoch_kernel_t<V, C, true>, 128, 0)
+                      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fusion_epoch_kernel_t<V, C, false>, 128, 0);
+  if (e != cudaSuccess || occ < 1) {
+    set_error("fusion epoch kernel: occupancy query failed (%s)", cudaGetErrorString(e));
+    return MPU_ERR_CUDA;
+  }
+  if ((reinterpret_cast<uintptr_t>(a.X) & 15) != 0) {
+    set_error("mpu_fusion_train_epoch: X must be 16-byte aligned");
+    return MPU_ERR_ARG;
+  }
+  // one 32-point chunk per warp and batch is the finest useful split; every block must be resident (spin barrier)
+  long long blocks = (a.batch + 127) / 128;
+  long long cap = (long long)sm_count() * occ;
+  static int env_cap = -1;
+  if (env_cap < 0) {
+    const char* ev = getenv("MPU_FUSION_EPOCH_BLOCKS");
+    env_cap = ev ? atoi(ev) : 0;
+  }
+  if (env_cap > 0 && env_cap < cap) cap = env_cap;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  FusionEpochArgs args = a;
+  void* params[] = {&args};
+  MPU_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)blocks), dim3(128), params, 0, st));
+  count_launch();
+  return MPU_OK;
+}
+
+static int fusion_epoch_dispatch(const FusionEpochArgs& a, int V, int C, cudaStream_t st, bool* handled) {
+  *handled = true;
+  if (V == 6) {
+    switch (C) {
+      case 2: return launch_fusion_epoch_t<6, 2>(a, st);
+      case 3: return launch_fusion_epoch_t<6, 3>(a, st);
+      case 4: return launch_fusion_epoch_t<6, 4>(a, st);
+      case 5: return launch_fusion_epoch_t<6, 5>(a, st);
+      case 6: return launch_fusion_epoch_t<6, 6>(a, st);
+      case 7: return launch_fusion_epoch_t<6, 7>(a, st);
+      case 8: return launch_fusion_epoch_t<6, 8>(a, st);
+      default: break;
+    }
+  }
+  if (V == 3 && C == 5) return launch_fusion_epoch_t<3, 5>(a, st);
+  *handled = false;
+  return MPU_OK;
 }
 
 template <int V, int C>
@@ -1463,13 +1727,39 @@ int mpu_fusion_train_step(const float* X, const unsigned char* y, const long lon
   return MPU_OK;
 }
 
+// layout of the caller's `counter` buffer (mpu_fusion_scratch_bytes() bytes, zeroed once): 16-byte arrival counter of
+// the per-batch kernel, then the persistent epoch kernel's barrier words and rotating accumulators
+static void fusion_epoch_buffers(unsigned int* counter, FusionEpochArgs& a) {
+  unsigned char* base = reinterpret_cast<unsigned char*>(counter) + 16;
+  a.bar = reinterpret_cast<unsigned long long*>(base);                       // 3 x u64 (64 bytes reserved)
+  a.acc3 = reinterpret_cast<double*>(base + 64);                             // [3][kMailDoubles]
+  a.tot3 = reinterpret_cast<double*>(base + 64 + 3 * kMailDoubles * sizeof(double));
+}
+
 int mpu_fusion_train_epoch(const float* X, const unsigned char* y, const long long* perm, long long n,
                            long long batch, int V, int C, float* W, float* b, float* m, float* v, double* accum,
                            unsigned int* counter, double* losses_out, float reg, float lr, float beta1, float beta2,
                            float eps, int first_step, void* stream) {
-  if (batch < 1 || n < 1) {
-    set_error("mpu_fusion_train_epoch: bad batch / point count");
+  if (!X || !y || !W || !b || !m || !v || !accum || !counter || batch < 1 || n < 1 || first_step < 1) {
+    set_error("mpu_fusion_train_epoch: bad arguments");
     return MPU_ERR_ARG;
+  }
+  // MPU_FUSION_EPOCH_PERSISTENT=0: one launch per batch instead of the persistent epoch kernel (read per call)
+  const char* env_p = getenv("MPU_FUSION_EPOCH_PERSISTENT");
+  const bool per_batch = env_p && atoi(env_p) == 0;
+  if (!per_batch) {
+    FusionEpochArgs a;
+    memset(&a, 0, sizeof(a));
+    a.X = X; a.y = y; a.perm = perm; a.n = n; a.batch = batch; a.n_batches = (n + batch - 1) / batch;
+    a.W = W; a.b = b; a.m = m; a.v = v;
+    fusion_epoch_buffers(counter, a);
+    a.losses_out = losses_out;
+    a.reg = reg; a.lr = lr; a.b1 = beta1; a.b2 = beta2; a.eps = eps;
+    a.first_step = first_step;
+    a.world = 1;
+    bool handled = false;
+    MPU_TRY(fusion_epoch_dispatch(a, V, C, reinterpret_cast<cudaStream_t>(stream), &handled));
+    if (handled) return MPU_OK;
   }
   int step = first_step;
   long long k = 0;
@@ -1505,6 +1795,25 @@ int mpu_fusion_train_epoch_peer(const float* X, const unsigned char* y, const lo
     return MPU_ERR_ARG;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  {
+    const char* env_p = getenv("MPU_FUSION_EPOCH_PERSISTENT");
+    const bool per_batch = env_p && atoi(env_p) == 0;
+    if (!per_batch) {
+      FusionEpochArgs a;
+      memset(&a, 0, sizeof(a));
+      a.X = X; a.y = y; a.perm = perm; a.n = n; a.batch = batch; a.n_batches = n_batches;
+      a.W = W; a.b = b; a.m = m; a.v = v;
+      fusion_epoch_buffers(counter, a);
+      a.losses_out = losses_out;
+      a.reg = reg; a.lr = lr; a.b1 = beta1; a.b2 = beta2; a.eps = eps;
+      a.first_step = first_step;
+      a.world = world; a.rank = rank; a.first_seq = first_seq;
+      for (int q = 0; q < world; ++q) a.mail[q] = reinterpret_cast<unsigned char*>(const_cast<void*>(h_peer_mail[q]));
+      bool handled = false;
+      MPU_TRY(fusion_epoch_dispatch(a, V, C, st, &handled));
+      if (handled) return MPU_OK;
+    }
+  }
   for (long long k = 0; k < n_batches; ++k) {
     const long long s0 = k * batch;
     // every rank launches exactly n_batches exchanges; a rank that ran out of points contributes one (zero-weight

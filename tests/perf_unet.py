@@ -45,8 +45,7 @@ def main():
         return [a.elapsed_time(b) for a, b in evs]
 
     def step():
-        model.forward_backward(x, y)
-        model.apply_gradients()
+        model.train_on_batch_async(x, y)  # the product step: forward + backward + Adam per range
 
     for _ in range(args.warmup):
         step()

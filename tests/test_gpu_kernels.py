@@ -224,3 +224,65 @@ def test_elastic_2d_against_reference_goldens_and_oracle():
     assert gw == ow and 0.33 in gw
     assert np.abs(gx.cpu().numpy() - np.stack(ox)).max() <= 2e-6
     assert np.array_equal(gy.cpu().numpy(), np.stack(oy))
+
+
+def test_fusion_persistent_epoch_equals_per_batch_launches(monkeypatch):
+    """mpu_fusion_train_epoch as ONE cooperative launch (grid barrier per batch, every block applies the same Adam
+    update to its own copy of the 35 parameters) against the one-launch-per-batch path and against the float64 oracle
+    (oracle/fusion.py: GDL gradients + Keras Adam), batch by batch, including a ragged last batch."""
+    import torch
+    from multiplanarunet_b200.models import FusionModel
+    from oracle import fusion
+    rng = np.random.RandomState(12)
+    N, V, C, B = 70000, 6, 5, 8192   # 9 batches, the last one with 4464 points
+    X = rng.rand(N, V, C).astype(np.float32)
+    X /= X.sum(-1, keepdims=True)
+    y = rng.randint(0, C, size=N).astype(np.uint8)
+    W0 = rng.uniform(0.5, 1.5, size=(V, C)).astype(np.float32)
+    b0 = (0.1 * rng.randn(C)).astype(np.float32)
+    Xd, yd = torch.as_tensor(X).cuda(), torch.as_tensor(y).cuda()
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("MPU_FUSION_EPOCH_PERSISTENT", mode)
+        fm = FusionModel(V, C)
+        fm.set_weights([W0, b0])
+        hist = fm.fit(Xd, yd, batch_size=B, epochs=2, shuffle=False)
+        torch.cuda.synchronize()
+        Wm, bm = fm.get_weights()
+        res[mode] = (np.asarray(Wm).copy(), np.asarray(bm).ravel().copy(), hist, fm.iterations)
+    monkeypatch.delenv("MPU_FUSION_EPOCH_PERSISTENT")
+    assert res["1"][3] == res["0"][3] == 18
+    assert np.abs(res["1"][0] - res["0"][0]).max() < 2e-6 and np.abs(res["1"][1] - res["0"][1]).max() < 2e-6
+    assert np.allclose(res["1"][2], res["0"][2], rtol=1e-6, atol=1e-9)
+    # oracle: 18 sequential Adam steps in float64
+    th = np.concatenate([W0.ravel(), b0]).astype(np.float64)
+    m, v = np.zeros_like(th), np.zeros_like(th)
+    t = 0
+    for ep in range(2):
+        for s in range(0, N, B):
+            Wc, bc = th[:V * C].reshape(V, C), th[V * C:]
+            _, dW, db = fusion.gdl_loss_and_grads(X[s:s + B], y[s:s + B], Wc.astype(np.float32), bc.astype(np.float32))
+            t += 1
+            th, m, v = fusion.adam_step(th, np.concatenate([dW.ravel(), db]), m, v, t, 1e-3)
+    err = max(np.abs(res["1"][0].ravel() - th[:V * C]).max(), np.abs(res["1"][1] - th[V * C:]).max())
+    assert err < 5e-5, err   # 18 steps of size 1e-3
+    # rows in order without an index (perm == NULL): same epoch as the arange permutation
+    import ctypes
+    from multiplanarunet_b200 import _C
+    fa, fb = FusionModel(V, C), FusionModel(V, C)
+    for f in (fa, fb):
+        f.set_weights([W0, b0])
+    fa.fit(Xd, yd, batch_size=B, epochs=1, shuffle=False)
+    fb.fit(Xd[:B], yd[:B], batch_size=B, epochs=1, shuffle=False)   # allocates the scratch buffers, one step
+    fb.set_weights([W0, b0])
+    fb._m.zero_()
+    fb._v.zero_()
+    losses = torch.zeros((N + B - 1) // B, dtype=torch.float64, device="cuda")
+    _C.check(_C.lib.mpu_fusion_train_epoch(_C.ptr(Xd), _C.ptr(yd), _C.ptr(None), ctypes.c_longlong(N),
+                                           ctypes.c_longlong(B), V, C, _C.ptr(fb.W), _C.ptr(fb.b), _C.ptr(fb._m),
+                                           _C.ptr(fb._v), _C.ptr(fb._accum), _C.ptr(fb._counter), _C.ptr(losses),
+                                           ctypes.c_float(fb.reg), ctypes.c_float(fb.lr), ctypes.c_float(fb.beta_1),
+                                           ctypes.c_float(fb.beta_2), ctypes.c_float(fb.epsilon), 1,
+                                           _C.current_stream()), "mpu_fusion_train_epoch")
+    torch.cuda.synchronize()
+    assert float((fa.W - fb.W).abs().max()) < 2e-6 and float((fa.b - fb.b).abs().max()) < 2e-6
