@@ -65,7 +65,12 @@ def entry_func(args=None):
     pairs = D.shard(pairs)  # every rank builds the points of its own volumes
     rng = np.random.RandomState(0)
     order = rng.permutation(len(pairs))
-    for r0 in range(0, len(order), a.images_per_round):
+    # round-robin shards differ by at most one volume: every rank runs the round count of the largest shard (a rank
+    # whose shard is exhausted contributes an empty point set) so the collectives inside fit / evaluate stay paired
+    n_pairs_max = torch.tensor([len(pairs)], device=model.device)
+    if D.world_size() > 1:
+        torch.distributed.all_reduce(n_pairs_max, op=torch.distributed.ReduceOp.MAX)
+    for r0 in range(0, int(n_pairs_max.item()), a.images_per_round):
         Xs, ys = [], []
         for j in order[r0:r0 + a.images_per_round]:
             ld, i = pairs[j]
@@ -96,7 +101,8 @@ def entry_func(args=None):
         best, wait = np.inf, 0
         for ep in range(a.epochs):
             fm.fit(X, y, batch_size=a.batch_size, epochs=1, verbose=0, index=tr, steps_per_epoch=steps)
-            loss = fm.evaluate(X[va], y[va]) if n_val else float("nan")   # val_loss drives early stopping (:199-203)
+            # val_loss drives early stopping (:199-203); evaluate() all-reduces, so a rank with no points still calls it
+            loss = fm.evaluate(X[va], y[va]) if (n_val or D.world_size() > 1) else float("nan")
             if loss < best - 1e-6:
                 best, wait = loss, 0
             else:

@@ -83,8 +83,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mtgemm_fwd_kernel(const __grid
   const uint32_t slab_bytes = (uint32_t)p.slab_rows * 128u;  // multiple of 1024
   const uint32_t a_base = smem_base;
   const uint32_t w_base = a_base + (uint32_t)NA * slab_bytes;
-  const uint32_t stg_off = (uint32_t)NA * slab_bytes + (uint32_t)NW * kWStageBytes;  // 2 x 16 KB staging
-  const uint32_t stg_half = (uint32_t)p.stg_px * 256u;                               // bytes of one half's staging
+  const uint32_t w_tile_bytes = (uint32_t)p.w_tile_bytes;       // one (chunk, tap) weight tile: box rows x 128 B
+  const uint32_t w_stage_bytes = 2u * w_tile_bytes;             // a ring stage carries two consecutive items
+  const uint32_t stg_off = (uint32_t)NA * slab_bytes + (uint32_t)NW * w_stage_bytes;
+  const uint32_t stg_half = (uint32_t)p.stg_px * (uint32_t)p.stg_ch * 2u;  // one half's staging: stg_px/2 pixel pairs x stg_ch x 4 B
   const uint32_t orow_off = stg_off + 2u * stg_half;                                 // int[256]
   const uint32_t bar_base = smem_base + orow_off + 1024u;
   auto a_full = [&](int s) { return bar_base + 8u * s; };
@@ -94,6 +96,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mtgemm_fwd_kernel(const __grid
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * NA + 2 * NW + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * NA + 2 * NW + 2 + s); };
   const uint32_t tmem_slot_off = orow_off + 1024u + 8u * (2 * NA + 2 * NW + 4);
+  const uint32_t vmask_off = tmem_slot_off + 16u;  // uint32[2][4]: valid-pixel bits of the tile, 32 pixels per word
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_al + tmem_slot_off);
 
   const int warp = threadIdx.x >> 5;
@@ -205,15 +208,15 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mtgemm_fwd_kernel(const __grid
         while (left > 0) {
           const int nit = left >= 2 ? 2 : 1;
           timed_wait(w_empty(ws), wph ^ 1u, prof ? &w1 : nullptr);
-          const uint32_t w_dst = w_base + (uint32_t)ws * kWStageBytes;
-          if (!(PROF && (p.dbg_flags & 4))) mbar_expect_tx(w_full(ws), (uint32_t)nit * kWTileBytes);
+          const uint32_t w_dst = w_base + (uint32_t)ws * w_stage_bytes;
+          if (!(PROF && (p.dbg_flags & 4))) mbar_expect_tx(w_full(ws), (uint32_t)nit * w_tile_bytes);
 #pragma unroll
           for (int i = 0; i < 2; ++i) {
             if (i < nit) {
               const int kcol = c < p.chunks0 ? c * 64 : p.kofs1 + (c - p.chunks0) * 64;
               // row (K-major: output channel row; MN-major: K row) of the tap's block in the weight matrix
               const int wr = p.groups[g].w_idx[t] * p.w_rows_per_tap + rbase;
-              const uint32_t dst = w_dst + (uint32_t)i * kWTileBytes;
+              const uint32_t dst = w_dst + (uint32_t)i * w_tile_bytes;
               if (PROF && (p.dbg_flags & 4)) {
                 // bring-up: no weight traffic
               } else if (!W_MN) {
@@ -280,7 +283,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mtgemm_fwd_kernel(const __grid
           const int nit = left >= 2 ? 2 : 1;
           timed_wait(w_full(ws), wph, prof ? &w1 : nullptr);
           tc_fence_after();
-          const uint32_t w_lo = w_lo0 + (uint32_t)ws * (kWStageBytes >> 4);
+          const uint32_t w_lo = w_lo0 + (uint32_t)ws * (w_stage_bytes >> 4);
 #pragma unroll
           for (int i = 0; i < 2; ++i) {
             if (i < nit) {
@@ -290,18 +293,16 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mtgemm_fwd_kernel(const __grid
                 a_lo = a_lo0 + (uint32_t)as * (slab_bytes >> 4);
                 ks = c == tail_c0 ? tail_k0 : (c == tail_c1 ? tail_k1 : 4);
               }
-              const uint64_t wd = w_hi | (uint64_t)(w_lo + (uint32_t)i * (kWTileBytes >> 4));
+              const uint64_t wd = w_hi | (uint64_t)(w_lo + (uint32_t)i * (w_tile_bytes >> 4));
               const uint64_t xd = x_hi | (uint64_t)(a_lo + sh);
-              if (ks == 4) {
-                mma_bf16_ss(d_tmem, wd, xd, idesc, acc);
-                mma_bf16_ss(d_tmem, wd + w_step, xd + 2, idesc, 1u);
-                mma_bf16_ss(d_tmem, wd + 2 * w_step, xd + 4, idesc, 1u);
-                mma_bf16_ss(d_tmem, wd + 3 * w_step, xd + 6, idesc, 1u);
-              } else {
-#pragma unroll 1
-                for (int kk = 0; kk < ks; ++kk)
-                  mma_bf16_ss(d_tmem, wd + (uint64_t)kk * w_step, xd + (uint64_t)(2 * kk), idesc, kk ? 1u : acc);
-              }
+              // 1..4 K=16 steps, descriptor offsets as immediates.  (A rolled loop for the short tail chunks cost
+              // ~215 cycles per MMA - R2UR + 64-bit multiply chains per iteration - which made level 0, where half of
+              // the items are 2-step tails of the 96-channel K, issue-bound: 161 cycles per MMA with nothing else
+              // running, profiles/r02_fwd_ablation.txt.)
+              mma_bf16_ss(d_tmem, wd, xd, idesc, acc);
+              if (ks >= 2) mma_bf16_ss(d_tmem, wd + w_step, xd + 2, idesc, 1u);
+              if (ks >= 3) mma_bf16_ss(d_tmem, wd + 2 * w_step, xd + 4, idesc, 1u);
+              if (ks >= 4) mma_bf16_ss(d_tmem, wd + 3 * w_step, xd + 6, idesc, 1u);
               acc = 1u;
               if (++t == ntaps) {  // last tap of the chunk: the slab is free once these MMAs retire
                 if (CL2) mma_commit_multicast(a_empty(as), (uint16_t)3);
@@ -334,14 +335,25 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mtgemm_fwd_kernel(const __grid
     __syncwarp();
   } else if (warp >= 4) {
     // ===== epilogue =====
+    // Thread = output channel (TMEM lane).  The 128 pixels of this half are read in four blocks of 32 columns, the
+    // tcgen05.ld of block k+1 in flight while block k is converted (the accumulator is released right after the last
+    // load has landed, not after the last conversion).  Conversion packs TWO pixels of the thread's channel per
+    // cvt.rn.bf16x2 (F2FP; the scalar form compiles to the quarter-rate F2F) and stores them as one 32-bit word:
+    // the staging buffer is laid out [pixel pair][channel] (4 B elements), so a warp's store is one conflict-free
+    // 128 B wavefront instead of two 64 B ones.  The row-wise copy-out un-interleaves the pairs with byte permutes.
     const int q = warp & 3;              // TMEM lane quarter: channels q*32 .. q*32+31 of the tile
     const int half = (warp - 4) >> 2;    // pixel half: columns half*128 .. +127
     const int et = threadIdx.x - 128 - half * 128;  // 0..127 inside the half
     const int ch_local = q * 32 + lane;
-    __nv_bfloat16* stg = reinterpret_cast<__nv_bfloat16*>(smem_al + stg_off + (uint32_t)half * stg_half);
+    const int CS = p.stg_ch;             // channels per staging row (128, or the tensor's width for a single narrow tile)
+    uint32_t* stg = reinterpret_cast<uint32_t*>(smem_al + stg_off + (uint32_t)half * stg_half);
     int* orow_s = reinterpret_cast<int*>(smem_al + orow_off) + half * 128;
+    volatile uint32_t* vm_s = reinterpret_cast<volatile uint32_t*>(smem_al + vmask_off) + half * 4;
+    const bool st_ok = ch_local < CS;
     const int plane = p.map.Hp * p.map.Wp;
     const bool prof_e = prof && warp == 4 && lane == 0;
+    const bool do_stats = p.stats != nullptr;
+    const bool do_relu = p.relu != 0;
     int acs = 0;
     uint32_t acph = 0;
     float s_sum = 0.f, s_sq = 0.f;
@@ -374,6 +386,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mtgemm_fwd_kernel(const __grid
 #pragma unroll
       for (int j = 0; j < 8; ++j) cs[j] = cy[j] = 0.f;
     };
+    const int SP = p.stg_px;
     for (int tile = unit0; tile < total_tiles; tile += unit_step) {
       const int m0 = pix_tile(tile) * kPT;
       const int n0 = ch_tile(tile) * 128;
@@ -382,7 +395,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mtgemm_fwd_kernel(const __grid
         flush_red();
         cs_ch = n0 + (lane & 15) * 8;
       }
-      if (p.stats && ch != s_ch) {  // channel tile changed: flush the register accumulators
+      if (do_stats && ch != s_ch) {  // channel tile changed: flush the register accumulators
         if (s_ch >= 0 && s_ch < p.n_valid) {
           atomicAdd(p.stats + s_ch, (double)s_sum);
           atomicAdd(p.stats + p.n_valid + s_ch, (double)s_sq);
@@ -390,7 +403,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mtgemm_fwd_kernel(const __grid
         s_sum = s_sq = 0.f;
         s_ch = ch;
       }
-      // output row (or -1) of pixel `et` of this half
+      // output row (or -1) of pixel `et` of this half, and the half's valid-pixel bit masks
       {
         const int m = m0 + half * 128 + et;
         int orow = -1;
@@ -404,6 +417,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mtgemm_fwd_kernel(const __grid
                    (p.map.s * (xa - 1) + p.map.px + 1);
         }
         orow_s[et] = orow;
+        const uint32_t bal = __ballot_sync(0xffffffffu, orow >= 0);
+        if (lane == 0) vm_s[q] = bal;
       }
       named_bar_sync(1 + half, 128);
       timed_wait(tfull_bar(acs), acph, prof_e ? &w0 : nullptr);
@@ -419,79 +434,132 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mtgemm_fwd_kernel(const __grid
         if (++acs == 2) { acs = 0; acph ^= 1u; }
         continue;
       }
-      // the 128 pixels of this half go through a small staging buffer in passes of SP = 64 or 32 pixels (16 / 8 KB
-      // per half): a 32 KB buffer per half would cost the weight ring its third stage, and for deep-K layers the
-      // 8 KB variant pays for a third activation slab
-      const int SP = p.stg_px, rows_w = SP >> 2;
-      for (int px0 = 0; px0 < 128; px0 += SP) {
-        if (px0) named_bar_sync(1 + half, 128);  // copy-out of the previous pass is done with the staging buffer
-        // a warp whose 32 channels all lie beyond the tensor (90 channels in a 128-row tile: warp q = 3) has nothing
-        // to convert or stage; it still takes part in the barriers and in the row-wise copy-out below
-        for (int c0 = 0; c0 < SP && warp_live; c0 += 32) {
-          uint32_t r[2][16];
-          tmem_ld16(t_row + (uint32_t)(px0 + c0), r[0]);  // two loads in flight before the wait
-          tmem_ld16(t_row + (uint32_t)(px0 + c0) + 16u, r[1]);
+      const int nchunk = min(16, (p.n_valid - n0 + 7) >> 3);
+      const int sub = lane >> 4, chunk = lane & 15;
+      const int pairs_w = SP >> 3;  // pixel pairs copied out by one warp per pass (SP / 2 pairs over 4 warps)
+
+      // one 32-pixel block of this thread's channel: bias + ReLU, bf16x2 packing, staging store, BatchNorm statistics
+      auto convert = [&](const uint32_t (&r)[2][16], int blk) {
+        const int pp0 = ((blk * 32) & (SP - 1)) >> 1;  // first pixel pair of the block inside the pass
+        const uint32_t vm = do_stats ? vm_s[blk] : 0u;
+        const bool all_valid = vm == 0xffffffffu;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            float v0 = __uint_as_float(r[h][2 * jj]) + bias;
+            float v1 = __uint_as_float(r[h][2 * jj + 1]) + bias;
+            if (do_relu) {
+              v0 = fmaxf(v0, 0.f);
+              v1 = fmaxf(v1, 0.f);
+            }
+            const __nv_bfloat162 pk = __floats2bfloat162_rn(v0, v1);  // .x (low half) = even pixel
+            const uint32_t u = *reinterpret_cast<const uint32_t*>(&pk);
+            if (st_ok) stg[(pp0 + h * 8 + jj) * CS + ch_local] = u;
+            if (do_stats) {
+              const float f0 = __uint_as_float(u << 16), f1 = __uint_as_float(u & 0xffff0000u);
+              if (all_valid) {
+                s_sum += f0;
+                s_sq = fmaf(f0, f0, s_sq);
+                s_sum += f1;
+                s_sq = fmaf(f1, f1, s_sq);
+              } else {
+                if ((vm >> (h * 16 + 2 * jj)) & 1u) {
+                  s_sum += f0;
+                  s_sq = fmaf(f0, f0, s_sq);
+                }
+                if ((vm >> (h * 16 + 2 * jj + 1)) & 1u) {
+                  s_sum += f1;
+                  s_sq = fmaf(f1, f1, s_sq);
+                }
+              }
+            }
+          }
+        }
+      };
+      // one stored row chunk: ReLU-backward mask, 16-byte store, optional column reductions
+      auto store_chunk = [&](int orow, uint4 val, uint4 mk) {
+        const long long o = (long long)orow;
+        if (p.mask) {
+          const __nv_bfloat16* mb = reinterpret_cast<const __nv_bfloat16*>(&mk);
+          __nv_bfloat16* vb = reinterpret_cast<__nv_bfloat16*>(&val);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (!(__bfloat162float(mb[j]) > 0.f)) vb[j] = __float2bfloat16_rn(0.f);
+        }
+        *reinterpret_cast<uint4*>(p.out + o * p.ldo + n0 + chunk * 8) = val;
+        if (do_red) {
+          const __nv_bfloat16* vb = reinterpret_cast<const __nv_bfloat16*>(&val);
+          float vf[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            vf[j] = __bfloat162float(vb[j]);
+            cs[j] += vf[j];
+          }
+          const int rc = n0 + chunk * 8 - p.red_col0;
+          if (p.red_y && rc >= 0 && rc < p.red_C) {
+            const uint4 yk = *reinterpret_cast<const uint4*>(p.red_y + o * p.red_ldy + rc);
+            const __nv_bfloat16* yb = reinterpret_cast<const __nv_bfloat16*>(&yk);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) cy[j] = fmaf(vf[j], __bfloat162float(yb[j]), cy[j]);
+          }
+        }
+      };
+      // row-wise copy-out of one pass: a warp instruction covers 2 pixel pairs x 16 chunks of 8 channels; every thread
+      // reads its 8 channels x 2 pixels (32 B), splits them into the even and the odd pixel's 16 bytes and stores both
+      auto copy_out = [&](int px0) {
+#pragma unroll 2
+        for (int pp = q * pairs_w + sub; pp < (q + 1) * pairs_w; pp += 2) {
+          const int o0 = orow_s[px0 + 2 * pp], o1 = orow_s[px0 + 2 * pp + 1];
+          if (chunk < nchunk && (o0 >= 0 || o1 >= 0)) {
+            const uint4 lo = *reinterpret_cast<const uint4*>(stg + pp * CS + chunk * 8);
+            const uint4 hi = *reinterpret_cast<const uint4*>(stg + pp * CS + chunk * 8 + 4);
+            uint4 mk0 = make_uint4(0, 0, 0, 0), mk1 = mk0;
+            if (p.mask) {  // both mask loads are issued before either is used
+              if (o0 >= 0) mk0 = *reinterpret_cast<const uint4*>(p.mask + (long long)o0 * p.ldm + n0 + chunk * 8);
+              if (o1 >= 0) mk1 = *reinterpret_cast<const uint4*>(p.mask + (long long)o1 * p.ldm + n0 + chunk * 8);
+            }
+            uint4 ev, od;
+            ev.x = __byte_perm(lo.x, lo.y, 0x5410); od.x = __byte_perm(lo.x, lo.y, 0x7632);
+            ev.y = __byte_perm(lo.z, lo.w, 0x5410); od.y = __byte_perm(lo.z, lo.w, 0x7632);
+            ev.z = __byte_perm(hi.x, hi.y, 0x5410); od.z = __byte_perm(hi.x, hi.y, 0x7632);
+            ev.w = __byte_perm(hi.z, hi.w, 0x5410); od.w = __byte_perm(hi.z, hi.w, 0x7632);
+            if (o0 >= 0) store_chunk(o0, ev, mk0);
+            if (o1 >= 0) store_chunk(o1, od, mk1);
+          }
+        }
+      };
+      // a warp whose 32 channels all lie beyond the tensor (90 channels in a 128-row tile: warp q = 3) has nothing to
+      // load, convert or stage; it still takes part in the barriers and in the row-wise copy-out
+      auto step = [&](const uint32_t (&cur)[2][16], uint32_t (&nxt)[2][16], int blk) {
+        const int pxb = blk * 32;
+        if (blk && (pxb & (SP - 1)) == 0) named_bar_sync(1 + half, 128);  // previous pass's copy-out is done with the staging buffer
+        if (warp_live) {
           tmem_ld_wait();
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float v = __uint_as_float(r[h][j]) + bias;
-              if (p.relu) v = fmaxf(v, 0.f);
-              const __nv_bfloat16 hb = __float2bfloat16_rn(v);
-              stg[(c0 + h * 16 + j) * 128 + ch_local] = hb;
-              if (p.stats && orow_s[px0 + c0 + h * 16 + j] >= 0) {
-                const float vr = __bfloat162float(hb);
-                s_sum += vr;
-                s_sq = fmaf(vr, vr, s_sq);
-              }
-            }
+          if (blk < 3) {
+            tmem_ld16(t_row + (uint32_t)(pxb + 32), nxt[0]);
+            tmem_ld16(t_row + (uint32_t)(pxb + 48), nxt[1]);
           }
         }
-        if (px0 + SP == 128) {
+        if (blk == 3) {
           tc_fence_before();
-          mbar_arrive(tempty_bar(acs));  // accumulator drained: the MMA warp may start the next tile
+          mbar_arrive(tempty_bar(acs));  // accumulator drained: the MMA warp may start the tile after next
         }
-        named_bar_sync(1 + half, 128);
-        // row-wise copy-out: 16 chunks of 16 B per pixel row (128 channels), 2 rows per warp instruction
-        {
-          const int nchunk = min(16, (p.n_valid - n0 + 7) >> 3);
-          const int sub = lane >> 4, chunk = lane & 15;
-          for (int r0 = q * rows_w; r0 < q * rows_w + rows_w; r0 += 2) {
-            const int rr = r0 + sub;
-            const int orow = orow_s[px0 + rr];
-            if (orow >= 0 && chunk < nchunk) {
-              uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 128 + chunk * 8);
-              const long long o = (long long)orow;
-              if (p.mask) {
-                const uint4 mk = *reinterpret_cast<const uint4*>(p.mask + o * p.ldm + n0 + chunk * 8);
-                const __nv_bfloat16* mb = reinterpret_cast<const __nv_bfloat16*>(&mk);
-                __nv_bfloat16* vb = reinterpret_cast<__nv_bfloat16*>(&val);
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                  if (!(__bfloat162float(mb[j]) > 0.f)) vb[j] = __float2bfloat16_rn(0.f);
-              }
-              *reinterpret_cast<uint4*>(p.out + o * p.ldo + n0 + chunk * 8) = val;
-              if (do_red) {
-                const __nv_bfloat16* vb = reinterpret_cast<const __nv_bfloat16*>(&val);
-                float vf[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  vf[j] = __bfloat162float(vb[j]);
-                  cs[j] += vf[j];
-                }
-                const int rc = n0 + chunk * 8 - p.red_col0;
-                if (p.red_y && rc >= 0 && rc < p.red_C) {
-                  const uint4 yk = *reinterpret_cast<const uint4*>(p.red_y + o * p.red_ldy + rc);
-                  const __nv_bfloat16* yb = reinterpret_cast<const __nv_bfloat16*>(&yk);
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) cy[j] = fmaf(vf[j], __bfloat162float(yb[j]), cy[j]);
-                }
-              }
-            }
-          }
+        if (warp_live) convert(cur, blk);
+        if (((pxb + 32) & (SP - 1)) == 0) {
+          named_bar_sync(1 + half, 128);
+          copy_out(pxb + 32 - SP);
         }
+      };
+      uint32_t ra[2][16], rb[2][16];
+      if (warp_live) {
+        tmem_ld16(t_row, ra[0]);
+        tmem_ld16(t_row + 16u, ra[1]);
       }
+      step(ra, rb, 0);
+      step(rb, ra, 1);
+      step(ra, rb, 2);
+      step(rb, ra, 3);
       named_bar_sync(1 + half, 128);  // staging + row table are reused by the next tile
       if (prof_e) w1 += clock64() - te0;
       if (++acs == 2) { acs = 0; acph ^= 1u; }
@@ -829,9 +897,16 @@ int fwd_setup(FwdParams& p, const FwdDesc& d) {
     p.kofs1 = d.C0;
   }
   p.w_mn = d.w_mn ? 1 : 0;
+  // A conv with a single, narrow channel tile (level 0: 96 physical channels) loads weight tiles of exactly its own
+  // rows and stages its outputs at its own width: 12 instead of 16 KB per tile and per 64-pixel staging pass, which is
+  // what pays for a third activation slab there.  (The MMA still reads 128 A rows; accumulator rows beyond the tensor
+  // are never stored, and rows of an MMA are independent.)
+  const int narrow = (d.n_phys < 128 && d.n_phys % 8 == 0) ? d.n_phys : 128;
+  p.stg_ch = narrow;
+  p.w_tile_bytes = d.w_mn ? (int)kWTileBytes : narrow * 128;
   if (!d.w_mn) {
     MPU_TRY(make_tmap_2d(&p.tmW, d.W, (uint64_t)d.w_taps * d.n_phys, (uint64_t)d.k_total,
-                         (uint64_t)d.k_total, 64, 128));
+                         (uint64_t)d.k_total, 64, narrow));
   } else {
     MPU_TRY(make_tmap_2d(&p.tmW, d.W, (uint64_t)d.w_taps * d.w_rows, (uint64_t)d.n_phys,
                          (uint64_t)d.n_phys, 64, 64));
@@ -864,7 +939,7 @@ int fwd_setup(FwdParams& p, const FwdDesc& d) {
   // what makes the tall slab fit
   const int budget = kSmemBudget - smem_reserve();
   auto fits = [&](int S, int stg_px) {
-    return 2 * slab_rows_for(S) * 128 + 3 * (int)kWStageBytes + 2 * stg_px * 256 + 1024 <= budget;
+    return 2 * slab_rows_for(S) * 128 + 3 * 2 * p.w_tile_bytes + 2 * stg_px * p.stg_ch * 2 + 1024 <= budget;
   };
   int bestS = 7;
   long long best_cost = (long long)count_groups(7, 3) * slab_rows_for(7);
@@ -952,13 +1027,28 @@ int launch_fwd(FwdParams& p, cudaStream_t stream) {
   // Measured alternative (MPU_FWD_NA=3 MPU_FWD_SP=32: a third slab paid for by 32-pixel passes): the MMA thread's
   // a_full waits drop from 12-20 % to 4 %, but its w_full waits rise by as much - no net gain on levels 2-3, 5 %
   // slower at 16x16 (profiles/r02_perf_gemm_pairs.txt).
-  int NA = 2;
-  if (const char* e = getenv("MPU_FWD_NA")) NA = atoi(e);  // bring-up override
-  if (NA >= 3 && p.ext_rows == 0) p.stg_px = 32;
-  if (const char* e = getenv("MPU_FWD_SP")) p.stg_px = atoi(e) == 32 ? 32 : 64;
-  const int fixed = 2 * p.stg_px * 256 + 1024;  // epilogue staging + row table
+  // Round 2, session 2 (profiles/r02_perf_gemm_epilogue.txt): where a slab serves only the 3 taps of one kernel row
+  // (levels 0-1: 6-12 MMAs per slab) two slab slots do not cover the refill round trip - the MMA thread waited 14-23 %
+  // of its time on a_full - so those convs take a THIRD slab whenever three weight stages still fit, with 32-pixel
+  // staging passes if that is what it takes.
   const int budget = kSmemBudget - smem_reserve();
-  int NW = (budget - fixed - NA * p.slab_rows * 128) / (int)kWStageBytes;   // stages of two weight tiles
+  const int stage_bytes = 2 * p.w_tile_bytes;
+  auto fixed_for = [&](int sp) { return 2 * sp * p.stg_ch * 2 + 1024; };  // epilogue staging + row table
+  auto nw_for = [&](int na, int sp) { return (budget - fixed_for(sp) - na * p.slab_rows * 128) / stage_bytes; };
+  int NA = 2;
+  if (const char* e = getenv("MPU_FWD_NA")) {  // bring-up override
+    NA = atoi(e);
+    if (NA >= 3 && p.ext_rows == 0) p.stg_px = 32;
+  } else if (p.ext_rows == 0) {
+    if (nw_for(3, p.stg_px) >= 3) {
+      NA = 3;
+    } else if (nw_for(3, 32) >= 3) {
+      NA = 3;
+      p.stg_px = 32;
+    }
+  }
+  if (const char* e = getenv("MPU_FWD_SP")) p.stg_px = atoi(e) == 32 ? 32 : 64;
+  int NW = nw_for(NA, p.stg_px);   // stages of two weight tiles
   if (NW > 8) NW = 8;
   p.items_per_tile = 0;
   for (int g = 0; g < p.ngroups; ++g) p.items_per_tile += p.groups[g].ntaps * (p.chunks0 + p.chunks1);

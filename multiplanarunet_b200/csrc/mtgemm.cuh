@@ -71,6 +71,8 @@ struct FwdParams {
   int red_ldy, red_col0, red_C;  //   sum g and sum g*y when this GEMM produces the gradient g at a BN output)
   int a_slots, w_slots;          // slab ring slots; weight ring stages (two tiles each)
   int stg_px;                    // pixels per epilogue staging pass (64 or 32)
+  int stg_ch;                    // channels per staging row: 128, or the tensor's own width for a single narrow tile
+  int w_tile_bytes;              // one weight tile in the ring: 16 KB, or (K-major, single narrow tile) n_phys x 128 B
   int items_per_tile;            // (group, chunk, tap) items of one output tile = weight tiles streamed per tile
   long long* dbg;                // optional [8] cycle counters written by CTA 0 (bring-up profiling)
   int dbg_flags;                 // bring-up only (env MPU_FWD_DEBUG): 1 = epilogue drains nothing, 2 = no slab loads,

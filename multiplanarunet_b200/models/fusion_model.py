@@ -146,9 +146,10 @@ class FusionModel(object):
         """Mean dice loss (without regulariser) over a point set, no update (validation_split of the reference's fit)."""
         import torch
         acc = torch.zeros_like(self._accum)
-        check(lib.mpu_fusion_grad_indexed(_C.ptr(X), _C.ptr(y), _C.ptr(None), ctypes.c_longlong(int(X.shape[0])),
-                                          self.n_inputs, self.n_classes, _C.ptr(self.W), _C.ptr(self.b), _C.ptr(acc),
-                                          _C.current_stream()), "mpu_fusion_grad_indexed")
+        if int(X.shape[0]) > 0:
+            check(lib.mpu_fusion_grad_indexed(_C.ptr(X), _C.ptr(y), _C.ptr(None), ctypes.c_longlong(int(X.shape[0])),
+                                              self.n_inputs, self.n_classes, _C.ptr(self.W), _C.ptr(self.b), _C.ptr(acc),
+                                              _C.current_stream()), "mpu_fusion_grad_indexed")
         tot = torch.stack([acc[-1], torch.tensor(float(X.shape[0]), dtype=torch.float64, device=self.device)])
         if self._distributed():
             torch.distributed.all_reduce(tot)
