@@ -603,9 +603,16 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
                : "memory");
 }
 
+// PROF: CTA 0 writes role timings to p.dbg (bring-up only): [0] producer waits on empty slots, [1] MMA thread waits on
+// full slots, [2] start -> all MMAs retired, [3] accumulator drain (TMEM -> red.global), [4] whole CTA, [5] prologue,
+// [6] K blocks of the CTA.
+template <bool PROF>
 __global__ void __launch_bounds__(kThreads, 1)
     mtgemm_wgrad_kernel(const __grid_constant__ WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
+  const bool prof = PROF && p.dbg != nullptr && blockIdx.x == 0;
+  const long long t_start = prof ? clock64() : 0;
+  long long pw = 0;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int S = p.stages;
   const int CA = p.CA;
@@ -624,15 +631,28 @@ __global__ void __launch_bounds__(kThreads, 1)
   // work decomposition: the CTAs that read the same pixel range (all kernel rows, output-channel tiles and
   // input-channel tiles of one K split) are neighbours in the grid, so they run in the same wave and share the
   // X / dY lines through L2 instead of re-streaming them from HBM (round 1: 2.4x the algorithmic DRAM bytes)
+  // Two regions: CTAs of the FULL ci tiles (CA atoms) first, then those of the partial last ci tile (fewer atoms:
+  // less work per K block), which get correspondingly longer K ranges so that every CTA of the grid
+  // runs for about the same time (wgrad_setup sizes both so that the grid fills whole waves).
   int w = blockIdx.x;
+  const int n_region1 = p.ngroups * p.co_tiles * p.ci_tiles_full * p.splits;
+  const bool part = w >= n_region1;
+  if (part) w -= n_region1;
   const int gi = w % p.ngroups;   w /= p.ngroups;
   const int co_t = w % p.co_tiles; w /= p.co_tiles;
-  const int ci_t = w % p.ci_tiles; w /= p.ci_tiles;
-  const int split = w;
+  int ci_t, split;
+  if (!part) {
+    ci_t = w % p.ci_tiles_full;
+    split = w / p.ci_tiles_full;
+  } else {
+    ci_t = p.ci_tiles_full;
+    split = w;
+  }
+  const int kbps = part ? p.kblocks_per_split_part : p.kblocks_per_split;
   const WgradGroup& grp = p.groups[gi];
   const int ci0 = ci_t * CA * 64, co0 = co_t * 128;
-  const int kb0 = split * p.kblocks_per_split;
-  const int kb1 = min(p.kblocks, kb0 + p.kblocks_per_split);
+  const int kb0 = split * kbps;
+  const int kb1 = min(p.kblocks, kb0 + kbps);
   const int nkb = max(0, kb1 - kb0);
   const int ncol = 64 * grp.ntaps;  // accumulator columns per ci atom (MMA N)
   // the last ci tile may hold fewer than CA atoms (181 channels = 3 atoms = tiles of 2 + 1): no loads, MMAs or
@@ -660,6 +680,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  const long long t_setup = prof ? clock64() : 0;
 
   if (warp == 0) {
     // TMA producer: one elected thread runs the whole role
@@ -668,7 +689,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       uint32_t ph = 0;
       for (int kb = kb0; kb < kb1; ++kb) {
         const int r0 = kb * 64;
-        mbar_wait(empty_bar(s), ph ^ 1u);
+        timed_wait(empty_bar(s), ph ^ 1u, prof ? &pw : nullptr);
         const uint32_t st = smem_base + (uint32_t)s * stage_bytes;
         // the second 64-channel half of the dY tile is not fetched when it lies beyond the tensor (its accumulator
         // rows are never stored; rows of an MMA are independent)
@@ -679,6 +700,11 @@ __global__ void __launch_bounds__(kThreads, 1)
           tma_load_2d(&p.tmX, full_bar(s), st + kWgABytes + (uint32_t)a * kWgAtomBytes, ci0 + a * 64,
                       r0 + grp.x_off);
         if (++s == S) { s = 0; ph ^= 1u; }
+      }
+      if (prof) {
+        p.dbg[0] = pw;
+        p.dbg[5] = t_setup - t_start;
+        p.dbg[6] = nkb;
       }
     }
     __syncwarp();
@@ -694,7 +720,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       uint32_t ph = 0;
       uint32_t acc = 0;
       for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait(full_bar(s), ph);
+        timed_wait(full_bar(s), ph, prof ? &pw : nullptr);
         tc_fence_after();
         const uint32_t st_lo = lo0 + (uint32_t)s * (stage_bytes >> 4);
         const uint64_t ad = a_hi | (uint64_t)st_lo;
@@ -711,37 +737,55 @@ __global__ void __launch_bounds__(kThreads, 1)
         if (++s == S) { s = 0; ph ^= 1u; }
       }
       mma_commit(done_bar);
+      if (prof) p.dbg[1] = pw;
     }
     __syncwarp();
-  } else if (warp >= 4) {
-    const int q = warp & 3;
+  }
+
+  // Accumulator drain by ALL eight warps (the producer / MMA / allocator warps have nothing left to do): warp w reads
+  // TMEM lane quarter w % 4 and every second 32-column block (w / 4), two tcgen05.ld in flight per wait, and adds the
+  // values into the flat gradient with 16-byte vector reductions.  A CTA's drain is serial with its main loop (384
+  // accumulator columns leave no room for a second buffer), so its length is pure overhead: 13-22k cycles with four
+  // warps and one load per wait (profiles/r02_perf_wgrad_waves.txt).
+  {
+    const int q = warp & 3, hsel = warp >> 2;
     mbar_wait(done_bar, 0);
     tc_fence_after();
-    if (nkb > 0) {
-      const int co = co0 + q * 32 + lane;
+    const long long t_done = (prof && warp == 4 && lane == 0) ? clock64() : 0;
+    const int co = co0 + q * 32 + lane;
+    const bool warp_live = co0 + q * 32 < p.co_valid;
+    if (nkb > 0 && warp_live) {
       for (int a = 0; a < CAh; ++a) {
         for (int j = 0; j < grp.ntaps; ++j) {
           // tap j sits at slab shift grp.shift[j] (shifts are consecutive 0..ntaps-1 by construction)
           const int tw = grp.w_idx[j];
+          const int cb = hsel * 32;  // this warp's 32-column block of the tap's 64 channels
           const uint32_t t_row =
-              tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * ncol + grp.shift[j] * 64);
-          float* row = p.dW + ((size_t)tw * p.w_rows_per_tap + co) * p.ldw + p.dw_col0 + ci0 + a * 64;
-          for (int c0 = 0; c0 < 64; c0 += 16) {
-            uint32_t r[16];
-            tmem_ld16(t_row + (uint32_t)c0, r);
-            tmem_ld_wait();
-            if (co < p.co_valid) {
+              tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * ncol + grp.shift[j] * 64 + cb);
+          float* row = p.dW + ((size_t)tw * p.w_rows_per_tap + co) * p.ldw + p.dw_col0 + ci0 + a * 64 + cb;
+          const int ci_base = ci0 + a * 64 + cb;
+          if (ci_base >= p.ci_valid) continue;  // (warp-uniform)
+          uint32_t r[2][16];
+          tmem_ld16(t_row, r[0]);
+          tmem_ld16(t_row + 16u, r[1]);
+          tmem_ld_wait();
+          if (co < p.co_valid) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
 #pragma unroll
               for (int v4 = 0; v4 < 4; ++v4) {
-                const int ci = ci0 + a * 64 + c0 + v4 * 4;
+                const int ci = ci_base + h * 16 + v4 * 4;
                 if (ci < p.ci_valid)  // ci_valid is a multiple of 8
-                  red_add_v4(row + c0 + v4 * 4, __uint_as_float(r[v4 * 4 + 0]), __uint_as_float(r[v4 * 4 + 1]),
-                             __uint_as_float(r[v4 * 4 + 2]), __uint_as_float(r[v4 * 4 + 3]));
+                  red_add_v4(row + h * 16 + v4 * 4, __uint_as_float(r[h][v4 * 4 + 0]), __uint_as_float(r[h][v4 * 4 + 1]),
+                             __uint_as_float(r[h][v4 * 4 + 2]), __uint_as_float(r[h][v4 * 4 + 3]));
               }
-            }
           }
         }
       }
+    }
+    if (prof && warp == 4 && lane == 0) {
+      p.dbg[2] = t_done - t_start;
+      p.dbg[3] = clock64() - t_done;
     }
   }
 
@@ -751,6 +795,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
+  if (prof && threadIdx.x == 0) p.dbg[4] = clock64() - t_start;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1167,12 +1212,73 @@ int wgrad_setup(WgradParams& p, const WgradDesc& d) {
   p.ci_tiles = (atoms + p.CA - 1) / p.CA;
   p.co_tiles = (d.Cy + 127) / 128;
   p.kblocks = (int)((d.rows_total + 63) / 64);
-  const int base = p.ci_tiles * p.co_tiles * p.ngroups;
-  int splits = d.splits > 0 ? d.splits : (2 * num_sms() + base - 1) / base;
-  if (splits < 1) splits = 1;
-  if (splits > p.kblocks) splits = p.kblocks;
-  p.kblocks_per_split = (p.kblocks + splits - 1) / splits;
-  p.splits = (p.kblocks + p.kblocks_per_split - 1) / p.kblocks_per_split;
+  // Split-K sizing.  A CTA owns its SM (shared memory + 384-512 TMEM columns), so the grid runs in waves of num_sms
+  // CTAs and a wave lasts as long as its slowest CTA.  Measured (profiles/r02_perf_wgrad_waves.txt): the main loop
+  // runs at 98-99 % of the tensor pipe (777-788 cycles per K block of 8 N=192 MMAs), but round 1's rule "about 2 CTAs
+  // per SM" produced 297 CTAs on 148 SMs for two of the five levels - a third, almost empty wave, i.e. 2/3 of the rate.
+  // Now: the partial last ci tile (181 channels = 2 + 1 atoms) gets K ranges longer by CA / its atom count, and the K
+  // range L per full CTA is the one that minimises  waves(L) x (L x cycles per K block + per-CTA overhead)  over
+  // the wave counts 1..12 (overhead = prologue + accumulator drain, ~12k cycles).
+  const int part_atoms = atoms % p.CA;                     // atoms of the partial ci tile (0: none)
+  p.ci_tiles_full = atoms / p.CA;
+  const int units_full = p.ci_tiles_full * p.co_tiles * p.ngroups;
+  const int units_part = part_atoms ? p.co_tiles * p.ngroups : 0;
+  auto ceil_div = [](long long a, long long b) { return (int)((a + b - 1) / b); };
+  // cycles per K block of a CTA with n atoms: the larger of its MMA time and of its operand bytes at the ~45 B/cycle a
+  // single SM pulls through TMA (a one-atom CTA still loads the whole 16 KB dY tile: it is load-bound at ~570 cycles,
+  // not the 384 its MMAs need)
+  int max_taps = 1;
+  for (int g = 0; g < p.ngroups; ++g) max_taps = p.groups[g].ntaps > max_taps ? p.groups[g].ntaps : max_taps;
+  auto cyc_kb_for = [&](int n_atoms) {
+    const double mma = n_atoms * 4.0 * (max_taps >= 2 ? 32.0 * max_taps : 64.0);
+    const double load = ((d.Cy > 64 ? 16384.0 : 8192.0) + n_atoms * (double)kWgAtomBytes) / 45.0;
+    return mma > load ? mma : load;
+  };
+  const double cyc_kb = cyc_kb_for(p.CA);
+  auto part_len = [&](int L) { return part_atoms ? (int)(L * cyc_kb / cyc_kb_for(part_atoms)) : L; };
+  auto ctas_for = [&](int L) {
+    return (long long)units_full * ceil_div(p.kblocks, L) +
+           (units_part ? (long long)units_part * ceil_div(p.kblocks, part_len(L)) : 0);
+  };
+  int L;
+  static int old_rule = -1;  // MPU_WG_OLD_SPLITS=1: round 1's "about two CTAs per SM" (same-box A/B measurements)
+  if (old_rule < 0) {
+    const char* e = getenv("MPU_WG_OLD_SPLITS");
+    old_rule = e ? atoi(e) : 0;
+  }
+  const int fixed_splits = d.splits > 0 ? d.splits
+                           : (old_rule ? (2 * num_sms() + p.ci_tiles * p.co_tiles * p.ngroups - 1) /
+                                             (p.ci_tiles * p.co_tiles * p.ngroups)
+                                       : 0);
+  if (fixed_splits > 0) {  // caller-fixed split count (tests): the same K range for every tile
+    int splits = fixed_splits > p.kblocks ? p.kblocks : fixed_splits;
+    L = ceil_div(p.kblocks, splits);
+    p.kblocks_per_split = L;
+    p.kblocks_per_split_part = L;
+  } else {
+    const double overhead = 12000.0;
+    const int sms = num_sms();
+    double best_t = 1e300;
+    L = p.kblocks;
+    for (int k = 1; k <= 12; ++k) {
+      int lo = 1, hi = p.kblocks;  // smallest K range whose grid fits k waves
+      if (ctas_for(hi) > (long long)k * sms) continue;
+      while (lo < hi) {
+        const int mid = (lo + hi) / 2;
+        if (ctas_for(mid) <= (long long)k * sms) hi = mid;
+        else lo = mid + 1;
+      }
+      const double t = (double)ceil_div(ctas_for(lo), sms) * (lo * cyc_kb + overhead);
+      if (t < best_t * 0.999) {
+        best_t = t;
+        L = lo;
+      }
+    }
+    p.kblocks_per_split = L;
+    p.kblocks_per_split_part = part_len(L) > p.kblocks ? p.kblocks : part_len(L);
+  }
+  p.splits = ceil_div(p.kblocks, p.kblocks_per_split);
+  p.splits_part = units_part ? ceil_div(p.kblocks, p.kblocks_per_split_part) : 0;
   p.dW = d.dW;
   p.ldw = d.ldw;
   p.w_rows_per_tap = d.w_rows_per_tap;
@@ -1190,13 +1296,15 @@ int launch_wgrad(WgradParams& p, cudaStream_t stream) {
   }
   p.stages = S;
   if (!g_wgrad_attr_set[cur_dev()]) {
-    MPU_CUDA(cudaFuncSetAttribute(mtgemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  kDynSmem));
+    MPU_CUDA(cudaFuncSetAttribute(mtgemm_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmem));
+    MPU_CUDA(cudaFuncSetAttribute(mtgemm_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmem));
     g_wgrad_attr_set[cur_dev()] = true;
   }
-  const int grid = p.ci_tiles * p.co_tiles * p.ngroups * p.splits;
+  const int grid = p.co_tiles * p.ngroups * (p.ci_tiles_full * p.splits + (p.ci_tiles - p.ci_tiles_full) * p.splits_part);
+  p.dbg = g_fwd_dbg;
   gemm_timer_begin(stream);
-  mtgemm_wgrad_kernel<<<grid, kThreads, kDynSmem - smem_reserve(), stream>>>(p);
+  if (p.dbg) mtgemm_wgrad_kernel<true><<<grid, kThreads, kDynSmem - smem_reserve(), stream>>>(p);
+  else mtgemm_wgrad_kernel<false><<<grid, kThreads, kDynSmem - smem_reserve(), stream>>>(p);
   gemm_timer_end(stream);
   count_launch();
   MPU_CUDA(cudaGetLastError());

@@ -111,9 +111,12 @@ struct WgradParams {
   WgradGroup groups[kMaxTaps];
   int CA;                        // 64-channel ci atoms per CTA (1 or 2)
   int ci_atoms;                  // 64-channel atoms of X in total (the last ci tile may hold fewer than CA)
-  int ci_tiles, co_tiles, splits;  // ci tiles of CA*64 channels, co tiles of 128 channels
+  int ci_tiles, co_tiles, splits;  // ci tiles of CA*64 channels, co tiles of 128 channels; K splits of the full ci tiles
+  int ci_tiles_full;             // ci tiles that hold all CA atoms (the partial last one, if any, follows)
+  int splits_part;               // K splits of the partial ci tile (fewer: its CTAs do less MMA work per K block)
   int kblocks;                   // total 64-row K blocks
   int kblocks_per_split;
+  int kblocks_per_split_part;
   float* dW;                     // [tap][co][ldw] fp32, accumulated with vector reductions
   int ldw;
   int w_rows_per_tap;
@@ -121,6 +124,7 @@ struct WgradParams {
   int ci_valid, co_valid;
   int stages;
   int BN;                        // unused (kept for the bring-up API)
+  long long* dbg;                // optional [8] role timings of CTA 0 (bring-up profiling, see the kernel)
 };
 
 struct WgradDesc {

@@ -179,6 +179,17 @@ def perf_wgrad_case(B, H, W, Cin, Cout, iters=10):
     ms = a.elapsed_time(b) / iters
     fl = 2.0 * B * H * W * 9 * Cin * Cout
     print("  wgrad perf B=%d %dx%d %d->%d: %.3f ms  %.1f TFLOP/s (algorithmic)" % (B, H, W, Cin, Cout, ms, fl / ms / 1e9))
+    # role timings of CTA 0 (profiling instantiation)
+    cnt = torch.zeros(8, dtype=torch.int64, device=dev)
+    lib.mpu_debug_set_fwd_profile(ctypes.c_void_p(cnt.data_ptr()))
+    run()
+    torch.cuda.synchronize()
+    lib.mpu_debug_set_fwd_profile(ctypes.c_void_p(0))
+    c = cnt.cpu().tolist()
+    tot = max(c[4], 1)
+    print("   CTA0 cycles %d (prologue %d, MMAs retired at %d, drain %d) | %d K blocks, %.0f cycles each | producer waits "
+          "empty %.0f%% | mma waits full %.0f%%" %
+          (tot, c[5], c[2], c[3], c[6], (c[2] - c[5]) / max(c[6], 1), 100 * c[0] / tot, 100 * c[1] / tot))
     return True
 
 
