@@ -433,16 +433,19 @@ __global__ void bn_bwd_params_kernel(const double* __restrict__ sums, const floa
 }
 
 // ---- first conv (CUDA cores) -------------------------------------------------------------------------
-// thread = a column of kRows vertically adjacent pixels: their (kRows+2) x 3 x CIN inputs sit in registers, the
-// weights in shared memory as fp32 [9*CIN][co_phys] and are read as warp-wide broadcasts - one pair of 16-byte
-// weight reads now feeds kRows x 8 FMAs (the one-pixel version was bound by the shared-memory pipe); output
-// channels are produced 8 at a time (one 16-byte store per pixel).
+// thread = (8-channel group cg, row lane rl) like the other per-pixel kernels, a work item = a band of kRows image rows
+// x RL consecutive pixels: the thread holds the (kRows+2) x 3 x CIN inputs of its column of kRows pixels in registers
+// and reads the weights of ITS channel group from shared memory (fp32 [9*CIN][co_phys]; a warp reads 32-byte runs of
+// consecutive groups, conflict-free): one pair of 16-byte weight reads feeds kRows x 8 FMAs.  A warp stores
+// 512 contiguous bytes (the round-1 mapping, thread = pixel with a loop over channel groups, wrote 16-byte pieces
+// 192 bytes apart and ran at 1.6 TB/s; this kernel only writes: 0.4 GB at 256^2, batch 32).
 constexpr int kFirstRows = 4;
 
 template <int CIN>
-__global__ void conv_first_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
-                                  const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, Geo g,
-                                  int co_phys) {
+__global__ void __launch_bounds__(256)
+    conv_first_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
+                      const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, Geo g, int co_phys, int CG,
+                      int RL) {
   constexpr int R = kFirstRows;
   extern __shared__ float4 cw4[];  // [9*CIN][co_phys] + bias[co_phys]
   float* cw = reinterpret_cast<float*>(cw4);
@@ -455,13 +458,15 @@ __global__ void conv_first_kernel(const __nv_bfloat16* __restrict__ x, const __n
   float* sb = cw + 9 * CIN * co_phys;
   for (int i = threadIdx.x; i < co_phys; i += blockDim.x) sb[i] = bias[i];
   __syncthreads();
-  const int CG = co_phys / 8;
+  const int cg = threadIdx.x % CG, rl = threadIdx.x / CG;
   const int Wp = g.W + 2;
   const int bands = (g.H + R - 1) / R;
+  const float4 b0 = *reinterpret_cast<const float4*>(sb + cg * 8);
+  const float4 b1 = *reinterpret_cast<const float4*>(sb + cg * 8 + 4);
   SegIter it;
-  it.init(blockIdx.x, gridDim.x, bands, (g.W + blockDim.x - 1) / blockDim.x);
+  it.init(blockIdx.x, gridDim.x, bands, (g.W + RL - 1) / RL);
   for (; it.n < g.B; it.next()) {
-    const int xx = it.seg * blockDim.x + threadIdx.x;
+    const int xx = it.seg * RL + rl;
     if (xx >= g.W) continue;
     const int y0 = it.yy * R;  // first image row of the band
     // padded row of pixel (y0 - 1, xx - 1): top-left input of the band's first pixel
@@ -483,45 +488,39 @@ __global__ void conv_first_kernel(const __nv_bfloat16* __restrict__ x, const __n
         }
       }
     }
-    for (int cg = 0; cg < CG; ++cg) {
-      float acc[R][8];
-      {
-        const float4 b0 = *reinterpret_cast<const float4*>(sb + cg * 8);
-        const float4 b1 = *reinterpret_cast<const float4*>(sb + cg * 8 + 4);
+    float acc[R][8];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      acc[r][0] = b0.x; acc[r][1] = b0.y; acc[r][2] = b0.z; acc[r][3] = b0.w;
+      acc[r][4] = b1.x; acc[r][5] = b1.y; acc[r][6] = b1.z; acc[r][7] = b1.w;
+    }
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int k = 0; k < 3 * CIN; ++k) {
+        const float* wr = cw + ((ky * 3) * CIN + k) * co_phys + cg * 8;  // tap (ky, k / CIN), channel k % CIN
+        const float4 w0 = *reinterpret_cast<const float4*>(wr);
+        const float4 w1 = *reinterpret_cast<const float4*>(wr + 4);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          acc[r][0] = b0.x; acc[r][1] = b0.y; acc[r][2] = b0.z; acc[r][3] = b0.w;
-          acc[r][4] = b1.x; acc[r][5] = b1.y; acc[r][6] = b1.z; acc[r][7] = b1.w;
+          const float xv = xs[r + ky][k];
+          acc[r][0] = fmaf(xv, w0.x, acc[r][0]);
+          acc[r][1] = fmaf(xv, w0.y, acc[r][1]);
+          acc[r][2] = fmaf(xv, w0.z, acc[r][2]);
+          acc[r][3] = fmaf(xv, w0.w, acc[r][3]);
+          acc[r][4] = fmaf(xv, w1.x, acc[r][4]);
+          acc[r][5] = fmaf(xv, w1.y, acc[r][5]);
+          acc[r][6] = fmaf(xv, w1.z, acc[r][6]);
+          acc[r][7] = fmaf(xv, w1.w, acc[r][7]);
         }
       }
 #pragma unroll
-      for (int ky = 0; ky < 3; ++ky)
+    for (int r = 0; r < R; ++r) {
+      if (y0 + r < g.H) {
+        Vec8 o;
 #pragma unroll
-        for (int k = 0; k < 3 * CIN; ++k) {
-          const float* wr = cw + ((ky * 3) * CIN + k) * co_phys + cg * 8;  // tap (ky, k / CIN), channel k % CIN
-          const float4 w0 = *reinterpret_cast<const float4*>(wr);
-          const float4 w1 = *reinterpret_cast<const float4*>(wr + 4);
-#pragma unroll
-          for (int r = 0; r < R; ++r) {
-            const float xv = xs[r + ky][k];
-            acc[r][0] = fmaf(xv, w0.x, acc[r][0]);
-            acc[r][1] = fmaf(xv, w0.y, acc[r][1]);
-            acc[r][2] = fmaf(xv, w0.z, acc[r][2]);
-            acc[r][3] = fmaf(xv, w0.w, acc[r][3]);
-            acc[r][4] = fmaf(xv, w1.x, acc[r][4]);
-            acc[r][5] = fmaf(xv, w1.y, acc[r][5]);
-            acc[r][6] = fmaf(xv, w1.z, acc[r][6]);
-            acc[r][7] = fmaf(xv, w1.w, acc[r][7]);
-          }
-        }
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        if (y0 + r < g.H) {
-          Vec8 o;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) o.v[j] = fmaxf(acc[r][j], 0.f);
-          store8(out + (row0 + (long long)(r + 1) * Wp + 1) * co_phys + cg * 8, o);
-        }
+        for (int j = 0; j < 8; ++j) o.v[j] = fmaxf(acc[r][j], 0.f);
+        store8(out + (row0 + (long long)(r + 1) * Wp + 1) * co_phys + cg * 8, o);
       }
     }
   }
@@ -533,6 +532,8 @@ __global__ void conv_first_kernel(const __nv_bfloat16* __restrict__ x, const __n
 __global__ void __launch_bounds__(256)
     conv_first_wgrad_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dz, Geo g,
                             int co_phys, int CG, int RL, float* __restrict__ dW, int ldw) {
+  constexpr int U = 4;  // pixels per thread and iteration: U dz rows + 9 U input taps in flight (with one pixel per
+                        // iteration the kernel ran at 1.45 TB/s, bound by the latency of its single 16-byte load)
   extern __shared__ float wred[];  // [RL][CG*8]
   const int tid = threadIdx.x;
   const int cg = tid % CG, rl = tid / CG;
@@ -544,17 +545,39 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
   SegIter it;
-  it.init(blockIdx.x, gridDim.x, g.H, (g.W + RL - 1) / RL);
+  it.init(blockIdx.x, gridDim.x, g.H, (g.W + U * RL - 1) / (U * RL));
   for (; it.n < g.B; it.next()) {
-    const int xx = it.seg * RL + rl;
-    if (xx >= g.W) continue;
-    const long long row = ((long long)it.n * (g.H + 2) + it.yy + 1) * Wp + xx + 1;
-    const Vec8 d = load8(dz + row * co_phys + cg * 8);
+    const int x0 = it.seg * (U * RL) + rl;
+    const long long row0 = ((long long)it.n * (g.H + 2) + it.yy + 1) * Wp + x0 + 1;
+    uint4 dr[U];
+    __nv_bfloat16 xr[U][9];
 #pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      const float xv = __bfloat162float(x[(row + (t / 3 - 1) * Wp + (t % 3 - 1)) * 8 + ci]);
+    for (int u = 0; u < U; ++u) {
+      if (x0 + u * RL < g.W) {
+        const long long row = row0 + u * RL;
+        dr[u] = *reinterpret_cast<const uint4*>(dz + row * co_phys + cg * 8);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[t][j] = fmaf(d.v[j], xv, acc[t][j]);
+        for (int t = 0; t < 9; ++t) xr[u][t] = x[(row + (t / 3 - 1) * Wp + (t % 3 - 1)) * 8 + ci];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (x0 + u * RL < g.W) {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&dr[u]);
+        float d[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __bfloat1622float2(h[j]);
+          d[2 * j] = f.x;
+          d[2 * j + 1] = f.y;
+        }
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const float xv = __bfloat162float(xr[u][t]);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[t][j] = fmaf(d[j], xv, acc[t][j]);
+        }
+      }
     }
   }
 #pragma unroll
@@ -577,24 +600,30 @@ constexpr int kHeadTile = 256;  // pixels per block iteration (= blockDim)
 
 // NC > 0: number of classes known at compile time (class loops fully unrolled, no predication);
 // NC == 0: generic path for up to kMaxCls classes.
-// TRAIN: phase A, thread = pixel: logits, softmax, loss, dlogits, dx; phase B, thread = (channel pair,
-// pixel segment): dWh[c][ci] += sum_p dlogit[p][c] * x[p][ci] from the tile's x (bf16, shared memory).
+// A block iteration handles a tile of 256 pixels.  The tile's x rows are copied into shared memory COOPERATIVELY
+// (consecutive threads fetch consecutive 16-byte pieces: x rows of one image line are contiguous in memory), then
+// thread = pixel computes logits, softmax, loss and dlogits from its shared-memory row; TRAIN: thread = (channel pair,
+// pixel segment) accumulates dWh[c][ci] += sum_p dlogit[p][c] * x[p][ci] from the tile, thread = pixel overwrites its
+// row of the tile with dx = dlogit * Wh, and the tile is written back cooperatively.  (Round 1's version read and
+// wrote the 192-byte rows per thread - 16-byte pieces 192 bytes apart across a warp - and ran at 1.9 TB/s.)
+// tile_x == 0 (inference with very wide inputs whose tile does not fit shared memory): x is read per thread.
 template <bool TRAIN, int NC>
 __global__ void __launch_bounds__(kHeadTile)
     head_kernel(const __nv_bfloat16* __restrict__ x, Geo g, int C, const float* __restrict__ Wh,
                 const float* __restrict__ bh, int ncls_rt, const uint8_t* __restrict__ labels,
                 const float* __restrict__ sample_w, float grad_scale, __nv_bfloat16* __restrict__ dx,
                 float* __restrict__ dWh, float* __restrict__ dbh, double* __restrict__ loss_sum,
-                float* __restrict__ probs) {
+                float* __restrict__ probs, int tile_x) {
   constexpr int MC = NC > 0 ? NC : kMaxCls;  // unrolled class loop bound
   constexpr int DLS = (MC + 3) & ~3;         // dlogit row stride (float4 reads)
   const int ncls = NC > 0 ? NC : ncls_rt;
   extern __shared__ float4 hsm4[];
-  // smem: Wh [ncls][C] f32 | bh [DLS] | (TRAIN) dl [256][DLS] f32 | xs [256][C+8] bf16
+  // smem: Wh [ncls][C] f32 | bh [DLS] | rows [256] i64 | (TRAIN) dl [256][DLS] f32 | xs [256][C+8] bf16
   float* sW = reinterpret_cast<float*>(hsm4);
   float* sB = sW + ((ncls * C + 3) & ~3);
-  float* dl = sB + DLS;
-  const int XS = C + 8;  // row stride of the x tile: +16 B keeps the 16-byte row writes off the same banks
+  long long* rows_s = reinterpret_cast<long long*>(sB + DLS);
+  float* dl = reinterpret_cast<float*>(rows_s + kHeadTile);
+  const int XS = C + 8;  // row stride of the x tile: +16 B keeps the 16-byte row accesses off the same banks
   __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(dl + (TRAIN ? kHeadTile * DLS : 0));
   for (int i = threadIdx.x; i < ncls * C; i += blockDim.x) sW[i] = Wh[i];
   for (int i = threadIdx.x; i < DLS; i += blockDim.x) sB[i] = i < ncls ? bh[i] : 0.f;
@@ -602,6 +631,7 @@ __global__ void __launch_bounds__(kHeadTile)
 
   const long long npix = g.pixels();
   const int Wp = g.W + 2;
+  const int CG = C / 8;
   const int C2 = C / 2;                          // channel pairs
   const int nseg = max(1, kHeadTile / C2);       // pixel segments of the weight-gradient pass
   const int rows_per_seg = (kHeadTile + nseg - 1) / nseg;
@@ -615,18 +645,35 @@ __global__ void __launch_bounds__(kHeadTile)
   for (long long p0 = (long long)blockIdx.x * kHeadTile; p0 < npix; p0 += (long long)gridDim.x * kHeadTile) {
     const long long pix = p0 + threadIdx.x;
     const bool valid = pix < npix;
+    const int nrows = (int)min((long long)kHeadTile, npix - p0);
+    long long row = 0;
+    int n = 0;
     if (valid) {
       // one division chain per tile and thread (tiles are 256x fewer than pixels)
-      const int n = (int)(pix / hw);
+      n = (int)(pix / hw);
       const int rem = (int)(pix - (long long)n * hw);
       const int yy = rem / g.W, xx = rem - yy * g.W;
-      const long long row = ((long long)n * (g.H + 2) + yy + 1) * Wp + xx + 1;
+      row = ((long long)n * (g.H + 2) + yy + 1) * Wp + xx + 1;
+    }
+    if (tile_x) {
+      rows_s[threadIdx.x] = row;
+      __syncthreads();
+      // cooperative, coalesced copy of the tile's x rows
+      for (int id = threadIdx.x; id < nrows * CG; id += kHeadTile) {
+        const int px = id / CG, cgi = id - px * CG;
+        *reinterpret_cast<uint4*>(xs + px * XS + cgi * 8) =
+            *reinterpret_cast<const uint4*>(x + rows_s[px] * C + cgi * 8);
+      }
+      __syncthreads();
+    }
+    float d[MC];
+    if (valid) {
       float z[MC];
 #pragma unroll
       for (int c = 0; c < MC; ++c) z[c] = sB[c];
       for (int k8 = 0; k8 < C; k8 += 8) {
-        const uint4 u = *reinterpret_cast<const uint4*>(x + row * C + k8);
-        if (TRAIN) *reinterpret_cast<uint4*>(xs + threadIdx.x * XS + k8) = u;
+        const uint4 u = tile_x ? *reinterpret_cast<const uint4*>(xs + threadIdx.x * XS + k8)
+                               : *reinterpret_cast<const uint4*>(x + row * C + k8);
         const __nv_bfloat162* hv = reinterpret_cast<const __nv_bfloat162*>(&u);
         float xv[8];
 #pragma unroll
@@ -678,7 +725,6 @@ __global__ void __launch_bounds__(kHeadTile)
         for (int c = 0; c < MC; ++c)
           if (c == lab) zy = z[c];
         lacc += (double)((logf(se) + mx - zy) * w);
-        float d[MC];
 #pragma unroll
         for (int c = 0; c < MC; ++c) {
           d[c] = (NC > 0 || c < ncls) ? (e[c] * inv - (c == lab ? 1.f : 0.f)) * w * grad_scale : 0.f;
@@ -687,33 +733,11 @@ __global__ void __launch_bounds__(kHeadTile)
         }
 #pragma unroll
         for (int c = MC; c < DLS; ++c) dl[threadIdx.x * DLS + c] = 0.f;
-        // dx[ci] = sum_c dlogit_c * Wh[c][ci]
-        for (int k8 = 0; k8 < C; k8 += 8) {
-          Vec8 o;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) o.v[j] = 0.f;
-#pragma unroll
-          for (int c = 0; c < MC; ++c) {
-            if (NC > 0 || c < ncls) {
-              const float4 w0 = *reinterpret_cast<const float4*>(sW + c * C + k8);
-              const float4 w1 = *reinterpret_cast<const float4*>(sW + c * C + k8 + 4);
-              o.v[0] = fmaf(d[c], w0.x, o.v[0]);
-              o.v[1] = fmaf(d[c], w0.y, o.v[1]);
-              o.v[2] = fmaf(d[c], w0.z, o.v[2]);
-              o.v[3] = fmaf(d[c], w0.w, o.v[3]);
-              o.v[4] = fmaf(d[c], w1.x, o.v[4]);
-              o.v[5] = fmaf(d[c], w1.y, o.v[5]);
-              o.v[6] = fmaf(d[c], w1.z, o.v[6]);
-              o.v[7] = fmaf(d[c], w1.w, o.v[7]);
-            }
-          }
-          store8(dx + row * C + k8, o);
-        }
       }
     }
     if (TRAIN) {
       __syncthreads();
-      const int nrows = (int)min((long long)kHeadTile, npix - p0);
+      // dWh partial sums from the tile
       if (threadIdx.x < nseg * C2) {
         const int cp = threadIdx.x % C2, seg = threadIdx.x / C2;
         const int r_lo = seg * rows_per_seg, r_hi = min(nrows, r_lo + rows_per_seg);
@@ -737,6 +761,37 @@ __global__ void __launch_bounds__(kHeadTile)
         }
       }
       __syncthreads();
+      // dx[ci] = sum_c dlogit_c * Wh[c][ci], written over the thread's own x row of the tile
+      if (valid) {
+        for (int k8 = 0; k8 < C; k8 += 8) {
+          Vec8 o;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o.v[j] = 0.f;
+#pragma unroll
+          for (int c = 0; c < MC; ++c) {
+            if (NC > 0 || c < ncls) {
+              const float4 w0 = *reinterpret_cast<const float4*>(sW + c * C + k8);
+              const float4 w1 = *reinterpret_cast<const float4*>(sW + c * C + k8 + 4);
+              o.v[0] = fmaf(d[c], w0.x, o.v[0]);
+              o.v[1] = fmaf(d[c], w0.y, o.v[1]);
+              o.v[2] = fmaf(d[c], w0.z, o.v[2]);
+              o.v[3] = fmaf(d[c], w0.w, o.v[3]);
+              o.v[4] = fmaf(d[c], w1.x, o.v[4]);
+              o.v[5] = fmaf(d[c], w1.y, o.v[5]);
+              o.v[6] = fmaf(d[c], w1.z, o.v[6]);
+              o.v[7] = fmaf(d[c], w1.w, o.v[7]);
+            }
+          }
+          store8(xs + threadIdx.x * XS + k8, o);
+        }
+      }
+      __syncthreads();
+      for (int id = threadIdx.x; id < nrows * CG; id += kHeadTile) {
+        const int px = id / CG, cgi = id - px * CG;
+        *reinterpret_cast<uint4*>(dx + rows_s[px] * C + cgi * 8) =
+            *reinterpret_cast<const uint4*>(xs + px * XS + cgi * 8);
+      }
+      __syncthreads();  // the tile and the row table are rewritten by the next iteration
     }
   }
   if (TRAIN) {
@@ -1067,12 +1122,16 @@ int launch_conv_first(const __nv_bfloat16* x, const __nv_bfloat16* w, const floa
     set_error("conv_first: weights do not fit in shared memory");
     return MPU_ERR_ARG;
   }
-  int threads = ((g.W + 31) / 32) * 32;
-  if (threads > 256) threads = 256;
-  const long long items = (long long)g.B * ((g.H + kFirstRows - 1) / kFirstRows) * ((g.W + threads - 1) / threads);
+  if (co_phys / 8 > 256) {
+    set_error("conv_first: co_phys=%d exceeds 2048 channels", co_phys);
+    return MPU_ERR_ARG;
+  }
+  int CG, RL, threads;
+  line_layout(co_phys, g.W, &CG, &RL, &threads);
+  const long long items = (long long)g.B * ((g.H + kFirstRows - 1) / kFirstRows) * ((g.W + RL - 1) / RL);
 #define MPU_CONV_FIRST(CIN)                                                                        \
   conv_first_kernel<CIN><<<resident_grid(conv_first_kernel<CIN>, threads, smem, items), threads, smem, st>>>( \
-      x, w, bias, out, g, co_phys)
+      x, w, bias, out, g, co_phys, CG, RL)
   switch (cin) {
     case 1: MPU_CONV_FIRST(1); break;
     case 2: MPU_CONV_FIRST(2); break;
@@ -1092,9 +1151,9 @@ int launch_conv_first_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dz, Geo
     return MPU_ERR_ARG;
   }
   int CG, RL, threads;
-  line_layout(co_phys, g.W, &CG, &RL, &threads);
+  line_layout(co_phys, (g.W + 3) / 4, &CG, &RL, &threads);
   const size_t smem = sizeof(float) * threads * 8;
-  const long long items = (long long)g.B * g.H * ((g.W + RL - 1) / RL);
+  const long long items = (long long)g.B * g.H * ((g.W + 4 * RL - 1) / (4 * RL));
   const int grid = resident_grid(conv_first_wgrad_kernel, threads, smem, items);
   conv_first_wgrad_kernel<<<dim3(grid, cin), threads, smem, st>>>(x, dz, g, co_phys, CG, RL, dW, ldw);
   count_launch();
@@ -1103,10 +1162,11 @@ int launch_conv_first_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dz, Geo
 }
 
 namespace {
-size_t head_smem(int C, int ncls, int mc, bool train) {
+size_t head_smem(int C, int ncls, int mc, bool train, bool tile_x) {
   const int dls = (mc + 3) & ~3;
-  size_t s = sizeof(float) * ((size_t)((ncls * C + 3) & ~3) + dls);
-  if (train) s += sizeof(float) * kHeadTile * dls + (size_t)kHeadTile * (C + 8) * 2;
+  size_t s = sizeof(float) * ((size_t)((ncls * C + 3) & ~3) + dls) + sizeof(long long) * kHeadTile;
+  if (train) s += sizeof(float) * kHeadTile * dls;
+  if (tile_x) s += (size_t)kHeadTile * (C + 8) * 2;
   return s;
 }
 
@@ -1114,7 +1174,9 @@ template <bool TRAIN, int NC>
 int launch_head(const __nv_bfloat16* x, Geo g, int C, const float* Wh, const float* bh, int ncls,
                 const uint8_t* labels, const float* sample_w, float grad_scale, __nv_bfloat16* dx,
                 float* dWh, float* dbh, double* loss_sum, float* probs, cudaStream_t st) {
-  const size_t smem = head_smem(C, ncls, NC > 0 ? NC : kMaxCls, TRAIN);
+  // inference with a very wide input: the x tile does not fit shared memory, rows are read per thread
+  const bool tile_x = TRAIN || head_smem(C, ncls, NC > 0 ? NC : kMaxCls, TRAIN, true) <= 96 * 1024;
+  const size_t smem = head_smem(C, ncls, NC > 0 ? NC : kMaxCls, TRAIN, tile_x);
   if (smem > 200 * 1024) {
     set_error("head: shared memory %zu too large (C=%d, n_classes=%d)", smem, C, ncls);
     return MPU_ERR_ARG;
@@ -1128,7 +1190,7 @@ int launch_head(const __nv_bfloat16* x, Geo g, int C, const float* Wh, const flo
   const long long tiles = (g.pixels() + kHeadTile - 1) / kHeadTile;
   const int grid = resident_grid(head_kernel<TRAIN, NC>, kHeadTile, smem, tiles);
   head_kernel<TRAIN, NC><<<grid, kHeadTile, smem, st>>>(x, g, C, Wh, bh, ncls, labels, sample_w, grad_scale,
-                                                       dx, dWh, dbh, loss_sum, probs);
+                                                       dx, dWh, dbh, loss_sum, probs, tile_x ? 1 : 0);
   count_launch();
   MPU_CUDA(cudaGetLastError());
   return MPU_OK;
