@@ -10,6 +10,7 @@ statistics, preprocessing/scaling.py:47-88), `.sample_weight`, `.predict_mode`.
 """
 import numpy as np
 
+from ..errors import ReadOnlyAttributeError
 from ..interpolation import ViewInterpolator, plane_basis, plane_basis_batch, view_offsets
 
 
@@ -38,9 +39,9 @@ class SyntheticImage(object):
         image = np.asarray(image, dtype=np.float32)
         if image.ndim == 3:
             image = image[..., None]
-        self.image = image
-        self.labels = None if labels is None else np.asarray(labels).astype(np.uint8)
-        self.affine = np.eye(4) if affine is None else np.asarray(affine, dtype=np.float64)
+        self._image = image
+        self._labels = None if labels is None else np.asarray(labels).astype(np.uint8)
+        self._affine = np.eye(4) if affine is None else np.asarray(affine, dtype=np.float64)
         self.shape = image.shape
         self.n_channels = image.shape[-1]
         self.predict_mode = labels is None
@@ -50,13 +51,67 @@ class SyntheticImage(object):
             pct = float(bg_value[:-3])
             bg_value = [float(np.percentile(image[..., c], pct)) for c in range(self.n_channels)]
         self.bg_value = bg_value
+        self.bg_class = bg_class
         self.scaler_center, self.scaler_scale = robust_scaler_stats(image)
-        self.interpolator = ViewInterpolator(image, self.labels, self.affine, bg_value=bg_value,
-                                             bg_class=bg_class, device=device)
+        # the device-resident interpolator is built on first use (needs a CUDA device; geometry and file handling of an
+        # ImagePair do not)
+        self._device = device
+        self._interpolator = None
+
+    # image / labels / affine are read-only like the reference's (image_pair.py:143-198)
+    @property
+    def image(self):
+        return self._image
+
+    @image.setter
+    def image(self, _):
+        raise ReadOnlyAttributeError("Manually setting the image attribute is not allowed. "
+                                     "Initialize a new ImagePair object.")
+
+    @property
+    def labels(self):
+        return self._labels
+
+    @labels.setter
+    def labels(self, _):
+        raise ReadOnlyAttributeError("Manually setting the labels attribute is not allowed. "
+                                     "Initialize a new ImagePair object.")
+
+    @property
+    def affine(self):
+        return self._affine
+
+    @affine.setter
+    def affine(self, _):
+        raise ReadOnlyAttributeError("Manually setting the affine attribute is not allowed. "
+                                     "Initialize a new ImagePair object.")
+
+    @property
+    def interpolator(self):
+        if self._interpolator is None:
+            self._interpolator = ViewInterpolator(self._image, self._labels, self._affine, bg_value=self.bg_value,
+                                                  bg_class=self.bg_class, device=self._device)
+        return self._interpolator
+
+    @interpolator.setter
+    def interpolator(self, value):
+        self._interpolator = value
+
+    @property
+    def center(self):
+        """Voxel-space centre (image_pair.py:234-240)."""
+        return (np.asarray(self.shape[:-1]) - 1) / 2
+
+    @property
+    def real_center(self):
+        """Scanner-space centre (image_pair.py:242-248)."""
+        return self._affine[:3, :3].dot(self.center) + self._affine[:3, -1]
 
     @property
     def real_shape(self):
-        pix = np.linalg.norm(self.affine[:3, :3], axis=0)
+        """Physical extent per axis: voxel counts x voxel sizes (image_pair.py:261-267, sample_grid.py:9-16; the voxel
+        sizes are the column norms of the affine, which is what a NIfTI header's pixdim holds)."""
+        pix = np.linalg.norm(self._affine[:3, :3], axis=0)
         return np.asarray(self.shape[:3]) * pix
 
 
