@@ -110,22 +110,33 @@ __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ x, long long row
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[0][j] = 0.f;
   const long long stride = (long long)gridDim.x * RL;
-  for (long long r = (long long)blockIdx.x * RL + rl; r < rows; r += 4 * stride) {
-    Vec8 v[4];
+  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+  auto issue = [&](long long r, uint4 (&v)[4]) {
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const long long rr = r + u * stride;
-      if (rr < rows) {
-        v[u] = load8(x + rr * ld + cg * 8);
-      } else {
+      v[u] = rr < rows ? *reinterpret_cast<const uint4*>(x + rr * ld + cg * 8) : zero4;
+    }
+  };
+  // the loads of the next iteration are in flight while this one is summed (see bn_bwd_kernel)
+  uint4 cur[4], nxt[4];
+  long long r = (long long)blockIdx.x * RL + rl;
+  if (r < rows) issue(r, cur);
+  for (; r < rows; r += 4 * stride) {
+    const bool more = r + 4 * stride < rows;
+    if (more) issue(r + 4 * stride, nxt);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[u].v[j] = 0.f;
+    for (int u = 0; u < 4; ++u) {
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&cur[u]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(h[j]);
+        acc[0][2 * j] += f.x;
+        acc[0][2 * j + 1] += f.y;
       }
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[0][j] += v[u].v[j];
+    for (int u = 0; u < 4; ++u) cur[u] = nxt[u];
   }
   block_reduce_store<1, float>(acc, CG, RL, C, out);
 }
@@ -207,7 +218,7 @@ struct SegIter {
 __global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
                                 const float* __restrict__ shift, __nv_bfloat16* __restrict__ b, Geo g,
                                 int C, int CG, int RL) {
-  constexpr int U = 4;  // independent 16-byte loads in flight per thread
+  constexpr int U = 4;  // independent 16-byte loads per thread and work item
   const int tid = threadIdx.x;
   const int cg = tid % CG, rl = tid / CG;
   float sc[8], sh[8];
@@ -217,22 +228,46 @@ __global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float
     sh[j] = shift[cg * 8 + j];
   }
   const int Wp = g.W + 2;
-  SegIter it;
-  it.init(blockIdx.x, gridDim.x, g.H, (g.W + U * RL - 1) / (U * RL));
-  for (; it.n < g.B; it.next()) {
-    const long long base = ((long long)it.n * (g.H + 2) + it.yy + 1) * Wp + 1;
+  auto base_of = [&](const SegIter& it) {
+    return ((long long)it.n * (g.H + 2) + it.yy + 1) * Wp + 1 + it.seg * (U * RL) + rl;
+  };
+  auto issue = [&](const SegIter& it, uint4 (&v)[U]) {
+    const long long base = base_of(it);
     const int x0 = it.seg * (U * RL) + rl;
-    Vec8 v[U];
 #pragma unroll
     for (int u = 0; u < U; ++u)
-      if (x0 + u * RL < g.W) v[u] = load8(y + (base + x0 + u * RL) * C + cg * 8);
+      if (x0 + u * RL < g.W) v[u] = *reinterpret_cast<const uint4*>(y + (base + u * RL) * C + cg * 8);
+  };
+  // the loads of the next work item are in flight while this one is scaled and stored (see bn_bwd_kernel)
+  SegIter it;
+  it.init(blockIdx.x, gridDim.x, g.H, (g.W + U * RL - 1) / (U * RL));
+  uint4 cur[U], nxt[U];
+  bool have = it.n < g.B;
+  if (have) issue(it, cur);
+  while (have) {
+    SegIter in = it;
+    in.next();
+    const bool have_n = in.n < g.B;
+    if (have_n) issue(in, nxt);
+    const long long base = base_of(it);
+    const int x0 = it.seg * (U * RL) + rl;
 #pragma unroll
     for (int u = 0; u < U; ++u)
       if (x0 + u * RL < g.W) {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&cur[u]);
+        Vec8 v;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[u].v[j] = fmaf(v[u].v[j], sc[j], sh[j]);
-        store8(b + (base + x0 + u * RL) * C + cg * 8, v[u]);
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __bfloat1622float2(h[j]);
+          v.v[2 * j] = fmaf(f.x, sc[2 * j], sh[2 * j]);
+          v.v[2 * j + 1] = fmaf(f.y, sc[2 * j + 1], sh[2 * j + 1]);
+        }
+        store8(b + (base + u * RL) * C + cg * 8, v);
       }
+    it = in;
+    have = have_n;
+#pragma unroll
+    for (int u = 0; u < U; ++u) cur[u] = nxt[u];
   }
 }
 
@@ -285,23 +320,82 @@ __global__ void bn_apply_pool_kernel(const __nv_bfloat16* __restrict__ y,
 // affine map dz = relu'(y) * (a*g + b*y + c):  a = gamma*rstd, b = -a*rstd*mgx, c = -a*mg - b*mu  where
 // mg = mean(g), mgx = mean(g*xhat) = rstd*(mean(g*y) - mu*mg).  Few per-thread coefficients keep the
 // register count low enough for 3 resident blocks per SM (these kernels are pure HBM streams).
+// V channels (8 or 4) per thread as one raw 16- or 8-byte register group
+template <int V>
+struct RawV;
+template <>
+struct RawV<8> {
+  typedef uint4 type;
+};
+template <>
+struct RawV<4> {
+  typedef uint2 type;
+};
+template <int V>
+__device__ __forceinline__ void unpackv(const typename RawV<V>::type& u, float (&r)[V]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int j = 0; j < V / 2; ++j) {
+    const float2 f = __bfloat1622float2(h[j]);
+    r[2 * j] = f.x;
+    r[2 * j + 1] = f.y;
+  }
+}
+template <int V>
+__device__ __forceinline__ typename RawV<V>::type packv(const float (&r)[V]) {
+  typename RawV<V>::type u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int j = 0; j < V / 2; ++j) h[j] = __floats2bfloat162_rn(r[2 * j], r[2 * j + 1]);
+  return u;
+}
+
+// Block-level reduction of per-thread V-channel partials over the RL row lanes, then atomics.
+template <int NVAL, typename OutT, int V>
+__device__ __forceinline__ void block_reduce_store_v(float (&acc)[NVAL][V], int CG, int RL, int C,
+                                                     OutT* out /*[NVAL][C]*/) {
+  extern __shared__ float red_smem[];  // [NVAL][RL][CG*V]
+  const int tid = threadIdx.x;
+  const int cg = tid % CG, rl = tid / CG;
+#pragma unroll
+  for (int n = 0; n < NVAL; ++n)
+#pragma unroll
+    for (int j = 0; j < V; ++j) red_smem[(n * RL + rl) * (CG * V) + cg * V + j] = acc[n][j];
+  __syncthreads();
+  for (int i = tid; i < NVAL * CG * V; i += blockDim.x) {
+    const int n = i / (CG * V), c = i % (CG * V);
+    float s = 0.f;
+    for (int r = 0; r < RL; ++r) s += red_smem[(n * RL + r) * (CG * V) + c];
+    atomicAdd(out + (size_t)n * C + c, (OutT)s);
+  }
+}
+
+// The loads of work item k+1 are issued (raw registers) BEFORE item k is processed: these kernels are pure HBM
+// streams, and with load -> wait -> compute -> store per item the bytes in flight per SM dropped to zero once per
+// iteration (3.1-4.6 TB/s under ncu where the simple streaming Adam kernel reaches 5.7).  The 2x2-window (POOL)
+// variants keep 9 loads per item and buffer set; they process a window in two halves of 4 channels so that two buffer
+// sets, the coefficients and the arg-max temporaries stay below the 170 registers that allow two resident blocks.
+// (Measured alternative: 4 channels per thread with 8-byte accesses - half the state per thread - ran 2x SLOWER.)
 template <bool POOL, bool APPLY>
-__global__ void __launch_bounds__(256, POOL ? 2 : 3)
+__global__ void __launch_bounds__(256) __maxnreg__(POOL ? 168 : 128)
     bn_bwd_kernel(BnBwdArgs a, int CG, int RL, const double* __restrict__ sums_in,
                   double* __restrict__ sums_out, __nv_bfloat16* __restrict__ dz, int phase_major,
                   float* __restrict__ dbias) {
+  constexpr int V = 8;              // channels per thread
   constexpr int U = POOL ? 1 : 2;
+  constexpr int NV = POOL ? 4 : U;  // pixels per work item and thread
+  typedef typename RawV<V>::type raw_t;
   const int tid = threadIdx.x;
   const int cg = tid % CG, rl = tid / CG;
   const int C = a.C;
   const Geo g = a.g;
   const int Wp = g.W + 2;
   const int hh = g.H / 2, wh = g.W / 2;
-  float sc[POOL ? 8 : 1], sh[POOL ? 8 : 1];
-  float ca[APPLY ? 8 : 1], cb[APPLY ? 8 : 1], cc[APPLY ? 8 : 1];
+  float sc[POOL ? V : 1], sh[POOL ? V : 1];
+  float ca[APPLY ? V : 1], cb[APPLY ? V : 1], cc[APPLY ? V : 1];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = cg * 8 + j;
+  for (int j = 0; j < V; ++j) {
+    const int c = cg * V + j;
     if (POOL) {
       sc[j] = a.scale[c];
       sh[j] = a.shift[c];
@@ -318,108 +412,179 @@ __global__ void __launch_bounds__(256, POOL ? 2 : 3)
       cc[j] = -k1 * mg - cb[j] * mu;
     }
   }
-  float acc[2][8];
+  float acc[2][V];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
+  for (int j = 0; j < V; ++j) acc[0][j] = acc[1][j] = 0.f;
   const long long rows_lo = (long long)g.B * (hh + 2) * (wh + 2);
 
   // one pixel: accumulate the reduction terms (pass 1) or write dz (pass 2)
-  auto emit = [&](const Vec8& gv, const Vec8& yv, int n, int yy, int xx, long long row) {
+  auto emit = [&](const float (&gv)[V], const float (&yv)[V], int n, int yy, int xx, long long row) {
     if (!APPLY) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        acc[0][j] += gv.v[j];
-        acc[1][j] = fmaf(gv.v[j], yv.v[j], acc[1][j]);
+      for (int j = 0; j < V; ++j) {
+        acc[0][j] += gv[j];
+        acc[1][j] = fmaf(gv[j], yv[j], acc[1][j]);
       }
     } else {
-      Vec8 o;
+      float o[V];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float v = fmaf(ca[j], gv.v[j], fmaf(cb[j], yv.v[j], cc[j]));
-        if (!(yv.v[j] > 0.f)) v = 0.f;
-        v = bf16_round(v);
-        o.v[j] = v;
-        acc[0][j] += v;
+      for (int j = 0; j < V; ++j) {
+        float v = fmaf(ca[j], gv[j], fmaf(cb[j], yv[j], cc[j]));
+        if (!(yv[j] > 0.f)) v = 0.f;
+        o[j] = v;
       }
+      // round to the stored bf16 values first (packed conversion): the bias-gradient sums are taken over those
+      const raw_t u = packv<V>(o);
+      float r[V];
+      unpackv<V>(u, r);
+#pragma unroll
+      for (int j = 0; j < V; ++j) acc[0][j] += r[j];
       long long orow = row;
       if (phase_major)  // pixel (n, yy, xx) of this level -> [phase][rows of the half-resolution level]
         orow = ((yy & 1) * 2 + (xx & 1)) * rows_lo + ((long long)n * (hh + 2) + (yy >> 1) + 1) * (wh + 2) +
                ((xx >> 1) + 1);
-      store8(dz + orow * C + cg * 8, o);
+      *reinterpret_cast<raw_t*>(dz + orow * C + cg * V) = u;
+    }
+  };
+
+  // raw loads of one work item
+  struct Raw {
+    raw_t y[NV], g[NV], gp;
+  };
+  raw_t zero;
+  memset(&zero, 0, sizeof(zero));
+  auto live = [&](const SegIter& it, int u) {  // does position u of the item exist?
+    return POOL ? (it.seg * RL + rl < wh) : (it.seg * (U * RL) + rl + u * RL < g.W);
+  };
+  auto row_of = [&](const SegIter& it, int u) -> long long {
+    if (POOL) {
+      const long long base = ((long long)it.n * (g.H + 2) + 2 * it.yy + 1) * Wp + (2 * (it.seg * RL + rl) + 1);
+      return base + (u >> 1) * Wp + (u & 1);
+    }
+    return ((long long)it.n * (g.H + 2) + it.yy + 1) * Wp + 1 + it.seg * (U * RL) + rl + u * RL;
+  };
+  auto issue = [&](const SegIter& it, Raw& r) {
+#pragma unroll
+    for (int u = 0; u < NV; ++u) {
+      r.y[u] = zero;
+      r.g[u] = zero;
+      if (live(it, u)) {
+        const long long row = row_of(it, u);
+        r.y[u] = *reinterpret_cast<const raw_t*>(a.y + row * C + cg * V);
+        if (a.gA) r.g[u] = *reinterpret_cast<const raw_t*>(a.gA + row * (long long)a.ldA + cg * V);
+      }
+    }
+    r.gp = zero;
+    if (POOL && a.gP && live(it, 0)) {
+      const long long prow = ((long long)it.n * (hh + 2) + it.yy + 1) * (wh + 2) + (it.seg * RL + rl + 1);
+      r.gp = *reinterpret_cast<const raw_t*>(a.gP + prow * C + cg * V);
+    }
+  };
+  auto consume = [&](const SegIter& it, const Raw& r) {
+    if (!live(it, 0)) return;  // (POOL: the whole window; line kernels: position 0 exists whenever any does)
+    if (POOL) {
+      uint4 outw[4];
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {  // channels hf*4 .. hf*4+3 of the thread's group
+        float yv[4][4], gv[4][4], gp[4];
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+          unpackv<4>(reinterpret_cast<const uint2*>(&r.y[d])[hf], yv[d]);
+          unpackv<4>(reinterpret_cast<const uint2*>(&r.g[d])[hf], gv[d]);
+        }
+        unpackv<4>(reinterpret_cast<const uint2*>(&r.gp)[hf], gp);
+        if (a.gP) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float best = -INFINITY;
+            int am = 0;
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+              const float bv = bf16_round(fmaf(yv[d][j], sc[hf * 4 + j], sh[hf * 4 + j]));
+              if (bv > best) {
+                best = bv;
+                am = d;
+              }
+            }
+#pragma unroll
+            for (int d = 0; d < 4; ++d)
+              if (am == d) gv[d][j] += gp[j];
+          }
+        }
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+          if (!APPLY) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              acc[0][hf * 4 + j] += gv[d][j];
+              acc[1][hf * 4 + j] = fmaf(gv[d][j], yv[d][j], acc[1][hf * 4 + j]);
+            }
+          } else {
+            float o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float v = fmaf(ca[hf * 4 + j], gv[d][j], fmaf(cb[hf * 4 + j], yv[d][j], cc[hf * 4 + j]));
+              if (!(yv[d][j] > 0.f)) v = 0.f;
+              o[j] = v;
+            }
+            const uint2 u = packv<4>(o);
+            float rr[4];
+            unpackv<4>(u, rr);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[0][hf * 4 + j] += rr[j];
+            reinterpret_cast<uint2*>(&outw[d])[hf] = u;
+          }
+        }
+      }
+      if (APPLY) {
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+          long long orow = row_of(it, d);
+          if (phase_major) {
+            const int yy = 2 * it.yy + (d >> 1), xx = 2 * (it.seg * RL + rl) + (d & 1);
+            orow = ((yy & 1) * 2 + (xx & 1)) * rows_lo + ((long long)it.n * (hh + 2) + (yy >> 1) + 1) * (wh + 2) +
+                   ((xx >> 1) + 1);
+          }
+          *reinterpret_cast<uint4*>(dz + orow * C + cg * 8) = outw[d];
+        }
+      }
+      return;
+    }
+    float yv[NV][V], gv[NV][V];
+#pragma unroll
+    for (int u = 0; u < NV; ++u) {
+      unpackv<V>(r.y[u], yv[u]);
+      unpackv<V>(r.g[u], gv[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < NV; ++u) {
+      if (!live(it, u)) continue;
+      emit(gv[u], yv[u], it.n, it.yy, it.seg * (U * RL) + rl + u * RL, row_of(it, u));
     }
   };
 
   SegIter it;
   it.init(blockIdx.x, gridDim.x, POOL ? hh : g.H, ((POOL ? wh : g.W) + U * RL - 1) / (U * RL));
-  for (; it.n < g.B; it.next()) {
-    if (POOL) {
-      const int jx = it.seg * RL + rl, iy = it.yy;
-      if (jx >= wh) continue;
-      const long long base = ((long long)it.n * (g.H + 2) + 2 * iy + 1) * Wp + (2 * jx + 1);
-      Vec8 yv[4], gv[4];
-#pragma unroll
-      for (int d = 0; d < 4; ++d) {
-        const long long row = base + (d >> 1) * Wp + (d & 1);
-        yv[d] = load8(a.y + row * C + cg * 8);
-        if (a.gA) {
-          gv[d] = load8(a.gA + row * (long long)a.ldA + cg * 8);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) gv[d].v[j] = 0.f;
-        }
-      }
-      if (a.gP) {
-        const long long prow = ((long long)it.n * (hh + 2) + iy + 1) * (wh + 2) + (jx + 1);
-        const Vec8 gp = load8(a.gP + prow * C + cg * 8);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float best = -INFINITY;
-          int am = 0;
-#pragma unroll
-          for (int d = 0; d < 4; ++d) {
-            const float bv = bf16_round(fmaf(yv[d].v[j], sc[j], sh[j]));
-            if (bv > best) {
-              best = bv;
-              am = d;
-            }
-          }
-#pragma unroll
-          for (int d = 0; d < 4; ++d)
-            if (am == d) gv[d].v[j] += gp.v[j];
-        }
-      }
-#pragma unroll
-      for (int d = 0; d < 4; ++d)
-        emit(gv[d], yv[d], it.n, 2 * iy + (d >> 1), 2 * jx + (d & 1), base + (d >> 1) * Wp + (d & 1));
-    } else {
-      const long long base = ((long long)it.n * (g.H + 2) + it.yy + 1) * Wp + 1;
-      const int x0 = it.seg * (U * RL) + rl;
-      Vec8 yv[U], gv[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (x0 + u * RL < g.W) {
-          const long long row = base + x0 + u * RL;
-          yv[u] = load8(a.y + row * C + cg * 8);
-          if (a.gA) {
-            gv[u] = load8(a.gA + row * (long long)a.ldA + cg * 8);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) gv[u].v[j] = 0.f;
-          }
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u)
-        if (x0 + u * RL < g.W) emit(gv[u], yv[u], it.n, it.yy, x0 + u * RL, base + x0 + u * RL);
-    }
+  Raw cur, nxt;
+  bool have = it.n < g.B;
+  if (have) issue(it, cur);
+  while (have) {
+    SegIter in = it;
+    in.next();
+    const bool have_n = in.n < g.B;
+    if (have_n) issue(in, nxt);
+    consume(it, cur);
+    it = in;
+    have = have_n;
+    cur = nxt;
   }
   if (!APPLY) {
-    block_reduce_store<2, double>(acc, CG, RL, C, sums_out);
+    block_reduce_store_v<2, double, V>(acc, CG, RL, C, sums_out);
   } else if (dbias) {
-    float acc1[1][8];
+    float acc1[1][V];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc1[0][j] = acc[0][j];
-    block_reduce_store<1, float>(acc1, CG, RL, C, dbias);
+    for (int j = 0; j < V; ++j) acc1[0][j] = acc[0][j];
+    block_reduce_store_v<1, float, V>(acc1, CG, RL, C, dbias);
   }
 }
 
@@ -1076,11 +1241,12 @@ int launch_bn_bwd(const BnBwdArgs& a, const double* sums_in, double* sums_out, _
                   int phase_major, float* dbias, cudaStream_t st) {
   int CG, RL, threads;
   const int span = POOL ? a.g.W / 2 : (a.g.W + 1) / 2;
-  line_layout(a.C, span, &CG, &RL, &threads);
+  const int V = 8;  // channels per thread (see the kernel)
+  line_layout(a.C * 8 / V, span, &CG, &RL, &threads);
   const int U = POOL ? 1 : 2;
   const long long items =
       (long long)a.g.B * (POOL ? a.g.H / 2 : a.g.H) * (((POOL ? a.g.W / 2 : a.g.W) + U * RL - 1) / (U * RL));
-  const size_t smem = sizeof(float) * (APPLY ? 1 : 2) * RL * CG * 8;
+  const size_t smem = sizeof(float) * (APPLY ? 1 : 2) * RL * CG * V;
   const int grid = resident_grid(bn_bwd_kernel<POOL, APPLY>, threads, smem, items);
   bn_bwd_kernel<POOL, APPLY><<<grid, threads, smem, st>>>(a, CG, RL, sums_in, sums_out, dz, phase_major, dbias);
   count_launch();
@@ -1090,6 +1256,10 @@ int launch_bn_bwd(const BnBwdArgs& a, const double* sums_in, double* sums_out, _
 }  // namespace
 
 int launch_bn_bwd_reduce(const BnBwdArgs& a, double* sums, cudaStream_t st) {
+  if (a.C / 4 > 256 && a.gP != nullptr) {
+    set_error("bn_bwd: C=%d exceeds 1024 channels on a pooled level", a.C);
+    return MPU_ERR_ARG;
+  }
   if (a.C / 8 > 256) {
     set_error("bn_bwd: C=%d exceeds 2048 channels", a.C);
     return MPU_ERR_ARG;
