@@ -377,7 +377,7 @@ __device__ __forceinline__ void block_reduce_store_v(float (&acc)[NVAL][V], int 
 // sets, the coefficients and the arg-max temporaries stay below the 170 registers that allow two resident blocks.
 // (Measured alternative: 4 channels per thread with 8-byte accesses - half the state per thread - ran 2x SLOWER.)
 template <bool POOL, bool APPLY>
-__global__ void __launch_bounds__(256) __maxnreg__(POOL ? 168 : 128)
+__global__ void __launch_bounds__(256) __maxnreg__(POOL ? 168 : 104)
     bn_bwd_kernel(BnBwdArgs a, int CG, int RL, const double* __restrict__ sums_in,
                   double* __restrict__ sums_out, __nv_bfloat16* __restrict__ dz, int phase_major,
                   float* __restrict__ dbias) {

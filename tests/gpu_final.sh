@@ -12,6 +12,7 @@ timeout 600 python bench.py --workload train_fusion --no-cpu-baseline > $out/ben
 timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum \
   --clock-control none --csv --log-file $out/launches_traffic.csv python tests/perf_unet.py --ncu > $out/ncu.log 2>&1
 python tests/ncu_traffic.py $out/launches_traffic.csv $out/gemm_traffic.json > $out/traffic_summary.txt 2>&1
+python tests/launch_summary.py $out/launches_traffic.csv > $out/launch_summary.txt 2>&1
 python - <<PY
 import json
 for f in ("bench_n1", "bench_reference", "bench_predict", "bench_fusion"):
