@@ -20,7 +20,47 @@ from oracle import ref_shim  # noqa: E402
 import golden_inputs as gi  # noqa: E402
 
 
+UNET_GRAPH_CASES = [
+    # name, kwargs of the reference's UNet(...), whether to store a forward pass
+    ("small", dict(n_classes=3, dim=32, n_channels=1, depth=4, complexity_factor=0.125), True),
+    ("rgb", dict(n_classes=2, dim=48, n_channels=3, depth=4, complexity_factor=0.25), True),
+    ("benchmark", dict(n_classes=5, dim=256, n_channels=1, depth=4, complexity_factor=2.0), False),
+]
+
+
+def unet_graph_goldens(out_dir):
+    """tests/golden/unet_graph_*.npz: the graph the reference's OWN `UNet.init_model` builds (mpunet/models/unet.py
+    executed unmodified under oracle/keras_shim.py) - layer names in creation order, parameter shapes, count_params,
+    receptive field, label crop - and, for the small cases, its inference output on seeded weights / inputs computed by
+    the shim's numpy layers."""
+    import json
+    from oracle import keras_shim
+    from oracle.unet import init_params
+    UNet = keras_shim.reference_unet_class()
+    for name, kw, forward in UNET_GRAPH_CASES:
+        model = UNet(logger=lambda *a, **k: None, **kw)
+        layers = [dict(name=l.name, cls=l.__class__.__name__,
+                       shapes={k: list(v.shape) for k, v in l.weights.items()},
+                       out=list(l.output.shape[1:])) for l in model.layers]
+        rec = dict(layers=json.dumps(layers), count_params=model.count_params(),
+                   trainable_params=model.trainable_count(),
+                   receptive_field=np.asarray(model.receptive_field), label_crop=np.asarray(model.label_crop))
+        if forward:
+            P = init_params(kw["n_classes"], kw["n_channels"], kw["depth"], kw["complexity_factor"], seed=1,
+                            randomize_bn=True)
+            for l in model.layers:
+                for k in l.weights:
+                    l.weights[k] = P[l.name][k]
+            x = gi.unet_graph_input(kw)
+            rec["probs"] = model.predict(x)
+        np.savez_compressed(os.path.join(out_dir, "unet_graph_%s.npz" % name), **rec)
+        print("unet_graph_%s: %d layers, %d parameters (%d trainable)" % (name, len(layers), rec["count_params"],
+                                                                         rec["trainable_params"]))
+
+
 def main():
+    if sys.argv[1:] == ["unet"]:  # only the network-graph fixtures
+        return unet_graph_goldens(os.path.join(ROOT, "tests", "golden"))
     m = ref_shim.modules()
     sg, vi = m.sample_grid, m.view_interpolator
     out_dir = os.path.join(ROOT, "tests", "golden")
@@ -156,6 +196,7 @@ def main():
         print("elastic_%s: mean |delta| %.4f, %d labels moved" % (case["name"], np.abs(o - im).mean(),
                                                                  int((l != lab).sum())))
     np.savez_compressed(os.path.join(out_dir, "elastic.npz"), **outs)
+    unet_graph_goldens(out_dir)
 
 
 if __name__ == "__main__":

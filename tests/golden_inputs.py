@@ -131,3 +131,17 @@ def batch_rule_inputs(case):
     cand_noise = rng.normal(scale=0.1, size=(case["B"], case["tries"], 3))
     bg = [float(np.float32(np.percentile(vol[..., 0], 1)))]
     return vol, lab, views, cand_view, cand_off, cand_noise, bg
+
+
+# ---- U-Net graph fixtures (tests/golden/unet_graph_*.npz, oracle/make_golden.py::unet_graph_goldens) ----
+UNET_GRAPH_CASES = {
+    "small": dict(n_classes=3, dim=32, n_channels=1, depth=4, complexity_factor=0.125),
+    "rgb": dict(n_classes=2, dim=48, n_channels=3, depth=4, complexity_factor=0.25),
+    "benchmark": dict(n_classes=5, dim=256, n_channels=1, depth=4, complexity_factor=2.0),
+}
+
+
+def unet_graph_input(kw, batch=2):
+    """Seeded input batch [B, dim, dim, n_channels] float32 of a U-Net graph case."""
+    rng = np.random.RandomState(7 + kw["dim"])
+    return rng.randn(batch, kw["dim"], kw["dim"], kw["n_channels"]).astype(np.float32)

@@ -87,3 +87,36 @@ def test_exact_voxel_grid_centre_matches_reference():
     # full-size volume: finite, close to the closed form
     m = voxel_grid_center_exact((256, 256, 256), gi.rotated_affine()[:3, :3])
     assert np.allclose(m, gi.rotated_affine()[:3, :3].dot(np.full(3, 127.5)), rtol=1e-13)
+
+
+def test_unet_matches_the_reference_graph_goldens():
+    """The product U-Net (C ABI, tcgen05 GEMMs) against tests/golden/unet_graph_*.npz: the inference output of the graph
+    that the reference's own UNet.init_model builds (mpunet/models/unet.py executed unmodified under
+    oracle/keras_shim.py), on seeded weights loaded BY KERAS LAYER NAME.  Probabilities within 5e-3 of the float64
+    reference-graph execution (the product stores bf16 activations; the bf16-emulating oracle pins the 1e-3 bar in
+    test_gpu_unet*.py), arg-max labels equal wherever the reference's top-2 margin exceeds twice that bar; the layer
+    names, parameter shapes and count_params are the reference's."""
+    import json
+    from multiplanarunet_b200.models import UNet
+    from oracle.unet import init_params
+    for name, kw in gi.UNET_GRAPH_CASES.items():
+        z = np.load(os.path.join(GOLD, "unet_graph_%s.npz" % name))
+        if "probs" not in z.files:
+            continue
+        model = UNet(max_batch=2, training=False, **kw)
+        assert model.count_params() == int(z["count_params"])
+        ref_layers = [l for l in json.loads(str(z["layers"])) if l["shapes"]]
+        mine = model.get_keras_weights()
+        assert [l["name"] for l in ref_layers] == list(mine.keys())
+        for l in ref_layers:
+            assert {k: list(np.shape(v)) for k, v in mine[l["name"]].items()} == l["shapes"], l["name"]
+        model.set_keras_weights(init_params(kw["n_classes"], kw["n_channels"], kw["depth"], kw["complexity_factor"],
+                                            seed=1, randomize_bn=True))
+        got = model.predict_on_batch(gi.unet_graph_input(kw))
+        ref = z["probs"]
+        assert got.shape == ref.shape
+        err = float(np.abs(got - ref).max())
+        assert err < 5e-3, (name, err)
+        top2 = np.sort(ref, axis=-1)[..., -2:]
+        sure = (top2[..., 1] - top2[..., 0]) > 1e-2
+        assert sure.mean() > 0.5 and np.array_equal(got.argmax(-1)[sure], ref.argmax(-1)[sure])

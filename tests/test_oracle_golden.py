@@ -221,3 +221,30 @@ def test_pairwise_tree_reproduces_numpy_sum_and_reference_centre():
         mean = np.array([combine(n, np.array([leaf_sum(real[s:s + l, r].tolist()) for s, l in zip(ls, ll)])) / n
                          for r in range(3)])
         assert np.array_equal(mean, z["mean_%d" % k]), (shape, kind)
+
+
+def test_unet_graph_matches_reference_goldens():
+    """tests/golden/unet_graph_*.npz were produced by running the reference's OWN UNet.init_model (mpunet/models/
+    unet.py:114-216, unmodified) under oracle/keras_shim.py: the oracle's layer table must be that graph - names in
+    creation order, kernel / BN shapes, parameter counts (62 050 512 trainable at the benchmark configuration) - and its fp32
+    inference output must equal the reference graph's, executed by the shim's numpy layers on the same seeded weights."""
+    import json
+    from oracle.unet import UNetOracle, count_params, init_params, layer_specs
+    for name, kw in gi.UNET_GRAPH_CASES.items():
+        z = np.load(os.path.join(GOLD, "unet_graph_%s.npz" % name))
+        ref_layers = [l for l in json.loads(str(z["layers"])) if l["shapes"]]
+        specs = layer_specs(kw["n_classes"], kw["n_channels"], kw["depth"], kw["complexity_factor"])
+        assert [l["name"] for l in ref_layers] == [s[0] for s in specs]
+        P = init_params(kw["n_classes"], kw["n_channels"], kw["depth"], kw["complexity_factor"], seed=1, randomize_bn=True)
+        for l in ref_layers:
+            assert {k: list(v.shape) for k, v in P[l["name"]].items()} == l["shapes"], l["name"]
+        assert count_params(P) == int(z["trainable_params"])
+        n_bn = sum(P[l["name"]]["gamma"].size for l in ref_layers if "gamma" in l["shapes"])
+        assert int(z["count_params"]) == count_params(P) + 2 * n_bn   # Keras counts the moving statistics too
+        assert not z["label_crop"].any()
+        if "probs" in z.files:
+            got = UNetOracle(kw["n_classes"], kw["n_channels"], kw["depth"], kw["complexity_factor"],
+                             params=P).predict(gi.unet_graph_input(kw))
+            assert got.shape == z["probs"].shape
+            assert np.abs(got - z["probs"]).max() < 1e-6
+    assert int(np.load(os.path.join(GOLD, "unet_graph_benchmark.npz"))["trainable_params"]) == 62050512

@@ -130,3 +130,28 @@ def test_elastic_augmenter_equals_reference():
         assert np.array_equal(a, b)
     for a, b in zip(ry, oy):
         assert np.array_equal(a, b)
+
+
+def test_unet_graph_is_the_references_own():
+    """The reference's UNet class, executed unmodified under oracle/keras_shim.py, against the oracle's layer table and
+    the product's filter rule over a sweep of configurations (names, shapes, parameter count, receptive field)."""
+    from multiplanarunet_b200.models.unet import unet_filters
+    from oracle import keras_shim
+    from oracle.unet import count_params, init_params, layer_specs
+    RefUNet = keras_shim.reference_unet_class()
+    for n_classes, n_channels, depth, cf, dim in [(3, 1, 4, 0.125, 32), (5, 1, 4, 2.0, 64), (2, 3, 4, 1.0, 64),
+                                                  (9, 2, 3, 0.5, 48), (4, 1, 2, 1.0, 16)]:
+        m = RefUNet(n_classes=n_classes, dim=dim, n_channels=n_channels, depth=depth, complexity_factor=cf,
+                    logger=lambda *a, **k: None)
+        ref = [(l.name, {k: tuple(v.shape) for k, v in l.weights.items()}) for l in m.layers if l.weights]
+        P = init_params(n_classes, n_channels, depth, cf)
+        assert [r[0] for r in ref] == [s[0] for s in layer_specs(n_classes, n_channels, depth, cf)]
+        for name, shapes in ref:
+            assert {k: tuple(v.shape) for k, v in P[name].items()} == shapes
+        assert m.trainable_count() == count_params(P)
+        enc = [m.get_layer("encoder_L%d_conv1" % i).filters for i in range(depth)] + [m.get_layer("bottom_conv1").filters]
+        assert enc == unet_filters(depth, cf)
+        assert not m.label_crop.any() and m.img_shape == (dim, dim, n_channels)
+    # the concatenation order of the up blocks is [skip, upsampled] (unet.py:167-169)
+    cat = m.get_layer("upsample_L0_concat")
+    assert [n.layer.name for n in cat.output.inputs] == ["encoder_L%d_BN" % (depth - 1), "upsample_L0_BN1"]
