@@ -696,7 +696,8 @@ __global__ void __launch_bounds__(256)
 // reduced over the block's row lanes through shared memory, then added with one atomic per value.
 __global__ void __launch_bounds__(256)
     conv_first_wgrad_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dz, Geo g,
-                            int co_phys, int CG, int RL, float* __restrict__ dW, int ldw) {
+                            int co_phys, int CG, int RL, float* __restrict__ dW, int ldw,
+                            float* __restrict__ dbias) {
   constexpr int U = 4;  // pixels per thread and iteration: U dz rows + 9 U input taps in flight (with one pixel per
                         // iteration the kernel ran at 1.45 TB/s, bound by the latency of its single 16-byte load)
   extern __shared__ float wred[];  // [RL][CG*8]
@@ -705,6 +706,9 @@ __global__ void __launch_bounds__(256)
   const int ci = blockIdx.y;
   const int Wp = g.W + 2;
   float acc[9][8];
+  float bs[8];  // column sums of dz: the conv's bias gradient (input channel 0's blocks only)
+#pragma unroll
+  for (int j = 0; j < 8; ++j) bs[j] = 0.f;
 #pragma unroll
   for (int t = 0; t < 9; ++t)
 #pragma unroll
@@ -737,6 +741,8 @@ __global__ void __launch_bounds__(256)
           d[2 * j + 1] = f.y;
         }
 #pragma unroll
+        for (int j = 0; j < 8; ++j) bs[j] += d[j];
+#pragma unroll
         for (int t = 0; t < 9; ++t) {
           const float xv = __bfloat162float(xr[u][t]);
 #pragma unroll
@@ -756,6 +762,16 @@ __global__ void __launch_bounds__(256)
       atomicAdd(dW + ((long long)t * co_phys + c) * ldw + ci, sum);
     }
     __syncthreads();
+  }
+  if (dbias != nullptr && ci == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wred[tid * 8 + j] = bs[j];
+    __syncthreads();
+    for (int c = tid; c < CG * 8; c += blockDim.x) {
+      float sum = 0.f;
+      for (int r = 0; r < RL; ++r) sum += wred[r * (CG * 8) + c];
+      atomicAdd(dbias + c, sum);
+    }
   }
 }
 
@@ -1315,7 +1331,7 @@ int launch_conv_first(const __nv_bfloat16* x, const __nv_bfloat16* w, const floa
 }
 
 int launch_conv_first_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dz, Geo g, int cin, int co_phys,
-                            float* dW, int ldw, cudaStream_t st) {
+                            float* dW, int ldw, float* dbias, cudaStream_t st) {
   if (cin < 1 || cin > 8 || co_phys % 8 || co_phys / 8 > 256) {
     set_error("conv_first_wgrad: cin=%d co_phys=%d unsupported", cin, co_phys);
     return MPU_ERR_ARG;
@@ -1325,7 +1341,7 @@ int launch_conv_first_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dz, Geo
   const size_t smem = sizeof(float) * threads * 8;
   const long long items = (long long)g.B * g.H * ((g.W + 4 * RL - 1) / (4 * RL));
   const int grid = resident_grid(conv_first_wgrad_kernel, threads, smem, items);
-  conv_first_wgrad_kernel<<<dim3(grid, cin), threads, smem, st>>>(x, dz, g, co_phys, CG, RL, dW, ldw);
+  conv_first_wgrad_kernel<<<dim3(grid, cin), threads, smem, st>>>(x, dz, g, co_phys, CG, RL, dW, ldw, dbias);
   count_launch();
   MPU_CUDA(cudaGetLastError());
   return MPU_OK;

@@ -59,8 +59,9 @@ int launch_conv_first(const __nv_bfloat16* x, const __nv_bfloat16* w, const floa
                       Geo g, int cin, int co_phys, cudaStream_t st);
 
 // Its weight gradient: dW[tap][co][ci] (row stride ldw floats per (tap, co)) += sum_p dz[p][co] * x[p+tap][ci].
+// dbias (optional): += column sums of dz, the conv's bias gradient, taken in the same pass
 int launch_conv_first_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dz, Geo g, int cin, int co_phys,
-                            float* dW, int ldw, cudaStream_t st);
+                            float* dW, int ldw, float* dbias, cudaStream_t st);
 
 // 1x1 conv + softmax head.  x = BN2 output of the last up block.
 int launch_head_infer(const __nv_bfloat16* x, Geo g, int C, const float* Wh /*[ncls][C]*/,

@@ -664,10 +664,15 @@ __global__ void __launch_bounds__(kThreads, 1)
     prefetch_tmap(&p.tmX);
     prefetch_tmap(&p.tmDY);
   }
+  // Column sums of dY (= the bias gradient of the conv whose weight gradient this is) are taken from the dY tiles as
+  // they pass through shared memory, by the four warps that otherwise idle until the drain - in the CTAs of the first
+  // kernel row and first ci tile only, whose K ranges cover every pixel row exactly once.  A stage of such a CTA is
+  // released by the MMA commit AND by these 128 readers.
+  const bool do_cs = p.bias_grad != nullptr && !part && gi == 0 && ci_t == 0;
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), do_cs ? 129 : 1);
     }
     mbar_init(done_bar, 1);
     fence_mbar_init();
@@ -740,6 +745,45 @@ __global__ void __launch_bounds__(kThreads, 1)
       if (prof) p.dbg[1] = pw;
     }
     __syncwarp();
+  } else if (warp >= 4 && do_cs) {
+    // dY tile in shared memory: two atoms of [64 pixel rows][64 channels] bf16, 128 B rows, 16-byte chunk c of row r
+    // stored at chunk position c ^ (r & 7).  Thread t sums channel chunk t & 15 (atom = chunk >> 3) over the rows
+    // (t >> 4) + 8 i: its rows all have the same r & 7, so its physical chunk position is fixed.
+    const int t = threadIdx.x - 128;
+    const int chunk = t & 15, rg = t >> 4;
+    const bool live = co0 + chunk * 8 < p.co_valid;  // (the second atom is not even loaded when it lies beyond the tensor)
+    const uint32_t toff = (uint32_t)(chunk >> 3) * 8192u + (uint32_t)rg * 128u + (uint32_t)(((chunk & 7) ^ rg) << 4);
+    float cs[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) cs[j] = 0.f;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int kb = 0; kb < nkb; ++kb) {
+      mbar_wait(full_bar(s), ph);
+      if (live) {
+        const uint8_t* st = smem_raw + (smem_base + (uint32_t)s * stage_bytes - smem_u32(smem_raw)) + toff;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint4 v = *reinterpret_cast<const uint4*>(st + i * 1024);
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = __bfloat1622float2(h[j]);
+            cs[2 * j] += f.x;
+            cs[2 * j + 1] += f.y;
+          }
+        }
+      }
+      mbar_arrive(empty_bar(s));
+      if (++s == S) { s = 0; ph ^= 1u; }
+    }
+    // row groups rg and rg ^ 1 sit 16 lanes apart in the same warp
+#pragma unroll
+    for (int j = 0; j < 8; ++j) cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], 16);
+    if (live && lane < 16) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(p.bias_grad + co0 + chunk * 8 + j, cs[j]);
+    }
   }
 
   // Accumulator drain by ALL eight warps (the producer / MMA / allocator warps have nothing left to do): warp w reads
@@ -1283,6 +1327,18 @@ int wgrad_setup(WgradParams& p, const WgradDesc& d) {
   p.ldw = d.ldw;
   p.w_rows_per_tap = d.w_rows_per_tap;
   p.dw_col0 = d.dw_col0;
+  p.bias_grad = d.bias_grad;
+  if (d.bias_grad) {
+    for (int g = 0; g < p.ngroups; ++g)
+      if (p.groups[g].dy_off != 0) {
+        set_error("wgrad_setup: bias_grad needs an unshifted dY (no phase planes)");
+        return MPU_ERR_ARG;
+      }
+    if (p.ci_tiles_full < 1) {
+      set_error("wgrad_setup: bias_grad needs at least one full ci tile");
+      return MPU_ERR_ARG;
+    }
+  }
   return MPU_OK;
 }
 

@@ -121,6 +121,7 @@ struct WgradParams {
   int ldw;
   int w_rows_per_tap;
   int dw_col0;                   // column offset (concat source 1)
+  float* bias_grad;              // optional [co_valid] += column sums of dY over all K rows (the conv's bias gradient)
   int ci_valid, co_valid;
   int stages;
   int BN;                        // unused (kept for the bring-up API)
@@ -135,6 +136,7 @@ struct WgradDesc {
   int BN;                        // 0 = choose
   int splits;                    // 0 = choose
   float* dW; int ldw, w_rows_per_tap, dw_col0;
+  float* bias_grad;              // optional: += column sums of dY (see WgradParams)
 };
 
 // Host helpers -----------------------------------------------------------------------------------

@@ -74,6 +74,7 @@ struct UNet {
   bf16* shadow = nullptr;    // bf16 copy of the whole flat parameter buffer (written by Adam); the forward
                              // GEMM operand of every 3x3 conv is a view into it
   bool dgrad_mn = true;      // dgrad reads the forward weights MN-major (no transposed copies)
+  int bias_colsum_pass = 0;  // 1 (MPU_BIAS_COLSUM): conv1 bias gradients by a separate column-sum pass over dz1
   int red_min_level = 99;    // levels >= this take BatchNorm-backward sums / bias column sums in the GEMM epilogue.
                              // OFF by default: measured slower at every level than the separate HBM passes, which
                              // overlap with the next GEMM, while the epilogue is on these GEMMs' critical path
@@ -416,8 +417,9 @@ static int gemm_dgrad3x3(UNet& u, const bf16* dz, const ConvL& L, Geo g, bf16* o
 }
 
 // dW[tap][co][col0 + ci] += sum_m X[m+off_tap][ci] * dZ[m][co]   (3x3 / 1-tap, same resolution)
+// bias_grad (optional): += column sums of dZ, taken from the dZ tiles inside the same kernel
 static int wgrad_same(const bf16* X, int Cx, int ldX, const bf16* dZ, int Cz, int ntap, Geo g,
-                      float* dW, int ldw, int co_phys, int col0, cudaStream_t st) {
+                      float* dW, int ldw, int co_phys, int col0, cudaStream_t st, float* bias_grad = nullptr) {
   int off[kMaxTaps] = {0}, widx[kMaxTaps];
   if (ntap == 9) taps3x3(g.Wp(), off);
   for (int t = 0; t < ntap; ++t) widx[t] = t;
@@ -428,6 +430,7 @@ static int wgrad_same(const bf16* X, int Cx, int ldX, const bf16* dZ, int Cz, in
   d.ntaps = ntap; d.tap_x_off = off; d.tap_dy_off = nullptr; d.tap_w = widx;
   d.rows_total = g.rows();
   d.dW = dW; d.ldw = ldw; d.w_rows_per_tap = co_phys; d.dw_col0 = col0;
+  d.bias_grad = bias_grad;
   WgradParams p;
   MPU_TRY(wgrad_setup(p, d));
   return launch_wgrad(p, st);
@@ -581,12 +584,16 @@ static int block_tail_backward(UNet& u, ConvL& c1, ConvL& c2, const bf16* xin0, 
   bias_red.csum_f = G + c1.b_off;
   MPU_TRY(gemm_dgrad3x3(u, dz2, c2, g, dz1, a1, C, st, fuse_red ? &bias_red : nullptr));
   MPU_TRY(fork_side(u, st, sb));  // dz1 is ready
-  if (!fuse_red) MPU_TRY(launch_colsum(dz1, g.rows(), C, C, G + c1.b_off, sb));
+  // ... or (default) by the weight-gradient kernel of conv1 itself, from the dz1 tiles it streams anyway: the separate
+  // column-sum pass (9 launches, 1.56 GB of DRAM reads per step) is only kept as a bring-up comparison
+  // (MPU_BIAS_COLSUM=1)
+  float* bg = (fuse_red || u.bias_colsum_pass) ? nullptr : G + c1.b_off;
+  if (!fuse_red && u.bias_colsum_pass) MPU_TRY(launch_colsum(dz1, g.rows(), C, C, G + c1.b_off, sb));
   if (!xin1 && cx0 == 8 && c1.k_phys == 8 && u.cfg.n_channels <= 4 && xin0 == u.x_in)
     // first conv of the network: K = 9 * n_channels is too thin for the tensor cores
-    MPU_TRY(launch_conv_first_wgrad(xin0, dz1, g, u.cfg.n_channels, c1.co_phys, G + c1.w_off, c1.k_phys, sb));
+    MPU_TRY(launch_conv_first_wgrad(xin0, dz1, g, u.cfg.n_channels, c1.co_phys, G + c1.w_off, c1.k_phys, bg, sb));
   else
-    MPU_TRY(wgrad_same(xin0, cx0, cx0, dz1, C, 9, g, G + c1.w_off, c1.k_phys, c1.co_phys, 0, sb));
+    MPU_TRY(wgrad_same(xin0, cx0, cx0, dz1, C, 9, g, G + c1.w_off, c1.k_phys, c1.co_phys, 0, sb, bg));
   if (xin1)
     MPU_TRY(wgrad_same(xin1, cx1, cx1, dz1, C, 9, g, G + c1.w_off, c1.k_phys, c1.co_phys, cx0, sb));
   if (dxin) MPU_TRY(gemm_dgrad3x3(u, dz1, c1, g, dxin, nullptr, 0, st, dxin_red));
@@ -758,6 +765,7 @@ int mpu_unet_create(const MpuUNetConfig* cfg, float* params, float* grads, float
   u->cfg = *cfg;
   if (const char* e = getenv("MPU_DGRAD_MN")) u->dgrad_mn = atoi(e) != 0;
   if (const char* e = getenv("MPU_EPI_RED_LEVEL")) u->red_min_level = atoi(e);
+  if (const char* e = getenv("MPU_BIAS_COLSUM")) u->bias_colsum_pass = atoi(e);
   if (const char* e = getenv("MPU_OVERLAP")) u->overlap = atoi(e) != 0;
   if (u->overlap) {
     bool ok = cudaStreamCreateWithFlags(&u->side, cudaStreamNonBlocking) == cudaSuccess;
