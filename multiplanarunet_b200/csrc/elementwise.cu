@@ -1367,11 +1367,14 @@ int launch_head(const __nv_bfloat16* x, Geo g, int C, const float* Wh, const flo
     set_error("head: shared memory %zu too large (C=%d, n_classes=%d)", smem, C, ncls);
     return MPU_ERR_ARG;
   }
-  static bool attr = false;  // one flag per instantiation
-  if (!attr) {
+  static bool attr[64] = {false};  // one flag per instantiation and device (the attribute is per device)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev = (dev >= 0 && dev < 64) ? dev : 0;
+  if (!attr[dev]) {
     MPU_CUDA(cudaFuncSetAttribute(head_kernel<TRAIN, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   200 * 1024));
-    attr = true;
+    attr[dev] = true;
   }
   const long long tiles = (g.pixels() + kHeadTile - 1) / kHeadTile;
   const int grid = resident_grid(head_kernel<TRAIN, NC>, kHeadTile, smem, tiles);
