@@ -12,7 +12,10 @@ What this pins and what it does not:
 
 Functional-API subset: Input, Conv2D, BatchNormalization, MaxPooling2D, UpSampling2D, Cropping2D, Concatenate, Reshape,
 Model(inputs, outputs) with .layers (creation order, like Keras), .get_layer, .count_params, .predict, .output;
-regularizers.l2.  Only `install()`ed by tests / oracle/make_golden.py; the GPU box has no /root/reference.
+regularizers.l2; a user-subclassable Layer (build / add_weight / call) and eager numpy versions of the elementary
+TensorFlow ops (reduce_sum / mean / max, square, multiply, where, one_hot, softmax, reciprocal ...) that
+`fusion_model.py` and `evaluate/loss_functions.py:23-31,207-246` are written in, so that the reference's FusionLayer.call,
+its weight regulariser and sparse_generalized_dice_loss run as written.  Only `install()`ed by tests / oracle/make_golden.py; the GPU box has no /root/reference.
 """
 import sys
 import types
@@ -308,6 +311,128 @@ class _L2(object):
         self.l2 = l2
 
 
+# ---- user-subclassable Layer + the handful of TensorFlow ops the fusion model and its loss use ------------------------
+class T(np.ndarray):
+    """ndarray with the two TensorFlow tensor methods the reference calls (get_shape / shape behave like a TensorShape
+    for indexing and len)."""
+
+    def get_shape(self):
+        return tuple(self.shape)
+
+
+def _t(x, dtype=None):
+    return np.asarray(x, dtype=dtype).view(T)
+
+
+class KerasLayer(Layer):
+    """tensorflow.keras.layers.Layer for subclasses that define build(input_shape) / call(x) (fusion_model.py:14-43)."""
+    auto_prefix = "layer"
+
+    def __init__(self, name=None, **kw):
+        super().__init__(name)
+        self.built = False
+        self.regularizers = {}
+
+    def add_weight(self, name, shape, initializer=None, trainable=True, regularizer=None, **kw):
+        arr = _t(initializer(shape) if initializer is not None else np.zeros(shape, np.float32))
+        self.weights[name] = arr
+        if regularizer is not None:
+            self.regularizers[name] = regularizer
+        return arr
+
+    def build(self, input_shape):
+        self.built = True
+
+    def __call__(self, x):
+        self.input = x
+        if not self.built:
+            self.build(tuple(x.shape))
+        shp = self.compute_output_shape(tuple(x.shape))
+        self.output = Node(tuple(shp), self, (x,))
+        return self.output
+
+    def run(self, xs):
+        return np.asarray(self.call(_t(xs[0], np.float32)))
+
+    def regularization_losses(self):
+        return [float(fn(self.weights[k])) for k, fn in self.regularizers.items()]
+
+
+def _constant(value):
+    return lambda shape: np.full(tuple(int(a) for a in shape), value, dtype=np.float32)
+
+
+class _Reduction(object):
+    NONE, SUM, SUM_OVER_BATCH_SIZE, AUTO = "none", "sum", "sum_over_batch_size", "auto"
+
+
+class _LossFunctionWrapper(object):
+    """tensorflow.python.keras.losses.LossFunctionWrapper: fn(y_true, y_pred, **kwargs) per sample, then the reduction
+    (SUM_OVER_BATCH_SIZE = mean over all per-sample values; an optional sample_weight multiplies them first)."""
+
+    def __init__(self, fn, reduction=_Reduction.AUTO, name=None, **kwargs):
+        self.fn, self.reduction, self.name, self._fn_kwargs = fn, reduction, name, kwargs
+
+    def __call__(self, y_true, y_pred, sample_weight=None):
+        per = np.asarray(self.fn(_t(y_true), _t(y_pred), **self._fn_kwargs))
+        if sample_weight is not None:
+            per = per * np.asarray(sample_weight).reshape((-1,) + (1,) * (per.ndim - 1))
+        if self.reduction == _Reduction.NONE:
+            return per
+        if self.reduction == _Reduction.SUM:
+            return per.sum()
+        return per.sum() / per.size
+
+
+def _tf_ops(tf):
+    """Eager numpy implementations of the elementary ops used by mpunet/models/fusion_model.py and
+    mpunet/evaluate/loss_functions.py:23-31,207-246 (reductions, elementwise math, one_hot, softmax, where)."""
+    def axis_of(axis):
+        if axis is None:
+            return None
+        if isinstance(axis, (int, np.integer)):
+            return int(axis)
+        return tuple(int(a) for a in axis)      # a range / list; () reduces nothing, as in TensorFlow
+
+    tf.float32, tf.float64, tf.uint8, tf.int32, tf.int64 = np.float32, np.float64, np.uint8, np.int32, np.int64
+    tf.convert_to_tensor = lambda x, dtype=None: _t(x, dtype)
+    tf.cast = lambda x, dtype: _t(np.asarray(x).astype(dtype))
+    tf.size = lambda x: np.asarray(x).size
+    tf.shape = lambda x: np.asarray(np.asarray(x).shape)
+    tf.reshape = lambda x, shape: _t(np.reshape(np.asarray(x), tuple(int(a) for a in np.asarray(shape))))
+    tf.equal = lambda a, b: np.asarray(a) == np.asarray(b)
+    tf.cond = lambda pred, true_fn, false_fn: true_fn() if bool(np.all(pred)) else false_fn()
+    tf.square = lambda x: _t(np.square(x))
+    tf.multiply = lambda a, b: _t(np.multiply(a, b))
+    tf.ones_like = lambda x: _t(np.ones_like(x))
+    tf.zeros_like = lambda x: _t(np.zeros_like(x))
+    tf.where = lambda c, a, b: _t(np.where(c, a, b))
+    tf.reduce_sum = lambda x, axis=None, keepdims=False: _t(np.sum(x, axis=axis_of(axis), keepdims=keepdims))
+    tf.reduce_mean = lambda x, axis=None, keepdims=False: _t(np.mean(x, axis=axis_of(axis), keepdims=keepdims))
+    tf.reduce_max = lambda x, axis=None, keepdims=False: _t(np.max(x, axis=axis_of(axis), keepdims=keepdims))
+
+    def one_hot(indices, depth, dtype=np.float32):
+        idx = np.asarray(indices).astype(np.int64)
+        out = np.zeros(idx.shape + (int(depth),), dtype=dtype)
+        np.put_along_axis(out, idx[..., None], 1, axis=-1)
+        return _t(out)
+    tf.one_hot = one_hot
+
+    def softmax(z, axis=-1):
+        z = np.asarray(z)
+        e = np.exp(z - z.max(axis=axis, keepdims=True))
+        return _t(e / e.sum(axis=axis, keepdims=True))
+    tf.nn = types.ModuleType("tensorflow.nn")
+    tf.nn.softmax = softmax
+    tf.math = types.ModuleType("tensorflow.math")
+    with np.errstate(divide="ignore"):
+        pass
+    tf.math.reciprocal = lambda x: _t(np.divide(1.0, np.asarray(x), out=np.full(np.shape(x), np.inf, dtype=np.asarray(x).dtype),
+                                               where=np.asarray(x) != 0))
+    tf.math.square = tf.square
+    tf.math.is_inf = lambda x: np.isinf(np.asarray(x))
+
+
 def install():
     """Registers the stand-in as tensorflow.keras.{models,layers,regularizers} (replacing ref_shim's bare stub, whose
     keras.utils.Sequence is kept) and restores the numpy aliases the reference still uses (np.int: conv_arithmetics.py:23)."""
@@ -323,12 +448,47 @@ def install():
     models.Model = Model
     regularizers = types.ModuleType("tensorflow.keras.regularizers")
     regularizers.l2 = _L2
-    for name, mod in (("layers", layers), ("models", models), ("regularizers", regularizers)):
+    layers.Layer = KerasLayer
+    initializers = types.ModuleType("tensorflow.keras.initializers")
+    initializers.constant = _constant
+    losses = types.ModuleType("tensorflow.keras.losses")
+    losses.Reduction = _Reduction
+    for name, mod in (("layers", layers), ("models", models), ("regularizers", regularizers),
+                      ("initializers", initializers), ("losses", losses)):
         sys.modules["tensorflow.keras." + name] = mod
         setattr(keras, name, mod)
     tf.keras = keras
+    _tf_ops(tf)
+    for name in ("tensorflow.python", "tensorflow.python.keras"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    pk_losses = types.ModuleType("tensorflow.python.keras.losses")
+    pk_losses.LossFunctionWrapper = _LossFunctionWrapper
+    sys.modules["tensorflow.python.keras.losses"] = pk_losses
     if not hasattr(np, "int"):
         np.int = int  # removed in numpy 1.24; the reference pins an older numpy
+
+
+def _load_reference_file(rel, modname):
+    import importlib.util
+    import os
+    from . import ref_shim
+    install()
+    spec = importlib.util.spec_from_file_location(modname, os.path.join(ref_shim.REF_ROOT, *rel.split("/")))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def reference_fusion_modules():
+    """(loss_functions module, fusion_model module) of the reference, loaded from their own files: the package
+    __init__s of mpunet.evaluate / mpunet.models would pull every metric and model family."""
+    lf = _load_reference_file("mpunet/evaluate/loss_functions.py", "_ref_loss_functions")
+    pkg = types.ModuleType("mpunet.evaluate")
+    pkg.__path__ = []
+    sys.modules.setdefault("mpunet.evaluate", pkg)
+    sys.modules["mpunet.evaluate.loss_functions"] = lf
+    fm = _load_reference_file("mpunet/models/fusion_model.py", "_ref_fusion_model")
+    return lf, fm
 
 
 def reference_unet_class():

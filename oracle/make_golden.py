@@ -58,9 +58,59 @@ def unet_graph_goldens(out_dir):
                                                                          rec["trainable_params"]))
 
 
+def fusion_goldens(out_dir):
+    """tests/golden/fusion_ref.npz: the reference's OWN FusionModel / FusionLayer.call (mpunet/models/fusion_model.py:
+    9-75), weight regulariser and sparse_generalized_dice_loss (mpunet/evaluate/loss_functions.py:207-246) executed
+    unmodified under oracle/keras_shim.py (eager numpy versions of the elementary TensorFlow ops they are written in):
+    probabilities, labels, the loss for the three `type_weight`s, and central-difference gradients of the reference
+    objective (float64) with respect to W and b."""
+    from oracle import keras_shim
+    lf, fm = keras_shim.reference_fusion_modules()
+    x, y, W, b = gi.fusion_inputs()
+    rec = {}
+    model = fm.FusionModel(n_inputs=W.shape[0], n_classes=W.shape[1], weight="uniform", logger=lambda *a, **k: None,
+                           verbose=False)
+    lay = model.layers[-1]
+    lay.W[...] = W
+    lay.b[...] = b
+    probs = model.predict(x)
+    rec["probs"] = probs
+    rec["labels"] = probs.argmax(-1).astype(np.uint8)
+    rec["n_weights"] = model.count_params()
+    rec["reg"] = np.asarray(sum(lay.regularization_losses()), dtype=np.float64)
+
+    def objective(Wv, bv, weight):
+        """mean per-point loss of the reference's loss function on the reference layer's float64 output"""
+        lay.weights["W"] = lay.W = keras_shim._t(Wv, np.float64)
+        lay.weights["b"] = lay.b = keras_shim._t(bv, np.float64)
+        p = lay.call(keras_shim._t(x, np.float64))
+        per = lf.sparse_generalized_dice_loss(keras_shim._t(y), p, weight)
+        return float(np.mean(per))
+
+    W64, b64 = W.astype(np.float64), b.astype(np.float64)
+    for weight in ("uniform", "simple", "square"):
+        rec["loss_" + weight] = np.asarray(objective(W64, b64, weight))
+    h = 1e-6
+    dW, db = np.zeros_like(W64), np.zeros_like(b64)
+    for idx in np.ndindex(*W64.shape):
+        d = np.zeros_like(W64)
+        d[idx] = h
+        dW[idx] = (objective(W64 + d, b64, "uniform") - objective(W64 - d, b64, "uniform")) / (2 * h)
+    for idx in np.ndindex(*b64.shape):
+        d = np.zeros_like(b64)
+        d[idx] = h
+        db[idx] = (objective(W64, b64 + d, "uniform") - objective(W64, b64 - d, "uniform")) / (2 * h)
+    rec["dW_uniform_fd"], rec["db_uniform_fd"] = dW, db
+    np.savez_compressed(os.path.join(out_dir, "fusion_ref.npz"), **rec)
+    print("fusion_ref: loss uniform %.6f simple %.6f square %.6f, |dW| %.3e" % (
+        rec["loss_uniform"], rec["loss_simple"], rec["loss_square"], np.abs(dW).max()))
+
+
 def main():
     if sys.argv[1:] == ["unet"]:  # only the network-graph fixtures
         return unet_graph_goldens(os.path.join(ROOT, "tests", "golden"))
+    if sys.argv[1:] == ["fusion"]:
+        return fusion_goldens(os.path.join(ROOT, "tests", "golden"))
     m = ref_shim.modules()
     sg, vi = m.sample_grid, m.view_interpolator
     out_dir = os.path.join(ROOT, "tests", "golden")
@@ -197,6 +247,7 @@ def main():
                                                                  int((l != lab).sum())))
     np.savez_compressed(os.path.join(out_dir, "elastic.npz"), **outs)
     unet_graph_goldens(out_dir)
+    fusion_goldens(out_dir)
 
 
 if __name__ == "__main__":

@@ -145,3 +145,14 @@ def unet_graph_input(kw, batch=2):
     """Seeded input batch [B, dim, dim, n_channels] float32 of a U-Net graph case."""
     rng = np.random.RandomState(7 + kw["dim"])
     return rng.randn(batch, kw["dim"], kw["dim"], kw["n_channels"]).astype(np.float32)
+
+
+# ---- fusion layer / generalized dice loss fixtures (tests/golden/fusion_ref.npz) ----
+def fusion_inputs(n=4096, n_views=6, n_classes=5, seed=11):
+    """Seeded softmax-like view predictions x [n, V, C] f32, labels y [n, 1] u8, weights W [V, C], bias b [1, C]."""
+    rng = np.random.RandomState(seed)
+    x = rng.dirichlet(0.4 * np.ones(n_classes), size=(n, n_views)).astype(np.float32)
+    y = rng.randint(0, n_classes, size=(n, 1)).astype(np.uint8)
+    W = rng.uniform(0.5, 1.5, (n_views, n_classes)).astype(np.float32)
+    b = (0.1 * rng.randn(1, n_classes)).astype(np.float32)
+    return x, y, W, b

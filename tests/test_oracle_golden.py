@@ -248,3 +248,22 @@ def test_unet_graph_matches_reference_goldens():
             assert got.shape == z["probs"].shape
             assert np.abs(got - z["probs"]).max() < 1e-6
     assert int(np.load(os.path.join(GOLD, "unet_graph_benchmark.npz"))["trainable_params"]) == 62050512
+
+
+def test_fusion_layer_and_dice_loss_match_reference_goldens():
+    """tests/golden/fusion_ref.npz: the reference's own FusionLayer.call, regulariser and sparse_generalized_dice_loss
+    (fusion_model.py:9-43, loss_functions.py:207-246) executed unmodified under oracle/keras_shim.py.  The oracle's
+    restatement must give the same probabilities / labels, the same loss, and its ANALYTIC gradients must equal the
+    central differences of the reference objective."""
+    from oracle import fusion
+    z = np.load(os.path.join(GOLD, "fusion_ref.npz"))
+    x, y, W, b = gi.fusion_inputs()
+    probs = fusion.fusion_forward(x, W, b)
+    assert np.abs(probs - z["probs"]).max() < 1e-6 and np.array_equal(probs.argmax(-1).astype(np.uint8), z["labels"])
+    assert int(z["n_weights"]) == W.size + b.size == 35
+    loss, dW, db = fusion.gdl_loss_and_grads(x, y, W, b, reg=0.0)
+    for weight in ("uniform", "simple", "square"):   # rank-2 inputs: every class weight is 1 whatever the type
+        assert abs(loss - float(z["loss_" + weight])) < 1e-9
+    assert np.abs(dW - z["dW_uniform_fd"]).max() < 1e-8 and np.abs(db.reshape(1, -1) - z["db_uniform_fd"]).max() < 1e-8
+    loss_r, _, _ = fusion.gdl_loss_and_grads(x, y, W, b, reg=1e-6)
+    assert abs((loss_r - loss) - float(z["reg"])) < 1e-12

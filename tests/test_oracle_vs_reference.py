@@ -155,3 +155,30 @@ def test_unet_graph_is_the_references_own():
     # the concatenation order of the up blocks is [skip, upsampled] (unet.py:167-169)
     cat = m.get_layer("upsample_L0_concat")
     assert [n.layer.name for n in cat.output.inputs] == ["encoder_L%d_BN" % (depth - 1), "upsample_L0_BN1"]
+
+
+def test_fusion_model_is_the_references_own():
+    """The reference's FusionModel / FusionLayer / reg / sparse_generalized_dice_loss, executed unmodified under
+    oracle/keras_shim.py, against the oracle on a sweep of shapes (incl. a 2-class, 3-view case and [N] labels)."""
+    from oracle import fusion, keras_shim
+    lf, fm = keras_shim.reference_fusion_modules()
+    for n, V, C, seed in [(512, 6, 5, 0), (300, 3, 2, 1), (64, 1, 4, 2)]:
+        rng = np.random.RandomState(seed)
+        x = rng.dirichlet(np.ones(C), size=(n, V)).astype(np.float32)
+        y = rng.randint(0, C, size=(n, 1)).astype(np.uint8)
+        W = rng.uniform(0.5, 1.5, (V, C)).astype(np.float32)
+        b = (0.1 * rng.randn(1, C)).astype(np.float32)
+        M = fm.FusionModel(n_inputs=V, n_classes=C, weight="uniform", logger=lambda *a, **k: None, verbose=False)
+        lay = M.layers[-1]
+        assert M.count_params() == V * C + C and lay.weights["W"].shape == (V, C) and lay.weights["b"].shape == (1, C)
+        assert float(lay.W.min()) == 1.0 and float(np.abs(lay.b).max()) == 0.0     # constant(1) / constant(0) init
+        lay.W[...] = W
+        lay.b[...] = b
+        p_ref = M.predict(x)
+        p = fusion.fusion_forward(x, W, b)
+        assert np.abs(p_ref - p).max() < 1e-6 and np.array_equal(p_ref.argmax(-1), p.argmax(-1))
+        loss, _, _ = fusion.gdl_loss_and_grads(x, y, W, b, reg=1e-6)
+        p64 = lay.call(keras_shim._t(x, np.float64))
+        ref_loss = float(M.loss(y, p64)) + sum(lay.regularization_losses())
+        assert abs(ref_loss - loss) < 1e-7
+        assert abs(float(M.loss(y.reshape(-1), p64)) - float(M.loss(y, p64))) < 1e-12   # [N] and [N, 1] labels
