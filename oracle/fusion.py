@@ -13,9 +13,12 @@ CPU restatement in numpy of the reference's multi-view mapping + fusion:
   * dice_all ...................... mpunet/evaluate/metrics.py:26-52
 
 map_real_space_pred is pinned against the unmodified reference source under oracle/ref_shim.py
-(tests/test_oracle_vs_reference.py, tests/golden/).  The fusion layer / loss live in TensorFlow in
-the reference (not installable here): "parity unpinned" for those - they follow the 3-line formulas
-at the cited lines.
+(tests/test_oracle_vs_reference.py, tests/golden/).  The fusion layer, its regulariser and the generalized dice
+loss are pinned against the reference's OWN FusionModel / FusionLayer.call / reg / sparse_generalized_dice_loss
+executed unmodified under oracle/keras_shim.py, which supplies eager numpy versions of the elementary TensorFlow
+ops those few lines are written in (tests/golden/fusion_ref.npz, incl. central-difference gradients of the
+reference objective for the analytic gradients below).  The Adam rule stays "parity unpinned" (it lives in
+TensorFlow, not in the reference tree).
 """
 import numpy as np
 

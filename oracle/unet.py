@@ -8,7 +8,10 @@ CPU restatement (torch-CPU, fp32) of the reference's 2D U-Net graph and train st
                                     Adam(lr 5e-5, eps 1e-8): bin/defaults/MultiPlanar/train_hparams.yaml:108,125-126,
                                     train/trainer.py:51-101,246-257
 
-PARITY UNPINNED: the arithmetic of these layers lives in TensorFlow 2.3.2 (requirements.txt:10), which
+GRAPH PINNED: layer order / names / filter counts / kernel sizes / concatenation order / parameter counts equal the
+graph that the reference's own UNet.init_model builds when executed unmodified under oracle/keras_shim.py
+(tests/golden/unet_graph_*.npz, tests/test_oracle_golden.py, tests/test_oracle_vs_reference.py).
+LAYER ARITHMETIC - PARITY UNPINNED: the arithmetic of these layers lives in TensorFlow 2.3.2 (requirements.txt:10), which
 cannot be installed here (no wheel for Python 3.12, no network) and the reference ships no golden
 vectors for the network.  Layer semantics restated from the TF/Keras 2.3
 documentation: Conv2D NHWC / HWIO cross-correlation, SAME padding = (k-1)//2 before, rest after
