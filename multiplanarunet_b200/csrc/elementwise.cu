@@ -3,6 +3,7 @@
 #include "common.h"
 
 #include <cstdio>
+#include <cstdlib>
 
 namespace mpu {
 
@@ -171,6 +172,43 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count
   if (rstd_out) rstd_out[c] = rstd;
 }
 
+// BN coefficients of one channel, computed by every thread for its own channels (the arithmetic of bn_finalize_kernel,
+// which this replaces on the U-Net's schedule: 13 tiny launches on the forward critical path per step).  `writer`
+// threads (one per channel: block 0, row lane 0) also store scale / shift / mean / rstd for the backward pass and
+// update the moving statistics; in training mode nobody else reads the moving statistics, so there is no race.
+__device__ __forceinline__ void bn_coef(const BnFin& f, int c, bool writer, float& sc, float& sh) {
+  if (f.no_write) {  // coefficients already finalised by a separate launch (bring-up comparison)
+    sc = f.scale[c];
+    sh = f.shift[c];
+    return;
+  }
+  float mean, var;
+  if (f.training) {
+    const double m = f.sums[c] / f.count;
+    double v = f.sums[f.C + c] / f.count - m * m;
+    if (v < 0) v = 0;
+    mean = (float)m;
+    var = (float)v;
+    if (writer) {
+      const double unbiased = f.count > 1 ? v * f.count / (f.count - 1) : v;
+      f.mmean[c] = f.mmean[c] * f.momentum + mean * (1.f - f.momentum);
+      f.mvar[c] = f.mvar[c] * f.momentum + (float)unbiased * (1.f - f.momentum);
+    }
+  } else {
+    mean = f.mmean[c];
+    var = f.mvar[c];
+  }
+  const float rstd = 1.0f / sqrtf(var + f.eps);
+  sc = f.gamma[c] * rstd;
+  sh = f.beta[c] - mean * sc;
+  if (writer) {
+    f.scale[c] = sc;
+    f.shift[c] = sh;
+    if (f.mean_out) f.mean_out[c] = mean;
+    if (f.rstd_out) f.rstd_out[c] = rstd;
+  }
+}
+
 // interior pixel index -> padded row
 __device__ __forceinline__ long long padded_row(const Geo& g, long long pix) {
   const int x = (int)(pix % g.W);
@@ -215,18 +253,14 @@ struct SegIter {
   }
 };
 
-__global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
-                                const float* __restrict__ shift, __nv_bfloat16* __restrict__ b, Geo g,
+__global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ y, BnFin f, __nv_bfloat16* __restrict__ b, Geo g,
                                 int C, int CG, int RL) {
   constexpr int U = 4;  // independent 16-byte loads per thread and work item
   const int tid = threadIdx.x;
   const int cg = tid % CG, rl = tid / CG;
   float sc[8], sh[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    sc[j] = scale[cg * 8 + j];
-    sh[j] = shift[cg * 8 + j];
-  }
+  for (int j = 0; j < 8; ++j) bn_coef(f, cg * 8 + j, blockIdx.x == 0 && rl == 0, sc[j], sh[j]);
   const int Wp = g.W + 2;
   auto base_of = [&](const SegIter& it) {
     return ((long long)it.n * (g.H + 2) + it.yy + 1) * Wp + 1 + it.seg * (U * RL) + rl;
@@ -272,8 +306,7 @@ __global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float
 }
 
 // window (2x2) version: writes the four BN outputs and their max into the half-resolution tensor.
-__global__ void bn_apply_pool_kernel(const __nv_bfloat16* __restrict__ y,
-                                     const float* __restrict__ scale, const float* __restrict__ shift,
+__global__ void bn_apply_pool_kernel(const __nv_bfloat16* __restrict__ y, BnFin f,
                                      __nv_bfloat16* __restrict__ b, __nv_bfloat16* __restrict__ pooled,
                                      Geo g, int C, int CG, int RL) {
   const int tid = threadIdx.x;
@@ -282,10 +315,7 @@ __global__ void bn_apply_pool_kernel(const __nv_bfloat16* __restrict__ y,
   const int Wp = g.W + 2;
   float sc[8], sh[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    sc[j] = scale[cg * 8 + j];
-    sh[j] = shift[cg * 8 + j];
-  }
+  for (int j = 0; j < 8; ++j) bn_coef(f, cg * 8 + j, blockIdx.x == 0 && rl == 0, sc[j], sh[j]);
   SegIter it;
   it.init(blockIdx.x, gridDim.x, h, (w + RL - 1) / RL);
   for (; it.n < g.B; it.next()) {
@@ -403,6 +433,11 @@ __global__ void __launch_bounds__(256) __maxnreg__(POOL ? 168 : 104)
     if (APPLY) {
       const double cnt = (double)g.pixels();
       const float mu = a.mean[c], rs = a.rstd[c];
+      if (a.dgamma != nullptr && blockIdx.x == 0 && rl == 0) {
+        // dbeta += sum g ; dgamma += sum g*xhat = rstd * (sum g*y - mu * sum g)   (was bn_bwd_params_kernel)
+        a.dbeta[c] += (float)sums_in[c];
+        a.dgamma[c] += (float)((double)rs * (sums_in[C + c] - (double)mu * sums_in[c]));
+      }
       const float mg = (float)(sums_in[c] / cnt);
       const float mgy = (float)(sums_in[C + c] / cnt);
       const float mgx = rs * (mgy - mu * mg);
@@ -1227,8 +1262,26 @@ int launch_bn_finalize(const double* sums, double count, const float* gamma, con
   return MPU_OK;
 }
 
-int launch_bn_apply(const __nv_bfloat16* y, const float* scale, const float* shift, __nv_bfloat16* b,
+// bring-up knob for same-box A/B measurements: MPU_BN_SEPARATE=1 runs bn_finalize / bn_bwd_params as the separate
+// single-block launches they were before being folded into the apply kernels
+static int bn_separate() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MPU_BN_SEPARATE");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+
+int launch_bn_apply(const __nv_bfloat16* y, const BnFin& f0, __nv_bfloat16* b,
                     __nv_bfloat16* pooled, Geo g, int C, cudaStream_t st) {
+  BnFin f = f0;
+  f.no_write = 0;
+  if (bn_separate()) {
+    MPU_TRY(launch_bn_finalize(f.sums, f.count, f.gamma, f.beta, f.mmean, f.mvar, f.eps, f.momentum, f.training, f.C,
+                               f.scale, f.shift, f.mean_out, f.rstd_out, st));
+    f.no_write = 1;   // (the apply kernel must then read the stored coefficients: the moving statistics have moved on)
+  }
   int CG, RL, threads;
   if (C / 8 > 256) {
     set_error("bn_apply: C=%d exceeds 2048 channels", C);
@@ -1238,12 +1291,12 @@ int launch_bn_apply(const __nv_bfloat16* y, const float* scale, const float* shi
     line_layout(C, g.W / 2, &CG, &RL, &threads);
     const long long items = (long long)g.B * (g.H / 2) * ((g.W / 2 + RL - 1) / RL);
     const int grid = resident_grid(bn_apply_pool_kernel, threads, 0, items);
-    bn_apply_pool_kernel<<<grid, threads, 0, st>>>(y, scale, shift, b, pooled, g, C, CG, RL);
+    bn_apply_pool_kernel<<<grid, threads, 0, st>>>(y, f, b, pooled, g, C, CG, RL);
   } else {
     line_layout(C, (g.W + 3) / 4, &CG, &RL, &threads);
     const long long items = (long long)g.B * g.H * ((g.W + 4 * RL - 1) / (4 * RL));
     const int grid = resident_grid(bn_apply_kernel, threads, 0, items);
-    bn_apply_kernel<<<grid, threads, 0, st>>>(y, scale, shift, b, g, C, CG, RL);
+    bn_apply_kernel<<<grid, threads, 0, st>>>(y, f, b, g, C, CG, RL);
   }
   count_launch();
   MPU_CUDA(cudaGetLastError());
@@ -1285,15 +1338,21 @@ int launch_bn_bwd_reduce(const BnBwdArgs& a, double* sums, cudaStream_t st) {
   return launch_bn_bwd<false, false>(a, nullptr, sums, nullptr, 0, nullptr, st);
 }
 
-int launch_bn_bwd_apply(const BnBwdArgs& a, const double* sums, __nv_bfloat16* dz, int phase_major,
+int launch_bn_bwd_apply(const BnBwdArgs& a0, const double* sums, __nv_bfloat16* dz, int phase_major,
                         float* dgamma, float* dbeta, float* dbias, cudaStream_t st) {
+  BnBwdArgs a = a0;  // the parameter gradients are added by block 0 of the apply kernel itself
+  const bool sep = bn_separate() != 0;
+  a.dgamma = sep ? nullptr : dgamma;
+  a.dbeta = sep ? nullptr : dbeta;
   if (a.gP != nullptr)
     MPU_TRY((launch_bn_bwd<true, true>(a, sums, nullptr, dz, phase_major, dbias, st)));
   else
     MPU_TRY((launch_bn_bwd<false, true>(a, sums, nullptr, dz, phase_major, dbias, st)));
-  bn_bwd_params_kernel<<<(a.C + 127) / 128, 128, 0, st>>>(sums, a.mean, a.rstd, a.C, dgamma, dbeta);
-  count_launch();
-  MPU_CUDA(cudaGetLastError());
+  if (sep) {
+    bn_bwd_params_kernel<<<(a.C + 127) / 128, 128, 0, st>>>(sums, a.mean, a.rstd, a.C, dgamma, dbeta);
+    count_launch();
+    MPU_CUDA(cudaGetLastError());
+  }
   return MPU_OK;
 }
 

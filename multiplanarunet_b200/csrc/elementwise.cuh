@@ -27,8 +27,21 @@ int launch_bn_finalize(const double* sums, double count, const float* gamma, con
                        float* moving_mean, float* moving_var, float eps, float momentum, int training,
                        int C, float* scale, float* shift, float* mean, float* rstd, cudaStream_t st);
 
+// What bn_finalize computes, handed to the apply kernels so that they derive the coefficients themselves (no separate
+// launch between the stats-producing GEMM and the apply pass): batch sums / count (training) or moving statistics
+// (inference) -> scale / shift; block 0 also stores scale / shift / mean / rstd and updates the moving statistics.
+struct BnFin {
+  const double* sums;            // [2][C] sum / sum of squares (training)
+  double count;
+  const float *gamma, *beta;
+  float *mmean, *mvar;           // moving statistics (updated in training mode)
+  float eps, momentum;
+  int training, C;
+  float *scale, *shift, *mean_out, *rstd_out;
+  int no_write;                  // set by launch_bn_apply (bring-up: coefficients finalised by a separate launch)
+};
 // b = y*scale + shift on interior pixels; optionally also the 2x2 max-pooled tensor (next level).
-int launch_bn_apply(const __nv_bfloat16* y, const float* scale, const float* shift, __nv_bfloat16* b,
+int launch_bn_apply(const __nv_bfloat16* y, const BnFin& f, __nv_bfloat16* b,
                     __nv_bfloat16* pooled, Geo g, int C, cudaStream_t st);
 
 struct BnBwdArgs {
@@ -39,6 +52,7 @@ struct BnBwdArgs {
   const float *scale, *shift, *mean, *rstd, *gamma;
   Geo g;
   int C;
+  float *dgamma, *dbeta;         // set by launch_bn_bwd_apply: parameter gradients, added by block 0 of the apply pass
 };
 // pass 1: sums[0][c] = sum g, sums[1][c] = sum g*xhat
 int launch_bn_bwd_reduce(const BnBwdArgs& a, double* sums, cudaStream_t st);

@@ -472,11 +472,14 @@ static int bn_forward(UNet& u, BnL& bn, const bf16* y, Geo g, bf16* b, bf16* poo
   const float* P = u.params;
   if (training && !stats_fused)
     MPU_TRY(launch_channel_stats(y, g.rows(), bn.c_phys, bn.c_phys, bn.sums, st));
-  MPU_TRY(launch_bn_finalize(bn.sums, (double)g.pixels(), P + bn.g_off, P + bn.b_off,
-                             u.bn_state + bn.m_off, u.bn_state + bn.v_off, u.cfg.bn_eps,
-                             u.cfg.bn_momentum, training, bn.c_phys, bn.scale, bn.shift, bn.mean, bn.rstd,
-                             st));
-  return launch_bn_apply(y, bn.scale, bn.shift, b, pooled, g, bn.c_phys, st);
+  BnFin f;
+  f.sums = bn.sums; f.count = (double)g.pixels();
+  f.gamma = P + bn.g_off; f.beta = P + bn.b_off;
+  f.mmean = u.bn_state + bn.m_off; f.mvar = u.bn_state + bn.v_off;
+  f.eps = u.cfg.bn_eps; f.momentum = u.cfg.bn_momentum;
+  f.training = training; f.C = bn.c_phys;
+  f.scale = bn.scale; f.shift = bn.shift; f.mean_out = bn.mean; f.rstd_out = bn.rstd;
+  return launch_bn_apply(y, f, b, pooled, g, bn.c_phys, st);
 }
 
 // bf16 operand copies that are NOT plain views of the shadow buffer: collapsed upsample-conv weights,
@@ -563,6 +566,7 @@ static int bn_backward(UNet& u, BnL& bn, const bf16* y, const bf16* gA, int ldA,
   a.gamma = u.params + bn.g_off;
   a.g = g;
   a.C = bn.c_phys;
+  a.dgamma = a.dbeta = nullptr;  // (set by launch_bn_bwd_apply)
   if (!sums_ready) MPU_TRY(launch_bn_bwd_reduce(a, bn.sums, st));
   return launch_bn_bwd_apply(a, bn.sums, dz, phase_major, u.grads + bn.g_off, u.grads + bn.b_off, dbias,
                              st);
