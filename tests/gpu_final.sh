@@ -24,7 +24,8 @@ for f in ("bench_n1", "bench_reference", "bench_predict", "bench_fusion"):
         print(f, "failed", e)
 PY
 cat $out/traffic_summary.txt
-# ncu --set full of the BatchNorm / elementwise kernels of one train step (summaries only)
+# ncu --set full of the BatchNorm / elementwise kernels of one train step (summaries only; ~7 minutes: only with a 2nd argument)
+[ -n "$2" ] || exit 0
 timeout 900 ncu --set full --clock-control none --profile-from-start off -k regex:"bn_|head_kernel|conv_first|adam" \
   -f -o $out/elementwise python tests/perf_unet.py --ncu > $out/ncu_elementwise.log 2>&1
 python tests/ncu_summary.py $out/elementwise.ncu-rep > $out/elementwise_summary.txt 2>&1
