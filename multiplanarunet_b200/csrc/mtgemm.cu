@@ -1,18 +1,23 @@
 // tcgen05 / TMA / TMEM multi-tap GEMM kernels (sm_100a). See mtgemm.cuh for the math.
 //
-// Measured facts these kernels are built around (B200, ncu + in-kernel cycle counters, profiles/):
-//   * a tcgen05.mma with both operands in shared memory costs ~165 cycles per issue whatever N is (the
-//     128-row A operand fetch), so every MMA is given the full N = 256: the forward/dgrad kernel puts
-//     the OUTPUT CHANNELS on the 128 MMA rows (weights = A operand) and 256 PIXELS on the columns;
-//   * issuing TMA / MMA from a divergent `lane == 0` branch makes ptxas wrap every UTCHMMA in an
-//     ELECT+BRA waterfall loop: producer / MMA warps run warp-uniform loops and issue from one
-//     elect.sync lane;
-//   * the 128B swizzle is applied on absolute shared-memory address bits: a descriptor whose start
-//     address is shifted by whole 128 B rows inside a TMA-written tile reads the shifted rows
-//     correctly with the base-offset field left at 0.  One activation "slab" load therefore serves
-//     the kx-1, kx, kx+1 taps of a 3x3 kernel row.
-//   * operand traffic L2 -> SM is the next bound (~42 B/clk/SM): slabs are shared across taps and
-//     rings of slabs / weight tiles keep the tensor pipe fed.
+// Measured facts these kernels are built around (B200; ncu, in-kernel cycle counters and tests/mma_issue_bench.cu,
+// evidence under profiles/, discussion in DESIGN.md section 3):
+//   * the tensor pipe costs N/2 cycles per M=128, K=16 MMA at full rate down to N=128 (4095 MAC/cycle/SM), whatever
+//     else the SM does (TMA refill, tcgen05.ld, row-shifted or MN-major descriptors); N=96 costs 64 cycles.  The
+//     forward/dgrad kernel therefore puts the OUTPUT CHANNELS on the 128 MMA rows (weights = A operand) and 256 PIXELS
+//     on the columns; wgrad stacks the three kx taps of a kernel row along N (N = 192);
+//   * what limits a main loop is the ISSUE path of the single issuing thread (~15 uniform-datapath instructions per
+//     MMA): one elect.sync at role entry and a plain single-thread loop inside, descriptor high words hoisted, K tails
+//     issued through unrolled immediates (a rolled loop cost ~215 cycles per MMA);
+//   * the 128B swizzle is applied on absolute shared-memory address bits: a descriptor whose start address is shifted
+//     by whole 128 B rows inside a TMA-written tile reads the shifted rows correctly with the base-offset field left
+//     at 0.  One activation "slab" load therefore serves the kx-1, kx, kx+1 taps of a 3x3 kernel row - or all nine taps
+//     where the padded image rows are short;
+//   * operand delivery L2 -> SM (~45-57 B/clk/SM through TMA) is the next bound on the fine levels: slabs are shared
+//     across taps (and across the two CTAs of a cluster by multicast), rings of three slabs / three or four weight
+//     stages cover the refill round trip;
+//   * the SM clock of sustained operation is set by the ~1 kW power cap (1.62-1.80 GHz of 1.965): wasted MMA work
+//     (padded rows) costs twice.
 #include "mtgemm.cuh"
 #include "ptx.cuh"
 #include "common.h"
