@@ -79,8 +79,16 @@ static constexpr uint32_t kStageHalfBytes = 64u * 256u;      // epilogue staging
 // CTAs' MMA threads (multicast arrive), so each producer knows both copies are free before it overwrites them.
 // RED: the epilogue additionally takes column reductions of the stored tile (FwdParams::csum_f / red_d); a separate
 // instantiation so that the plain kernels carry neither its registers nor its branches.
-template <bool W_MN, bool PROF, bool CL2, bool RED>
+// CLM (cluster mode): 0 = independent CTAs; 1 = "CL2" above (the two channel tiles of one pixel tile share every slab);
+// 2 = the two CTAs of a cluster work on two ADJACENT PIXEL TILES of the SAME channel tile and share the WEIGHT stream:
+// each stage of the weight ring carries two (chunk, tap) tiles, CTA rank r fetches tile r and multicasts it to both
+// (a conv with a single channel tile - level 0 - cannot share slabs, and its weights are re-streamed for every one of
+// its 8256 pixel tiles); a weight stage is released by the commits of both MMA threads.
+template <bool W_MN, bool PROF, int CLM, bool RED>
 __global__ void __launch_bounds__(kFwdThreads, 1) mtgemm_fwd_kernel(const __grid_constant__ FwdParams p) {
+  constexpr bool CL2 = CLM == 1;   // slab sharing
+  constexpr bool CLW = CLM == 2;   // weight sharing
+  constexpr bool CLUSTER = CLM != 0;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -123,7 +131,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mtgemm_fwd_kernel(const __grid
     }
     for (int s = 0; s < NW; ++s) {
       mbar_init(w_full(s), 1);
-      mbar_init(w_empty(s), 1);
+      mbar_init(w_empty(s), CLW ? 2 : 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
@@ -137,18 +145,22 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mtgemm_fwd_kernel(const __grid
   }
   tc_fence_before();
   __syncthreads();
-  if (CL2) cluster_sync_all();  // the partner's barriers are initialised before anything is multicast to them
+  if (CLUSTER) cluster_sync_all();  // the partner's barriers are initialised before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   // Work units: plain mode - one (pixel tile, channel tile) per CTA and step, channel tile fastest; cluster mode - one
   // (pixel tile, channel-tile PAIR) per cluster and step, CTA rank r takes channel tile 2 * pair + r.
-  const int crank = CL2 ? (int)cluster_ctarank() : 0;
+  // weight-sharing mode - one (pixel-tile PAIR, channel tile) per cluster and step, CTA rank r takes pixel tile
+  // 2 * pair + r (with an odd number of pixel tiles the last pair's second tile lies beyond the tensor: its CTA runs the
+  // whole protocol on zero-filled slabs and stores nothing).
+  const int crank = CLUSTER ? (int)cluster_ctarank() : 0;
   const int n_div = CL2 ? (p.n_tiles >> 1) : p.n_tiles;
-  const int total_tiles = p.m_tiles * n_div;
-  const int unit0 = CL2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  const int unit_step = CL2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  auto pix_tile = [&](int unit) { return unit / n_div; };
+  const int m_div = CLW ? ((p.m_tiles + 1) >> 1) : p.m_tiles;
+  const int total_tiles = m_div * n_div;
+  const int unit0 = CLUSTER ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int unit_step = CLUSTER ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  auto pix_tile = [&](int unit) { return CLW ? (unit / n_div) * 2 + crank : unit / n_div; };
   auto ch_tile = [&](int unit) { return CL2 ? (unit % n_div) * 2 + crank : unit % n_div; };
   const int kchunks = p.chunks0 + p.chunks1;
   const bool prof = PROF && p.dbg != nullptr && blockIdx.x == 0;
@@ -224,6 +236,15 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mtgemm_fwd_kernel(const __grid
               const uint32_t dst = w_dst + (uint32_t)i * w_tile_bytes;
               if (PROF && (p.dbg_flags & 4)) {
                 // bring-up: no weight traffic
+              } else if (CLW) {  // tile i of the stage is fetched by CTA rank i and delivered to both CTAs
+                if (i == crank) {
+                  if (!W_MN) {
+                    tma_load_2d_multicast(&p.tmW, w_full(ws), dst, kcol, wr, (uint16_t)3);
+                  } else {
+                    tma_load_2d_multicast(&p.tmW, w_full(ws), dst, n0, wr + kcol, (uint16_t)3);
+                    tma_load_2d_multicast(&p.tmW, w_full(ws), dst + 8192u, n0 + 64, wr + kcol, (uint16_t)3);
+                  }
+                }
               } else if (!W_MN) {
                 tma_load_2d(&p.tmW, w_full(ws), dst, kcol, wr);
               } else {  // two 64-channel atoms of [64 K rows][64 channels]
@@ -323,7 +344,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mtgemm_fwd_kernel(const __grid
               sh = (uint32_t)p.groups[g].shift[t] * 8u;
             }
           }
-          mma_commit(w_empty(ws));
+          if (CLW) mma_commit_multicast(w_empty(ws), (uint16_t)3);
+          else mma_commit(w_empty(ws));
           left -= nit;
           if (++ws == NW) { ws = 0; wph ^= 1u; }
         }
@@ -582,7 +604,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mtgemm_fwd_kernel(const __grid
 
   tc_fence_before();
   __syncthreads();
-  if (CL2) cluster_sync_all();  // no CTA leaves while its partner may still multicast data or arrivals into it
+  if (CLUSTER) cluster_sync_all();  // no CTA leaves while its partner may still multicast data or arrivals into it
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -936,14 +958,19 @@ static int cur_dev() {
   return (dev >= 0 && dev < 64) ? dev : 0;
 }
 typedef void (*FwdKernel)(const FwdParams);
-static FwdKernel fwd_kernel_for(bool w_mn, bool prof, bool cl2, bool red) {
-  if (red) return w_mn ? mtgemm_fwd_kernel<true, false, false, true> : mtgemm_fwd_kernel<false, false, false, true>;
-  if (cl2) {
-    if (prof) return w_mn ? mtgemm_fwd_kernel<true, true, true, false> : mtgemm_fwd_kernel<false, true, true, false>;
-    return w_mn ? mtgemm_fwd_kernel<true, false, true, false> : mtgemm_fwd_kernel<false, false, true, false>;
+// clm: cluster mode 0 / 1 (slab sharing) / 2 (weight sharing)
+static FwdKernel fwd_kernel_for(bool w_mn, bool prof, int clm, bool red) {
+  if (red) return w_mn ? mtgemm_fwd_kernel<true, false, 0, true> : mtgemm_fwd_kernel<false, false, 0, true>;
+  if (clm == 1) {
+    if (prof) return w_mn ? mtgemm_fwd_kernel<true, true, 1, false> : mtgemm_fwd_kernel<false, true, 1, false>;
+    return w_mn ? mtgemm_fwd_kernel<true, false, 1, false> : mtgemm_fwd_kernel<false, false, 1, false>;
   }
-  if (prof) return w_mn ? mtgemm_fwd_kernel<true, true, false, false> : mtgemm_fwd_kernel<false, true, false, false>;
-  return w_mn ? mtgemm_fwd_kernel<true, false, false, false> : mtgemm_fwd_kernel<false, false, false, false>;
+  if (clm == 2) {
+    if (prof) return w_mn ? mtgemm_fwd_kernel<true, true, 2, false> : mtgemm_fwd_kernel<false, true, 2, false>;
+    return w_mn ? mtgemm_fwd_kernel<true, false, 2, false> : mtgemm_fwd_kernel<false, false, 2, false>;
+  }
+  if (prof) return w_mn ? mtgemm_fwd_kernel<true, true, 0, false> : mtgemm_fwd_kernel<false, true, 0, false>;
+  return w_mn ? mtgemm_fwd_kernel<true, false, 0, false> : mtgemm_fwd_kernel<false, false, 0, false>;
 }
 // clusters of 2 that can be co-resident with this kernel's shared-memory footprint (per device; 0 = cluster launch
 // not possible, fall back to independent CTAs)
@@ -960,6 +987,7 @@ static int g_fwd_no_slab = 0;
 static int g_fwd_cl2 = 1;   // MPU_FWD_CL2: 0 = never launch slab-sharing clusters, 1 = whenever the conv has an even
                             // number of channel tiles (default: +5 % at level 1, +2 % at level 3, neutral at 16x16;
                             // profiles/r02_perf_gemm_cluster.txt), 2 = only where the 9-tap slab does not fit
+static int g_fwd_clw = 0;   // MPU_FWD_CLW: weight-sharing clusters (see launch_fwd); measured neutral -> off by default
 static int g_fwd_wide = 1;  // MPU_FWD_WIDE=0: never build slabs taller than 264 rows (bring-up comparison)
 static long long* g_fwd_dbg = nullptr;
 extern "C" void mpu_debug_set_fwd_mode(int no_slab) { g_fwd_no_slab = no_slab; }
@@ -972,6 +1000,7 @@ int fwd_setup(FwdParams& p, const FwdDesc& d) {
     if (const char* e = getenv("MPU_FWD_NO_SLAB")) g_fwd_no_slab = atoi(e);
     if (const char* e = getenv("MPU_FWD_WIDE")) g_fwd_wide = atoi(e);
     if (const char* e = getenv("MPU_FWD_CL2")) g_fwd_cl2 = atoi(e);
+    if (const char* e = getenv("MPU_FWD_CLW")) g_fwd_clw = atoi(e);
     env_read = true;
   }
   memset(&p, 0, sizeof(p));
@@ -1155,24 +1184,37 @@ int launch_fwd(FwdParams& p, cudaStream_t stream) {
   p.m_tiles = (p.M_rows + kPT - 1) / kPT;
   p.n_tiles = (p.n_valid + 127) / 128;
   if (!g_fwd_attr_set[cur_dev()]) {
-    for (int i = 0; i < 16; ++i)
-      MPU_CUDA(cudaFuncSetAttribute(fwd_kernel_for(i & 1, i & 2, i & 4, i & 8),
+    for (int i = 0; i < 4; ++i)
+      for (int clm = 0; clm < 3; ++clm)
+        MPU_CUDA(cudaFuncSetAttribute(fwd_kernel_for(i & 1, i & 2, clm, false),
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmem));
+    for (int i = 0; i < 2; ++i)
+      MPU_CUDA(cudaFuncSetAttribute(fwd_kernel_for(i & 1, false, 0, true),
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmem));
     g_fwd_attr_set[cur_dev()] = true;
   }
   const int smem = kDynSmem - smem_reserve();
-  // Cluster mode (two CTAs share every activation slab through TMA multicast): needs an even number of channel
-  // tiles (levels 1, 3, 4 at complexity_factor 2).
+  // Cluster modes (pairs of CTAs sharing one operand stream through TMA multicast).  1: the two channel tiles of a pixel
+  // tile share every activation slab - needs an even number of channel tiles (levels 1, 3, 4 at complexity_factor 2).
+  // 2: two adjacent pixel tiles of one channel tile share the weight stream - used where there is a single channel
+  // tile (level 0), whose weights are otherwise re-fetched for every pixel tile (MPU_FWD_CLW: 0 = never [default],
+  // 1 = single channel tile, 2 = also instead of mode 1 on the 3-tap-slab levels).  Built, parity-green and measured
+  // NEUTRAL (profiles/r02_perf_gemm_weight_sharing.txt: level 0 853 vs 847 TFLOP/s, 180->90 938 vs 932, level 1 with
+  // mode 2 instead of mode 1 899 vs 907; step 26.47 vs 26.33-26.44 ms): the 7-8 % the MMA thread waits for weights at
+  // level 0 is ring latency, not fetch bandwidth.  Off by default: independent CTAs do not run in lockstep.
   const bool red = p.csum_f != nullptr || p.red_d != nullptr;  // (own instantiation: neither profiled nor clustered)
-  bool cl2 = !red && p.n_tiles >= 2 && (p.n_tiles & 1) == 0 &&
-             (g_fwd_cl2 == 1 || (g_fwd_cl2 == 2 && p.ext_rows == 0));
+  int clm = 0;
+  if (!red && p.n_tiles >= 2 && (p.n_tiles & 1) == 0 && (g_fwd_cl2 == 1 || (g_fwd_cl2 == 2 && p.ext_rows == 0)))
+    clm = 1;
+  if (!red && g_fwd_clw >= 1 && p.n_tiles == 1 && p.m_tiles >= 2 && p.items_per_tile >= 2) clm = 2;
+  if (!red && g_fwd_clw >= 2 && p.m_tiles >= 2 && p.items_per_tile >= 2 && p.ext_rows == 0) clm = 2;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cudaLaunchAttribute attr[1];
   cfg.blockDim = dim3(kFwdThreads, 1, 1);
   cfg.dynamicSmemBytes = (size_t)smem;
   cfg.stream = stream;
-  if (cl2) {
+  if (clm) {
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
@@ -1183,18 +1225,19 @@ int launch_fwd(FwdParams& p, cudaStream_t stream) {
     if (!g_max_clusters_set[dev]) {
       cfg.gridDim = dim3(2 * (num_sms() / 2), 1, 1);
       int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, fwd_kernel_for(p.w_mn != 0, false, true, false), &cfg) != cudaSuccess) {
+      if (cudaOccupancyMaxActiveClusters(&n, fwd_kernel_for(p.w_mn != 0, false, 1, false), &cfg) != cudaSuccess) {
         cudaGetLastError();
         n = 0;
       }
       g_max_clusters[dev] = n;
       g_max_clusters_set[dev] = true;
     }
-    if (g_max_clusters[dev] < 1) cl2 = false;
+    if (g_max_clusters[dev] < 1) clm = 0;
   }
-  const int units = cl2 ? p.m_tiles * (p.n_tiles / 2) : p.m_tiles * p.n_tiles;
+  const int units = clm == 1 ? p.m_tiles * (p.n_tiles / 2)
+                             : (clm == 2 ? ((p.m_tiles + 1) / 2) * p.n_tiles : p.m_tiles * p.n_tiles);
   int grid;
-  if (cl2) {
+  if (clm) {
     const int nc = units < g_max_clusters[cur_dev()] ? units : g_max_clusters[cur_dev()];
     grid = 2 * nc;
   } else {
@@ -1204,7 +1247,7 @@ int launch_fwd(FwdParams& p, cudaStream_t stream) {
   }
   cfg.gridDim = dim3(grid, 1, 1);
   gemm_timer_begin(stream);
-  MPU_CUDA(cudaLaunchKernelEx(&cfg, fwd_kernel_for(p.w_mn != 0, p.dbg != nullptr && !red, cl2, red), p));
+  MPU_CUDA(cudaLaunchKernelEx(&cfg, fwd_kernel_for(p.w_mn != 0, p.dbg != nullptr && !red, clm, red), p));
   gemm_timer_end(stream);
   count_launch();
   MPU_CUDA(cudaGetLastError());
