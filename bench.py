@@ -262,6 +262,7 @@ def predict_config(args, where):
     return {"workload": "mp predict of one synthetic %d^3 x 1ch volume: 6 views x %d planes of %dx%d, U-Net inference "
                         "(complexity_factor %g, %d classes) + nearest mapping + fusion + argmax" % (
                             args.dim, args.dim + 20, args.dim, args.dim, args.cf, args.classes), "where": where,
+            "planes_per_inference_call": getattr(args, "predict_batch", None),
             "l2_policy": "every view streams >2 GB of activations; no explicit flush"}
 
 
@@ -422,6 +423,9 @@ def main():
     ap.add_argument("--cf", type=float, default=2.0)
     ap.add_argument("--dim", type=int, default=256)
     ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--predict-batch", type=int, default=92,
+                    help="planes per U-Net inference call of --workload predict (276 planes per view = 3 x 92: fuller "
+                         "waves of the persistent GEMM kernels on the coarse levels than 32-plane calls)")
     ap.add_argument("--classes", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
@@ -474,7 +478,8 @@ def main():
             dist.destroy_process_group()
         return
 
-    model = UNet(n_classes=args.classes, dim=dim, n_channels=1, complexity_factor=args.cf, max_batch=B,
+    model = UNet(n_classes=args.classes, dim=dim, n_channels=1, complexity_factor=args.cf,
+                 max_batch=args.predict_batch if args.workload == "predict" else B,
                  training=args.workload == "train", seed=0, device=dev)
     if args.workload == "predict":
         clocks = ClockSampler(local) if rank == 0 else None

@@ -68,7 +68,10 @@ def entry_func(args=None):
         images = [loader.get(i) for i in D.shard(list(range(len(loader))))]  # independent volumes shard
     views = np.load(os.path.join(base_dir, "views.npz"))["arr_0"]
     weights = get_best_model(os.path.join(base_dir, "model"))
-    model = models.__dict__[build["model_class_name"]](max_batch=32, training=False, **build)
+    # 92 planes per inference call (a 256-plane-wide stack has 276 planes = 3 x 92): fuller waves of the persistent GEMM
+    # kernels on the coarse levels than with 32 (bench.py --workload predict --predict-batch)
+    model = models.__dict__[build["model_class_name"]](max_batch=int(os.environ.get("MPU_PREDICT_BATCH", "92")),
+                                                       training=False, **build)
     model.load_weights(weights)
     W = b = None
     if not a.sum_fusion:
