@@ -182,3 +182,70 @@ def test_fusion_model_is_the_references_own():
         ref_loss = float(M.loss(y, p64)) + sum(lay.regularization_losses())
         assert abs(ref_loss - loss) < 1e-7
         assert abs(float(M.loss(y.reshape(-1), p64)) - float(M.loss(y, p64))) < 1e-12   # [N] and [N, 1] labels
+
+
+def test_auditor_equals_reference(tmp_path):
+    """The reference's Auditor (image/auditor.py:73-260, unmodified; nibabel.load replaced by an adapter over NIfTI files
+    laid out from the specification) against the package's: sample dim, real-space span, channels, classes - incl. a
+    case where the span is shrunk (nearest valid dim < 0.9 x span / resolution) and multi-channel volumes."""
+    import sys
+    import types
+    from oracle import ref_shim
+    from test_image_pair_cpu import nifti1_bytes
+    from multiplanarunet_b200.image import Auditor
+    from multiplanarunet_b200.image.nifti import read_nifti
+    ref_shim.install()
+
+    class _Hdr(dict):
+        def get_zooms(self):
+            return tuple(self["pixdim"][1:4])
+
+    class _Img(object):
+        def __init__(self, path):
+            self._data, self.affine, h = read_nifti(path)
+            self.shape = self._data.shape
+            self.header = _Hdr(pixdim=np.asarray(h["pixdim"], dtype=np.float32))
+
+        def get_data_dtype(self):
+            return self._data.dtype
+
+        def get_data(self):
+            return self._data
+
+        get_fdata = get_data
+
+    nib = sys.modules["nibabel"]
+    saved = nib.load
+    nib.load = _Img
+    try:
+        import importlib
+        ref_auditor = importlib.import_module("mpunet.image.auditor")
+        rng = np.random.RandomState(5)
+        cases = [
+            ([((96, 110, 80), (1.0, 1.0, 1.5)), ((128, 100, 90), (0.9, 0.9, 1.2))], 1),
+            ([((300, 280, 40), (0.5, 0.5, 4.0)), ((256, 256, 36), (0.6, 0.6, 4.5)), ((320, 300, 44), (0.45, 0.45, 4.0))], 1),
+            ([((64, 64, 64), (2.0, 2.0, 2.0))], 3),
+            ([((700, 650, 600), (1.0, 1.0, 1.0))], 1),      # span / res far above max_dim: the span is shrunk
+        ]
+        for ci, (vols, n_ch) in enumerate(cases):
+            ims, labs = [], []
+            for vi, (shape, pix) in enumerate(vols):
+                small = tuple(max(4, s // 16) for s in shape)       # keep the files tiny: scale voxel size up instead
+                pix_s = tuple(p * s / q for p, s, q in zip(pix, shape, small))
+                data = rng.randn(*(small + ((n_ch,) if n_ch > 1 else ()))).astype(np.float64)
+                aff = np.diag(list(pix_s) + [1.0])
+                p_im = tmp_path / ("c%d_im%d.nii" % (ci, vi))
+                p_im.write_bytes(nifti1_bytes(data, aff))
+                lab = rng.randint(0, 4 + ci, size=small).astype(np.float64)
+                lab.flat[:4 + ci] = np.arange(4 + ci)                # every class present
+                p_lab = tmp_path / ("c%d_lab%d.nii" % (ci, vi))
+                p_lab.write_bytes(nifti1_bytes(lab, aff))
+                ims.append(str(p_im))
+                labs.append(str(p_lab))
+            ref = ref_auditor.Auditor(ims, labs, logger=lambda *a, **k: None)
+            mine = Auditor(ims, labs)
+            assert mine.sample_dim_2D == int(ref.sample_dim_2D), ci
+            assert abs(mine.real_space_span_2D - float(ref.real_space_span_2D)) < 1e-4 * float(ref.real_space_span_2D), ci
+            assert mine.n_channels == ref.n_channels == n_ch and mine.n_classes == ref.n_classes == 4 + ci
+    finally:
+        nib.load = saved
