@@ -17,11 +17,17 @@ def _models_in(model_dir):
 
 
 def get_best_model(model_dir):
-    """Highest val_dice in `@epoch_XX_val_dice_Y` names, else model_weights (utils.py:88-110)."""
+    """Best checkpoint by the reference's rule (utils.py:88-110): the first of the name patterns `@epoch*val_dice*`
+    (highest score), `@epoch*val_loss*` (lowest), `@epoch*dice*` (highest), `@epoch*loss*` (lowest) that matches any
+    file decides; the score is the first decimal number in the file name; otherwise `model_weights.*`."""
+    if len(os.listdir(model_dir)) == 0:
+        raise OSError("Model dir {} is empty.".format(model_dir))
     models = _models_in(model_dir)
-    if models:
-        scores = [float(re.findall(r"val_dice_(\d+\.\d+)", os.path.basename(m))[0]) for m in models]
-        return os.path.abspath(models[int(np.argmax(scores))])
+    for key, pick in (("val_dice", np.argmax), ("val_loss", np.argmin), ("dice", np.argmax), ("loss", np.argmin)):
+        cand = [m for m in models if key in os.path.basename(m)]
+        if cand:
+            scores = [float(re.findall(r"(\d+[.]\d+)", os.path.basename(m))[0]) for m in cand]
+            return os.path.abspath(cand[int(pick(np.array(scores)))])
     for ext in WEIGHT_EXTS:
         p = os.path.join(model_dir, "model_weights" + ext)
         if os.path.exists(p):

@@ -1,5 +1,7 @@
 """Pins the oracle against the LIVE reference source where it is present (this container only; the
 GPU box has no /root/reference, so these tests skip there).  Wider sweep than the golden fixtures."""
+import os
+
 import numpy as np
 import pytest
 
@@ -249,3 +251,40 @@ def test_auditor_equals_reference(tmp_path):
             assert mine.n_channels == ref.n_channels == n_ch and mine.n_classes == ref.n_classes == 4 + ci
     finally:
         nib.load = saved
+
+
+def test_view_sampling_and_model_selection_equal_reference(ref, tmp_path):
+    """Host helpers on the path of `mp train` / `mp predict`, against the reference functions themselves:
+    sample_random_views_with_angle_restriction (sample_grid.py:133-173; same RNG consumption => identical views.npz for a
+    seed), get_best_model / get_last_model (utils/utils.py:88-130) over checkpoint-name layouts."""
+    import importlib
+    from multiplanarunet_b200.interpolation import sample_random_views_with_angle_restriction
+    from multiplanarunet_b200.utils.utils import get_best_model, get_last_model
+    for seed, n, ang in [(0, 6, 60), (1, 6, 60), (2, 3, 75), (3, 9, 40)]:
+        np.random.seed(seed)
+        want = ref.sample_grid.sample_random_views_with_angle_restriction(n, ang, logger=lambda *a, **k: None)
+        np.random.seed(seed)
+        got = sample_random_views_with_angle_restriction(n, ang)
+        assert np.array_equal(got, want)
+    ru = importlib.import_module("mpunet.utils")
+    layouts = [
+        ["@epoch_03_val_dice_0.71230.h5", "@epoch_10_val_dice_0.80011.h5", "@epoch_07_val_dice_0.79000.h5"],
+        ["@epoch_02_val_loss_0.91000.h5", "@epoch_05_val_loss_0.35000.h5"],
+        ["@epoch_04_dice_0.50000.h5", "@epoch_09_dice_0.45000.h5"],
+        ["@epoch_01_loss_1.25000.h5", "@epoch_12_loss_0.75000.h5", "model_weights.h5"],
+        ["model_weights.h5"],
+    ]
+    for i, names in enumerate(layouts):
+        d = tmp_path / ("m%d" % i)
+        d.mkdir()
+        for nme in names:
+            (d / nme).write_bytes(b"x")
+        assert os.path.basename(get_best_model(str(d))) == os.path.basename(ru.get_best_model(str(d)))
+        mine, theirs = get_last_model(str(d)), ru.get_last_model(str(d))
+        assert os.path.basename(mine[0]) == os.path.basename(theirs[0]) and int(mine[1]) == int(theirs[1])
+    empty = tmp_path / "empty"
+    empty.mkdir()
+    with pytest.raises(OSError):
+        get_best_model(str(empty))
+    with pytest.raises(OSError):
+        ru.get_best_model(str(empty))
