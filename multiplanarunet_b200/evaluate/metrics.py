@@ -91,20 +91,12 @@ def dice_all(y_true, y_pred, smooth=1.0, n_classes=None, ignore_zero=True, skip_
 
 
 def compute_dice(tp, rel, sel):
-    """precision / recall / dice per class from accumulated counts, zero where undefined
-    (callbacks/validation.py:60-90)."""
-    tp = np.asarray(tp)
-    rel = np.asarray(rel)
-    sel = np.asarray(sel)
-    sel_mask = sel > 0
-    rel_mask = rel > 0
-    precisions = np.zeros(shape=tp.shape, dtype=np.float32)
-    recalls = np.zeros_like(precisions)
-    dices = np.zeros_like(precisions)
-    precisions[sel_mask] = tp[sel_mask] / sel[sel_mask]
-    recalls[rel_mask] = tp[rel_mask] / rel[rel_mask]
-    intrs = 2 * precisions * recalls
-    union = precisions + recalls
-    m = union > 0
-    dices[m] = intrs[m] / union[m]
-    return precisions, recalls, dices
+    """Per-class precision tp / sel, recall tp / rel and their harmonic mean (dice) from accumulated confusion counts;
+    a class without selected (relevant) pixels gets precision (recall) 0, and dice 0 when both vanish.  float32 results,
+    bit-equal to `Validation._compute_dice` (callbacks/validation.py:60-90; pinned in tests/test_oracle_vs_reference.py)."""
+    tp, rel, sel = (np.asarray(a, dtype=np.float64) for a in (tp, rel, sel))
+    precision = np.divide(tp, sel, out=np.zeros_like(tp), where=sel > 0).astype(np.float32)
+    recall = np.divide(tp, rel, out=np.zeros_like(tp), where=rel > 0).astype(np.float32)
+    both = precision + recall
+    dice = np.divide(2 * precision * recall, both, out=np.zeros_like(both), where=both > 0)
+    return precision, recall, dice

@@ -288,3 +288,49 @@ def test_view_sampling_and_model_selection_equal_reference(ref, tmp_path):
         get_best_model(str(empty))
     with pytest.raises(OSError):
         ru.get_best_model(str(empty))
+
+
+def test_validation_metrics_equal_reference():
+    """compute_dice against the reference's Validation._compute_dice (callbacks/validation.py:60-90, loaded from its own
+    file with a stub for tensorflow.keras.callbacks.Callback), bit for bit, incl. classes without relevant / selected
+    pixels; and the confusion counts of its counting thread (:91-131) against the oracle's integer counts."""
+    import queue
+    import sys
+    import threading
+    import types
+    from collections import defaultdict
+    from oracle import keras_shim, metrics as ometrics
+    from multiplanarunet_b200.evaluate.metrics import compute_dice
+    keras_shim.install()
+    cb = types.ModuleType("tensorflow.keras.callbacks")
+    cb.Callback = type("Callback", (object,), {})
+    sys.modules["tensorflow.keras.callbacks"] = cb
+    sys.modules["tensorflow.keras"].callbacks = cb
+    em = keras_shim._load_reference_file("mpunet/evaluate/metrics.py", "_ref_evaluate_metrics")
+    pkg = sys.modules.setdefault("mpunet.evaluate", types.ModuleType("mpunet.evaluate"))
+    pkg.dice_all = em.dice_all
+    sys.modules["mpunet.evaluate.metrics"] = em
+    val = keras_shim._load_reference_file("mpunet/callbacks/validation.py", "_ref_callbacks_validation")
+    rng = np.random.RandomState(9)
+    for n_classes in (2, 5, 9):
+        rel = rng.randint(0, 5000, n_classes).astype(np.uint64)
+        sel = rng.randint(0, 5000, n_classes).astype(np.uint64)
+        rel[rng.randint(n_classes)] = 0
+        sel[rng.randint(n_classes)] = 0
+        tp = np.minimum(rel, sel) // 2
+        want = val.Validation._compute_dice(tp=tp, rel=rel, sel=sel)
+        got = compute_dice(tp=tp, rel=rel, sel=sel)
+        for w, g in zip(want, got):
+            assert g.dtype == w.dtype == np.float32 and np.array_equal(g, w)
+    # the counting thread of the reference on two batches == the oracle's counts
+    n_classes = 4
+    q = queue.Queue()
+    preds = [rng.rand(3, 16, 16, n_classes).astype(np.float32) for _ in range(2)]
+    trues = [rng.randint(0, n_classes, (3, 16, 16, 1)).astype(np.uint8) for _ in range(2)]
+    for p, t in zip(preds, trues):
+        q.put(([p], [t]))
+    TPs, relv, selv = (defaultdict(lambda: np.zeros(n_classes, np.uint64)) for _ in range(3))
+    val.Validation._count_cm_elements_from_queue(q, 2, TPs, relv, selv, ["t"], [n_classes], threading.Lock())
+    tp2, rel2, sel2 = ometrics.cm_counts(np.concatenate([t.ravel() for t in trues]),
+                                        np.concatenate([p.argmax(-1).ravel() for p in preds]), n_classes)
+    assert np.array_equal(TPs["t"], tp2) and np.array_equal(relv["t"], rel2) and np.array_equal(selv["t"], sel2)
