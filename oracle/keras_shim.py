@@ -449,6 +449,9 @@ def install():
     regularizers = types.ModuleType("tensorflow.keras.regularizers")
     regularizers.l2 = _L2
     layers.Layer = KerasLayer
+    # any other layer name (Cropping3D, Conv3D ... of the model families outside the hot path) resolves to an inert
+    # placeholder class, so that reference modules which merely IMPORT those families can be loaded (PEP 562)
+    layers.__getattr__ = lambda name: type(name, (Layer,), {})
     initializers = types.ModuleType("tensorflow.keras.initializers")
     initializers.constant = _constant
     losses = types.ModuleType("tensorflow.keras.losses")

@@ -334,3 +334,41 @@ def test_validation_metrics_equal_reference():
     tp2, rel2, sel2 = ometrics.cm_counts(np.concatenate([t.ravel() for t in trues]),
                                         np.concatenate([p.argmax(-1).ravel() for p in preds]), n_classes)
     assert np.array_equal(TPs["t"], tp2) and np.array_equal(relv["t"], rel2) and np.array_equal(selv["t"], sel2)
+
+
+def test_cli_flags_and_defaults_equal_reference():
+    """Every `mp` script on the path exposes exactly the reference's command-line surface: the same option strings,
+    argparse action types and defaults (mpunet/bin/{train,predict,train_fusion,init_project,predict_3D}.py parsers,
+    imported from the reference under the shim and compared field by field)."""
+    import importlib
+    import sys
+    import types
+    from oracle import keras_shim
+    keras_shim.install()
+    if "ruamel" not in sys.modules:      # hyperparameters/hparams.py imports it at module level; not needed by the parsers
+        ry = types.ModuleType("ruamel.yaml")
+        ry.YAML = type("YAML", (object,), {})
+        rm = types.ModuleType("ruamel")
+        rm.yaml = ry
+        sys.modules["ruamel"], sys.modules["ruamel.yaml"] = rm, ry
+
+    def surface(parser):
+        return {(a.option_strings[0] if a.option_strings else a.dest): (tuple(a.option_strings), type(a).__name__,
+                                                                        a.default, a.nargs, a.type)
+                for a in parser._actions if a.dest != "help"}
+
+    checked = 0
+    for name, fn in [("train", "get_argparser"), ("predict", "get_argparser"), ("train_fusion", "get_argparser"),
+                     ("init_project", "get_parser"), ("predict_3D", "get_argparser")]:
+        try:
+            ref_mod = importlib.import_module("mpunet.bin." + name)
+        except Exception as e:  # a model family outside the path failed to import under the shim
+            if name in ("train", "predict"):
+                raise
+            continue
+        mine = importlib.import_module("multiplanarunet_b200.bin." + name)
+        want = surface(getattr(ref_mod, fn)())
+        got = surface(getattr(mine, fn if hasattr(mine, fn) else "get_argparser")())
+        assert got == want, (name, {k: (want.get(k), got.get(k)) for k in set(want) | set(got) if want.get(k) != got.get(k)})
+        checked += 1
+    assert checked >= 4
