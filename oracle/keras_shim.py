@@ -460,6 +460,16 @@ def install():
                       ("initializers", initializers), ("losses", losses)):
         sys.modules["tensorflow.keras." + name] = mod
         setattr(keras, name, mod)
+    # inert stand-ins for the keras sub-modules that reference modules outside the arithmetic path import at load time
+    # (callbacks, optimizers, metrics, activations, backend ...): any attribute resolves to a placeholder class
+    for name in ("callbacks", "optimizers", "metrics", "activations", "backend", "utils"):
+        mod = sys.modules.get("tensorflow.keras." + name) or types.ModuleType("tensorflow.keras." + name)
+        if "__getattr__" not in mod.__dict__:
+            mod.__getattr__ = lambda attr, _m=name: type(attr, (object,), {})
+        sys.modules["tensorflow.keras." + name] = mod
+        setattr(keras, name, mod)
+    if "__getattr__" not in losses.__dict__:
+        losses.__getattr__ = lambda attr: type(attr, (object,), {})
     tf.keras = keras
     _tf_ops(tf)
     for name in ("tensorflow.python", "tensorflow.python.keras"):
