@@ -378,3 +378,58 @@ def test_cli_flags_and_defaults_equal_reference():
         assert got == want, (name, {k: (want.get(k), got.get(k)) for k in set(want) | set(got) if want.get(k) != got.get(k)})
         checked += 1
     assert checked == 5, checked
+
+
+def test_output_bias_initialisation_equals_reference():
+    """set_bias_weights (utils/utils.py:205-242: bias of the softmax layer from class frequencies, biased_output_layer of
+    train_hparams.yaml) against the reference function, on given class counts and on counts estimated from label maps."""
+    import contextlib
+    import importlib
+    from multiplanarunet_b200.utils.utils import set_bias_weights
+    from oracle import ref_shim
+    ref_shim.install()
+    if not hasattr(np, "int"):
+        np.int = int  # utils.py:221 (removed in numpy 1.24; the reference pins an older numpy)
+    ru = importlib.import_module("mpunet.utils.utils")
+
+    def softmax():
+        pass
+
+    class Lay(object):
+        activation = softmax
+
+        def __init__(self, n):
+            self.w = [np.zeros((1, 1, 8, n), np.float32), np.zeros(n, np.float32)]
+
+        def get_weights(self):
+            return [w.copy() for w in self.w]
+
+        def set_weights(self, ws):
+            self.w = [np.asarray(w) for w in ws]
+
+    class Img(object):
+        def __init__(self, lab):
+            self.labels = lab
+
+    class Queue(object):                         # what the reference's estimate path needs from a data queue
+        def __init__(self, images):
+            self.dataset, self._i = images, 0
+
+        @contextlib.contextmanager
+        def get_random_image(self):
+            im = self.dataset[self._i % len(self.dataset)]
+            self._i += 1
+            yield im
+
+    quiet = lambda *a, **k: None
+    for counts in ([700, 120, 90, 60, 30], [1, 1], [10 ** 9, 5, 7]):
+        a, b = Lay(len(counts)), Lay(len(counts))
+        ru.set_bias_weights(a, None, class_counts=np.asarray(counts), logger=quiet)
+        set_bias_weights(b, None, class_counts=np.asarray(counts), logger=quiet)
+        assert np.allclose(a.w[-1], b.w[-1], rtol=1e-6, atol=1e-7) and abs(np.linalg.norm(b.w[-1]) - 1.0) < 1e-6
+    rng = np.random.RandomState(2)
+    images = [Img(rng.randint(0, 4, (6, 7, 5)).astype(np.uint8)) for _ in range(3)]
+    a, b = Lay(4), Lay(4)
+    ru.set_bias_weights(a, Queue(images), logger=quiet)
+    set_bias_weights(b, images, logger=quiet)
+    assert np.allclose(a.w[-1], b.w[-1], rtol=1e-6, atol=1e-7)
