@@ -661,19 +661,35 @@ __global__ void __launch_bounds__(kThreads, 1)
   // Two regions: CTAs of the FULL ci tiles (CA atoms) first, then those of the partial last ci tile (fewer atoms:
   // less work per K block), which get correspondingly longer K ranges so that every CTA of the grid
   // runs for about the same time (wgrad_setup sizes both so that the grid fills whole waves).
+  // With an order table (wgrad_setup) consecutive groups of ngroups x co_tiles CTAs are (ci tile, K split) entries
+  // sorted by the first pixel row they read, partial-tile entries interleaved with the full ones: launched last, as a
+  // separate region, the partial tile's CTAs re-read the whole dY tensor from DRAM long after the full tiles streamed
+  // it (level 1: 850 MB per launch for 400 MB of operands, profiles/r02_launches_trainstep_traffic.csv).
   int w = blockIdx.x;
-  const int n_region1 = p.ngroups * p.co_tiles * p.ci_tiles_full * p.splits;
-  const bool part = w >= n_region1;
-  if (part) w -= n_region1;
-  const int gi = w % p.ngroups;   w /= p.ngroups;
-  const int co_t = w % p.co_tiles; w /= p.co_tiles;
-  int ci_t, split;
-  if (!part) {
-    ci_t = w % p.ci_tiles_full;
-    split = w / p.ci_tiles_full;
+  bool part;
+  int gi, co_t, ci_t, split;
+  if (p.n_entries > 0) {
+    const int per = p.ngroups * p.co_tiles;
+    const uint32_t ent = p.order[w / per];
+    w %= per;
+    gi = w % p.ngroups;
+    co_t = w / p.ngroups;
+    part = (ent >> 31) != 0;
+    ci_t = part ? p.ci_tiles_full : (int)((ent >> 16) & 0x7fffu);
+    split = (int)(ent & 0xffffu);
   } else {
-    ci_t = p.ci_tiles_full;
-    split = w;
+    const int n_region1 = p.ngroups * p.co_tiles * p.ci_tiles_full * p.splits;
+    part = w >= n_region1;
+    if (part) w -= n_region1;
+    gi = w % p.ngroups;   w /= p.ngroups;
+    co_t = w % p.co_tiles; w /= p.co_tiles;
+    if (!part) {
+      ci_t = w % p.ci_tiles_full;
+      split = w / p.ci_tiles_full;
+    } else {
+      ci_t = p.ci_tiles_full;
+      split = w;
+    }
   }
   const int kbps = part ? p.kblocks_per_split_part : p.kblocks_per_split;
   const WgradGroup& grp = p.groups[gi];
@@ -1371,6 +1387,34 @@ int wgrad_setup(WgradParams& p, const WgradDesc& d) {
   }
   p.splits = ceil_div(p.kblocks, p.kblocks_per_split);
   p.splits_part = units_part ? ceil_div(p.kblocks, p.kblocks_per_split_part) : 0;
+  // launch order of the (ci tile, K split) entries: by first K block, partial-tile entries interleaved
+  p.n_entries = 0;
+  {
+    static int no_order = -1;  // MPU_WG_NO_ORDER=1: partial-tile CTAs as a separate region at the end (same-box A/B)
+    if (no_order < 0) {
+      const char* e = getenv("MPU_WG_NO_ORDER");
+      no_order = e ? atoi(e) : 0;
+    }
+    const int n = p.ci_tiles_full * p.splits + p.splits_part;
+    if (!no_order && p.splits_part > 0 && n <= kWgMaxEntries && p.splits < 65536 && p.ci_tiles_full < 32768) {
+      struct Ent { int kb0; uint32_t code; };
+      Ent ents[kWgMaxEntries];
+      int m = 0;
+      for (int sp = 0; sp < p.splits; ++sp)
+        for (int ct = 0; ct < p.ci_tiles_full; ++ct)
+          ents[m++] = {sp * p.kblocks_per_split, ((uint32_t)ct << 16) | (uint32_t)sp};
+      for (int sp = 0; sp < p.splits_part; ++sp)
+        ents[m++] = {sp * p.kblocks_per_split_part, 0x80000000u | (uint32_t)sp};
+      for (int i = 1; i < m; ++i)  // stable insertion sort by first K block (full tiles before the partial one on ties)
+        for (int j = i; j > 0 && ents[j].kb0 < ents[j - 1].kb0; --j) {
+          const Ent t = ents[j];
+          ents[j] = ents[j - 1];
+          ents[j - 1] = t;
+        }
+      for (int i = 0; i < m; ++i) p.order[i] = ents[i].code;
+      p.n_entries = m;
+    }
+  }
   p.dW = d.dW;
   p.ldw = d.ldw;
   p.w_rows_per_tap = d.w_rows_per_tap;

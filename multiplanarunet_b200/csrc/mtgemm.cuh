@@ -105,6 +105,8 @@ struct WgradGroup {
   int w_idx[3];                  // tap index inside dW
 };
 
+constexpr int kWgMaxEntries = 512;
+
 struct WgradParams {
   CUtensorMap tmX, tmDY;         // X box {64 ch, 72 rows}; dY box {64 ch, 64 rows}
   int ngroups;
@@ -126,6 +128,8 @@ struct WgradParams {
   int stages;
   int BN;                        // unused (kept for the bring-up API)
   long long* dbg;                // optional [8] role timings of CTA 0 (bring-up profiling, see the kernel)
+  int n_entries;                 // > 0: launch order table below is used (else full tiles first, partial tile last)
+  uint32_t order[kWgMaxEntries]; // per group of ngroups x co_tiles CTAs: bit 31 partial tile, bits 16-30 ci tile, 0-15 split
 };
 
 struct WgradDesc {
