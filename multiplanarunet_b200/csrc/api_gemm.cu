@@ -135,4 +135,32 @@ int mpu_mtgemm_wgrad(const void* X, long long rowsX, int Cx, int ldX, const void
   return launch_wgrad(p, reinterpret_cast<cudaStream_t>(stream));
 }
 
+// Bring-up / test entry (not part of include/mpunet_b200.h): the work decomposition wgrad_setup would choose for a
+// weight-gradient GEMM of these shapes, without touching a device.  out[0..11] = grid, splits, splits_part,
+// kblocks_per_split, kblocks_per_split_part, kblocks, ci_tiles_full, ci_tiles, co_tiles, ngroups, n_entries, CA;
+// out[12 .. 12 + n_entries) = the launch-order table.  `out` holds at least 12 + 512 ints.
+int mpu_debug_wgrad_plan(int Cx, int Cy, long long rows_total, int ntaps, const int* tap_x_off, const int* tap_dy_off,
+                         int* out) {
+  if (!out || !tap_x_off || ntaps < 1 || ntaps > kMaxTaps) {
+    set_error("mpu_debug_wgrad_plan: bad arguments");
+    return MPU_ERR_ARG;
+  }
+  int widx[kMaxTaps];
+  for (int t = 0; t < ntaps; ++t) widx[t] = t;
+  WgradDesc d;
+  memset(&d, 0, sizeof(d));
+  d.Cx = Cx; d.Cy = Cy; d.ntaps = ntaps;
+  d.tap_x_off = tap_x_off; d.tap_dy_off = tap_dy_off; d.tap_w = widx;
+  d.rows_total = rows_total;
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  MPU_TRY(wgrad_plan(p, d));
+  out[0] = p.co_tiles * p.ngroups * (p.ci_tiles_full * p.splits + (p.ci_tiles - p.ci_tiles_full) * p.splits_part);
+  out[1] = p.splits; out[2] = p.splits_part; out[3] = p.kblocks_per_split; out[4] = p.kblocks_per_split_part;
+  out[5] = p.kblocks; out[6] = p.ci_tiles_full; out[7] = p.ci_tiles; out[8] = p.co_tiles; out[9] = p.ngroups;
+  out[10] = p.n_entries; out[11] = p.CA;
+  for (int i = 0; i < p.n_entries; ++i) out[12 + i] = (int)p.order[i];
+  return MPU_OK;
+}
+
 }  // extern "C"

@@ -1282,6 +1282,13 @@ int wgrad_setup(WgradParams& p, const WgradDesc& d) {
   }
   MPU_TRY(make_tmap_2d(&p.tmX, d.X, (uint64_t)d.rowsX, (uint64_t)d.Cx, (uint64_t)d.ldX, 64, kWgSlabRows));
   MPU_TRY(make_tmap_2d(&p.tmDY, d.dY, (uint64_t)d.rowsDY, (uint64_t)d.Cy, (uint64_t)d.ldDY, 64, 64));
+  return wgrad_plan(p, d);
+}
+
+// Work decomposition of one weight-gradient GEMM (tap groups, tiles, split-K sizing, launch order): pure host
+// arithmetic on the shapes - no device, no tensor maps - so that it can be tested on its own (mpu_debug_wgrad_plan,
+// tests/test_cabi.py).
+int wgrad_plan(WgradParams& p, const WgradDesc& d) {
   // sort taps by (dy_off, x_off); a group = taps of one dY plane at CONSECUTIVE rows (shift 0,1,2):
   // they become the N atoms of one MMA
   int order[kMaxTaps];

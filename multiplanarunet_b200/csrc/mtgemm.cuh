@@ -152,6 +152,7 @@ int fwd_setup(FwdParams& p, const FwdDesc& d);
 int launch_fwd(FwdParams& p, cudaStream_t stream);
 int pick_bn(int n_valid);
 int wgrad_setup(WgradParams& p, const WgradDesc& d);
+int wgrad_plan(WgradParams& p, const WgradDesc& d);   // the shape-only part of wgrad_setup (p zero-initialised)
 int launch_wgrad(WgradParams& p, cudaStream_t stream);
 int num_sms();
 
